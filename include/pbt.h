@@ -1,0 +1,272 @@
+/*
+ * pbt.h — C-ABI of libpbt.so, the B200 (sm_100a) native library behind the
+ * patch-based-training hot path (GeneratorJ forward/backward, masked patch
+ * sampler, full-frame inference).
+ *
+ * The reference (Mega-Gorilla/Video-to-Video_Few-Shot-Patch-Based-Training) is
+ * pure Python and has NO FFI layer of its own; every entry point below states
+ * the reference call site (file:line, relative to the reference root) whose
+ * arithmetic it replaces.  INTEGRATION.md shows the ctypes binding a reference
+ * maintainer would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch / C++ types cross this boundary
+ *  - every device pointer is owned by the caller (PyTorch allocates); the
+ *    library allocates nothing and keeps no state
+ *  - all work is enqueued on the caller's stream (a cudaStream_t passed as
+ *    void*); no call synchronises; all are CUDA-graph capturable
+ *  - return value: 0 = ok, negative = pbt_status error (pbt_error_string)
+ *  - there is no CPU fallback: without a CUDA device every compute call
+ *    returns PBT_ERR_CUDA
+ *
+ * Activation layout "P8" (planar, 8-channel interleaved, 16-bit elements):
+ *      act[n][c/8][y][x][c%8]        C is a multiple of 8
+ * i.e. each group of 8 channels is one H*W plane of 16-byte pixels.  A view
+ * onto a channel range of a wider tensor is expressed by offsetting `ptr` by
+ * whole planes and keeping the parent's `img_stride`.
+ * fp32 tensors in "P8F" layout use the same indexing with 4-byte elements.
+ */
+#ifndef PBT_H_
+#define PBT_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PBT_ABI_VERSION 1
+
+typedef enum {
+  PBT_OK = 0,
+  PBT_ERR_ARG = -1,      /* bad shape / alignment / enum */
+  PBT_ERR_CUDA = -2,     /* CUDA runtime or driver error (incl. no device) */
+  PBT_ERR_UNSUPPORTED = -3,
+  PBT_ERR_SMEM = -4      /* configuration does not fit shared/tensor memory */
+} pbt_status;
+
+typedef enum { PBT_BF16 = 0, PBT_FP16 = 1 } pbt_dtype;
+typedef enum { PBT_ACT_NONE = 0, PBT_ACT_RELU = 1, PBT_ACT_LEAKY02 = 2 } pbt_act_kind;
+
+/* 16-bit P8 activation view. */
+typedef struct {
+  void*   ptr;         /* device pointer, 16-byte aligned; NULL = absent */
+  int32_t n, c, h, w;  /* c multiple of 8 */
+  int64_t img_stride;  /* elements between consecutive images */
+} pbt_act_t;
+
+int         pbt_abi_version(void);
+const char* pbt_error_string(int status);
+/* last CUDA error text seen by this thread's most recent failing call */
+const char* pbt_last_cuda_error(void);
+
+/* ------------------------------------------------------------------------
+ * Convolution as implicit GEMM on tcgen05 tensor cores (TMA-fed, TMEM fp32
+ * accumulators).  Replaces every nn.Conv2d of GeneratorJ:
+ *   src/models/generator.py:41,49 (ResNetBlock), :126 (conv11), :133,136
+ *   (smoothers), :141 (output, fused as `head`), :171 (_make_conv_block),
+ *   :200 (_make_upconv_block).
+ * One entry point serves forward and dgrad (dgrad = the same stride-1 conv
+ * with tap-flipped, channel-transposed packed weights).
+ *
+ * The conv is stride 1 with explicit top/left padding; output spatial size ==
+ * input spatial size.  Stride-2 layers are expressed by the caller as 2x2
+ * stride-1 convs over a space-to-depth input (see pbt_norm_apply s2d output).
+ *
+ * Packed weights (`wpack`, 16-bit): for channel block cb (blk_c channels,
+ * last block may be shorter), tap t = ky*kw+kx:
+ *      w[cb][t][k/8][cout][k%8]      k = channel inside the block
+ * `blk_c` must be 16, 32 or 64 and a multiple of 16; cin multiple of 16.
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  pbt_act_t   in;            /* [n, cin, h, w] */
+  const void* wpack;
+  int32_t     cout;          /* multiple of 16, <= 256 */
+  int32_t     kh, kw, pad_t, pad_l;
+  int32_t     blk_c;         /* channels per K block: 16 / 32 / 64 */
+  int32_t     tiles_per_cta; /* T in {1,2,3}: x-adjacent 8x16 pixel tiles sharing one haloed smem region; (8T+kw-1) <= 32 */
+  int32_t     dtype;         /* pbt_dtype of in / wpack / out / mask */
+  /* epilogue, applied in this order */
+  const float* bias;         /* [cout] or NULL */
+  int32_t      act;          /* pbt_act_kind */
+  const float* post_scale;   /* [cout] affine after act (eval BatchNorm), or NULL */
+  const float* post_shift;
+  pbt_act_t    mask;         /* v = mask>0 ? v : 0 (ReLU backward); ptr NULL = off */
+  const float* addend32;     /* P8F [n,cout,h,w] added before store, or NULL */
+  float*       out32;        /* P8F fp32 store, or NULL */
+  pbt_act_t    out;          /* 16-bit store, ptr NULL = off */
+  float*       stats_partial;/* [n][tiles][2][cout] per-tile (sum, sumsq) of the stored values, or NULL */
+  /* fused 1x1 head: tanh(head_w . v + head_b) -> fp32 NCHW [n,3,h,w]  (src/models/generator.py:141-144) */
+  const float* head_w;       /* [3][cout] or NULL */
+  const float* head_b;       /* [3] */
+  float*       head_out;
+  int32_t      head_tanh;    /* 1 = apply tanh */
+  int32_t      debug_flags;  /* bring-up only; 0 in production */
+} pbt_conv_desc_t;
+
+/* number of stats tiles per image for a given geometry (tiles_x*tiles_y) */
+int pbt_conv_num_tiles(int32_t h, int32_t w, int32_t tiles_per_cta);
+int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Weight gradient: dW[t][ci][co] += sum_pixels X[pix+t][ci] * dY[pix][co]
+ * (autograd of the convs above; fires at lightning_model.py:241).
+ * Output `dw` is fp32 [kh*kw][cin][cout], ACCUMULATED into (caller zeroes),
+ * scaled by *inv_scale (device scalar, NULL = 1).
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  pbt_act_t   x;             /* conv input  [n, cin, h, w] */
+  pbt_act_t   dy;            /* grad of conv output [n, cout, h, w] */
+  int32_t     kh, kw, pad_t, pad_l;
+  int32_t     dtype;
+  float*      dw;            /* fp32 [kh*kw][cin][cout] */
+  const float* inv_scale;
+  int32_t     debug_flags;
+} pbt_wgrad_desc_t;
+int pbt_conv_wgrad(const pbt_wgrad_desc_t* d, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Normalisation statistics (nn.InstanceNorm2d eps 1e-5 affine=False,
+ * src/models/generator.py:36,87,178,204; nn.BatchNorm2d(64) :135).
+ * partial: [n][tiles][2][c] from pbt_conv_fwd.
+ * instance mode: scale[n][c] = rstd, shift[n][c] = -mean*rstd
+ * batch mode   : statistics pooled over n; scale = gamma*rstd, shift = beta -
+ *                mean*scale written for every n; running_mean/var updated
+ *                (momentum, unbiased var) when non-NULL.
+ * mean_out/rstd_out ([n][c], optional) are kept for the backward pass.
+ * ---------------------------------------------------------------------- */
+int pbt_norm_finalize(const float* partial, int32_t n, int32_t tiles, int32_t c,
+                      int64_t count_per_image, float eps, int32_t batch_mode,
+                      const float* gamma, const float* beta,
+                      float* running_mean, float* running_var, float momentum,
+                      float* scale, float* shift, float* mean_out, float* rstd_out,
+                      void* stream);
+
+/* y = act(x*scale[n][c] + shift[n][c]) (+ residual32); any of the outputs may be absent.
+ * Replaces the InstanceNorm/BatchNorm + LeakyReLU/ReLU + residual add modules
+ * (src/models/generator.py:36-58,93,99,103,116,120,135).
+ * out_s2d (optional) receives the same values space-to-depth'ed:
+ *   [n, 4*c, h/2, w/2], plane = ((y&1)*2+(x&1))*(c/8) + c/8-index. */
+typedef struct {
+  pbt_act_t    x;
+  const float* scale;       /* [n][c] (or [c] when per_channel) ; NULL = identity */
+  const float* shift;
+  int32_t      per_channel; /* 1: scale/shift indexed [c] only */
+  int32_t      act;
+  const float* residual32;  /* P8F or NULL */
+  pbt_act_t    out;         /* 16-bit y */
+  pbt_act_t    out_relu;    /* 16-bit relu(y) */
+  float*       out32;       /* P8F y */
+  pbt_act_t    out_s2d;     /* 16-bit y, space-to-depth */
+  int32_t      dtype;
+} pbt_norm_apply_desc_t;
+int pbt_norm_apply(const pbt_norm_apply_desc_t* d, void* stream);
+
+/* Bilinear x2 upsample, align_corners=True (src/models/generator.py:13), on a P8 view. */
+int pbt_upsample2x(const pbt_act_t* in, const pbt_act_t* out, int32_t dtype, void* stream);
+/* its transpose (autograd): gin[h,w] (16-bit and/or fp32 P8F) = sum of gout[2h,2w] contributions */
+int pbt_upsample2x_bwd(const pbt_act_t* gout, const pbt_act_t* gin16, float* gin32, int32_t dtype, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Backward of (norm -> act [-> + residual]) blocks.
+ *  g = ga (16-bit P8, optionally s2d-indexed) + gb16 + gb32 (any may be absent)
+ *  xhat = x*scale+shift ; gact = g * act'(xhat)
+ *  reduce: sums[n][c] = (sum gact, sum gact*xhat) over h*w   (batch mode: over n too)
+ *  apply : dx = k[n][c] * (gact - s1/cnt - xhat*s2/cnt), k = rstd (instance) or gamma*rstd (batch)
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  pbt_act_t    x;           /* raw conv output saved by the forward pass */
+  const float* scale;       /* as given to pbt_norm_apply */
+  const float* shift;
+  int32_t      per_channel;
+  int32_t      act;
+  pbt_act_t    ga;          /* grad wrt y, 16-bit */
+  int32_t      ga_is_s2d;   /* ga is [n,4c,h/2,w/2] space-to-depth of the logical grad */
+  pbt_act_t    gb16;        /* second 16-bit addend or absent */
+  const float* gb32;        /* fp32 P8F addend or NULL */
+  float*       sums;        /* [n][2][c] (instance) or [2][c] (batch) fp32, zeroed by caller */
+  const float* kmul;        /* [n][c] or [c]: rstd or gamma*rstd */
+  int64_t      count;       /* elements per statistic (h*w or n*h*w) */
+  int32_t      batch_mode;
+  pbt_act_t    dx;          /* 16-bit output of apply */
+  int32_t      dtype;
+} pbt_norm_bwd_desc_t;
+int pbt_norm_bwd_reduce(const pbt_norm_bwd_desc_t* d, void* stream);
+int pbt_norm_bwd_apply(const pbt_norm_bwd_desc_t* d, void* stream);
+
+/* Backward of the fused head (tanh(1x1 conv), src/models/generator.py:141-144) and of the
+ * ReLU in front of it:  gz = gy*(1-y^2)*gscale ; dW[3][c] += gz (x) s ; db += gz ;
+ * gs = (s>0) ? W^T gz : 0 -> 16-bit P8 ; dbias_prev[c] += sum gs (bias grad of the conv that made s).
+ * gy, y: fp32 NCHW [n,3,h,w]; s: P8 [n,c,h,w]; grads fp32 accumulated (caller zeroes),
+ * left multiplied by gscale (undo with inv_scale). */
+int pbt_head_bwd(const float* gy, const float* y, const pbt_act_t* s, const float* head_w,
+                 const float* gscale, int32_t head_tanh,
+                 float* dw, float* db, const pbt_act_t* gs, float* dbias_prev,
+                 int32_t dtype, void* stream);
+
+/* per-channel sum over n,h,w of a 16-bit P8 tensor, accumulated into out[c] times *inv_scale (bias grads) */
+int pbt_channel_sum(const pbt_act_t* g, float* out, const float* inv_scale, int32_t dtype, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Layout / dtype conversion at the module boundary
+ * (GeneratorJ.forward takes NCHW fp32/fp16: src/models/generator.py:210).
+ * ---------------------------------------------------------------------- */
+/* x NCHW (fp32 if src_is_half==0 else fp16) [n,c,h,w] -> P8 `out` (out.c >= c, extra channels zeroed) */
+int pbt_nchw_to_p8(const void* x, int32_t src_is_half, int32_t n, int32_t c, int32_t h, int32_t w,
+                   const pbt_act_t* out, int32_t dtype, void* stream);
+/* P8 (first c channels) -> NCHW fp32 */
+int pbt_p8_to_nchw_f32(const pbt_act_t* in, int32_t c, float* out, float mul, int32_t dtype, void* stream);
+/* P8F fp32 -> NCHW fp32 */
+int pbt_p8f_to_nchw_f32(const float* in, int32_t n, int32_t c_total, int32_t c, int32_t h, int32_t w, float* out, void* stream);
+
+/* uint8 HWC frame -> P8 in [-1,1] : ToTensor + Normalize(0.5,0.5) (generator.py:91-95,584-616) */
+int pbt_u8hwc_to_p8(const uint8_t* img, int32_t n, int32_t h, int32_t w, int32_t c,
+                    const pbt_act_t* out, int32_t dtype, void* stream);
+/* fp32 NCHW [-1,1] -> uint8 HWC : clamp, (x+1)*127.5, round (generator.py:643-647) */
+int pbt_nchw_to_u8hwc(const float* y, int32_t n, int32_t c, int32_t h, int32_t w, uint8_t* out, void* stream);
+/* uint8 HWC -> fp32 CHW exactly as torchvision ToTensor + Normalize(0.5, 0.5) (src/data/dataset.py:34-38) */
+int pbt_u8hwc_to_norm_chw(const uint8_t* img, int32_t h, int32_t w, int32_t c, float* out, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Patch sampler gather (StyleTransferDataset._cut_patch + default_collate +
+ * torch.cat, src/data/dataset.py:209-232,262-273; lightning_model.py:211-221).
+ * For every patch b and source s:
+ *    out_s[b][:, 0:hx-hn, 0:xx-xn] = src_s[img_b][:, hn:hx, xn:xx], rest 0,
+ *    hn=max(0,y-P/2) hx=min(y+P/2,H-1) xn=max(0,x-P/2) xx=min(x+P/2,W-1)
+ * src_ptrs: device array [n_src][n_images] of const float* (CHW fp32, 3 channels... `ch` each)
+ * img_hw  : device array [n_images][2] int32 (H, W)
+ * pos     : device array [n_patches][3] int32 (img, y, x)
+ * outs    : host array [n_src] of float* ; out_ch_off/out_ch_total give the
+ *           channel slot of each source inside its output tensor so that
+ *           'pre' and the guides land concatenated (dim=1) in one tensor.
+ * ---------------------------------------------------------------------- */
+int pbt_patch_gather(const float* const* src_ptrs, int32_t n_src, int32_t n_images, int32_t ch,
+                     const int32_t* img_hw, const int32_t* pos, int32_t n_patches, int32_t patch,
+                     float* const* outs, const int32_t* out_ch_off, const int32_t* out_ch_total,
+                     void* stream);
+
+/* 7x7 box-sum != 0 of a binary mask (dilation), src/data/dataset.py:157-170: out[y][x] = 1 if any
+ * mask pixel > 0 in the 7x7 window. mask: uint8 [h][w] (already thresholded 0/255). */
+int pbt_mask_dilate7(const uint8_t* mask, int32_t h, int32_t w, uint8_t* out, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Loss / optimiser tail helpers.
+ * ---------------------------------------------------------------------- */
+/* max |g| over count fp32 values -> *out (device); used for dynamic fp16 gradient scaling */
+int pbt_absmax_f32(const float* g, int64_t count, float* out, void* stream);
+/* scale[0] = 2^k with amax*2^k in [target/2, target], scale[1] = 1/scale[0] (scale[0]=1 when amax==0) */
+int pbt_make_grad_scale(const float* amax, float target, float* scale2, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Host-side sampler bookkeeping (no CUDA): order-statistics tree that replaces
+ * `valid_indices_left[img].pop(center_idx)` (src/data/dataset.py:254-256), which
+ * is the c-th smallest not-yet-used index.  `tree` is caller-owned int32[n+1].
+ * ---------------------------------------------------------------------- */
+void    pbt_ostree_reset(int32_t* tree, int32_t n);
+/* returns the k-th (0-based) remaining index and removes it; -1 if k is out of range */
+int32_t pbt_ostree_take(int32_t* tree, int32_t n, int32_t k);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBT_H_ */

@@ -1,0 +1,192 @@
+"""ctypes binding of libpbt.so (C-ABI declared in include/pbt.h).
+
+There is deliberately no fallback: if the library is missing, or a call returns
+a non-zero status, a RuntimeError is raised.  Only raw pointers, sizes and the
+current CUDA stream handle cross this boundary.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libpbt.so")
+
+BF16, FP16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+
+_TORCH_DTYPE = {BF16: torch.bfloat16, FP16: torch.float16}
+
+
+def torch_dtype(dt: int) -> torch.dtype:
+    return _TORCH_DTYPE[dt]
+
+
+class Act(C.Structure):
+    """pbt_act_t — 16-bit P8 activation view."""
+
+    _fields_ = [("ptr", C.c_void_p), ("n", C.c_int32), ("c", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+                ("img_stride", C.c_int64)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [
+        ("inp", Act), ("wpack", C.c_void_p), ("cout", C.c_int32),
+        ("kh", C.c_int32), ("kw", C.c_int32), ("pad_t", C.c_int32), ("pad_l", C.c_int32),
+        ("blk_c", C.c_int32), ("tiles_per_cta", C.c_int32), ("dtype", C.c_int32),
+        ("bias", C.c_void_p), ("act", C.c_int32), ("post_scale", C.c_void_p), ("post_shift", C.c_void_p),
+        ("mask", Act), ("addend32", C.c_void_p), ("out32", C.c_void_p), ("out", Act),
+        ("stats_partial", C.c_void_p), ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("head_out", C.c_void_p),
+        ("head_tanh", C.c_int32), ("debug_flags", C.c_int32),
+    ]
+
+
+class WgradDesc(C.Structure):
+    _fields_ = [
+        ("x", Act), ("dy", Act), ("kh", C.c_int32), ("kw", C.c_int32), ("pad_t", C.c_int32), ("pad_l", C.c_int32),
+        ("dtype", C.c_int32), ("dw", C.c_void_p), ("inv_scale", C.c_void_p), ("debug_flags", C.c_int32),
+    ]
+
+
+class NormApplyDesc(C.Structure):
+    _fields_ = [
+        ("x", Act), ("scale", C.c_void_p), ("shift", C.c_void_p), ("per_channel", C.c_int32), ("act", C.c_int32),
+        ("residual32", C.c_void_p), ("out", Act), ("out_relu", Act), ("out32", C.c_void_p), ("out_s2d", Act),
+        ("dtype", C.c_int32),
+    ]
+
+
+class NormBwdDesc(C.Structure):
+    _fields_ = [
+        ("x", Act), ("scale", C.c_void_p), ("shift", C.c_void_p), ("per_channel", C.c_int32), ("act", C.c_int32),
+        ("ga", Act), ("ga_is_s2d", C.c_int32), ("gb16", Act), ("gb32", C.c_void_p), ("sums", C.c_void_p),
+        ("kmul", C.c_void_p), ("count", C.c_int64), ("batch_mode", C.c_int32), ("dx", Act), ("dtype", C.c_int32),
+    ]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libpbt.so once; fail loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"native library {LIB_PATH} is missing — run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU or PyTorch fallback for the hot path)")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+    sig = {
+        "pbt_abi_version": (C.c_int, []),
+        "pbt_error_string": (C.c_char_p, [C.c_int]),
+        "pbt_last_cuda_error": (C.c_char_p, []),
+        "pbt_conv_num_tiles": (C.c_int, [i32, i32, i32]),
+        "pbt_conv_fwd": (C.c_int, [C.POINTER(ConvDesc), vp]),
+        "pbt_conv_wgrad": (C.c_int, [C.POINTER(WgradDesc), vp]),
+        "pbt_norm_finalize": (C.c_int, [vp, i32, i32, i32, i64, f32, i32, vp, vp, vp, vp, f32, vp, vp, vp, vp, vp]),
+        "pbt_norm_apply": (C.c_int, [C.POINTER(NormApplyDesc), vp]),
+        "pbt_upsample2x": (C.c_int, [C.POINTER(Act), C.POINTER(Act), i32, vp]),
+        "pbt_upsample2x_bwd": (C.c_int, [C.POINTER(Act), C.POINTER(Act), vp, i32, vp]),
+        "pbt_norm_bwd_reduce": (C.c_int, [C.POINTER(NormBwdDesc), vp]),
+        "pbt_norm_bwd_apply": (C.c_int, [C.POINTER(NormBwdDesc), vp]),
+        "pbt_head_bwd": (C.c_int, [vp, vp, C.POINTER(Act), vp, vp, i32, vp, vp, C.POINTER(Act), vp, i32, vp]),
+        "pbt_channel_sum": (C.c_int, [C.POINTER(Act), vp, vp, i32, vp]),
+        "pbt_nchw_to_p8": (C.c_int, [vp, i32, i32, i32, i32, i32, C.POINTER(Act), i32, vp]),
+        "pbt_p8_to_nchw_f32": (C.c_int, [C.POINTER(Act), i32, vp, f32, i32, vp]),
+        "pbt_p8f_to_nchw_f32": (C.c_int, [vp, i32, i32, i32, i32, i32, vp, vp]),
+        "pbt_u8hwc_to_p8": (C.c_int, [vp, i32, i32, i32, i32, C.POINTER(Act), i32, vp]),
+        "pbt_nchw_to_u8hwc": (C.c_int, [vp, i32, i32, i32, i32, vp, vp]),
+        "pbt_u8hwc_to_norm_chw": (C.c_int, [vp, i32, i32, i32, vp, vp]),
+        "pbt_patch_gather": (C.c_int, [vp, i32, i32, i32, vp, vp, i32, i32, vp, vp, vp, vp]),
+        "pbt_mask_dilate7": (C.c_int, [vp, i32, i32, vp, vp]),
+        "pbt_absmax_f32": (C.c_int, [vp, i64, vp, vp]),
+        "pbt_make_grad_scale": (C.c_int, [vp, f32, vp, vp]),
+        "pbt_ostree_reset": (None, [vp, i32]),
+        "pbt_ostree_take": (i32, [vp, i32, i32]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)  # AttributeError here = header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    if L.pbt_abi_version() != 1:
+        raise RuntimeError("libpbt.so ABI version mismatch")
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = [
+    "pbt_abi_version", "pbt_error_string", "pbt_last_cuda_error", "pbt_conv_num_tiles", "pbt_conv_fwd",
+    "pbt_conv_wgrad", "pbt_norm_finalize", "pbt_norm_apply", "pbt_upsample2x", "pbt_upsample2x_bwd",
+    "pbt_norm_bwd_reduce", "pbt_norm_bwd_apply", "pbt_head_bwd", "pbt_channel_sum", "pbt_nchw_to_p8",
+    "pbt_p8_to_nchw_f32", "pbt_p8f_to_nchw_f32", "pbt_u8hwc_to_p8", "pbt_nchw_to_u8hwc", "pbt_u8hwc_to_norm_chw",
+    "pbt_patch_gather", "pbt_mask_dilate7", "pbt_absmax_f32", "pbt_make_grad_scale", "pbt_ostree_reset",
+    "pbt_ostree_take",
+]
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        L = lib()
+        raise RuntimeError(f"{what} failed: {L.pbt_error_string(status).decode()} — {L.pbt_last_cuda_error().decode()}")
+
+
+def stream_ptr() -> int:
+    """Handle of torch's current CUDA stream (all native work is enqueued there)."""
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+class P8:
+    """A 16-bit activation tensor in the P8 layout [n][c/8][h][w][8] plus channel-range views."""
+
+    __slots__ = ("t", "n", "c", "h", "w", "plane0", "planes_total")
+
+    def __init__(self, t: torch.Tensor, c: int | None = None, plane0: int = 0):
+        assert t.dim() == 5 and t.shape[4] == 8 and t.is_contiguous()
+        self.t = t
+        self.n, self.planes_total, self.h, self.w = t.shape[0], t.shape[1], t.shape[2], t.shape[3]
+        self.plane0 = plane0
+        self.c = (self.planes_total - plane0) * 8 if c is None else c
+        assert self.c % 8 == 0 and plane0 + self.c // 8 <= self.planes_total
+
+    @staticmethod
+    def empty(n, c, h, w, dt, device="cuda", zero=False) -> "P8":
+        f = torch.zeros if zero else torch.empty
+        return P8(f((n, c // 8, h, w, 8), dtype=torch_dtype(dt), device=device))
+
+    def view(self, c0: int, c: int) -> "P8":
+        """channels [c0, c0+c) of this tensor (multiples of 8)"""
+        assert c0 % 8 == 0 and c % 8 == 0
+        return P8(self.t, c, self.plane0 + c0 // 8)
+
+    def act(self) -> Act:
+        off = self.plane0 * self.h * self.w * 8 * self.t.element_size()
+        return Act(self.t.data_ptr() + off, self.n, self.c, self.h, self.w, self.planes_total * self.h * self.w * 8)
+
+    def to_nchw(self) -> torch.Tensor:
+        """fp32 NCHW copy via plain torch ops (tests / debugging only)."""
+        v = self.t[:, self.plane0:self.plane0 + self.c // 8]
+        return v.permute(0, 1, 4, 2, 3).reshape(self.n, self.c, self.h, self.w).float()
+
+    @staticmethod
+    def from_nchw(x: torch.Tensor, dt: int, c_pad: int | None = None) -> "P8":
+        """torch-op construction (tests / debugging only)."""
+        n, c, h, w = x.shape
+        cp = c_pad or ((c + 7) // 8 * 8)
+        xp = torch.zeros((n, cp, h, w), dtype=torch_dtype(dt), device=x.device)
+        xp[:, :c] = x.to(torch_dtype(dt))
+        return P8(xp.reshape(n, cp // 8, 8, h, w).permute(0, 1, 3, 4, 2).contiguous())
+
+
+NULL_ACT = Act(None, 0, 0, 0, 0, 0)
+
+
+def act_or_null(p: "P8 | None") -> Act:
+    return NULL_ACT if p is None else p.act()

@@ -1,0 +1,865 @@
+// elementwise.cu — HBM-bound kernels around the tensor-core convs: layout/dtype conversion,
+// normalisation finalize/apply (+activation, residual, space-to-depth), bilinear x2 upsample and its
+// transpose, normalisation backward (reduce + apply), fused head backward, small reductions.
+// All kernels move one P8 pixel chunk (8 channels = 16 B) per thread access: coalesced 128-bit
+// loads/stores, grid-stride loops sized to a multiple of the SM count.
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace pbt {
+
+constexpr int kEwThreads = 256;
+
+static inline int ew_grid(long long items) {
+  long long blocks = (items + kEwThreads - 1) / kEwThreads;
+  long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+struct ActView {
+  uint8_t* ptr;
+  long long img_stride;  // elements
+  int n, c, h, w;
+};
+static inline ActView view(const pbt_act_t& t) {
+  ActView v;
+  v.ptr = static_cast<uint8_t*>(t.ptr);
+  v.img_stride = t.img_stride;
+  v.n = t.n; v.c = t.c; v.h = t.h; v.w = t.w;
+  return v;
+}
+__device__ __forceinline__ uint4* chunk_ptr(const ActView& v, int n, int plane, long long pix) {
+  return reinterpret_cast<uint4*>(v.ptr + 2 * ((long long)n * v.img_stride + ((long long)plane * v.h * v.w + pix) * 8));
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == PBT_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == PBT_ACT_LEAKY02) return v > 0.f ? v : 0.2f * v;
+  return v;
+}
+__device__ __forceinline__ float act_grad(float xhat, int act) {
+  if (act == PBT_ACT_RELU) return xhat > 0.f ? 1.f : 0.f;
+  if (act == PBT_ACT_LEAKY02) return xhat > 0.f ? 1.f : 0.2f;
+  return 1.f;
+}
+
+// ------------------------------------------------------------------ NCHW -> P8
+template <int DT, bool SRC_HALF>
+__global__ void nchw_to_p8_kernel(const void* __restrict__ x, int n, int c, int h, int w, ActView out) {
+  const long long hw = (long long)h * w;
+  const int planes = out.c / 8;
+  const long long total = (long long)n * planes * hw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i % hw;
+    const int pl = (int)((i / hw) % planes);
+    const int ni = (int)(i / (hw * planes));
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int ch = pl * 8 + k;
+      float v = 0.f;
+      if (ch < c) {
+        const long long src = ((long long)ni * c + ch) * hw + pix;
+        v = SRC_HALF ? __half2float(static_cast<const __half*>(x)[src]) : static_cast<const float*>(x)[src];
+      }
+      f[k] = v;
+    }
+    *chunk_ptr(out, ni, pl, pix) = pack8<DT>(f);
+  }
+}
+
+template <int DT>
+__global__ void p8_to_nchw_kernel(ActView in, int c, float* __restrict__ out, float mul) {
+  const long long hw = (long long)in.h * in.w;
+  const int planes = (c + 7) / 8;
+  const long long total = (long long)in.n * planes * hw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i % hw;
+    const int pl = (int)((i / hw) % planes);
+    const int ni = (int)(i / (hw * planes));
+    float f[8];
+    unpack8<DT>(*chunk_ptr(in, ni, pl, pix), f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int ch = pl * 8 + k;
+      if (ch < c) out[((long long)ni * c + ch) * hw + pix] = f[k] * mul;
+    }
+  }
+}
+
+__global__ void p8f_to_nchw_kernel(const float* __restrict__ in, int n, int c_total, int c, int h, int w,
+                                   float* __restrict__ out) {
+  const long long hw = (long long)h * w;
+  const int planes = (c + 7) / 8;
+  const long long total = (long long)n * planes * hw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i % hw;
+    const int pl = (int)((i / hw) % planes);
+    const int ni = (int)(i / (hw * planes));
+    const float* src = in + (((long long)ni * (c_total / 8) + pl) * hw + pix) * 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int ch = pl * 8 + k;
+      if (ch < c) out[((long long)ni * c + ch) * hw + pix] = src[k];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ uint8 frames
+__device__ __forceinline__ float u8_to_norm(uint8_t u) {
+  // torchvision ToTensor (x/255) then Normalize(0.5, 0.5): (v - 0.5) / 0.5, each step rounded to fp32
+  return __fdiv_rn(__fsub_rn(__fdiv_rn((float)u, 255.f), 0.5f), 0.5f);
+}
+
+template <int DT>
+__global__ void u8hwc_to_p8_kernel(const uint8_t* __restrict__ img, int n, int h, int w, int c, ActView out) {
+  const long long hw = (long long)h * w;
+  const int planes = out.c / 8;
+  const long long total = (long long)n * planes * hw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i % hw;
+    const int pl = (int)((i / hw) % planes);
+    const int ni = (int)(i / (hw * planes));
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int ch = pl * 8 + k;
+      f[k] = ch < c ? u8_to_norm(img[((long long)ni * hw + pix) * c + ch]) : 0.f;
+    }
+    *chunk_ptr(out, ni, pl, pix) = pack8<DT>(f);
+  }
+}
+
+__global__ void nchw_to_u8hwc_kernel(const float* __restrict__ y, int n, int c, int h, int w, uint8_t* __restrict__ out) {
+  const long long hw = (long long)h * w;
+  const long long total = (long long)n * hw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i % hw;
+    const int ni = (int)(i / hw);
+    for (int ch = 0; ch < c; ++ch) {
+      float v = y[((long long)ni * c + ch) * hw + pix];
+      v = fminf(fmaxf(v, -1.f), 1.f);
+      v = fminf(fmaxf((v + 1.f) * 127.5f, 0.f), 255.f);
+      out[i * c + ch] = (uint8_t)rintf(v);
+    }
+  }
+}
+
+__global__ void u8hwc_to_norm_chw_kernel(const uint8_t* __restrict__ img, int h, int w, int c, float* __restrict__ out) {
+  const long long hw = (long long)h * w;
+  const long long total = hw * c;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i % hw;
+    const int ch = (int)(i / hw);
+    out[i] = u8_to_norm(img[pix * c + ch]);
+  }
+}
+
+__global__ void mask_dilate7_kernel(const uint8_t* __restrict__ m, int h, int w, uint8_t* __restrict__ out) {
+  const long long total = (long long)h * w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int y = (int)(i / w), x = (int)(i % w);
+    int any = 0;
+    for (int dy = -3; dy <= 3; ++dy) {
+      const int yy = y + dy;
+      if (yy < 0 || yy >= h) continue;
+      for (int dx = -3; dx <= 3; ++dx) {
+        const int xx = x + dx;
+        if (xx < 0 || xx >= w) continue;
+        any |= m[(long long)yy * w + xx];
+      }
+    }
+    out[i] = any ? 1 : 0;
+  }
+}
+
+// ------------------------------------------------------------------ norm finalize
+// one block per (image, 32-channel group) in instance mode; per 32-channel group in batch mode
+__global__ void norm_finalize_kernel(const float* __restrict__ partial, int n, int tiles, int c, long long count_per_image,
+                                     float eps, int batch_mode, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, float* running_mean, float* running_var, float momentum,
+                                     float* __restrict__ scale, float* __restrict__ shift, float* mean_out, float* rstd_out) {
+  __shared__ double s_sum[8][32], s_sq[8][32];
+  const int cg = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int row = threadIdx.x >> 5;  // 0..7
+  const int img = batch_mode ? 0 : blockIdx.y;
+  const int n_lo = batch_mode ? 0 : img, n_hi = batch_mode ? n : img + 1;
+  double a = 0.0, b = 0.0;
+  if (cg < c) {
+    for (int ni = n_lo; ni < n_hi; ++ni)
+      for (int t = row; t < tiles; t += 8) {
+        const float* pp = partial + ((long long)ni * tiles + t) * 2 * c;
+        a += (double)pp[cg];
+        b += (double)pp[c + cg];
+      }
+  }
+  s_sum[row][threadIdx.x & 31] = a;
+  s_sq[row][threadIdx.x & 31] = b;
+  __syncthreads();
+  if (row == 0 && cg < c) {
+    for (int r2 = 1; r2 < 8; ++r2) {
+      a += s_sum[r2][threadIdx.x];
+      b += s_sq[r2][threadIdx.x];
+    }
+    const double cnt = (double)count_per_image * (batch_mode ? n : 1);
+    const double mean = a / cnt;
+    double var = b / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float meanf = (float)mean;
+    if (batch_mode) {
+      const float g = gamma ? gamma[cg] : 1.f, be = beta ? beta[cg] : 0.f;
+      const float sc = g * rstd, sh = be - meanf * sc;
+      for (int ni = 0; ni < n; ++ni) {
+        scale[(long long)ni * c + cg] = sc;
+        shift[(long long)ni * c + cg] = sh;
+      }
+      if (mean_out) mean_out[cg] = meanf;
+      if (rstd_out) rstd_out[cg] = rstd;
+      if (running_mean) {
+        const double unbiased = cnt > 1.0 ? var * cnt / (cnt - 1.0) : var;
+        running_mean[cg] = (1.f - momentum) * running_mean[cg] + momentum * meanf;
+        running_var[cg] = (1.f - momentum) * running_var[cg] + momentum * (float)unbiased;
+      }
+    } else {
+      scale[(long long)img * c + cg] = rstd;
+      shift[(long long)img * c + cg] = -meanf * rstd;
+      if (mean_out) mean_out[(long long)img * c + cg] = meanf;
+      if (rstd_out) rstd_out[(long long)img * c + cg] = rstd;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ norm apply
+struct NormApplyK {
+  ActView x, out, out_relu, out_s2d;
+  const float* scale;
+  const float* shift;
+  int per_channel, act;
+  const float* residual32;
+  float* out32;
+};
+
+template <int DT>
+__global__ void norm_apply_kernel(NormApplyK p) {
+  const long long hw = (long long)p.x.h * p.x.w;
+  const int planes = p.x.c / 8;
+  const long long total = (long long)p.x.n * planes * hw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i % hw;
+    const int pl = (int)((i / hw) % planes);
+    const int ni = (int)(i / (hw * planes));
+    float f[8];
+    unpack8<DT>(*chunk_ptr(p.x, ni, pl, pix), f);
+    if (p.scale) {
+      const long long so = (p.per_channel ? 0 : (long long)ni * p.x.c) + pl * 8;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = fmaf(f[k], __ldg(&p.scale[so + k]), __ldg(&p.shift[so + k]));
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = apply_act(f[k], p.act);
+    const long long dense = (((long long)ni * planes + pl) * hw + pix) * 8;
+    if (p.residual32) {
+      const float4 a0 = *reinterpret_cast<const float4*>(p.residual32 + dense);
+      const float4 a1 = *reinterpret_cast<const float4*>(p.residual32 + dense + 4);
+      f[0] += a0.x; f[1] += a0.y; f[2] += a0.z; f[3] += a0.w;
+      f[4] += a1.x; f[5] += a1.y; f[6] += a1.z; f[7] += a1.w;
+    }
+    if (p.out32) {
+      *reinterpret_cast<float4*>(p.out32 + dense) = make_float4(f[0], f[1], f[2], f[3]);
+      *reinterpret_cast<float4*>(p.out32 + dense + 4) = make_float4(f[4], f[5], f[6], f[7]);
+    }
+    if (p.out.ptr || p.out_s2d.ptr) {
+      const uint4 u = pack8<DT>(f);
+      if (p.out.ptr) *chunk_ptr(p.out, ni, pl, pix) = u;
+      if (p.out_s2d.ptr) {
+        const int y = (int)(pix / p.x.w), x = (int)(pix % p.x.w);
+        const int phase = (y & 1) * 2 + (x & 1);
+        *chunk_ptr(p.out_s2d, ni, phase * planes + pl, (long long)(y >> 1) * p.out_s2d.w + (x >> 1)) = u;
+      }
+    }
+    if (p.out_relu.ptr) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f);
+      *chunk_ptr(p.out_relu, ni, pl, pix) = pack8<DT>(f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ bilinear x2 (align_corners=True)
+__device__ __forceinline__ void src_index(int dst, float scale, int in_size, int& i0, int& i1, float& l1) {
+  const float s = scale * (float)dst;
+  i0 = (int)s;
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  l1 = s - (float)i0;
+}
+
+template <int DT>
+__global__ void upsample2x_kernel(ActView in, ActView out) {
+  const int oh = out.h, ow = out.w;
+  const long long ohw = (long long)oh * ow;
+  const int planes = in.c / 8;
+  const float sy = oh > 1 ? (float)(in.h - 1) / (float)(oh - 1) : 0.f;
+  const float sx = ow > 1 ? (float)(in.w - 1) / (float)(ow - 1) : 0.f;
+  const long long total = (long long)in.n * planes * ohw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i % ohw;
+    const int pl = (int)((i / ohw) % planes);
+    const int ni = (int)(i / (ohw * planes));
+    const int Y = (int)(pix / ow), X = (int)(pix % ow);
+    int y0, y1, x0, x1;
+    float ly, lx;
+    src_index(Y, sy, in.h, y0, y1, ly);
+    src_index(X, sx, in.w, x0, x1, lx);
+    float a[8], b[8], c[8], d[8], r[8];
+    unpack8<DT>(*chunk_ptr(in, ni, pl, (long long)y0 * in.w + x0), a);
+    unpack8<DT>(*chunk_ptr(in, ni, pl, (long long)y0 * in.w + x1), b);
+    unpack8<DT>(*chunk_ptr(in, ni, pl, (long long)y1 * in.w + x0), c);
+    unpack8<DT>(*chunk_ptr(in, ni, pl, (long long)y1 * in.w + x1), d);
+    const float hy = 1.f - ly, hx = 1.f - lx;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] = hy * (hx * a[k] + lx * b[k]) + ly * (hx * c[k] + lx * d[k]);
+    *chunk_ptr(out, ni, pl, pix) = pack8<DT>(r);
+  }
+}
+
+// transpose of the above: each low-res pixel gathers the high-res gradients that read it
+template <int DT>
+__global__ void upsample2x_bwd_kernel(ActView gout, ActView gin16, float* gin32, int ih, int iw) {
+  const int oh = gout.h, ow = gout.w;
+  const long long ihw = (long long)ih * iw;
+  const int planes = gout.c / 8;
+  const float sy = oh > 1 ? (float)(ih - 1) / (float)(oh - 1) : 0.f;
+  const float sx = ow > 1 ? (float)(iw - 1) / (float)(ow - 1) : 0.f;
+  const long long total = (long long)gout.n * planes * ihw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i % ihw;
+    const int pl = (int)((i / ihw) % planes);
+    const int ni = (int)(i / (ihw * planes));
+    const int y = (int)(pix / iw), x = (int)(pix % iw);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    const int Ylo = max(0, 2 * y - 3), Yhi = min(oh - 1, 2 * y + 4);
+    const int Xlo = max(0, 2 * x - 3), Xhi = min(ow - 1, 2 * x + 4);
+    for (int Y = Ylo; Y <= Yhi; ++Y) {
+      int y0, y1;
+      float ly;
+      src_index(Y, sy, ih, y0, y1, ly);
+      float wy = 0.f;
+      if (y0 == y) wy += 1.f - ly;
+      if (y1 == y) wy += ly;
+      if (wy == 0.f) continue;
+      for (int X = Xlo; X <= Xhi; ++X) {
+        int x0, x1;
+        float lx;
+        src_index(X, sx, iw, x0, x1, lx);
+        float wx = 0.f;
+        if (x0 == x) wx += 1.f - lx;
+        if (x1 == x) wx += lx;
+        if (wx == 0.f) continue;
+        float g[8];
+        unpack8<DT>(*chunk_ptr(gout, ni, pl, (long long)Y * ow + X), g);
+        const float wgt = wy * wx;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf(wgt, g[k], acc[k]);
+      }
+    }
+    if (gin16.ptr) *chunk_ptr(gin16, ni, pl, pix) = pack8<DT>(acc);
+    if (gin32) {
+      float* dst = gin32 + (((long long)ni * planes + pl) * ihw + pix) * 8;
+      *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ norm backward
+struct NormBwdK {
+  ActView x, ga, gb16, dx;
+  const float* mean;   // "scale"/"shift" of the ABI carry rstd and -mean*rstd (xhat = x*scale + shift)
+  const float* shift;
+  int per_channel, act, ga_is_s2d, batch_mode;
+  const float* gb32;
+  float* sums;
+  const float* kmul;
+  float inv_count;
+};
+
+template <int DT>
+__device__ __forceinline__ void load_gact(const NormBwdK& p, int ni, int pl, long long pix, int planes, long long hw,
+                                          float* gact, float* xhat) {
+  float xr[8];
+  unpack8<DT>(*chunk_ptr(p.x, ni, pl, pix), xr);
+  const long long so = (p.per_channel ? 0 : (long long)ni * p.x.c) + pl * 8;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) xhat[k] = fmaf(xr[k], __ldg(&p.mean[so + k]), __ldg(&p.shift[so + k]));
+  float g[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) g[k] = 0.f;
+  if (p.ga.ptr) {
+    float t[8];
+    if (p.ga_is_s2d) {
+      const int y = (int)(pix / p.x.w), x = (int)(pix % p.x.w);
+      const int phase = (y & 1) * 2 + (x & 1);
+      unpack8<DT>(*chunk_ptr(p.ga, ni, phase * planes + pl, (long long)(y >> 1) * p.ga.w + (x >> 1)), t);
+    } else {
+      unpack8<DT>(*chunk_ptr(p.ga, ni, pl, pix), t);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g[k] += t[k];
+  }
+  if (p.gb16.ptr) {
+    float t[8];
+    unpack8<DT>(*chunk_ptr(p.gb16, ni, pl, pix), t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g[k] += t[k];
+  }
+  if (p.gb32) {
+    const float* s = p.gb32 + (((long long)ni * planes + pl) * hw + pix) * 8;
+    const float4 a0 = *reinterpret_cast<const float4*>(s), a1 = *reinterpret_cast<const float4*>(s + 4);
+    g[0] += a0.x; g[1] += a0.y; g[2] += a0.z; g[3] += a0.w;
+    g[4] += a1.x; g[5] += a1.y; g[6] += a1.z; g[7] += a1.w;
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) gact[k] = g[k] * act_grad(xhat[k], p.act);
+}
+
+// grid: (chunks, planes, n); each block reduces a pixel range of one (image, plane)
+template <int DT>
+__global__ void norm_bwd_reduce_kernel(NormBwdK p) {
+  const long long hw = (long long)p.x.h * p.x.w;
+  const int planes = p.x.c / 8;
+  const int pl = blockIdx.y, ni = blockIdx.z;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s1[k] = s2[k] = 0.f;
+  for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < hw; pix += (long long)gridDim.x * blockDim.x) {
+    float gact[8], xhat[8];
+    load_gact<DT>(p, ni, pl, pix, planes, hw, gact, xhat);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      s1[k] += gact[k];
+      s2[k] = fmaf(gact[k], xhat[k], s2[k]);
+    }
+  }
+  __shared__ float red[kEwThreads / 32][16];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], o);
+      s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], o);
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      red[wid][k] = s1[k];
+      red[wid][8 + k] = s2[k];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    float t = 0.f;
+    for (int w2 = 0; w2 < kEwThreads / 32; ++w2) t += red[w2][threadIdx.x];
+    const int which = threadIdx.x >> 3, k = threadIdx.x & 7;
+    float* dst = p.sums + (p.batch_mode ? 0 : (long long)ni * 2 * p.x.c) + (long long)which * p.x.c + pl * 8 + k;
+    atomicAdd(dst, t);
+  }
+}
+
+template <int DT>
+__global__ void norm_bwd_apply_kernel(NormBwdK p) {
+  const long long hw = (long long)p.x.h * p.x.w;
+  const int planes = p.x.c / 8;
+  const long long total = (long long)p.x.n * planes * hw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i % hw;
+    const int pl = (int)((i / hw) % planes);
+    const int ni = (int)(i / (hw * planes));
+    float gact[8], xhat[8], r[8];
+    load_gact<DT>(p, ni, pl, pix, planes, hw, gact, xhat);
+    const float* sp = p.sums + (p.batch_mode ? 0 : (long long)ni * 2 * p.x.c) + pl * 8;
+    const long long ko = (p.per_channel ? 0 : (long long)ni * p.x.c) + pl * 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float m1 = __ldg(&sp[k]) * p.inv_count, m2 = __ldg(&sp[p.x.c + k]) * p.inv_count;
+      r[k] = __ldg(&p.kmul[ko + k]) * (gact[k] - m1 - xhat[k] * m2);
+    }
+    *chunk_ptr(p.dx, ni, pl, pix) = pack8<DT>(r);
+  }
+}
+
+// ------------------------------------------------------------------ head backward
+// grid: (chunks, planes of s); block reduces dW[3][8], dbias_prev[8] (+ db[3] on plane 0)
+template <int DT>
+__global__ void head_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ y, ActView s,
+                                const float* __restrict__ head_w, const float* __restrict__ gscale, int head_tanh,
+                                float* dw, float* db, ActView gs, float* dbias_prev) {
+  const long long hw = (long long)s.h * s.w;
+  const long long total = (long long)s.n * hw;
+  const int pl = blockIdx.y;
+  const int C = s.c;
+  const float sc = gscale ? __ldg(gscale) : 1.f;
+  float w0[8], w1[8], w2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    w0[k] = __ldg(&head_w[pl * 8 + k]);
+    w1[k] = __ldg(&head_w[C + pl * 8 + k]);
+    w2[k] = __ldg(&head_w[2 * C + pl * 8 + k]);
+  }
+  float acc[35];
+#pragma unroll
+  for (int k = 0; k < 35; ++k) acc[k] = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i % hw;
+    const int ni = (int)(i / hw);
+    float gz[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const long long o = ((long long)ni * 3 + j) * hw + pix;
+      const float yy = y[o];
+      gz[j] = gy[o] * (head_tanh ? (1.f - yy * yy) : 1.f) * sc;
+    }
+    float sv[8], g[8];
+    unpack8<DT>(*chunk_ptr(s, ni, pl, pix), sv);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      acc[k] = fmaf(gz[0], sv[k], acc[k]);
+      acc[8 + k] = fmaf(gz[1], sv[k], acc[8 + k]);
+      acc[16 + k] = fmaf(gz[2], sv[k], acc[16 + k]);
+      const float gk = sv[k] > 0.f ? (w0[k] * gz[0] + w1[k] * gz[1] + w2[k] * gz[2]) : 0.f;
+      g[k] = gk;
+    }
+    const uint4 u = pack8<DT>(g);
+    *chunk_ptr(gs, ni, pl, pix) = u;
+    unpack8<DT>(u, g);  // bias grad sums what the dgrad/wgrad kernels will actually see
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[24 + k] += g[k];
+    acc[32] += gz[0];
+    acc[33] += gz[1];
+    acc[34] += gz[2];
+  }
+  __shared__ float red[kEwThreads / 32][35];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 35; ++k) {
+    float v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[wid][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 35) {
+    float t = 0.f;
+    for (int w2 = 0; w2 < kEwThreads / 32; ++w2) t += red[w2][threadIdx.x];
+    const int k = threadIdx.x;
+    if (k < 24) atomicAdd(&dw[(k >> 3) * C + pl * 8 + (k & 7)], t);
+    else if (k < 32) { if (dbias_prev) atomicAdd(&dbias_prev[pl * 8 + (k - 24)], t); }
+    else if (pl == 0) atomicAdd(&db[k - 32], t);
+  }
+}
+
+// grid: (chunks, planes)
+template <int DT>
+__global__ void channel_sum_kernel(ActView g, float* out, const float* __restrict__ inv_scale) {
+  const long long hw = (long long)g.h * g.w;
+  const long long total = (long long)g.n * hw;
+  const int pl = blockIdx.y;
+  float s[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s[k] = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    float f[8];
+    unpack8<DT>(*chunk_ptr(g, (int)(i / hw), pl, i % hw), f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[k] += f[k];
+  }
+  __shared__ float red[kEwThreads / 32][8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+    if (lane == 0) red[wid][k] = s[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float t = 0.f;
+    for (int w2 = 0; w2 < kEwThreads / 32; ++w2) t += red[w2][threadIdx.x];
+    atomicAdd(&out[pl * 8 + threadIdx.x], t * (inv_scale ? __ldg(inv_scale) : 1.f));
+  }
+}
+
+__global__ void absmax_kernel(const float* __restrict__ g, long long count, float* out) {
+  float m = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(g[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));  // m >= 0: int order == float order
+}
+
+__global__ void make_grad_scale_kernel(const float* amax, float target, float* scale2) {
+  const float a = *amax;
+  float s = 1.f;
+  if (a > 0.f && isfinite(a)) {
+    int e;
+    frexpf(target / a, &e);  // target/a = f * 2^e, f in [0.5,1)
+    s = ldexpf(1.f, e - 1);  // largest power of two <= target/a
+  }
+  scale2[0] = s;
+  scale2[1] = 1.f / s;
+}
+
+}  // namespace pbt
+
+using namespace pbt;
+
+#define DISPATCH_DT(dtype, ...)                              \
+  do {                                                       \
+    if ((dtype) == PBT_BF16) { constexpr int DT = 0; __VA_ARGS__; } \
+    else if ((dtype) == PBT_FP16) { constexpr int DT = 1; __VA_ARGS__; } \
+    else { pbt::set_last_error("bad dtype"); return PBT_ERR_ARG; } \
+  } while (0)
+
+static bool act_ok(const pbt_act_t& t) { return t.ptr && aligned16(t.ptr) && t.c % 8 == 0 && t.img_stride % 8 == 0 && t.n > 0 && t.h > 0 && t.w > 0; }
+
+extern "C" int pbt_nchw_to_p8(const void* x, int32_t src_is_half, int32_t n, int32_t c, int32_t h, int32_t w,
+                              const pbt_act_t* out, int32_t dtype, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  PBT_REQUIRE(x && out && act_ok(*out), "nchw_to_p8: bad tensors");
+  PBT_REQUIRE(out->n == n && out->h == h && out->w == w && out->c >= c, "nchw_to_p8: shape mismatch");
+  const long long items = (long long)n * (out->c / 8) * h * w;
+  DISPATCH_DT(dtype, {
+    if (src_is_half) nchw_to_p8_kernel<DT, true><<<ew_grid(items), kEwThreads, 0, st>>>(x, n, c, h, w, view(*out));
+    else nchw_to_p8_kernel<DT, false><<<ew_grid(items), kEwThreads, 0, st>>>(x, n, c, h, w, view(*out));
+  });
+  PBT_CUDA_CHECK(cudaGetLastError());
+  return PBT_OK;
+}
+
+extern "C" int pbt_p8_to_nchw_f32(const pbt_act_t* in, int32_t c, float* out, float mul, int32_t dtype, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  PBT_REQUIRE(in && out && act_ok(*in) && c > 0 && c <= in->c, "p8_to_nchw: bad tensors");
+  const long long items = (long long)in->n * ((c + 7) / 8) * in->h * in->w;
+  DISPATCH_DT(dtype, p8_to_nchw_kernel<DT><<<ew_grid(items), kEwThreads, 0, st>>>(view(*in), c, out, mul));
+  PBT_CUDA_CHECK(cudaGetLastError());
+  return PBT_OK;
+}
+
+extern "C" int pbt_p8f_to_nchw_f32(const float* in, int32_t n, int32_t c_total, int32_t c, int32_t h, int32_t w, float* out,
+                                   void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  PBT_REQUIRE(in && out && c_total % 8 == 0 && c <= c_total && n > 0, "p8f_to_nchw: bad tensors");
+  const long long items = (long long)n * ((c + 7) / 8) * h * w;
+  p8f_to_nchw_kernel<<<ew_grid(items), kEwThreads, 0, st>>>(in, n, c_total, c, h, w, out);
+  PBT_CUDA_CHECK(cudaGetLastError());
+  return PBT_OK;
+}
+
+extern "C" int pbt_u8hwc_to_p8(const uint8_t* img, int32_t n, int32_t h, int32_t w, int32_t c, const pbt_act_t* out,
+                               int32_t dtype, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  PBT_REQUIRE(img && out && act_ok(*out), "u8hwc_to_p8: bad tensors");
+  PBT_REQUIRE(out->n == n && out->h == h && out->w == w && out->c >= c, "u8hwc_to_p8: shape mismatch");
+  const long long items = (long long)n * (out->c / 8) * h * w;
+  DISPATCH_DT(dtype, u8hwc_to_p8_kernel<DT><<<ew_grid(items), kEwThreads, 0, st>>>(img, n, h, w, c, view(*out)));
+  PBT_CUDA_CHECK(cudaGetLastError());
+  return PBT_OK;
+}
+
+extern "C" int pbt_nchw_to_u8hwc(const float* y, int32_t n, int32_t c, int32_t h, int32_t w, uint8_t* out, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  PBT_REQUIRE(y && out && n > 0 && c > 0, "nchw_to_u8hwc: bad tensors");
+  nchw_to_u8hwc_kernel<<<ew_grid((long long)n * h * w), kEwThreads, 0, st>>>(y, n, c, h, w, out);
+  PBT_CUDA_CHECK(cudaGetLastError());
+  return PBT_OK;
+}
+
+extern "C" int pbt_u8hwc_to_norm_chw(const uint8_t* img, int32_t h, int32_t w, int32_t c, float* out, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  PBT_REQUIRE(img && out && h > 0 && w > 0 && c > 0, "u8hwc_to_norm_chw: bad tensors");
+  u8hwc_to_norm_chw_kernel<<<ew_grid((long long)h * w * c), kEwThreads, 0, st>>>(img, h, w, c, out);
+  PBT_CUDA_CHECK(cudaGetLastError());
+  return PBT_OK;
+}
+
+extern "C" int pbt_mask_dilate7(const uint8_t* mask, int32_t h, int32_t w, uint8_t* out, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  PBT_REQUIRE(mask && out && h > 0 && w > 0, "mask_dilate7: bad tensors");
+  mask_dilate7_kernel<<<ew_grid((long long)h * w), kEwThreads, 0, st>>>(mask, h, w, out);
+  PBT_CUDA_CHECK(cudaGetLastError());
+  return PBT_OK;
+}
+
+extern "C" int pbt_norm_finalize(const float* partial, int32_t n, int32_t tiles, int32_t c, int64_t count_per_image, float eps,
+                                 int32_t batch_mode, const float* gamma, const float* beta, float* running_mean,
+                                 float* running_var, float momentum, float* scale, float* shift, float* mean_out,
+                                 float* rstd_out, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  PBT_REQUIRE(partial && scale && shift && n > 0 && tiles > 0 && c > 0 && count_per_image > 0, "norm_finalize: bad arguments");
+  dim3 grid(ceil_div(c, 32), batch_mode ? 1 : n);
+  norm_finalize_kernel<<<grid, 256, 0, st>>>(partial, n, tiles, c, count_per_image, eps, batch_mode, gamma, beta, running_mean,
+                                            running_var, momentum, scale, shift, mean_out, rstd_out);
+  PBT_CUDA_CHECK(cudaGetLastError());
+  return PBT_OK;
+}
+
+extern "C" int pbt_norm_apply(const pbt_norm_apply_desc_t* d, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  PBT_REQUIRE(d && act_ok(d->x), "norm_apply: bad input");
+  PBT_REQUIRE((d->scale == nullptr) == (d->shift == nullptr), "norm_apply: scale/shift must come together");
+  NormApplyK p;
+  memset(&p, 0, sizeof(p));
+  p.x = view(d->x);
+  auto same = [&](const pbt_act_t& t) { return t.n == d->x.n && t.c >= d->x.c && t.h == d->x.h && t.w == d->x.w && act_ok(t); };
+  if (d->out.ptr) { PBT_REQUIRE(same(d->out), "norm_apply: out shape mismatch"); p.out = view(d->out); }
+  if (d->out_relu.ptr) { PBT_REQUIRE(same(d->out_relu), "norm_apply: out_relu shape mismatch"); p.out_relu = view(d->out_relu); }
+  if (d->out_s2d.ptr) {
+    PBT_REQUIRE(d->x.h % 2 == 0 && d->x.w % 2 == 0 && d->out_s2d.h == d->x.h / 2 && d->out_s2d.w == d->x.w / 2 &&
+                    d->out_s2d.c >= 4 * d->x.c && d->out_s2d.n == d->x.n && act_ok(d->out_s2d),
+                "norm_apply: out_s2d shape mismatch");
+    p.out_s2d = view(d->out_s2d);
+  }
+  p.scale = d->scale; p.shift = d->shift; p.per_channel = d->per_channel; p.act = d->act;
+  p.residual32 = d->residual32; p.out32 = d->out32;
+  const long long items = (long long)d->x.n * (d->x.c / 8) * d->x.h * d->x.w;
+  DISPATCH_DT(d->dtype, norm_apply_kernel<DT><<<ew_grid(items), kEwThreads, 0, st>>>(p));
+  PBT_CUDA_CHECK(cudaGetLastError());
+  return PBT_OK;
+}
+
+extern "C" int pbt_upsample2x(const pbt_act_t* in, const pbt_act_t* out, int32_t dtype, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  PBT_REQUIRE(in && out && act_ok(*in) && act_ok(*out), "upsample2x: bad tensors");
+  PBT_REQUIRE(out->h == 2 * in->h && out->w == 2 * in->w && out->n == in->n && out->c >= in->c, "upsample2x: shape mismatch");
+  const long long items = (long long)in->n * (in->c / 8) * out->h * out->w;
+  DISPATCH_DT(dtype, upsample2x_kernel<DT><<<ew_grid(items), kEwThreads, 0, st>>>(view(*in), view(*out)));
+  PBT_CUDA_CHECK(cudaGetLastError());
+  return PBT_OK;
+}
+
+extern "C" int pbt_upsample2x_bwd(const pbt_act_t* gout, const pbt_act_t* gin16, float* gin32, int32_t dtype, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  PBT_REQUIRE(gout && act_ok(*gout) && gout->h % 2 == 0 && gout->w % 2 == 0, "upsample2x_bwd: bad gout");
+  const int ih = gout->h / 2, iw = gout->w / 2;
+  ActView g16;
+  memset(&g16, 0, sizeof(g16));
+  if (gin16 && gin16->ptr) {
+    PBT_REQUIRE(act_ok(*gin16) && gin16->h == ih && gin16->w == iw && gin16->n == gout->n && gin16->c >= gout->c,
+                "upsample2x_bwd: gin16 shape mismatch");
+    g16 = view(*gin16);
+  }
+  PBT_REQUIRE(g16.ptr || gin32, "upsample2x_bwd: no output");
+  const long long items = (long long)gout->n * (gout->c / 8) * ih * iw;
+  DISPATCH_DT(dtype, upsample2x_bwd_kernel<DT><<<ew_grid(items), kEwThreads, 0, st>>>(view(*gout), g16, gin32, ih, iw));
+  PBT_CUDA_CHECK(cudaGetLastError());
+  return PBT_OK;
+}
+
+static int fill_norm_bwd(const pbt_norm_bwd_desc_t* d, NormBwdK& p) {
+  PBT_REQUIRE(d && act_ok(d->x) && d->scale && d->shift && d->sums, "norm_bwd: bad arguments");
+  memset(&p, 0, sizeof(p));
+  p.x = view(d->x);
+  if (d->ga.ptr) {
+    if (d->ga_is_s2d)
+      PBT_REQUIRE(act_ok(d->ga) && d->ga.h * 2 == d->x.h && d->ga.w * 2 == d->x.w && d->ga.c >= 4 * d->x.c && d->ga.n == d->x.n,
+                  "norm_bwd: s2d grad shape mismatch");
+    else
+      PBT_REQUIRE(act_ok(d->ga) && d->ga.h == d->x.h && d->ga.w == d->x.w && d->ga.c >= d->x.c && d->ga.n == d->x.n,
+                  "norm_bwd: grad shape mismatch");
+    p.ga = view(d->ga);
+  }
+  if (d->gb16.ptr) {
+    PBT_REQUIRE(act_ok(d->gb16) && d->gb16.h == d->x.h && d->gb16.w == d->x.w && d->gb16.c >= d->x.c && d->gb16.n == d->x.n,
+                "norm_bwd: gb16 shape mismatch");
+    p.gb16 = view(d->gb16);
+  }
+  p.mean = d->scale; p.shift = d->shift; p.per_channel = d->per_channel; p.act = d->act;
+  p.ga_is_s2d = d->ga_is_s2d; p.batch_mode = d->batch_mode; p.gb32 = d->gb32; p.sums = d->sums; p.kmul = d->kmul;
+  PBT_REQUIRE(d->count > 0, "norm_bwd: count must be positive");
+  p.inv_count = (float)(1.0 / (double)d->count);
+  return PBT_OK;
+}
+
+extern "C" int pbt_norm_bwd_reduce(const pbt_norm_bwd_desc_t* d, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  NormBwdK p;
+  int rc = fill_norm_bwd(d, p);
+  if (rc) return rc;
+  const long long hw = (long long)d->x.h * d->x.w;
+  int chunks = (int)((hw + kEwThreads * 4 - 1) / (kEwThreads * 4));
+  if (chunks < 1) chunks = 1;
+  if (chunks > 64) chunks = 64;
+  dim3 grid(chunks, d->x.c / 8, d->x.n);
+  DISPATCH_DT(d->dtype, norm_bwd_reduce_kernel<DT><<<grid, kEwThreads, 0, st>>>(p));
+  PBT_CUDA_CHECK(cudaGetLastError());
+  return PBT_OK;
+}
+
+extern "C" int pbt_norm_bwd_apply(const pbt_norm_bwd_desc_t* d, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  NormBwdK p;
+  int rc = fill_norm_bwd(d, p);
+  if (rc) return rc;
+  PBT_REQUIRE(d->kmul && act_ok(d->dx) && d->dx.h == d->x.h && d->dx.w == d->x.w && d->dx.c >= d->x.c && d->dx.n == d->x.n,
+              "norm_bwd_apply: dx shape mismatch");
+  p.dx = view(d->dx);
+  const long long items = (long long)d->x.n * (d->x.c / 8) * d->x.h * d->x.w;
+  DISPATCH_DT(d->dtype, norm_bwd_apply_kernel<DT><<<ew_grid(items), kEwThreads, 0, st>>>(p));
+  PBT_CUDA_CHECK(cudaGetLastError());
+  return PBT_OK;
+}
+
+extern "C" int pbt_head_bwd(const float* gy, const float* y, const pbt_act_t* s, const float* head_w, const float* gscale,
+                            int32_t head_tanh, float* dw, float* db, const pbt_act_t* gs, float* dbias_prev, int32_t dtype,
+                            void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  PBT_REQUIRE(gy && y && s && gs && head_w && dw && db && act_ok(*s) && act_ok(*gs), "head_bwd: bad tensors");
+  PBT_REQUIRE(gs->n == s->n && gs->h == s->h && gs->w == s->w && gs->c >= s->c, "head_bwd: gs shape mismatch");
+  const long long items = (long long)s->n * s->h * s->w;
+  int chunks = (int)((items + kEwThreads * 8 - 1) / (kEwThreads * 8));
+  if (chunks < 1) chunks = 1;
+  if (chunks > 2 * num_sms()) chunks = 2 * num_sms();
+  dim3 grid(chunks, s->c / 8);
+  DISPATCH_DT(dtype, head_bwd_kernel<DT><<<grid, kEwThreads, 0, st>>>(gy, y, view(*s), head_w, gscale, head_tanh, dw, db,
+                                                                      view(*gs), dbias_prev));
+  PBT_CUDA_CHECK(cudaGetLastError());
+  return PBT_OK;
+}
+
+extern "C" int pbt_channel_sum(const pbt_act_t* g, float* out, const float* inv_scale, int32_t dtype, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  PBT_REQUIRE(g && out && act_ok(*g), "channel_sum: bad tensors");
+  const long long items = (long long)g->n * g->h * g->w;
+  int chunks = (int)((items + kEwThreads * 8 - 1) / (kEwThreads * 8));
+  if (chunks < 1) chunks = 1;
+  if (chunks > 2 * num_sms()) chunks = 2 * num_sms();
+  dim3 grid(chunks, g->c / 8);
+  DISPATCH_DT(dtype, channel_sum_kernel<DT><<<grid, kEwThreads, 0, st>>>(view(*g), out, inv_scale));
+  PBT_CUDA_CHECK(cudaGetLastError());
+  return PBT_OK;
+}
+
+extern "C" int pbt_absmax_f32(const float* g, int64_t count, float* out, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  PBT_REQUIRE(g && out && count > 0, "absmax: bad arguments");
+  PBT_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(float), st));
+  absmax_kernel<<<ew_grid(count), kEwThreads, 0, st>>>(g, count, out);
+  PBT_CUDA_CHECK(cudaGetLastError());
+  return PBT_OK;
+}
+
+extern "C" int pbt_make_grad_scale(const float* amax, float target, float* scale2, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  PBT_REQUIRE(amax && scale2 && target > 0.f, "make_grad_scale: bad arguments");
+  make_grad_scale_kernel<<<1, 1, 0, st>>>(amax, target, scale2);
+  PBT_CUDA_CHECK(cudaGetLastError());
+  return PBT_OK;
+}

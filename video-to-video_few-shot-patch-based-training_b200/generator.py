@@ -1,0 +1,415 @@
+"""Drop-in ``GeneratorJ`` (reference src/models/generator.py:60-239) running on hand-written sm_100a kernels.
+
+Same constructor, same ``state_dict`` keys/shapes (the module tree is rebuilt in the reference's
+registration order so that a given torch seed initialises the weights bit-for-bit identically), same
+``forward(x[N,Cin,H,W]) -> [N,3,H,W]`` contract incl. autograd.  The nn.Conv2d / norm sub-modules are only
+parameter containers: the arithmetic runs through libpbt.so (tcgen05 implicit-GEMM convolutions with fused
+epilogues, HBM-bound elementwise kernels) in the P8 activation layout.  No PyTorch / CPU fallback exists:
+on a non-CUDA tensor forward raises.
+
+Data flow of one forward (reference :210-239; fused differently):
+  x -> P8 into the tail channels of the conv11 input buffer `cat11` (torch.cat :230 is never executed)
+  initial 7x7 conv (+IN stats) -> norm+lrelu -> cat11[conv0 slot] and a space-to-depth copy
+  downsample convs as 2x2 stride-1 convs over the space-to-depth tensors (stride 2 without strided TMA)
+  7 residual blocks: conv -> IN stats -> norm(+relu / +residual, fp32 residual stream)
+  decoder: bilinear x2 of [out, skip] written straight into the next conv's input buffer (cat :228-229)
+  conv11 7x7 (+bias, relu) -> smoothers (BN: batch stats in train, folded affine in eval) -> 1x1+tanh fused
+  into the last conv's epilogue.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from . import ops
+from ._native import ACT_LEAKY, ACT_NONE, ACT_RELU, BF16, FP16, P8
+
+EPS = 1e-5
+
+
+class UpsamplingLayer(nn.Module):
+    """parameter-free x2 bilinear (align_corners=True) stage; kept so module indices match the reference"""
+
+    def __init__(self, channels: int):
+        super().__init__()
+        self.layer = nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True)
+
+
+class ResNetBlock(nn.Module):
+    """container for `block.{1,4}` conv parameters (reference :18-58)"""
+
+    def __init__(self, channels: int, norm_layer: Optional[str] = "instance_norm", use_bias: bool = False):
+        super().__init__()
+        norm = _norm_cls(norm_layer)
+        seq: List[nn.Module] = []
+        for _ in range(2):
+            seq += [nn.ReLU(inplace=False), nn.Conv2d(channels, channels, 3, 1, 1, bias=use_bias)]
+            if norm is not None:
+                seq.append(norm(channels))
+        self.block = nn.Sequential(*seq)
+
+
+def _norm_cls(name):
+    return {"batch_norm": nn.BatchNorm2d, "instance_norm": nn.InstanceNorm2d}.get(name)
+
+
+def _pad16(c: int) -> int:
+    return (c + 15) // 16 * 16
+
+
+class GeneratorJ(nn.Module):
+    #: operand dtype of the tensor-core path: "bf16" | "fp16" (class default; per-instance attribute overrides)
+    operand_dtype = "fp16"
+
+    def __init__(self, input_channels: int = 3, additional_channels: Optional[Dict[str, Any]] = None,
+                 filters: List[int] = [32, 64, 128, 128, 128, 64], norm_layer: str = "instance_norm",
+                 use_bias: bool = False, resnet_blocks: int = 7, tanh: bool = True, append_smoothers: bool = True,
+                 input_size: int = 256):
+        super().__init__()
+        filters = [int(f) for f in filters]
+        self.input_size = input_size
+        self.append_smoothers = append_smoothers
+        self.input_channels = int(input_channels)
+        self.filters = filters
+        self.norm_layer = norm_layer
+        self.use_tanh = bool(tanh)
+        norm = _norm_cls(norm_layer)
+
+        def conv_block(cin, cout, k, s, p, act):
+            mods: List[nn.Module] = [nn.Conv2d(cin, cout, k, s, p, bias=use_bias)]
+            if norm is not None:
+                mods.append(norm(cout))
+            mods.append(act)
+            return nn.Sequential(*mods)
+
+        def up_block(cin, cout):
+            mods: List[nn.Module] = [UpsamplingLayer(cin), nn.Conv2d(cin, cout, 3, 1, 1, bias=use_bias)]
+            if norm is not None:
+                mods.append(norm(cout))
+            mods.append(nn.ReLU(inplace=False))
+            return nn.Sequential(*mods)
+
+        f = filters
+        self.initial_conv = conv_block(self.input_channels, f[0], 7, 1, 3, nn.LeakyReLU(0.2, inplace=False))
+        self.downsample1 = conv_block(f[0], f[1], 3, 2, 1, nn.LeakyReLU(0.2, inplace=False))
+        self.downsample2 = conv_block(f[1], f[2], 3, 2, 1, nn.LeakyReLU(0.2, inplace=False))
+        self.resnet_blocks = nn.ModuleList([ResNetBlock(f[2], norm_layer, use_bias) for _ in range(int(resnet_blocks))])
+        self.upsample2 = up_block(f[2] + f[2], f[4])
+        self.upsample1 = up_block(f[4] + f[1], f[4])
+        self.conv11 = nn.Sequential(nn.Conv2d(f[0] + f[4] + self.input_channels, f[5], 7, 1, 3, bias=use_bias),
+                                    nn.ReLU(inplace=False))
+        if append_smoothers:
+            self.smoothers = nn.Sequential(nn.Conv2d(f[5], f[5], 3, padding=1, bias=use_bias), nn.ReLU(inplace=False),
+                                           nn.BatchNorm2d(f[5]),
+                                           nn.Conv2d(f[5], f[5], 3, padding=1, bias=use_bias), nn.ReLU(inplace=False))
+        head: List[nn.Module] = [nn.Conv2d(f[5], 3, 1, bias=True)]
+        if tanh:
+            head.append(nn.Tanh())
+        self.output = nn.Sequential(*head)
+        self.apply(self._init_weights)
+        self._engine: Optional[_Engine] = None
+
+    @staticmethod
+    def _init_weights(m: nn.Module):
+        # reference :149-154 — N(0, 0.02) conv weights, zero biases
+        if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)):
+            nn.init.normal_(m.weight.data, 0.0, 0.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias.data, 0.0)
+
+    # ------------------------------------------------------------------ forward
+    def _check_supported(self):
+        f = self.filters
+        if self.norm_layer != "instance_norm":
+            raise NotImplementedError("native GeneratorJ supports norm_layer='instance_norm' only (the reference default)")
+        if any(c % 16 for c in (f[0], f[1], f[2], f[4], f[5])) or max(f) > 256 or 2 * f[2] > 256:
+            raise NotImplementedError(f"native GeneratorJ needs filter counts that are multiples of 16 and <= 256, got {f}")
+        if not self.append_smoothers:
+            raise NotImplementedError("native GeneratorJ is built for append_smoothers=True (the reference default)")
+
+    def forward(self, x: Tensor) -> Tensor:
+        if not x.is_cuda:
+            raise RuntimeError("GeneratorJ (B200-native) has no CPU path: move the module and its input to a CUDA device")
+        if x.dim() != 4 or x.shape[1] != self.input_channels:
+            raise ValueError(f"expected input [N,{self.input_channels},H,W], got {tuple(x.shape)}")
+        if x.shape[2] % 4 or x.shape[3] % 4:
+            raise ValueError("H and W must be multiples of 4 (skip connections of the reference mismatch otherwise)")
+        self._check_supported()
+        if self._engine is None:
+            self._engine = _Engine(self)
+        params = _param_list(self)
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        if need_grad:
+            y = _GeneratorFn.apply(x, self, *params)
+        else:
+            y = self._engine.forward(x, save=False)
+        return y if y.dtype == x.dtype else y.to(x.dtype)
+
+
+def _param_list(g: GeneratorJ) -> List[nn.Parameter]:
+    return list(g.parameters())
+
+
+class _GeneratorFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gen, *params):
+        ctx.gen = gen
+        ctx.x_needs_grad = x.requires_grad
+        y = gen._engine.forward(x, save=True)
+        ctx.mark_non_differentiable()
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (y,) = ctx.saved_tensors
+        if ctx.x_needs_grad:
+            raise NotImplementedError("gradient w.r.t. the generator input is not computed by the native path "
+                                      "(the reference training never uses it)")
+        grads = ctx.gen._engine.backward(gy.contiguous().float(), y)
+        return (None, None, *grads)
+
+
+class _Workspace:
+    """all device buffers for one (N, H, W) problem size"""
+
+    def __init__(self, eng: "_Engine", n: int, h: int, w: int, train: bool):
+        g, dt = eng.gen, eng.dt
+        f = g.filters
+        cp = eng.cin_p
+        dev = eng.device
+        self.n, self.h, self.w, self.train = n, h, w, train
+        h2, w2, h4, w4 = h // 2, w // 2, h // 4, w // 4
+        nb = len(g.resnet_blocks)
+        E = lambda c, hh, ww, zero=False: P8.empty(n, c, hh, ww, dt, device=dev, zero=zero)  # noqa: E731
+        self.cat11 = E(f[4] + f[0] + cp, h, w, zero=True)
+        self.raw0 = E(f[0], h, w)
+        self.s2d0 = E(4 * f[0], h2, w2)
+        self.raw1 = E(f[1], h2, w2)
+        self.c1cat = E(f[4] + f[1], h2, w2)
+        self.s2d1 = E(4 * f[1], h4, w4)
+        self.raw2 = E(f[2], h4, w4)
+        self.c2cat = E(2 * f[2], h4, w4)
+        k = nb if train else 1
+        self.rawA = [E(f[2], h4, w4) for _ in range(k)]
+        self.rawB = [E(f[2], h4, w4) for _ in range(k)]
+        self.hmid = [E(f[2], h4, w4) for _ in range(k)]
+        self.a = [E(f[2], h4, w4) for _ in range((nb + 1) if train else 2)]
+        self.r = [torch.empty((n, f[2] // 8, h4, w4, 8), device=dev) for _ in range(2)]
+        self.u2in = E(2 * f[2], h2, w2)
+        self.rawU2 = E(f[4], h2, w2)
+        self.u1in = E(f[4] + f[1], h, w)
+        self.rawU1 = E(f[4], h, w)
+        self.c11 = E(f[5], h, w)
+        self.s0 = E(f[5], h, w)
+        self.s0n = E(f[5], h, w)
+        self.s3 = E(f[5], h, w) if train else None
+        self.y = torch.empty((n, 3, h, w), device=dev)
+        # norm statistics: name -> (partial, scale, shift)
+        self.stats: Dict[str, Any] = {}
+
+    def stat(self, name: str, c: int, hh: int, ww: int, T: int, dev):
+        if name not in self.stats:
+            tiles = ops.conv_num_tiles(hh, ww, T)
+            self.stats[name] = dict(tiles=tiles, partial=torch.empty((self.n, tiles, 2, c), device=dev),
+                                    scale=torch.empty((self.n, c), device=dev), shift=torch.empty((self.n, c), device=dev))
+        return self.stats[name]
+
+
+class _Engine:
+    """orchestrates the native kernels for one GeneratorJ instance (host glue only)"""
+
+    def __init__(self, gen: GeneratorJ):
+        self.gen = gen
+        od = getattr(gen, "operand_dtype", "fp16")
+        self.dt = {"bf16": BF16, "fp16": FP16}[od]
+        self.cin_p = _pad16(gen.input_channels)
+        self.device = next(gen.parameters()).device
+        self._ws: Dict[Any, _Workspace] = {}
+        self._wcache: Dict[str, Any] = {}
+        self._wkey = None
+        self.grad_scale_target = 1024.0 if self.dt == FP16 else 0.0  # dynamic power-of-two gradient scaling (fp16 only)
+
+    # -------------------------------------------------------------- helpers
+    def workspace(self, n, h, w, train) -> _Workspace:
+        key = (n, h, w, train)
+        ws = self._ws.get(key)
+        if ws is None:
+            if len(self._ws) >= 4:
+                self._ws.clear()
+            ws = _Workspace(self, n, h, w, train)
+            self._ws[key] = ws
+        return ws
+
+    @staticmethod
+    def _T(pref: int, w: int) -> int:
+        return max(1, min(pref, (w + 7) // 8))
+
+    def _blk(self, cin: int) -> int:
+        return 32 if cin % 32 == 0 or cin > 32 else 16
+
+    def _weights(self, with_dgrad: bool):
+        """packed 16-bit weights, rebuilt only when a parameter changed (version counters)"""
+        g = self.gen
+        key = tuple((p.data_ptr(), p._version) for p in g.parameters()) + (with_dgrad,)
+        if key == self._wkey:
+            return self._wcache
+        f, dt, cp = g.filters, self.dt, self.cin_p
+        W: Dict[str, Any] = {}
+
+        def fwd(name, w, cin_pad):
+            w = w.detach().float()
+            W[name] = ops.pack_conv_weight(w, cin_pad, self._blk(cin_pad), dt)
+            return w
+
+        def dgr(name, w, cout_keep=None):
+            wt = ops.dgrad_weight(w)  # [cin, cout, kh, kw] flipped
+            if cout_keep is not None:
+                wt = wt[:cout_keep]
+            co = wt.shape[0]
+            pad = _pad16(co) - co
+            if pad:
+                wt = torch.cat([wt, wt.new_zeros((pad,) + tuple(wt.shape[1:]))], 0)
+            W[name + ".d"] = ops.pack_conv_weight(wt.contiguous(), wt.shape[1], self._blk(wt.shape[1]), dt)
+
+        fwd("initial", g.initial_conv[0].weight, cp)
+        w1 = ops.s2d_weight(g.downsample1[0].weight.detach().float())
+        w2 = ops.s2d_weight(g.downsample2[0].weight.detach().float())
+        fwd("down1", w1, 4 * f[0])
+        fwd("down2", w2, 4 * f[1])
+        for i, blk in enumerate(g.resnet_blocks):
+            wa = fwd(f"res{i}.a", blk.block[1].weight, f[2])
+            wb = fwd(f"res{i}.b", blk.block[4].weight, f[2])
+            if with_dgrad:
+                dgr(f"res{i}.a", wa)
+                dgr(f"res{i}.b", wb)
+        wu2 = fwd("up2", g.upsample2[1].weight, 2 * f[2])
+        wu1 = fwd("up1", g.upsample1[1].weight, f[4] + f[1])
+        # conv11 input order = [out(f4), conv0(f0), x(cin)] — identical to the reference cat (:230), zero padded
+        w11 = fwd("conv11", g.conv11[0].weight, f[4] + f[0] + cp)
+        ws0 = fwd("smooth0", g.smoothers[0].weight, f[5])
+        ws3 = fwd("smooth3", g.smoothers[3].weight, f[5])
+        if with_dgrad:
+            dgr("down1", w1)
+            dgr("down2", w2)
+            dgr("up2", wu2)
+            dgr("up1", wu1)
+            dgr("conv11", w11, cout_keep=f[4] + f[0])
+            dgr("smooth0", ws0)
+            dgr("smooth3", ws3)
+        W["head_w"] = g.output[0].weight.detach().float().reshape(3, f[5]).contiguous()
+        W["head_b"] = g.output[0].bias.detach().float().contiguous()
+
+        def bias(m):
+            return None if m.bias is None else m.bias.detach().float().contiguous()
+
+        W["b11"], W["bs0"], W["bs3"] = bias(g.conv11[0]), bias(g.smoothers[0]), bias(g.smoothers[3])
+        self._wcache, self._wkey = W, key
+        return W
+
+    # -------------------------------------------------------------- forward
+    def forward(self, x: Tensor, save: bool) -> Tensor:
+        g, dt, dev = self.gen, self.dt, self.device
+        f = g.filters
+        n, _, h, w = x.shape
+        h2, w2, h4, w4 = h // 2, w // 2, h // 4, w // 4
+        train_bn = g.training
+        ws = self.workspace(n, h, w, save)
+        W = self._weights(with_dgrad=save)
+        cp = self.cin_p
+        x = x.contiguous()
+        if x.dtype not in (torch.float32, torch.float16):
+            x = x.float()
+
+        def conv_in(name, xin, cout, k, pad, raw, T_pref):
+            """conv (bias skipped: a constant per channel is removed by the following InstanceNorm) + IN statistics"""
+            T = self._T(T_pref, xin.w)
+            st = ws.stat(name, cout, xin.h, xin.w, T, dev)
+            ops.conv_fwd(xin, W[name], cout, k, k, pad, pad, dt, blk_c=self._blk(xin.c), tiles_per_cta=T, out=raw,
+                         stats_partial=st["partial"])
+            ops.norm_finalize(st["partial"], n, st["tiles"], cout, xin.h * xin.w, st["scale"], st["shift"], eps=EPS)
+            return st
+
+        # input -> tail channels of cat11 (pad channels zeroed every call)
+        xin = ws.cat11.view(f[4] + f[0], cp)
+        ops.nchw_to_p8(x, xin, dt)
+        # encoder
+        st = conv_in("initial", xin, f[0], 7, 3, ws.raw0, 3)
+        ops.norm_apply(ws.raw0, dt, scale=st["scale"], shift=st["shift"], act=ACT_LEAKY, out=ws.cat11.view(f[4], f[0]),
+                       out_s2d=ws.s2d0)
+        st = conv_in("down1", ws.s2d0, f[1], 2, 1, ws.raw1, 2)
+        ops.norm_apply(ws.raw1, dt, scale=st["scale"], shift=st["shift"], act=ACT_LEAKY, out=ws.c1cat.view(f[4], f[1]),
+                       out_s2d=ws.s2d1)
+        st = conv_in("down2", ws.s2d1, f[2], 2, 1, ws.raw2, 2)
+        nb = len(g.resnet_blocks)
+        r_cur, r_nxt = ws.r[0], ws.r[1]
+        a_of = (lambda i: ws.a[i]) if save else (lambda i: ws.a[i % 2])
+        last16 = ws.c2cat.view(0, f[2])
+        if nb == 0:
+            ops.norm_apply(ws.raw2, dt, scale=st["scale"], shift=st["shift"], act=ACT_LEAKY, out=ws.c2cat.view(f[2], f[2]))
+            ops.norm_apply(ws.raw2, dt, scale=st["scale"], shift=st["shift"], act=ACT_LEAKY, out=last16)
+        else:
+            ops.norm_apply(ws.raw2, dt, scale=st["scale"], shift=st["shift"], act=ACT_LEAKY, out=ws.c2cat.view(f[2], f[2]),
+                           out32=r_cur, out_relu=a_of(0))
+        # residual blocks: r_{b+1} = r_b + IN(convB(relu(IN(convA(relu(r_b))))))
+        for b in range(nb):
+            k = b if save else 0
+            st = conv_in(f"res{b}.a", a_of(b), f[2], 3, 1, ws.rawA[k], 2)
+            ops.norm_apply(ws.rawA[k], dt, scale=st["scale"], shift=st["shift"], act=ACT_RELU, out=ws.hmid[k])
+            st = conv_in(f"res{b}.b", ws.hmid[k], f[2], 3, 1, ws.rawB[k], 2)
+            lastb = b == nb - 1
+            ops.norm_apply(ws.rawB[k], dt, scale=st["scale"], shift=st["shift"], act=ACT_NONE, residual32=r_cur,
+                           out32=None if lastb else r_nxt, out=last16 if lastb else None,
+                           out_relu=a_of(b + 1) if (not lastb or save) else None)
+            r_cur, r_nxt = r_nxt, r_cur
+        # decoder
+        ops.upsample2x(ws.c2cat, ws.u2in, dt)
+        st = conv_in("up2", ws.u2in, f[4], 3, 1, ws.rawU2, 2)
+        ops.norm_apply(ws.rawU2, dt, scale=st["scale"], shift=st["shift"], act=ACT_RELU, out=ws.c1cat.view(0, f[4]))
+        ops.upsample2x(ws.c1cat, ws.u1in, dt)
+        st = conv_in("up1", ws.u1in, f[4], 3, 1, ws.rawU1, 2)
+        ops.norm_apply(ws.rawU1, dt, scale=st["scale"], shift=st["shift"], act=ACT_RELU, out=ws.cat11.view(0, f[4]))
+        # conv11 + smoothers + fused head
+        ops.conv_fwd(ws.cat11, W["conv11"], f[5], 7, 7, 3, 3, dt, blk_c=32, tiles_per_cta=self._T(3, w), bias=W["b11"],
+                     act=ACT_RELU, out=ws.c11)
+        bn = g.smoothers[2]
+        T3 = self._T(3, w)
+        if train_bn:
+            st = ws.stat("bn", f[5], h, w, T3, dev)
+            ops.conv_fwd(ws.c11, W["smooth0"], f[5], 3, 3, 1, 1, dt, blk_c=32, tiles_per_cta=T3, bias=W["bs0"], act=ACT_RELU,
+                         out=ws.s0, stats_partial=st["partial"])
+            if "mean" not in st:
+                st["mean"] = torch.empty((f[5],), device=dev)
+                st["rstd"] = torch.empty((f[5],), device=dev)
+            ops.norm_finalize(st["partial"], n, st["tiles"], f[5], h * w, st["scale"], st["shift"], eps=bn.eps,
+                              batch_mode=True, gamma=bn.weight.detach().float(), beta=bn.bias.detach().float(),
+                              running_mean=bn.running_mean, running_var=bn.running_var,
+                              momentum=bn.momentum if bn.momentum is not None else 0.1, mean_out=st["mean"],
+                              rstd_out=st["rstd"])
+            bn.num_batches_tracked += 1
+            ops.norm_apply(ws.s0, dt, scale=st["scale"], shift=st["shift"], act=ACT_NONE, out=ws.s0n)
+        else:
+            # eval: fold BatchNorm's running statistics into the epilogue of smoothers.0 (after its ReLU)
+            rstd = torch.rsqrt(bn.running_var.float() + bn.eps)
+            sc = (bn.weight.detach().float() * rstd).contiguous()
+            sh = (bn.bias.detach().float() - bn.running_mean.float() * sc).contiguous()
+            ops.conv_fwd(ws.c11, W["smooth0"], f[5], 3, 3, 1, 1, dt, blk_c=32, tiles_per_cta=T3, bias=W["bs0"], act=ACT_RELU,
+                         post_scale=sc, post_shift=sh, out=ws.s0n)
+            if save:
+                raise RuntimeError("autograd through GeneratorJ in eval() mode is not supported by the native path")
+        y = ws.y if not save else torch.empty_like(ws.y)
+        ops.conv_fwd(ws.s0n, W["smooth3"], f[5], 3, 3, 1, 1, dt, blk_c=32, tiles_per_cta=T3, bias=W["bs3"], act=ACT_RELU,
+                     out=ws.s3 if save else None, head_w=W["head_w"], head_b=W["head_b"], head_out=y, head_tanh=g.use_tanh)
+        if save:
+            self._saved = (ws, W)
+            return y
+        return y.clone() if False else y
+
+    # -------------------------------------------------------------- backward
+    def backward(self, gy: Tensor, y: Tensor):
+        """returns gradients for `list(gen.parameters())` in order"""
+        from .generator_bwd import generator_backward
+        return generator_backward(self, gy, y)

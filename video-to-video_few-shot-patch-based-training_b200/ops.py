@@ -1,0 +1,216 @@
+"""Thin Python wrappers over the C-ABI ops of libpbt.so plus the host-side weight packing.
+
+Every function enqueues native CUDA work on torch's current stream and returns
+immediately; PyTorch only owns the buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _native as nv
+from ._native import ACT_LEAKY, ACT_NONE, ACT_RELU, BF16, FP16, P8, Act, act_or_null, check, lib, ptr, stream_ptr
+
+__all__ = [
+    "pack_conv_weight", "s2d_weight", "s2d_weight_grad", "dgrad_weight", "conv_fwd", "conv_wgrad", "conv_num_tiles",
+    "norm_finalize", "norm_apply", "upsample2x", "upsample2x_bwd", "norm_bwd", "head_bwd", "channel_sum", "nchw_to_p8",
+    "p8_to_nchw", "p8f_to_nchw", "u8hwc_to_p8", "nchw_to_u8hwc", "u8hwc_to_norm_chw", "patch_gather", "mask_dilate7",
+    "absmax", "make_grad_scale",
+]
+
+
+# ----------------------------------------------------------------------------- weights
+def pack_conv_weight(w: torch.Tensor, cin_pad: int, blk_c: int, dt: int) -> torch.Tensor:
+    """[cout, cin, kh, kw] fp32 -> flat 16-bit buffer  w[cb][tap][k/8][cout][k%8]  (see include/pbt.h)."""
+    cout, cin, kh, kw = w.shape
+    assert cin_pad % 16 == 0 and cin_pad >= cin and cout % 16 == 0
+    wp = w.new_zeros((cout, cin_pad, kh, kw))
+    wp[:, :cin] = w
+    t = wp.permute(2, 3, 1, 0).reshape(kh * kw, cin_pad, cout)  # [tap][ci][co]
+    chunks = []
+    for c0 in range(0, cin_pad, blk_c):
+        c1 = min(c0 + blk_c, cin_pad)
+        blk = t[:, c0:c1].reshape(kh * kw, (c1 - c0) // 8, 8, cout).permute(0, 1, 3, 2)  # [tap][k8][co][8]
+        chunks.append(blk.reshape(-1))
+    return torch.cat(chunks).to(nv.torch_dtype(dt)).contiguous()
+
+
+def dgrad_weight(w: torch.Tensor) -> torch.Tensor:
+    """weights of the stride-1 conv that maps dY -> dX: channel-transposed, tap-flipped."""
+    return w.transpose(0, 1).flip(2, 3).contiguous()
+
+
+_S2D_TAPS = ((0, 1, 0), (1, 0, 1), (1, 1, 2))  # (s2d tap, phase, original 3x3 tap)
+
+
+def s2d_weight(w: torch.Tensor) -> torch.Tensor:
+    """3x3 stride-2 pad-1 kernel [co, c, 3, 3] -> equivalent 2x2 stride-1 (pad top/left 1) kernel over the
+    space-to-depth input [co, 4c, 2, 2]; channel = ((y&1)*2 + (x&1))*c + ci."""
+    co, c = w.shape[0], w.shape[1]
+    w2 = w.new_zeros((co, 4 * c, 2, 2))
+    for ty, py, dy in _S2D_TAPS:
+        for tx, px, dx in _S2D_TAPS:
+            ph = py * 2 + px
+            w2[:, ph * c:(ph + 1) * c, ty, tx] = w[:, :, dy, dx]
+    return w2
+
+
+def s2d_weight_grad(dw2: torch.Tensor, c: int) -> torch.Tensor:
+    """inverse of s2d_weight for gradients: [co, 4c, 2, 2] -> [co, c, 3, 3]."""
+    co = dw2.shape[0]
+    dw = dw2.new_zeros((co, c, 3, 3))
+    for ty, py, dy in _S2D_TAPS:
+        for tx, px, dx in _S2D_TAPS:
+            ph = py * 2 + px
+            dw[:, :, dy, dx] = dw2[:, ph * c:(ph + 1) * c, ty, tx]
+    return dw
+
+
+# ----------------------------------------------------------------------------- convolution
+def conv_num_tiles(h: int, w: int, tiles_per_cta: int) -> int:
+    return lib().pbt_conv_num_tiles(h, w, tiles_per_cta)
+
+
+def conv_fwd(x: P8, wpack: torch.Tensor, cout: int, kh: int, kw: int, pad_t: int, pad_l: int, dt: int, *,
+             blk_c: int = 32, tiles_per_cta: int = 2, bias=None, act: int = ACT_NONE, post_scale=None, post_shift=None,
+             mask: P8 | None = None, addend32=None, out32=None, out: P8 | None = None, stats_partial=None,
+             head_w=None, head_b=None, head_out=None, head_tanh: bool = True, debug_flags: int = 0) -> None:
+    d = nv.ConvDesc()
+    d.inp = x.act()
+    d.wpack = wpack.data_ptr()
+    d.cout, d.kh, d.kw, d.pad_t, d.pad_l = cout, kh, kw, pad_t, pad_l
+    d.blk_c, d.tiles_per_cta, d.dtype = blk_c, tiles_per_cta, dt
+    d.bias, d.act = ptr(bias), act
+    d.post_scale, d.post_shift = ptr(post_scale), ptr(post_shift)
+    d.mask = act_or_null(mask)
+    d.addend32, d.out32 = ptr(addend32), ptr(out32)
+    d.out = act_or_null(out)
+    d.stats_partial = ptr(stats_partial)
+    d.head_w, d.head_b, d.head_out, d.head_tanh = ptr(head_w), ptr(head_b), ptr(head_out), int(head_tanh)
+    d.debug_flags = debug_flags
+    check(lib().pbt_conv_fwd(C.byref(d), stream_ptr()), "pbt_conv_fwd")
+
+
+def conv_wgrad(x: P8, dy: P8, kh: int, kw: int, pad_t: int, pad_l: int, dt: int, dw: torch.Tensor, inv_scale=None,
+               debug_flags: int = 0) -> None:
+    """dw: fp32 [kh*kw, cin, cout], accumulated into."""
+    d = nv.WgradDesc()
+    d.x, d.dy = x.act(), dy.act()
+    d.kh, d.kw, d.pad_t, d.pad_l, d.dtype = kh, kw, pad_t, pad_l, dt
+    d.dw, d.inv_scale, d.debug_flags = dw.data_ptr(), ptr(inv_scale), debug_flags
+    check(lib().pbt_conv_wgrad(C.byref(d), stream_ptr()), "pbt_conv_wgrad")
+
+
+# ----------------------------------------------------------------------------- normalisation
+def norm_finalize(partial, n, tiles, c, count_per_image, scale, shift, *, eps=1e-5, batch_mode=False, gamma=None,
+                  beta=None, running_mean=None, running_var=None, momentum=0.1, mean_out=None, rstd_out=None) -> None:
+    check(lib().pbt_norm_finalize(partial.data_ptr(), n, tiles, c, count_per_image, eps, int(batch_mode), ptr(gamma),
+                                  ptr(beta), ptr(running_mean), ptr(running_var), momentum, scale.data_ptr(),
+                                  shift.data_ptr(), ptr(mean_out), ptr(rstd_out), stream_ptr()), "pbt_norm_finalize")
+
+
+def norm_apply(x: P8, dt: int, *, scale=None, shift=None, per_channel=False, act=ACT_NONE, residual32=None,
+               out: P8 | None = None, out_relu: P8 | None = None, out32=None, out_s2d: P8 | None = None) -> None:
+    d = nv.NormApplyDesc()
+    d.x = x.act()
+    d.scale, d.shift, d.per_channel, d.act = ptr(scale), ptr(shift), int(per_channel), act
+    d.residual32 = ptr(residual32)
+    d.out, d.out_relu, d.out32, d.out_s2d = act_or_null(out), act_or_null(out_relu), ptr(out32), act_or_null(out_s2d)
+    d.dtype = dt
+    check(lib().pbt_norm_apply(C.byref(d), stream_ptr()), "pbt_norm_apply")
+
+
+def upsample2x(x: P8, out: P8, dt: int) -> None:
+    a, b = x.act(), out.act()
+    check(lib().pbt_upsample2x(C.byref(a), C.byref(b), dt, stream_ptr()), "pbt_upsample2x")
+
+
+def upsample2x_bwd(gout: P8, dt: int, gin16: P8 | None = None, gin32=None) -> None:
+    a, b = gout.act(), act_or_null(gin16)
+    check(lib().pbt_upsample2x_bwd(C.byref(a), C.byref(b), ptr(gin32), dt, stream_ptr()), "pbt_upsample2x_bwd")
+
+
+def norm_bwd(x: P8, dt: int, *, scale, shift, per_channel=False, act=ACT_NONE, ga: P8 | None = None, ga_is_s2d=False,
+             gb16: P8 | None = None, gb32=None, sums, kmul, count: int, batch_mode=False, dx: P8) -> None:
+    """reduce + apply of the (norm -> act) backward; `sums` must be zeroed by the caller."""
+    d = nv.NormBwdDesc()
+    d.x = x.act()
+    d.scale, d.shift, d.per_channel, d.act = ptr(scale), ptr(shift), int(per_channel), act
+    d.ga, d.ga_is_s2d, d.gb16, d.gb32 = act_or_null(ga), int(ga_is_s2d), act_or_null(gb16), ptr(gb32)
+    d.sums, d.kmul, d.count, d.batch_mode = sums.data_ptr(), kmul.data_ptr(), count, int(batch_mode)
+    d.dx, d.dtype = dx.act(), dt
+    check(lib().pbt_norm_bwd_reduce(C.byref(d), stream_ptr()), "pbt_norm_bwd_reduce")
+    check(lib().pbt_norm_bwd_apply(C.byref(d), stream_ptr()), "pbt_norm_bwd_apply")
+
+
+def head_bwd(gy, y, s: P8, head_w, dt: int, *, gscale=None, head_tanh=True, dw, db, gs: P8, dbias_prev=None) -> None:
+    a, b = s.act(), gs.act()
+    check(lib().pbt_head_bwd(gy.data_ptr(), y.data_ptr(), C.byref(a), head_w.data_ptr(), ptr(gscale), int(head_tanh),
+                             dw.data_ptr(), db.data_ptr(), C.byref(b), ptr(dbias_prev), dt, stream_ptr()), "pbt_head_bwd")
+
+
+def channel_sum(g: P8, out, dt: int, inv_scale=None) -> None:
+    a = g.act()
+    check(lib().pbt_channel_sum(C.byref(a), out.data_ptr(), ptr(inv_scale), dt, stream_ptr()), "pbt_channel_sum")
+
+
+# ----------------------------------------------------------------------------- layout / dtype
+def nchw_to_p8(x: torch.Tensor, out: P8, dt: int) -> None:
+    assert x.is_contiguous() and x.dtype in (torch.float32, torch.float16)
+    n, c, h, w = x.shape
+    a = out.act()
+    check(lib().pbt_nchw_to_p8(x.data_ptr(), int(x.dtype == torch.float16), n, c, h, w, C.byref(a), dt, stream_ptr()),
+          "pbt_nchw_to_p8")
+
+
+def p8_to_nchw(x: P8, c: int, out: torch.Tensor, dt: int, mul: float = 1.0) -> None:
+    a = x.act()
+    check(lib().pbt_p8_to_nchw_f32(C.byref(a), c, out.data_ptr(), mul, dt, stream_ptr()), "pbt_p8_to_nchw_f32")
+
+
+def p8f_to_nchw(x32: torch.Tensor, c: int, out: torch.Tensor) -> None:
+    n, planes, h, w, _ = x32.shape
+    check(lib().pbt_p8f_to_nchw_f32(x32.data_ptr(), n, planes * 8, c, h, w, out.data_ptr(), stream_ptr()),
+          "pbt_p8f_to_nchw_f32")
+
+
+def u8hwc_to_p8(img: torch.Tensor, out: P8, dt: int) -> None:
+    n, h, w, c = img.shape
+    a = out.act()
+    check(lib().pbt_u8hwc_to_p8(img.data_ptr(), n, h, w, c, C.byref(a), dt, stream_ptr()), "pbt_u8hwc_to_p8")
+
+
+def nchw_to_u8hwc(y: torch.Tensor, out: torch.Tensor) -> None:
+    n, c, h, w = y.shape
+    check(lib().pbt_nchw_to_u8hwc(y.data_ptr(), n, c, h, w, out.data_ptr(), stream_ptr()), "pbt_nchw_to_u8hwc")
+
+
+def u8hwc_to_norm_chw(img: torch.Tensor, out: torch.Tensor) -> None:
+    h, w, c = img.shape
+    check(lib().pbt_u8hwc_to_norm_chw(img.data_ptr(), h, w, c, out.data_ptr(), stream_ptr()), "pbt_u8hwc_to_norm_chw")
+
+
+def mask_dilate7(mask: torch.Tensor, out: torch.Tensor) -> None:
+    h, w = mask.shape
+    check(lib().pbt_mask_dilate7(mask.data_ptr(), h, w, out.data_ptr(), stream_ptr()), "pbt_mask_dilate7")
+
+
+def patch_gather(src_table: torch.Tensor, n_src: int, n_images: int, ch: int, img_hw: torch.Tensor, pos: torch.Tensor,
+                 patch: int, outs, ch_off, ch_total) -> None:
+    """src_table: int64 device tensor [n_src, n_images] of fp32 CHW image pointers."""
+    n_patches = pos.shape[0]
+    out_ptrs = (C.c_void_p * n_src)(*[o.data_ptr() for o in outs])
+    offs = (C.c_int32 * n_src)(*ch_off)
+    tots = (C.c_int32 * n_src)(*ch_total)
+    check(lib().pbt_patch_gather(src_table.data_ptr(), n_src, n_images, ch, img_hw.data_ptr(), pos.data_ptr(), n_patches,
+                                 patch, C.cast(out_ptrs, C.c_void_p), C.cast(offs, C.c_void_p), C.cast(tots, C.c_void_p),
+                                 stream_ptr()), "pbt_patch_gather")
+
+
+def absmax(g: torch.Tensor, out: torch.Tensor) -> None:
+    check(lib().pbt_absmax_f32(g.data_ptr(), g.numel(), out.data_ptr(), stream_ptr()), "pbt_absmax_f32")
+
+
+def make_grad_scale(amax: torch.Tensor, target: float, scale2: torch.Tensor) -> None:
+    check(lib().pbt_make_grad_scale(amax.data_ptr(), target, scale2.data_ptr(), stream_ptr()), "pbt_make_grad_scale")
