@@ -176,8 +176,8 @@ int pbt_upsample2x_bwd(const pbt_act_t* gout, const pbt_act_t* gin16, float* gin
  * ---------------------------------------------------------------------- */
 typedef struct {
   pbt_act_t    x;           /* raw conv output saved by the forward pass */
-  const float* scale;       /* as given to pbt_norm_apply */
-  const float* shift;
+  const float* scale;       /* rstd and -mean*rstd, so that xhat = x*scale + shift (for InstanceNorm these are */
+  const float* shift;       /* exactly the arrays given to pbt_norm_apply)                                    */
   int32_t      per_channel;
   int32_t      act;
   pbt_act_t    ga;          /* grad wrt y, 16-bit */
@@ -190,6 +190,7 @@ typedef struct {
   int32_t      batch_mode;
   pbt_act_t    dx;          /* 16-bit output of apply */
   int32_t      dtype;
+  int32_t      relu_mask_x; /* 1: dx is additionally zeroed where x <= 0 (x is itself a ReLU output, e.g. BatchNorm input) */
 } pbt_norm_bwd_desc_t;
 int pbt_norm_bwd_reduce(const pbt_norm_bwd_desc_t* d, void* stream);
 int pbt_norm_bwd_apply(const pbt_norm_bwd_desc_t* d, void* stream);

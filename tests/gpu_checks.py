@@ -200,22 +200,30 @@ def check_u8(dt=FP16):
     img = torch.randint(0, 256, (2, 10, 14, 3), generator=g, device="cuda", dtype=torch.uint8)
     out = P8.empty(2, 16, 10, 14, dt)
     ops.u8hwc_to_p8(img, out, dt)
-    ref = ((img.permute(0, 3, 1, 2).float() / 255.0) - 0.5) / 0.5
-    ok = bool((out.to_nchw()[:, :3] == ref.to(torch_dtype(dt)).float()).all()) and bool((out.to_nchw()[:, 3:] == 0).all())
+    # reference arithmetic on the CPU (true IEEE division, as ToTensor/Normalize do in the reference's
+    # dataset; torch's CUDA kernels divide by a scalar through a reciprocal multiply and differ in the last bit)
+    ref = (((img.cpu().permute(0, 3, 1, 2).float() / 255.0) - 0.5) / 0.5).cuda()
+    msgs = []
+    if not (bool((out.to_nchw()[:, :3] == ref.to(torch_dtype(dt)).float()).all()) and bool((out.to_nchw()[:, 3:] == 0).all())):
+        msgs.append("u8hwc_to_p8 mismatch")
     chw = torch.empty((3, 10, 14), device="cuda")
-    ops.u8hwc_to_norm_chw(img[0], chw)
-    ok &= bool((chw == ref[0]).all())  # bit exact vs ToTensor+Normalize arithmetic
+    ops.u8hwc_to_norm_chw(img[0].contiguous(), chw)
+    if not bool((chw == ref[0]).all()):  # bit exact vs ToTensor+Normalize arithmetic
+        msgs.append(f"u8hwc_to_norm_chw mismatch max={float((chw - ref[0]).abs().max()):.3g}")
     y = torch.randn((2, 3, 10, 14), generator=g, device="cuda") * 0.8
     u8 = torch.empty((2, 10, 14, 3), device="cuda", dtype=torch.uint8)
     ops.nchw_to_u8hwc(y, u8)
-    exp = ((y.clamp(-1, 1) + 1) * 127.5).clamp(0, 255).permute(0, 2, 3, 1).round().to(torch.uint8)
-    ok &= bool((u8 == exp).all())
+    yc = y.cpu()
+    exp = ((yc.clamp(-1, 1) + 1) * 127.5).clamp(0, 255).permute(0, 2, 3, 1).round().to(torch.uint8).cuda()
+    if not bool((u8 == exp).all()):
+        msgs.append(f"nchw_to_u8hwc mismatch n={int((u8 != exp).sum())}")
     m = (torch.rand((37, 53), generator=g, device="cuda") > 0.97).to(torch.uint8) * 255
     d = torch.empty_like(m)
     ops.mask_dilate7(m, d)
     expd = (F.conv2d((m.float() / 255.0)[None, None], torch.ones((1, 1, 7, 7), device="cuda"), padding=3)[0, 0] != 0)
-    ok &= bool((d.bool() == expd).all())
-    return ok, 0.0, ""
+    if not bool((d.bool() == expd).all()):
+        msgs.append("mask_dilate7 mismatch")
+    return not msgs, 0.0, "; ".join(msgs)
 
 
 def check_norm(dt=BF16, batch_mode=False):

@@ -1,0 +1,123 @@
+"""GPU parity of every native op (through the C-ABI) against float64 restatements — see tests/gpu_checks.py."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    import gpu_checks as gc
+    from pbt_b200._native import ACT_LEAKY, ACT_RELU, BF16, FP16
+
+CONV_CASES = [
+    dict(cin=16, cout=16),
+    dict(cin=64, cout=16, blk_c=32),
+    dict(cin=48, cout=16, blk_c=32),
+    dict(cin=16, cout=160),
+    dict(cin=16, cout=16, dt=1),
+    dict(cin=16, cout=32, kh=7, kw=7, pad_t=3, pad_l=3),
+    dict(cin=32, cout=16, kh=2, kw=2, pad_t=1, pad_l=1, blk_c=32),
+    dict(cin=32, cout=16, kh=2, kw=2, pad_t=0, pad_l=0, blk_c=32),
+    dict(n=2, cin=32, cout=64, h=48, w=72, kh=7, kw=7, pad_t=3, pad_l=3, T=3, blk_c=32),
+    dict(n=3, cin=128, cout=128, h=20, w=20, kh=3, kw=3, pad_t=1, pad_l=1, T=2, blk_c=32),
+    dict(n=5, cin=128, cout=128, h=8, w=8, kh=3, kw=3, pad_t=1, pad_l=1, T=1, blk_c=64),
+    dict(n=2, cin=32, cout=32, h=16, w=16, kh=3, kw=3, pad_t=1, pad_l=1, T=2, blk_c=32, in_off=16, in_extra=8, out_off=8,
+         out_extra=16),
+    dict(cin=176, cout=64, h=32, w=32, kh=7, kw=7, pad_t=3, pad_l=3, T=3, blk_c=32),
+    dict(cin=256, cout=128, h=16, w=16, kh=3, kw=3, pad_t=1, pad_l=1, T=2, blk_c=32),
+    dict(cin=32, cout=32, h=16, w=16, kh=3, kw=3, pad_t=1, pad_l=1, T=2, blk_c=32, bias=True, act=1),
+    dict(cin=32, cout=32, h=16, w=16, kh=3, kw=3, pad_t=1, pad_l=1, T=2, blk_c=32, bias=True, act=2, affine=True,
+         integer=False),
+    dict(cin=32, cout=32, h=16, w=24, kh=3, kw=3, pad_t=1, pad_l=1, T=2, blk_c=32, mask=True, addend=True, out32=True),
+    dict(cin=32, cout=32, h=16, w=24, kh=3, kw=3, pad_t=1, pad_l=1, T=2, blk_c=32, out32=True, store16=False),
+    dict(n=2, cin=32, cout=64, h=24, w=40, kh=3, kw=3, pad_t=1, pad_l=1, T=2, blk_c=32, stats=True),
+    dict(n=2, cin=32, cout=128, h=20, w=20, kh=3, kw=3, pad_t=1, pad_l=1, T=2, blk_c=32, stats=True, integer=False),
+    dict(n=2, cin=64, cout=64, h=16, w=24, kh=3, kw=3, pad_t=1, pad_l=1, T=2, blk_c=32, bias=True, act=1, head=True,
+         integer=False),
+    dict(cin=128, cout=128, h=32, w=32, kh=3, kw=3, pad_t=1, pad_l=1, T=2, blk_c=32, integer=False, dt=1),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
+def test_conv_fwd(case):
+    ok, err, msg = gc.check_conv(**case)
+    assert ok, f"err={err} {msg}"
+
+
+WGRAD_CASES = [
+    dict(cin=16, cout=16),
+    dict(cin=128, cout=16),
+    dict(cin=16, cout=128),
+    dict(cin=16, cout=16, kh=3, kw=3, pad_t=1, pad_l=1),
+    dict(n=2, cin=128, cout=128, h=32, w=32, kh=3, kw=3, pad_t=1, pad_l=1),
+    dict(cin=176, cout=64, h=32, w=32, kh=7, kw=7, pad_t=3, pad_l=3),
+    dict(n=3, cin=256, cout=128, h=20, w=20, kh=2, kw=2, pad_t=1, pad_l=1),
+    dict(cin=192, cout=128, h=24, w=24, kh=3, kw=3, pad_t=1, pad_l=1, dt=1, integer=False, inv_scale=0.25),
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
+def test_conv_wgrad(case):
+    ok, err, msg = gc.check_wgrad(**case)
+    assert ok, f"err={err} {msg}"
+
+
+@pytest.mark.parametrize("dt", [0, 1])
+def test_layout_roundtrip(dt):
+    assert gc.check_layout_roundtrip(dt=dt)[0]
+
+
+def test_u8_and_mask_kernels():
+    ok, _, msg = gc.check_u8()
+    assert ok, msg
+
+
+@pytest.mark.parametrize("kw", [dict(dt=0), dict(dt=1), dict(dt=1, batch_mode=True)])
+def test_norm_finalize_apply(kw):
+    ok, err, msg = gc.check_norm(**kw)
+    assert ok, msg
+
+
+@pytest.mark.parametrize("dt", [0, 1])
+def test_upsample_and_transpose(dt):
+    ok, err, msg = gc.check_upsample(dt=dt)
+    assert ok, msg
+
+
+@pytest.mark.parametrize("kw", [dict(dt=1), dict(dt=1, s2d=True), dict(dt=1, batch_mode=True), dict(dt=0)])
+def test_norm_backward(kw):
+    ok, err, msg = gc.check_norm_bwd(**kw)
+    assert ok, msg
+
+
+@pytest.mark.parametrize("dt", [0, 1])
+def test_head_backward(dt):
+    ok, err, msg = gc.check_head_bwd(dt=dt)
+    assert ok, msg
+
+
+def test_grad_scale():
+    ok, _, msg = gc.check_grad_scale()
+    assert ok, msg
+
+
+@pytest.mark.parametrize("kw", [dict(patch=32), dict(patch=80, n_patches=9), dict(patch=7, n_patches=9)])
+def test_patch_gather_bit_exact(kw):
+    assert gc.check_gather(**kw)[0]
+
+
+def test_patch_gather_empty_batch():
+    from pbt_b200 import ops
+    t = torch.zeros((1, 1), dtype=torch.int64, device="cuda")
+    hw = torch.zeros((1, 2), dtype=torch.int32, device="cuda")
+    pos = torch.zeros((0, 3), dtype=torch.int32, device="cuda")
+    out = torch.zeros((0, 3, 8, 8), device="cuda")
+    ops.patch_gather(t, 1, 1, 3, hw, pos, 8, [out], [0], [3])  # must be a no-op, not an error
+
+
+def test_bad_arguments_raise():
+    from pbt_b200 import ops
+    from pbt_b200._native import P8
+    x = P8.empty(1, 24, 16, 16, 0)  # cin not a multiple of 16
+    w = torch.zeros(16 * 24 * 2, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="cin must be a multiple of 16"):
+        ops.conv_fwd(x, w, 16, 1, 1, 0, 0, 0, blk_c=16, tiles_per_cta=1, out=P8.empty(1, 16, 16, 16, 0))

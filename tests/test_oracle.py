@@ -1,0 +1,153 @@
+"""Pins the oracle (oracle/*.py) to fixtures produced by the UNMODIFIED reference (oracle/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import generator_oracle as go
+from oracle import sampler_oracle as so
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def trained_sd():
+    z = np.load(os.path.join(GOLD, "gen_c3_trained.npz"))
+    return {k: torch.from_numpy(z[k]) for k in z.files}
+
+
+@pytest.fixture(scope="module")
+def vec():
+    return np.load(os.path.join(GOLD, "gen_c3_vectors.npz"))
+
+
+def test_state_dict_layout(trained_sd):
+    # 48 parameter tensors + 3 BatchNorm buffers, Cin = 3
+    assert len(trained_sd) == 51
+    assert trained_sd["initial_conv.0.weight"].shape == (32, 3, 7, 7)
+    assert trained_sd["conv11.0.weight"].shape == (64, 163, 7, 7)
+    assert trained_sd["smoothers.2.num_batches_tracked"].dtype == torch.int64
+
+
+def test_generator_eval_matches_reference(trained_sd, vec):
+    y = go.generator_forward(trained_sd, torch.from_numpy(vec["x"]), training=False)
+    assert (y - torch.from_numpy(vec["y_eval"])).abs().max().item() < 2e-5
+
+
+def test_generator_full_frame_matches_reference(trained_sd, vec):
+    y = go.generator_forward(trained_sd, torch.from_numpy(vec["frame"]), training=False)
+    assert (y - torch.from_numpy(vec["y_frame"])).abs().max().item() < 5e-5
+
+
+def test_generator_train_and_grads_match_reference(trained_sd, vec):
+    x, tgt = torch.from_numpy(vec["x"]), torch.from_numpy(vec["target"])
+    y, loss, grads = go.loss_and_grads(trained_sd, x, tgt)
+    assert (y - torch.from_numpy(vec["y_train"])).abs().max().item() < 2e-5
+    assert abs(loss.item() - float(vec["loss"])) < 1e-5
+    for k, g in grads.items():
+        ref_norm = float(vec["gnorm_" + k])
+        assert abs(float(g.double().norm()) - ref_norm) <= 2e-4 * max(ref_norm, 1e-6) + 1e-7, k
+        if "g_" + k in vec.files:
+            ref = torch.from_numpy(vec["g_" + k])
+            assert (g - ref).abs().max().item() <= 1e-4 * max(float(vec["gmax_" + k]), 1e-7) + 1e-7, k
+        else:
+            flat = g.reshape(-1)
+            sub = flat[:: max(1, flat.numel() // 4096)]
+            assert (sub - torch.from_numpy(vec["gs_" + k])).abs().max().item() <= 1e-4 * float(vec["gmax_" + k]) + 1e-7, k
+
+
+def test_bn_running_stats_update(trained_sd, vec):
+    sd = {k: v.clone() for k, v in trained_sd.items()}
+    st = {"running_mean": sd["smoothers.2.running_mean"], "running_var": sd["smoothers.2.running_var"],
+          "num_batches_tracked": sd["smoothers.2.num_batches_tracked"]}
+    go.generator_forward(sd, torch.from_numpy(vec["x"]), training=True, bn_state=st)
+    assert torch.allclose(st["running_mean"], torch.from_numpy(vec["bn_rm_after"]), atol=1e-5)
+    assert torch.allclose(st["running_var"], torch.from_numpy(vec["bn_rv_after"]), atol=1e-5)
+
+
+def test_adam_clip_step_matches_torch():
+    torch.manual_seed(3)
+    p = {"a": torch.randn(7, 5), "b": torch.randn(11)}
+    tp = [torch.nn.Parameter(v.clone()) for v in p.values()]
+    opt = torch.optim.Adam(tp, lr=4e-4, betas=(0.9, 0.999), weight_decay=1e-5)
+    st = go.AdamState(list(p))
+    for _ in range(3):
+        g = {k: torch.randn_like(v) for k, v in p.items()}
+        for q, gg in zip(tp, g.values()):
+            q.grad = gg.clone()
+        torch.nn.utils.clip_grad_norm_(tp, 0.5)
+        opt.step()
+        go.clip_grad_norm(g, 0.5)
+        st.step(p, g)
+    for q, v in zip(tp, p.values()):
+        assert torch.allclose(q.detach(), v, atol=1e-7)
+
+
+def test_frame_to_uint8():
+    y = torch.tensor([[[[-1.2, -1.0, 0.0]], [[0.003, 0.5, 1.0]], [[2.0, -0.5, 0.999]]]])
+    u = go.frame_to_uint8(y)
+    assert u.shape == (1, 1, 3, 3) and u.dtype == torch.uint8
+    assert u[0, 0, :, 0].tolist() == [0, 0, 128] and u[0, 0, 2, 1] == 255
+
+
+# ------------------------------------------------------------------------------- sampler
+def _mini(name):
+    return os.path.join(GOLD, "mini_dataset", name)
+
+
+@pytest.fixture(scope="module")
+def sampler_gold():
+    return np.load(os.path.join(GOLD, "sampler_golden.npz"))
+
+
+def test_sampler_draws_and_patches_match_reference(sampler_gold):
+    s = so.OracleSampler(_mini("input"), _mini("output"), _mini("mask"), 32,
+                         additional_channels={"guide": {"path": _mini("guide"), "depth": 3}})
+    assert len(s) == int(sampler_gold["length"])
+    assert [len(v) for v in s.valid] == sampler_gold["n_valid"].tolist()
+    log = sampler_gold["log"]
+    np.random.seed(123)
+    items = []
+    for (idx, img, y, x) in log:
+        it = s[int(idx)]
+        assert s.last_patch_positions[0] == [int(y), int(x)]
+        items.append(it)
+    # image 3 has fewer valid centres than draws: the refill path was exercised
+    assert (log[:, 1] == 3).sum() > sampler_gold["n_valid"][3]
+    for bi in range(2):
+        for key in ("pre", "post", "channel_guide"):
+            ref = sampler_gold[f"b{bi}_{key}"]
+            got = np.stack([items[bi * 8 + j][key] for j in range(8)])
+            assert np.array_equal(ref, got), (bi, key)
+
+
+def test_cut_patch_edge_cases():
+    z = np.load(os.path.join(GOLD, "cutpatch_golden.npz"))
+    img = z["image"]
+    n = 0
+    for key in z.files:
+        if key == "image":
+            continue
+        P, y, x = (int(v) for v in key[1:].split("_"))
+        assert np.array_equal(so.cut_patch(img, y, x, P), z[key]), key
+        n += 1
+    assert n == 21
+
+
+def test_dilate7_equals_conv_nonzero():
+    rng = np.random.RandomState(0)
+    m = (rng.rand(40, 57) > 0.97).astype(np.uint8)
+    ref = torch.nn.functional.conv2d(torch.from_numpy(m)[None, None].float(), torch.ones(1, 1, 7, 7), padding=3)[0, 0] != 0
+    assert np.array_equal(so.dilate7(m).astype(bool), ref.numpy())
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/test_dataset/miku_train_sorce"), reason="reference sample data absent")
+def test_sampler_on_reference_sample_data():
+    z = np.load(os.path.join(GOLD, "sampler_miku_golden.npz"))
+    d = "/root/reference/test_dataset/miku_train_sorce"
+    s = so.OracleSampler(os.path.join(d, "input"), os.path.join(d, "output"), os.path.join(d, "mask"), 32)
+    assert [len(v) for v in s.valid] == z["n_valid"].tolist() and len(s) == int(z["length"])
+    np.random.seed(0)
+    for (idx, img, y, x) in z["log"]:
+        assert s.draw(int(idx)) == (int(img), int(y), int(x))

@@ -63,6 +63,7 @@ class NormBwdDesc(C.Structure):
         ("x", Act), ("scale", C.c_void_p), ("shift", C.c_void_p), ("per_channel", C.c_int32), ("act", C.c_int32),
         ("ga", Act), ("ga_is_s2d", C.c_int32), ("gb16", Act), ("gb32", C.c_void_p), ("sums", C.c_void_p),
         ("kmul", C.c_void_p), ("count", C.c_int64), ("batch_mode", C.c_int32), ("dx", Act), ("dtype", C.c_int32),
+        ("relu_mask_x", C.c_int32),
     ]
 
 

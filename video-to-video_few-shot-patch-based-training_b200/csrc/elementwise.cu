@@ -141,7 +141,7 @@ __global__ void nchw_to_u8hwc_kernel(const float* __restrict__ y, int n, int c, 
     for (int ch = 0; ch < c; ++ch) {
       float v = y[((long long)ni * c + ch) * hw + pix];
       v = fminf(fmaxf(v, -1.f), 1.f);
-      v = fminf(fmaxf((v + 1.f) * 127.5f, 0.f), 255.f);
+      v = fminf(fmaxf(__fmul_rn(__fadd_rn(v, 1.f), 127.5f), 0.f), 255.f);
       out[i * c + ch] = (uint8_t)rintf(v);
     }
   }
@@ -382,7 +382,7 @@ struct NormBwdK {
   ActView x, ga, gb16, dx;
   const float* mean;   // "scale"/"shift" of the ABI carry rstd and -mean*rstd (xhat = x*scale + shift)
   const float* shift;
-  int per_channel, act, ga_is_s2d, batch_mode;
+  int per_channel, act, ga_is_s2d, batch_mode, relu_mask_x;
   const float* gb32;
   float* sums;
   const float* kmul;
@@ -391,8 +391,7 @@ struct NormBwdK {
 
 template <int DT>
 __device__ __forceinline__ void load_gact(const NormBwdK& p, int ni, int pl, long long pix, int planes, long long hw,
-                                          float* gact, float* xhat) {
-  float xr[8];
+                                          float* gact, float* xhat, float* xr) {
   unpack8<DT>(*chunk_ptr(p.x, ni, pl, pix), xr);
   const long long so = (p.per_channel ? 0 : (long long)ni * p.x.c) + pl * 8;
 #pragma unroll
@@ -438,8 +437,8 @@ __global__ void norm_bwd_reduce_kernel(NormBwdK p) {
 #pragma unroll
   for (int k = 0; k < 8; ++k) s1[k] = s2[k] = 0.f;
   for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < hw; pix += (long long)gridDim.x * blockDim.x) {
-    float gact[8], xhat[8];
-    load_gact<DT>(p, ni, pl, pix, planes, hw, gact, xhat);
+    float gact[8], xhat[8], xr[8];
+    load_gact<DT>(p, ni, pl, pix, planes, hw, gact, xhat, xr);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       s1[k] += gact[k];
@@ -482,14 +481,15 @@ __global__ void norm_bwd_apply_kernel(NormBwdK p) {
     const long long pix = i % hw;
     const int pl = (int)((i / hw) % planes);
     const int ni = (int)(i / (hw * planes));
-    float gact[8], xhat[8], r[8];
-    load_gact<DT>(p, ni, pl, pix, planes, hw, gact, xhat);
+    float gact[8], xhat[8], r[8], xr[8];
+    load_gact<DT>(p, ni, pl, pix, planes, hw, gact, xhat, xr);
     const float* sp = p.sums + (p.batch_mode ? 0 : (long long)ni * 2 * p.x.c) + pl * 8;
     const long long ko = (p.per_channel ? 0 : (long long)ni * p.x.c) + pl * 8;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float m1 = __ldg(&sp[k]) * p.inv_count, m2 = __ldg(&sp[p.x.c + k]) * p.inv_count;
       r[k] = __ldg(&p.kmul[ko + k]) * (gact[k] - m1 - xhat[k] * m2);
+      if (p.relu_mask_x && !(xr[k] > 0.f)) r[k] = 0.f;
     }
     *chunk_ptr(p.dx, ni, pl, pix) = pack8<DT>(r);
   }
@@ -782,7 +782,7 @@ static int fill_norm_bwd(const pbt_norm_bwd_desc_t* d, NormBwdK& p) {
     p.gb16 = view(d->gb16);
   }
   p.mean = d->scale; p.shift = d->shift; p.per_channel = d->per_channel; p.act = d->act;
-  p.ga_is_s2d = d->ga_is_s2d; p.batch_mode = d->batch_mode; p.gb32 = d->gb32; p.sums = d->sums; p.kmul = d->kmul;
+  p.ga_is_s2d = d->ga_is_s2d; p.batch_mode = d->batch_mode; p.relu_mask_x = d->relu_mask_x; p.gb32 = d->gb32; p.sums = d->sums; p.kmul = d->kmul;
   PBT_REQUIRE(d->count > 0, "norm_bwd: count must be positive");
   p.inv_count = (float)(1.0 / (double)d->count);
   return PBT_OK;

@@ -159,7 +159,6 @@ class _GeneratorFn(torch.autograd.Function):
         ctx.gen = gen
         ctx.x_needs_grad = x.requires_grad
         y = gen._engine.forward(x, save=True)
-        ctx.mark_non_differentiable()
         ctx.save_for_backward(y)
         return y
 
@@ -207,7 +206,6 @@ class _Workspace:
         self.s0 = E(f[5], h, w)
         self.s0n = E(f[5], h, w)
         self.s3 = E(f[5], h, w) if train else None
-        self.y = torch.empty((n, 3, h, w), device=dev)
         # norm statistics: name -> (partial, scale, shift)
         self.stats: Dict[str, Any] = {}
 
@@ -363,7 +361,7 @@ class _Engine:
             lastb = b == nb - 1
             ops.norm_apply(ws.rawB[k], dt, scale=st["scale"], shift=st["shift"], act=ACT_NONE, residual32=r_cur,
                            out32=None if lastb else r_nxt, out=last16 if lastb else None,
-                           out_relu=a_of(b + 1) if (not lastb or save) else None)
+                           out_relu=None if lastb else a_of(b + 1))
             r_cur, r_nxt = r_nxt, r_cur
         # decoder
         ops.upsample2x(ws.c2cat, ws.u2in, dt)
@@ -400,13 +398,12 @@ class _Engine:
                          post_scale=sc, post_shift=sh, out=ws.s0n)
             if save:
                 raise RuntimeError("autograd through GeneratorJ in eval() mode is not supported by the native path")
-        y = ws.y if not save else torch.empty_like(ws.y)
+        y = torch.empty((n, 3, h, w), device=dev)  # fresh result tensor: callers may keep it across calls
         ops.conv_fwd(ws.s0n, W["smooth3"], f[5], 3, 3, 1, 1, dt, blk_c=32, tiles_per_cta=T3, bias=W["bs3"], act=ACT_RELU,
                      out=ws.s3 if save else None, head_w=W["head_w"], head_b=W["head_b"], head_out=y, head_tanh=g.use_tanh)
         if save:
             self._saved = (ws, W)
-            return y
-        return y.clone() if False else y
+        return y
 
     # -------------------------------------------------------------- backward
     def backward(self, gy: Tensor, y: Tensor):

@@ -1,0 +1,177 @@
+"""Backward pass of the native GeneratorJ (autograd of reference src/models/generator.py:210-239, which
+fires inside ``manual_backward`` at lightning_model.py:241).
+
+Hand-scheduled reverse sweep over the buffers the forward pass saved:
+  per conv   : wgrad (tcgen05, K = pixels) + dgrad (the forward implicit-GEMM kernel with tap-flipped,
+               channel-transposed weights; ReLU masks / residual fan-in fused into its epilogue)
+  per norm   : two-kernel InstanceNorm/BatchNorm backward (reduce, apply) with the activation derivative,
+               skip-connection fan-in and the space-to-depth indexing of the stride-2 layers folded in
+  upsample   : gather form of the transposed bilinear x2
+All 16-bit gradient tensors carry a power-of-two scale S chosen from max|dL/dy| (fp16 operands only); the
+fp32 parameter gradients are unscaled inside the producing kernels.
+"""
+from __future__ import annotations
+
+from typing import List
+
+import torch
+
+from . import ops
+from ._native import ACT_LEAKY, ACT_NONE, ACT_RELU, P8
+
+
+def _wgrad_to_param(dw: torch.Tensor, cout: int, cin: int, kh: int, kw: int) -> torch.Tensor:
+    """[taps, cin_pad, cout] -> [cout, cin, kh, kw]"""
+    return dw[:, :cin].permute(2, 1, 0).reshape(cout, cin, kh, kw).contiguous()
+
+
+def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor) -> List[torch.Tensor]:
+    g, dt, dev = eng.gen, eng.dt, eng.device
+    ws, W = eng._saved
+    f = g.filters
+    cp = eng.cin_p
+    n, h, w = ws.n, ws.h, ws.w
+    h2, w2, h4, w4 = h // 2, w // 2, h // 4, w // 4
+    nb = len(g.resnet_blocks)
+    if nb == 0:
+        raise NotImplementedError("native backward needs at least one residual block")
+    E = lambda c, hh, ww: P8.empty(n, c, hh, ww, dt, device=dev)  # noqa: E731
+    Z = lambda *shape: torch.zeros(shape, device=dev)  # noqa: E731
+
+    # ---- gradient scale (fp16 only): S = 2^k with max|gy|*S in (target/2, target]
+    scale2 = None
+    gscale = inv = None
+    if eng.grad_scale_target > 0:
+        amax = torch.empty(1, device=dev)
+        scale2 = torch.empty(2, device=dev)
+        ops.absmax(gy, amax)
+        ops.make_grad_scale(amax, eng.grad_scale_target, scale2)
+        gscale, inv = scale2[0:1], scale2[1:2]
+
+    def T_of(pref, ww):
+        return eng._T(pref, ww)
+
+    def dgrad(name, gin: P8, cout, k, pad, out=None, T_pref=2, **kw):
+        """conv of the output gradient with the transposed/flipped kernel -> gradient of the conv input"""
+        acc_stride = (cout + 31) // 32 * 32
+        T = T_of(T_pref, gin.w)
+        while T > 1 and T * acc_stride > 512:
+            T -= 1
+        ops.conv_fwd(gin, W[name + ".d"], cout, k, k, k - 1 - pad, k - 1 - pad, dt, blk_c=eng._blk(gin.c), tiles_per_cta=T,
+                     out=out, **kw)
+
+    def wgrad(x: P8, dy: P8, k, pad):
+        dw = Z(k * k, x.c, dy.c)
+        ops.conv_wgrad(x, dy, k, k, pad, pad, dt, dw, inv_scale=inv)
+        return dw
+
+    def in_bwd(x: P8, st, act, dx: P8, count, **kw):
+        sums = Z(n, 2, x.c)
+        ops.norm_bwd(x, dt, scale=st["scale"], shift=st["shift"], act=act, sums=sums, kmul=st["scale"], count=count, dx=dx, **kw)
+
+    grads = {}
+
+    # ---- head (1x1 + tanh) and the ReLU of smoothers.3
+    dw_out, db_out, db_s3 = Z(3, f[5]), Z(3), Z(f[5])
+    g_s3 = E(f[5], h, w)
+    ops.head_bwd(gy, y, ws.s3, W["head_w"], dt, gscale=gscale, head_tanh=g.use_tanh, dw=dw_out, db=db_out, gs=g_s3,
+                 dbias_prev=db_s3)
+    if inv is not None:
+        dw_out, db_out, db_s3 = dw_out * inv, db_out * inv, db_s3 * inv
+    grads["output.0.weight"] = dw_out.reshape(3, f[5], 1, 1)
+    grads["output.0.bias"] = db_out
+    # ---- smoothers.3
+    grads["smoothers.3.weight"] = _wgrad_to_param(wgrad(ws.s0n, g_s3, 3, 1), f[5], f[5], 3, 3)
+    grads["smoothers.3.bias"] = db_s3
+    g_s0n = E(f[5], h, w)
+    dgrad("smooth3", g_s3, f[5], 3, 1, out=g_s0n, T_pref=3)
+    # ---- BatchNorm (batch statistics) + the ReLU in front of it
+    st = ws.stats["bn"]
+    bn = g.smoothers[2]
+    bn_rstd, bn_mean = st["rstd"], st["mean"]
+    bn_sums = Z(2, f[5])
+    g_s0 = E(f[5], h, w)
+    ops.norm_bwd(ws.s0, dt, scale=bn_rstd, shift=(-bn_mean * bn_rstd).contiguous(), per_channel=True, act=ACT_NONE, ga=g_s0n,
+                 sums=bn_sums, kmul=(bn.weight.detach().float() * bn_rstd).contiguous(), count=n * h * w, batch_mode=True,
+                 dx=g_s0, relu_mask_x=True)
+    grads["smoothers.2.weight"] = bn_sums[1] * inv if inv is not None else bn_sums[1].clone()
+    grads["smoothers.2.bias"] = bn_sums[0] * inv if inv is not None else bn_sums[0].clone()
+    db_s0 = Z(f[5])
+    ops.channel_sum(g_s0, db_s0, dt, inv_scale=inv)
+    # ---- smoothers.0
+    grads["smoothers.0.weight"] = _wgrad_to_param(wgrad(ws.c11, g_s0, 3, 1), f[5], f[5], 3, 3)
+    grads["smoothers.0.bias"] = db_s0
+    g_c11 = E(f[5], h, w)
+    dgrad("smooth0", g_s0, f[5], 3, 1, out=g_c11, T_pref=3, mask=ws.c11)
+    db_11 = Z(f[5])
+    ops.channel_sum(g_c11, db_11, dt, inv_scale=inv)
+    # ---- conv11 (input = cat11 = [up1 | conv0 | x])
+    cin11 = f[4] + f[0] + g.input_channels
+    grads["conv11.0.weight"] = _wgrad_to_param(wgrad(ws.cat11, g_c11, 7, 3), f[5], cin11, 7, 7)
+    grads["conv11.0.bias"] = db_11
+    g_cat = E(f[4] + f[0], h, w)
+    dgrad("conv11", g_c11, f[4] + f[0], 7, 3, out=g_cat, T_pref=3)
+    del g_c11, g_s0, g_s0n, g_s3
+    # ---- upsample1 block
+    g_rawU1 = E(f[4], h, w)
+    in_bwd(ws.rawU1, ws.stats["up1"], ACT_RELU, g_rawU1, h * w, ga=g_cat.view(0, f[4]))
+    grads["upsample1.1.weight"] = _wgrad_to_param(wgrad(ws.u1in, g_rawU1, 3, 1), f[4], f[4] + f[1], 3, 3)
+    g_u1in = E(f[4] + f[1], h, w)
+    dgrad("up1", g_rawU1, f[4] + f[1], 3, 1, out=g_u1in)
+    del g_rawU1
+    g_c1cat = E(f[4] + f[1], h2, w2)
+    ops.upsample2x_bwd(g_u1in, dt, gin16=g_c1cat)
+    del g_u1in
+    # ---- upsample2 block
+    g_rawU2 = E(f[4], h2, w2)
+    in_bwd(ws.rawU2, ws.stats["up2"], ACT_RELU, g_rawU2, h2 * w2, ga=g_c1cat.view(0, f[4]))
+    grads["upsample2.1.weight"] = _wgrad_to_param(wgrad(ws.u2in, g_rawU2, 3, 1), f[4], 2 * f[2], 3, 3)
+    g_u2in = E(2 * f[2], h2, w2)
+    dgrad("up2", g_rawU2, 2 * f[2], 3, 1, out=g_u2in)
+    g_r = torch.empty((n, f[2] // 8, h4, w4, 8), device=dev)          # fp32 gradient of the residual stream
+    g_c2skip = E(f[2], h4, w4)
+    ops.upsample2x_bwd(g_u2in.view(0, f[2]), dt, gin32=g_r)
+    ops.upsample2x_bwd(g_u2in.view(f[2], f[2]), dt, gin16=g_c2skip)
+    del g_u2in, g_rawU2
+    # ---- residual blocks, last to first
+    g_raw = E(f[2], h4, w4)
+    g_h = E(f[2], h4, w4)
+    for b in range(nb - 1, -1, -1):
+        in_bwd(ws.rawB[b], ws.stats[f"res{b}.b"], ACT_NONE, g_raw, h4 * w4, gb32=g_r)
+        grads[f"resnet_blocks.{b}.block.4.weight"] = _wgrad_to_param(wgrad(ws.hmid[b], g_raw, 3, 1), f[2], f[2], 3, 3)
+        dgrad(f"res{b}.b", g_raw, f[2], 3, 1, out=g_h)
+        in_bwd(ws.rawA[b], ws.stats[f"res{b}.a"], ACT_RELU, g_raw, h4 * w4, ga=g_h)
+        grads[f"resnet_blocks.{b}.block.1.weight"] = _wgrad_to_param(wgrad(ws.a[b], g_raw, 3, 1), f[2], f[2], 3, 3)
+        # g_r <- g_r + relu'(r_b) * dgrad   (in place: every element is read then written by the same thread)
+        dgrad(f"res{b}.a", g_raw, f[2], 3, 1, out=None, mask=ws.a[b], addend32=g_r, out32=g_r)
+    # ---- downsample2 (conv2 feeds the residual stream and the decoder skip)
+    g_raw2 = E(f[2], h4, w4)
+    in_bwd(ws.raw2, ws.stats["down2"], ACT_LEAKY, g_raw2, h4 * w4, gb16=g_c2skip, gb32=g_r)
+    dw2 = wgrad(ws.s2d1, g_raw2, 2, 1)                                   # [4, 4*f1, f2]
+    grads["downsample2.0.weight"] = ops.s2d_weight_grad(dw2.permute(2, 1, 0).reshape(f[2], 4 * f[1], 2, 2), f[1])
+    g_s2d1 = E(4 * f[1], h4, w4)
+    dgrad("down2", g_raw2, 4 * f[1], 2, 1, out=g_s2d1)
+    # ---- downsample1
+    g_raw1 = E(f[1], h2, w2)
+    in_bwd(ws.raw1, ws.stats["down1"], ACT_LEAKY, g_raw1, h2 * w2, ga=g_s2d1, ga_is_s2d=True, gb16=g_c1cat.view(f[4], f[1]))
+    dw1 = wgrad(ws.s2d0, g_raw1, 2, 1)
+    grads["downsample1.0.weight"] = ops.s2d_weight_grad(dw1.permute(2, 1, 0).reshape(f[1], 4 * f[0], 2, 2), f[0])
+    g_s2d0 = E(4 * f[0], h2, w2)
+    dgrad("down1", g_raw1, 4 * f[0], 2, 1, out=g_s2d0)
+    # ---- initial conv
+    g_raw0 = E(f[0], h, w)
+    in_bwd(ws.raw0, ws.stats["initial"], ACT_LEAKY, g_raw0, h * w, ga=g_s2d0, ga_is_s2d=True, gb16=g_cat.view(f[4], f[0]))
+    dw0 = wgrad(ws.cat11.view(f[4] + f[0], cp), g_raw0, 7, 3)
+    grads["initial_conv.0.weight"] = _wgrad_to_param(dw0, f[0], g.input_channels, 7, 7)
+
+    # ---- assemble in parameter order; a bias in front of an affine-less InstanceNorm has exactly zero gradient
+    out: List[torch.Tensor] = []
+    for name, p in g.named_parameters():
+        gr = grads.get(name)
+        if gr is None:
+            if name.endswith(".bias"):
+                gr = torch.zeros_like(p)
+            else:
+                raise RuntimeError(f"no gradient produced for {name}")
+        out.append(gr.reshape(p.shape).to(p.dtype))
+    return out

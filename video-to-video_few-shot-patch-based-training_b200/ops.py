@@ -132,14 +132,15 @@ def upsample2x_bwd(gout: P8, dt: int, gin16: P8 | None = None, gin32=None) -> No
 
 
 def norm_bwd(x: P8, dt: int, *, scale, shift, per_channel=False, act=ACT_NONE, ga: P8 | None = None, ga_is_s2d=False,
-             gb16: P8 | None = None, gb32=None, sums, kmul, count: int, batch_mode=False, dx: P8) -> None:
+             gb16: P8 | None = None, gb32=None, sums, kmul, count: int, batch_mode=False, dx: P8,
+             relu_mask_x=False) -> None:
     """reduce + apply of the (norm -> act) backward; `sums` must be zeroed by the caller."""
     d = nv.NormBwdDesc()
     d.x = x.act()
     d.scale, d.shift, d.per_channel, d.act = ptr(scale), ptr(shift), int(per_channel), act
     d.ga, d.ga_is_s2d, d.gb16, d.gb32 = act_or_null(ga), int(ga_is_s2d), act_or_null(gb16), ptr(gb32)
     d.sums, d.kmul, d.count, d.batch_mode = sums.data_ptr(), kmul.data_ptr(), count, int(batch_mode)
-    d.dx, d.dtype = dx.act(), dt
+    d.dx, d.dtype, d.relu_mask_x = dx.act(), dt, int(relu_mask_x)
     check(lib().pbt_norm_bwd_reduce(C.byref(d), stream_ptr()), "pbt_norm_bwd_reduce")
     check(lib().pbt_norm_bwd_apply(C.byref(d), stream_ptr()), "pbt_norm_bwd_apply")
 
