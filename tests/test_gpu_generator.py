@@ -91,24 +91,34 @@ def test_train_forward_and_one_step_gradients(trained_sd, vec, dtype):
     assert torch.allclose(g.smoothers[2].running_var.cpu(), torch.from_numpy(vec["bn_rv_after"]), rtol=2e-2, atol=2e-3)
     # full per-parameter gradients from the oracle (itself pinned to the reference in test_oracle.py)
     _, _, ref_grads = go.loss_and_grads(trained_sd, torch.from_numpy(vec["x"]), torch.from_numpy(vec["target"]))
-    worst = (0.0, "", 1e9, "")
+    worst_rel, worst_ps, rows = (0.0, ""), (1e9, ""), []
+    lim = MAX_ABS if dtype == "fp16" else 3 * MAX_ABS
+    ps_lim = PSNR_MIN if dtype == "fp16" else 35.0
+    before_in = ("initial_conv.0.bias", "downsample1.0.bias", "downsample2.0.bias", "upsample1.1.bias", "upsample2.1.bias")
+    failures = []
     for k, p in g.named_parameters():
         ref = ref_grads[k]
         got = p.grad.detach().cpu()
-        peak = float(ref.abs().max())
-        gnorm_ref = float(vec["gnorm_" + k])
-        if peak < 1e-9 or gnorm_ref < 1e-7:   # biases in front of InstanceNorm: exact zeros vs round-off noise
-            assert float(got.abs().max()) <= 1e-6, k
+        if k in before_in or (k.startswith("resnet_blocks.") and k.endswith(".bias")):
+            # a bias in front of an affine-less InstanceNorm has a mathematically zero gradient: the native path
+            # returns exact zeros, the reference returns float round-off noise far below its weight gradients
+            wref = float(ref_grads[k.replace(".bias", ".weight")].abs().max())
+            assert float(got.abs().max()) == 0.0, k
+            assert float(ref.abs().max()) <= 1e-3 * wref, (k, float(ref.abs().max()), wref)
             continue
+        peak = float(ref.abs().max())
         rel = float((got - ref).abs().max()) / peak
         ps = psnr(got, ref, peak)
-        if rel > worst[0]:
-            worst = (rel, k, worst[2], worst[3])
-        if ps < worst[2]:
-            worst = (worst[0], worst[1], ps, k)
-        lim = MAX_ABS if dtype == "fp16" else 3 * MAX_ABS
-        assert rel <= lim and ps >= (PSNR_MIN if dtype == "fp16" else 35.0), (k, rel, ps)
-    print(f"{dtype} grads: worst rel max-abs {worst[0]:.4f} ({worst[1]}), worst PSNR {worst[2]:.1f} dB ({worst[3]})")
+        rows.append(f"   {k:38s} rel_max_abs={rel:.5f} psnr={ps:.1f}")
+        if rel > worst_rel[0]:
+            worst_rel = (rel, k)
+        if ps < worst_ps[0]:
+            worst_ps = (ps, k)
+        if not (rel <= lim and ps >= ps_lim):
+            failures.append((k, rel, ps))
+    print("\n".join(rows))
+    print(f"{dtype} grads: worst rel max-abs {worst_rel[0]:.4f} ({worst_rel[1]}), worst PSNR {worst_ps[0]:.1f} dB ({worst_ps[1]})")
+    assert not failures, failures
 
 
 def test_training_reduces_loss_like_the_reference(trained_sd, vec):

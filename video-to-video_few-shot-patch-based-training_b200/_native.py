@@ -129,7 +129,11 @@ EXPORTED_SYMBOLS = [
 ]
 
 
+LAUNCHES = [0]  # native kernel launches issued through this binding (bench.py reports it)
+
+
 def check(status: int, what: str) -> None:
+    LAUNCHES[0] += 1
     if status != 0:
         L = lib()
         raise RuntimeError(f"{what} failed: {L.pbt_error_string(status).decode()} — {L.pbt_last_cuda_error().decode()}")

@@ -230,6 +230,8 @@ class _Engine:
         self._wcache: Dict[str, Any] = {}
         self._wkey = None
         self.grad_scale_target = 1024.0 if self.dt == FP16 else 0.0  # dynamic power-of-two gradient scaling (fp16 only)
+        self.grad_hook = None     # callable(name, grad) fired as each parameter gradient is produced (data parallel)
+        self.kernel_timer = None  # bench.py: list collecting CUDA-event pairs around the dominant kernel (conv11)
 
     # -------------------------------------------------------------- helpers
     def workspace(self, n, h, w, train) -> _Workspace:
@@ -309,17 +311,21 @@ class _Engine:
         return W
 
     # -------------------------------------------------------------- forward
-    def forward(self, x: Tensor, save: bool) -> Tensor:
+    def forward(self, x: Tensor, save: bool, u8_hwc: bool = False) -> Tensor:
+        """x: NCHW float (module contract) or, with u8_hwc, uint8 frames [N,H,W,Cin] normalised on load"""
         g, dt, dev = self.gen, self.dt, self.device
         f = g.filters
-        n, _, h, w = x.shape
+        if u8_hwc:
+            n, h, w, _ = x.shape
+        else:
+            n, _, h, w = x.shape
         h2, w2, h4, w4 = h // 2, w // 2, h // 4, w // 4
         train_bn = g.training
         ws = self.workspace(n, h, w, save)
         W = self._weights(with_dgrad=save)
         cp = self.cin_p
         x = x.contiguous()
-        if x.dtype not in (torch.float32, torch.float16):
+        if not u8_hwc and x.dtype not in (torch.float32, torch.float16):
             x = x.float()
 
         def conv_in(name, xin, cout, k, pad, raw, T_pref):
@@ -333,7 +339,10 @@ class _Engine:
 
         # input -> tail channels of cat11 (pad channels zeroed every call)
         xin = ws.cat11.view(f[4] + f[0], cp)
-        ops.nchw_to_p8(x, xin, dt)
+        if u8_hwc:
+            ops.u8hwc_to_p8(x, xin, dt)   # ToTensor + Normalize(0.5, 0.5) fused into the layout conversion
+        else:
+            ops.nchw_to_p8(x, xin, dt)
         # encoder
         st = conv_in("initial", xin, f[0], 7, 3, ws.raw0, 3)
         ops.norm_apply(ws.raw0, dt, scale=st["scale"], shift=st["shift"], act=ACT_LEAKY, out=ws.cat11.view(f[4], f[0]),
@@ -371,8 +380,15 @@ class _Engine:
         st = conv_in("up1", ws.u1in, f[4], 3, 1, ws.rawU1, 2)
         ops.norm_apply(ws.rawU1, dt, scale=st["scale"], shift=st["shift"], act=ACT_RELU, out=ws.cat11.view(0, f[4]))
         # conv11 + smoothers + fused head
+        ev = self.kernel_timer
+        if ev is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         ops.conv_fwd(ws.cat11, W["conv11"], f[5], 7, 7, 3, 3, dt, blk_c=32, tiles_per_cta=self._T(3, w), bias=W["b11"],
                      act=ACT_RELU, out=ws.c11)
+        if ev is not None:
+            e1.record()
+            ev.append((e0, e1))
         bn = g.smoothers[2]
         T3 = self._T(3, w)
         if train_bn:

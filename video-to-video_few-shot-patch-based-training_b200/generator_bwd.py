@@ -20,6 +20,9 @@ from . import ops
 from ._native import ACT_LEAKY, ACT_NONE, ACT_RELU, P8
 
 
+_BIAS_BEFORE_IN = ("initial_conv.", "downsample1.", "downsample2.", "resnet_blocks.", "upsample1.", "upsample2.")
+
+
 def _wgrad_to_param(dw: torch.Tensor, cout: int, cin: int, kh: int, kw: int) -> torch.Tensor:
     """[taps, cin_pad, cout] -> [cout, cin, kh, kw]"""
     return dw[:, :cin].permute(2, 1, 0).reshape(cout, cin, kh, kw).contiguous()
@@ -69,7 +72,19 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor) -> List[torch.Ten
         sums = Z(n, 2, x.c)
         ops.norm_bwd(x, dt, scale=st["scale"], shift=st["shift"], act=act, sums=sums, kmul=st["scale"], count=count, dx=dx, **kw)
 
-    grads = {}
+    hook = getattr(eng, "grad_hook", None)   # data-parallel training: parallel.GradAllReduce.grad_ready
+
+    class _Grads(dict):
+        def __setitem__(self, k, v):
+            super().__setitem__(k, v)
+            if hook is not None:
+                hook(k, v)
+
+    grads = _Grads()
+    # a bias in front of an affine-less InstanceNorm has exactly zero gradient: publish those first
+    for name, p in g.named_parameters():
+        if name.endswith(".bias") and name.startswith(_BIAS_BEFORE_IN):
+            grads[name] = torch.zeros_like(p, dtype=torch.float32)
 
     # ---- head (1x1 + tanh) and the ReLU of smoothers.3
     dw_out, db_out, db_s3 = Z(3, f[5]), Z(3), Z(f[5])
@@ -164,14 +179,11 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor) -> List[torch.Ten
     dw0 = wgrad(ws.cat11.view(f[4] + f[0], cp), g_raw0, 7, 3)
     grads["initial_conv.0.weight"] = _wgrad_to_param(dw0, f[0], g.input_channels, 7, 7)
 
-    # ---- assemble in parameter order; a bias in front of an affine-less InstanceNorm has exactly zero gradient
+    # ---- assemble in parameter order
     out: List[torch.Tensor] = []
     for name, p in g.named_parameters():
         gr = grads.get(name)
         if gr is None:
-            if name.endswith(".bias"):
-                gr = torch.zeros_like(p)
-            else:
-                raise RuntimeError(f"no gradient produced for {name}")
+            raise RuntimeError(f"no gradient produced for {name}")
         out.append(gr.reshape(p.shape).to(p.dtype))
     return out

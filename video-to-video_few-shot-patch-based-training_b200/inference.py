@@ -1,0 +1,79 @@
+"""Full-frame video stylisation: the generator applied to whole frames (north-star path; the reference's
+per-tile loop generator.py:500-555 is replaced by one GeneratorJ.forward per frame), frames sharded across
+ranks with no collective (see parallel.shard_range).
+
+Per frame on the device:  uint8 HWC -> [ToTensor+Normalize fused into the P8 layout conversion] -> generator ->
+[clamp, (x+1)*127.5, round fused into the uint8 HWC store]   (reference generator.py:584-616,643-647).
+`stylize_host` adds the pinned-host <-> device copies, double-buffered on two streams so that the copies of
+frame i+1 / i-1 overlap the convolutions of frame i.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+from .generator import GeneratorJ, _Engine
+
+
+class FrameStylizer:
+    def __init__(self, gen: GeneratorJ):
+        if not next(gen.parameters()).is_cuda:
+            raise RuntimeError("FrameStylizer needs the generator on a CUDA device (no CPU path)")
+        self.gen = gen.eval()
+        gen._check_supported()
+        if gen._engine is None:
+            gen._engine = _Engine(gen)
+        self.eng = gen._engine
+        self.device = self.eng.device
+        self._streams = None
+
+    @torch.no_grad()
+    def stylize_device(self, frames_u8: torch.Tensor, out_u8: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """frames_u8: device uint8 [N,H,W,Cin] -> device uint8 [N,H,W,3]; one generator pass per frame"""
+        n, h, w, c = frames_u8.shape
+        if c != self.gen.input_channels:
+            raise ValueError(f"expected {self.gen.input_channels} channels, got {c}")
+        if out_u8 is None:
+            out_u8 = torch.empty((n, h, w, 3), dtype=torch.uint8, device=self.device)
+        for i in range(n):
+            y = self.eng.forward(frames_u8[i:i + 1], save=False, u8_hwc=True)
+            ops.nchw_to_u8hwc(y, out_u8[i:i + 1])
+        return out_u8
+
+    @torch.no_grad()
+    def stylize_host(self, frames_pinned: torch.Tensor, out_pinned: torch.Tensor) -> None:
+        """pinned host uint8 [N,H,W,Cin] -> pinned host uint8 [N,H,W,3], copies overlapped with compute"""
+        if not (frames_pinned.is_pinned() and out_pinned.is_pinned()):
+            raise ValueError("stylize_host needs pinned host buffers")
+        n, h, w, c = frames_pinned.shape
+        if self._streams is None:
+            self._streams = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
+        copy_in, copy_out = self._streams
+        main = torch.cuda.current_stream(self.device)
+        dev_in = [torch.empty((1, h, w, c), dtype=torch.uint8, device=self.device) for _ in range(2)]
+        dev_out = [torch.empty((1, h, w, 3), dtype=torch.uint8, device=self.device) for _ in range(2)]
+        in_ready = [torch.cuda.Event() for _ in range(2)]
+        in_free = [torch.cuda.Event() for _ in range(2)]
+        out_ready = [torch.cuda.Event() for _ in range(2)]
+        out_free = [torch.cuda.Event() for _ in range(2)]
+        for e in in_free + out_free:
+            e.record(main)
+        for i in range(n):
+            b = i & 1
+            with torch.cuda.stream(copy_in):
+                copy_in.wait_event(in_free[b])
+                dev_in[b].copy_(frames_pinned[i:i + 1], non_blocking=True)
+                in_ready[b].record(copy_in)
+            main.wait_event(in_ready[b])
+            main.wait_event(out_free[b])
+            y = self.eng.forward(dev_in[b], save=False, u8_hwc=True)
+            ops.nchw_to_u8hwc(y, dev_out[b])
+            in_free[b].record(main)
+            out_ready[b].record(main)
+            with torch.cuda.stream(copy_out):
+                copy_out.wait_event(out_ready[b])
+                out_pinned[i:i + 1].copy_(dev_out[b], non_blocking=True)
+                out_free[b].record(copy_out)
+        main.wait_stream(copy_out)
