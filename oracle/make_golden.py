@@ -124,7 +124,15 @@ def generator_golden(ds_miku):
     dl = DataLoader(ds_miku, batch_size=40, shuffle=True, num_workers=0)
     l1 = torch.nn.L1Loss()
     losses = []
-    for it, batch in enumerate(dl):
+    trained = os.path.join(GOLD, "gen_c3_trained.npz")
+    if os.path.exists(trained) and "--retrain" not in sys.argv:
+        z = np.load(trained)
+        G.load_state_dict({k: torch.from_numpy(z[k]) for k in z.files})
+        losses = list(np.load(os.path.join(GOLD, "gen_c3_vectors.npz"))["train_losses"])
+        dl_train = []
+    else:
+        dl_train = dl
+    for it, batch in enumerate(dl_train):
         opt.zero_grad()
         loss = l1(G(batch["pre"]), batch["post"]) * 4.0
         loss.backward()
@@ -136,10 +144,13 @@ def generator_golden(ds_miku):
         if it >= 99:
             break
     sd = {k: v.detach().clone() for k, v in G.state_dict().items()}
-    np.savez(os.path.join(GOLD, "gen_c3_trained.npz"), **{k: v.numpy() for k, v in sd.items()})
-    # vectors: a fresh batch of real patches
+    if dl_train:
+        np.savez(trained, **{k: v.numpy() for k, v in sd.items()})
+    # vectors: a fresh batch of real patches at the C1 batch size (40 x 32x32)
+    torch.manual_seed(11)
+    np.random.seed(11)
     batch = next(iter(dl))
-    x, tgt = batch["pre"][:8].clone(), batch["post"][:8].clone()
+    x, tgt = batch["pre"].clone(), batch["post"].clone()
     G.train()
     G.zero_grad()
     y_train = G(x)

@@ -61,11 +61,11 @@ extern "C" int pbt_patch_gather(const float* const* src_ptrs, int32_t n_src, int
                                 const int32_t* img_hw, const int32_t* pos, int32_t n_patches, int32_t patch,
                                 float* const* outs, const int32_t* out_ch_off, const int32_t* out_ch_total, void* stream_) {
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  if (n_patches == 0) return PBT_OK;  // empty batch: nothing to do (pointers may legitimately be null)
+  PBT_REQUIRE(n_patches > 0, "patch_gather: negative patch count");
   PBT_REQUIRE(src_ptrs && img_hw && pos && outs && out_ch_off && out_ch_total, "patch_gather: null argument");
   PBT_REQUIRE(n_src >= 1 && n_src <= kMaxSrc, "patch_gather: n_src must be in [1,8]");
   PBT_REQUIRE(n_images > 0 && ch > 0 && patch > 0, "patch_gather: bad sizes");
-  if (n_patches == 0) return PBT_OK;  // empty batch: nothing to do
-  PBT_REQUIRE(n_patches > 0, "patch_gather: negative patch count");
   GatherOut o;
   for (int s = 0; s < n_src; ++s) {
     PBT_REQUIRE(outs[s] != nullptr, "patch_gather: null output");

@@ -1,0 +1,92 @@
+"""A ~150-line stand-in for pytorch_lightning.Trainer (not installed in this image) that drives the
+reference-shaped ``StyleTransferModel``: setup -> train_dataloader -> training_step, manual optimisation,
+`{'state_dict': ...}` checkpoints with the `generator.` key prefix the inference driver expects
+(reference generator.py:115-118,180), top-k on g_total_loss + last.ckpt (reference train.py:22-31), early
+stopping on the epoch mean (train.py:39-46).  With WORLD_SIZE > 1 (torchrun, one process per GPU) the
+generator gradients are mean all-reduced over NCCL before clipping (parallel.GradAllReduce)."""
+from __future__ import annotations
+
+import os
+import time
+from typing import Any, Dict, List, Optional
+
+import torch
+
+from .parallel import GradAllReduce, init_distributed
+
+
+class Trainer:
+    def __init__(self, max_epochs: int = 50, max_steps: Optional[int] = None, output_dir: str = "outputs",
+                 log_every_n_steps: int = 10, save_top_k: int = 3, early_stopping_patience: Optional[int] = None,
+                 steps_per_epoch: Optional[int] = None, devices: int = 1, **_ignored: Any):
+        self.max_epochs, self.max_steps = max_epochs, max_steps
+        self.ckpt_dir = os.path.join(output_dir, "checkpoints")
+        self.log_every = log_every_n_steps
+        self.save_top_k = save_top_k
+        self.patience = early_stopping_patience
+        self.steps_per_epoch = steps_per_epoch
+        self.rank, self.world, self.local = init_distributed()
+        if devices and devices > 1 and self.world == 1:
+            print(f"[trainer] devices={devices} requested: launch with `torchrun --nproc-per-node {devices} train.py ...`; "
+                  "running on one GPU")
+        self.global_step = 0
+        self.logged: Dict[str, float] = {}
+        self._best: List[tuple] = []
+
+    # Lightning-style logging sink used by StyleTransferModel.log / log_dict
+    def log(self, name: str, value) -> None:
+        self.logged[name] = float(value)
+
+    def save_checkpoint(self, model, path: str) -> None:
+        if self.rank == 0:
+            os.makedirs(os.path.dirname(path), exist_ok=True)
+            torch.save({"state_dict": model.state_dict(), "global_step": self.global_step}, path)
+
+    def fit(self, model) -> None:
+        model.trainer = self
+        model.to(torch.device("cuda", self.local))
+        model.setup("fit")
+        opts = model.configure_optimizers()
+        model._optimizers = opts
+        gen = model.generator
+        if self.world > 1:
+            gen(torch.zeros(1, gen.input_channels, 16, 16, device=torch.device("cuda", self.local)))  # builds the engine
+            model.grad_sync = GradAllReduce(list(gen.named_parameters()), world=self.world)
+            gen._engine.grad_hook = model.grad_sync.grad_ready
+        loader = model.train_dataloader()
+        bad_epochs, best_epoch_loss = 0, float("inf")
+        model.train()
+        for epoch in range(self.max_epochs):
+            t0, losses = time.time(), []
+            for batch_idx, batch in enumerate(loader):
+                out = model.training_step(batch, batch_idx)
+                self.global_step += 1
+                losses.append(float(out["loss"]) if self.global_step % self.log_every == 0 or batch_idx == 0 else None)
+                if self.rank == 0 and self.global_step % self.log_every == 0:
+                    msg = " ".join(f"{k}={v:.4f}" for k, v in sorted(self.logged.items()))
+                    print(f"[epoch {epoch} step {self.global_step}] {msg}", flush=True)
+                if (self.max_steps and self.global_step >= self.max_steps) or \
+                        (self.steps_per_epoch and batch_idx + 1 >= self.steps_per_epoch):
+                    break
+            vals = [v for v in losses if v is not None]
+            epoch_loss = sum(vals) / max(1, len(vals))
+            if self.rank == 0:
+                print(f"[epoch {epoch}] g_total_loss={epoch_loss:.4f} ({time.time() - t0:.1f}s)", flush=True)
+                name = os.path.join(self.ckpt_dir, f"style_transfer-epoch={epoch:02d}-g_total_loss={epoch_loss:.4f}.ckpt")
+                self.save_checkpoint(model, name)
+                self.save_checkpoint(model, os.path.join(self.ckpt_dir, "last.ckpt"))
+                self._best = sorted(self._best + [(epoch_loss, name)])
+                for _, stale in self._best[self.save_top_k:]:
+                    if os.path.exists(stale):
+                        os.remove(stale)
+                self._best = self._best[:self.save_top_k]
+            if epoch_loss < best_epoch_loss - 1e-12:
+                best_epoch_loss, bad_epochs = epoch_loss, 0
+            else:
+                bad_epochs += 1
+            if self.patience is not None and bad_epochs > self.patience:
+                if self.rank == 0:
+                    print(f"[trainer] early stop: g_total_loss did not improve for {bad_epochs} epochs")
+                break
+            if self.max_steps and self.global_step >= self.max_steps:
+                break
