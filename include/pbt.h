@@ -135,7 +135,7 @@ int pbt_conv_wgrad(const pbt_wgrad_desc_t* d, void* stream);
  *                (momentum, unbiased var) when non-NULL.
  * mean_out/rstd_out ([n][c], optional) are kept for the backward pass.
  * ---------------------------------------------------------------------- */
-int pbt_norm_finalize(const float* partial, int32_t n, int32_t tiles, int32_t c,
+int pbt_norm_finalize(const float* partial /* consumed: folded in place */, int32_t n, int32_t tiles, int32_t c,
                       int64_t count_per_image, float eps, int32_t batch_mode,
                       const float* gamma, const float* beta,
                       float* running_mean, float* running_var, float momentum,

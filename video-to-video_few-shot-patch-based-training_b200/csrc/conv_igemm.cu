@@ -13,10 +13,14 @@
 //  * UMMA A operand (K-major, no swizzle): row r of the 128-row tile = pixel (r>>3, r&7); the 8 rows
 //    of a core matrix are 8 x-adjacent pixels (16 B apart), core matrices along M are image rows
 //    (SBO = haloed row pitch), core matrices along K are channel planes (LBO = plane pitch).
-//  * B operand: pre-packed weights [blk][tap][k/8][cout][8] streamed by 1-D bulk copies through a ring.
+//  * B operand: pre-packed weights [blk][tap][k/8][cout][8] streamed by 1-D bulk copies through a ring whose
+//    stages hold a GROUP of taps (one full/empty barrier round trip per group, not per tap).
 //  * fp32 accumulators in TMEM (T accumulators of `cout` columns); M=128, N=cout, K=16 per instruction.
 //  * warp roles: warp 0 = TMA/bulk producer, warp 1 = TMEM owner + single-thread MMA issuer,
 //    warps 2..5 = epilogue (TMEM -> registers -> fused bias/act/affine/mask/residual/stats/1x1-head -> global).
+//  * the issuing thread is the critical resource (one tcgen05.mma per 16..64 tensor cycles): the kernel is
+//    templated on T and on the K steps per channel block so that the issue loop is fully unrolled and each MMA
+//    costs two 32-bit adds on the low descriptor words.
 #include "internal.h"
 #include "ptx.cuh"
 
@@ -26,11 +30,12 @@ struct ConvKParams {
   int n_img, H, W;
   int blk_p, n_blk, Cp;
   int KH, KW, pad_t, pad_l;
-  int T, NC, acc_stride, tmem_cols;
+  int NC, acc_stride, tmem_cols;
   int tiles_x, tiles_y;
   int BW, BH;
+  int dt;
   uint32_t idesc;
-  int a_stages, b_stages;
+  int a_stages, b_stages, b_group;
   uint32_t a_stage_bytes, b_stage_bytes;
   const uint8_t* wpack;
   const float* bias;
@@ -86,7 +91,15 @@ __device__ __forceinline__ float warp_colsum16(const float* v, int lane) {
   return d;
 }
 
-template <int DT>
+__device__ __forceinline__ void unpack8_rt(int dt, const uint4& u, float* f) {
+  if (dt == 0) unpack8<0>(u, f);
+  else unpack8<1>(u, f);
+}
+__device__ __forceinline__ uint4 pack8_rt(int dt, const float* f) { return dt == 0 ? pack8<0>(f) : pack8<1>(f); }
+
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+
+template <int T, int KB>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvKParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -108,9 +121,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvKParams p
   const int rem = blockIdx.x - n * tiles_per_img;
   const int tyi = rem / p.tiles_x;
   const int txi = rem - tyi * p.tiles_x;
-  const int x0 = txi * 8 * p.T;
+  const int x0 = txi * 8 * T;
   const int y0 = tyi * 16;
   const int ntaps = p.KH * p.KW;
+  const int ngroups = (ntaps + p.b_group - 1) / p.b_group;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.a_stages; ++i) {
@@ -134,7 +148,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvKParams p
   if (warp == 0) {
     // ------------------------------------------------------------ producer
     if (elect_one()) {
-      int bi = 0;  // running B-chunk counter
+      int bi = 0;  // running B-group counter
       for (int cb = 0; cb < p.n_blk; ++cb) {
         const int sa = cb % p.a_stages;
         const uint32_t pa = (uint32_t)(cb / p.a_stages) & 1u;
@@ -145,12 +159,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvKParams p
         const int pib = min(p.blk_p, p.Cp - cb * p.blk_p);
         const uint32_t chunk = (uint32_t)(pib * p.NC * 16);
         const uint8_t* wsrc = p.wpack + (size_t)cb * ntaps * ((size_t)p.blk_p * p.NC * 16);
-        for (int tap = 0; tap < ntaps; ++tap, ++bi) {
+        for (int g = 0; g < ngroups; ++g, ++bi) {
           const int sb = bi % p.b_stages;
           const uint32_t pb = (uint32_t)(bi / p.b_stages) & 1u;
+          const int tap0 = g * p.b_group;
+          const int nt = min(p.b_group, ntaps - tap0);
           mbar_wait(&b_empty[sb], pb ^ 1u);
-          mbar_arrive_expect_tx(&b_full[sb], chunk);
-          bulk_load_1d(sB + (size_t)sb * p.b_stage_bytes, wsrc + (size_t)tap * chunk, chunk, &b_full[sb]);
+          mbar_arrive_expect_tx(&b_full[sb], chunk * (uint32_t)nt);
+          // the taps of a group are contiguous in the packed weights: one bulk copy per group
+          bulk_load_1d(sB + (size_t)sb * p.b_stage_bytes, wsrc + (size_t)tap0 * chunk, chunk * (uint32_t)nt, &b_full[sb]);
         }
       }
     }
@@ -159,38 +176,48 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvKParams p
     if (elect_one()) {
       const uint32_t plane_bytes = (uint32_t)(p.BH * p.BW * 16);
       const uint32_t row_bytes = (uint32_t)(p.BW * 16);
-      const uint32_t a_lbo = (p.debug_flags & 1) ? row_bytes : plane_bytes;
-      const uint32_t a_sbo = (p.debug_flags & 1) ? plane_bytes : row_bytes;
       const uint32_t b_kstride = (uint32_t)(p.NC * 16);
-      const uint32_t b_lbo = (p.debug_flags & 2) ? 128u : b_kstride;
-      const uint32_t b_sbo = (p.debug_flags & 2) ? b_kstride : 128u;
+      // descriptor words: lo = addr>>4 | (LBO>>4)<<16 ; hi = SBO>>4 | version(1)<<14
+      const uint32_t a_lo_const = ((plane_bytes >> 4) & 0x3FFF) << 16;
+      const uint32_t a_hi = ((row_bytes >> 4) & 0x3FFF) | (1u << 14);
+      const uint32_t b_lo_const = ((b_kstride >> 4) & 0x3FFF) << 16;
+      const uint32_t b_hi = (128u >> 4) | (1u << 14);
+      const uint32_t a_kstep = (2u * plane_bytes) >> 4;  // two channel planes per K=16
+      const uint32_t b_kstep = (2u * b_kstride) >> 4;
+      const uint32_t acc_stride = (uint32_t)p.acc_stride;
+      const uint32_t idesc = p.idesc;
       int bi = 0;
       for (int cb = 0; cb < p.n_blk; ++cb) {
         const int sa = cb % p.a_stages;
         const uint32_t pa = (uint32_t)(cb / p.a_stages) & 1u;
         mbar_wait(&a_full[sa], pa);
         tc_fence_after();
-        const uint32_t a_base = smem_u32(sA + (size_t)sa * p.a_stage_bytes);
+        const uint32_t a_base = (smem_u32(sA + (size_t)sa * p.a_stage_bytes) >> 4) | a_lo_const;
         const int pib = min(p.blk_p, p.Cp - cb * p.blk_p);
         const int k16n = pib >> 1;
-        for (int tap = 0; tap < ntaps; ++tap, ++bi) {
+        const uint32_t chunk16 = (uint32_t)(pib * p.NC);  // bytes/16 of one tap's weights
+        int dy = 0, dx = 0;
+        for (int g = 0; g < ngroups; ++g, ++bi) {
           const int sb = bi % p.b_stages;
           const uint32_t pb = (uint32_t)(bi / p.b_stages) & 1u;
+          const int nt = min(p.b_group, ntaps - g * p.b_group);
           mbar_wait(&b_full[sb], pb);
           tc_fence_after();
-          const int dy = tap / p.KW;
-          const int dx = tap - dy * p.KW;
-          const uint32_t b_base = smem_u32(sB + (size_t)sb * p.b_stage_bytes);
-          const uint32_t a_tap = a_base + (uint32_t)((dy * p.BW + dx) * 16);
-          const uint32_t first = (cb == 0 && tap == 0) ? 0u : 1u;
-          for (int t = 0; t < p.T; ++t) {
-            const uint32_t d_tmem = tmem_base + (uint32_t)(t * p.acc_stride);
-            for (int k = 0; k < k16n; ++k) {
-              const uint64_t adesc = make_smem_desc(a_tap + (uint32_t)(t * 128) + (uint32_t)(2 * k) * plane_bytes,
-                                                    a_lbo, a_sbo);
-              const uint64_t bdesc = make_smem_desc(b_base + (uint32_t)(2 * k) * b_kstride, b_lbo, b_sbo);
-              umma_f16(d_tmem, adesc, bdesc, p.idesc, (k == 0) ? first : 1u);
+          uint32_t b_lo = (smem_u32(sB + (size_t)sb * p.b_stage_bytes) >> 4) | b_lo_const;
+          for (int j = 0; j < nt; ++j) {
+            const uint32_t a_tap = a_base + (uint32_t)(dy * p.BW + dx);
+            const uint32_t first = (cb == 0 && g == 0 && j == 0) ? 0u : 1u;
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+#pragma unroll
+              for (int k = 0; k < KB; ++k) {
+                if (k < k16n)
+                  umma_f16(tmem_base + (uint32_t)t * acc_stride, desc64(a_tap + (uint32_t)(t * 8) + (uint32_t)k * a_kstep, a_hi),
+                           desc64(b_lo + (uint32_t)k * b_kstep, b_hi), idesc, (k == 0) ? first : 1u);
+              }
             }
+            b_lo += chunk16;
+            if (++dx == p.KW) { dx = 0; ++dy; }
           }
           umma_commit(&b_empty[sb]);
         }
@@ -202,6 +229,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvKParams p
     // ------------------------------------------------------------ epilogue (warps 2..5)
     const int q = warp & 3;  // TMEM lane quadrant this warp may read
     const int NC = p.NC;
+    const int dt = p.dt;
     const bool do_stats = p.stats_partial != nullptr;
     float* my_stats = s_stats + (size_t)q * 2 * NC;
     if (do_stats) {
@@ -217,7 +245,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvKParams p
     mbar_wait(acc_full, 0);
     tc_fence_after();
 
-    for (int t = 0; t < p.T; ++t) {
+    for (int t = 0; t < T; ++t) {
       const int x = x0 + 8 * t + tx;
       const bool valid = (y < p.H) && (x < p.W);
       const long long pix = (long long)y * p.W + x;
@@ -251,7 +279,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvKParams p
               const uint4 m = *reinterpret_cast<const uint4*>(
                   p.mask + 2 * ((long long)n * p.mask_img_stride + ((long long)(c0 / 8 + hh) * plane_px + pix) * 8));
               float mf[8];
-              unpack8<DT>(m, mf);
+              unpack8_rt(dt, m, mf);
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[hh * 8 + i] = mf[i] > 0.f ? v[hh * 8 + i] : 0.f;
             }
@@ -278,14 +306,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvKParams p
         }
         if (p.out) {
           // round to the storage type; statistics and the head see the rounded values
-          const uint4 u0 = pack8<DT>(v), u1 = pack8<DT>(v + 8);
+          const uint4 u0 = pack8_rt(dt, v), u1 = pack8_rt(dt, v + 8);
           if (valid) {
             uint8_t* ob = p.out + 2 * ((long long)n * p.out_img_stride + ((long long)(c0 / 8) * plane_px + pix) * 8);
             *reinterpret_cast<uint4*>(ob) = u0;
             *reinterpret_cast<uint4*>(ob + 2 * plane_px * 8) = u1;
           }
-          unpack8<DT>(u0, v);
-          unpack8<DT>(u1, v + 8);
+          unpack8_rt(dt, u0, v);
+          unpack8_rt(dt, u1, v + 8);
         }
         if (p.head_w) {
 #pragma unroll
@@ -345,6 +373,23 @@ static int pow2_cols(int c) {
   return v;
 }
 
+template <int T, int KB>
+static int launch_conv(const CUtensorMap& tmap, const ConvKParams& p, int grid, uint32_t smem_bytes, cudaStream_t stream) {
+  PBT_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<T, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  conv_igemm_kernel<T, KB><<<grid, kThreads, smem_bytes, stream>>>(tmap, p);
+  PBT_CUDA_CHECK(cudaGetLastError());
+  return PBT_OK;
+}
+
+template <int T>
+static int launch_conv_kb(int kb, const CUtensorMap& tmap, const ConvKParams& p, int grid, uint32_t smem, cudaStream_t s) {
+  switch (kb) {
+    case 1: return launch_conv<T, 1>(tmap, p, grid, smem, s);
+    case 2: return launch_conv<T, 2>(tmap, p, grid, smem, s);
+    default: return launch_conv<T, 4>(tmap, p, grid, smem, s);
+  }
+}
+
 }  // namespace pbt
 
 using namespace pbt;
@@ -378,19 +423,19 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
   p.blk_p = d->blk_c / 8;
   p.n_blk = ceil_div(p.Cp, p.blk_p);
   p.KH = d->kh; p.KW = d->kw; p.pad_t = d->pad_t; p.pad_l = d->pad_l;
-  p.T = d->tiles_per_cta;
+  const int T = d->tiles_per_cta;
   p.NC = d->cout;
+  p.dt = d->dtype;
   p.acc_stride = (int)round_up((uint32_t)p.NC, 32);
-  p.tmem_cols = pow2_cols(p.T * p.acc_stride);
+  p.tmem_cols = pow2_cols(T * p.acc_stride);
   PBT_REQUIRE(p.tmem_cols <= 512, "conv: tiles_per_cta*cout exceeds tensor memory (512 columns)");
-  p.BW = 8 * p.T + p.KW - 1;
+  p.BW = 8 * T + p.KW - 1;
   p.BH = 16 + p.KH - 1;
   PBT_REQUIRE(p.BW <= 32, "conv: haloed tile wider than 32 pixels (reduce tiles_per_cta)");
-  p.tiles_x = ceil_div(p.W, 8 * p.T);
+  p.tiles_x = ceil_div(p.W, 8 * T);
   p.tiles_y = ceil_div(p.H, 16);
   p.idesc = make_idesc_f16(128, p.NC, d->dtype == PBT_BF16 ? 1 : 0, 0, 0);
   p.a_stage_bytes = round_up((uint32_t)(p.blk_p * p.BH * p.BW * 16), 128);
-  p.b_stage_bytes = round_up((uint32_t)(p.blk_p * p.NC * 16), 128);
   p.a_stages = p.n_blk > 1 ? 2 : 1;
   p.wpack = static_cast<const uint8_t*>(d->wpack);
   p.bias = d->bias; p.act = d->act; p.post_scale = d->post_scale; p.post_shift = d->post_shift;
@@ -413,13 +458,26 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
   PBT_REQUIRE(!d->head_w || (d->head_b && d->head_out), "conv: head needs head_b and head_out");
   p.debug_flags = d->debug_flags;
 
-  // shared memory budget: A ring + B ring + barriers + tmem slot + stats scratch
+  // shared memory budget: A ring + B ring (groups of taps) + barriers + tmem slot + stats scratch.
+  // Aim at two co-resident CTAs per SM (one CTA's epilogue/prologue overlaps the other's main loop).
   const uint32_t tail = 8u * (2 * 2 + 2 * 8 + 1) + 16 + (uint32_t)(4 * 2 * p.NC * 4) + 128;
   const uint32_t a_total = (uint32_t)p.a_stages * p.a_stage_bytes;
-  int b_stages = 6;
-  const uint32_t budget = 110 * 1024;  // aim at two co-resident CTAs per SM
-  while (b_stages > 2 && a_total + (uint32_t)b_stages * p.b_stage_bytes + tail > budget) --b_stages;
-  p.b_stages = b_stages;
+  const uint32_t chunk = (uint32_t)(p.blk_p * p.NC * 16);  // one tap of one channel block
+  const int ntaps = p.KH * p.KW;
+  const uint32_t budget = 112 * 1024;
+  int group = (int)(16384u / chunk);
+  if (group < 1) group = 1;
+  if (group > ntaps) group = ntaps;
+  int stages = 4;
+  auto fits = [&](int g, int s) { return a_total + (uint32_t)s * round_up((uint32_t)g * chunk, 128) + tail <= budget; };
+  while (!fits(group, stages) && (stages > 2 || group > 1)) {
+    if (stages > 2) --stages;
+    else --group;
+  }
+  if (d->debug_flags & 4) group = 1;  // bring-up: one tap per stage
+  p.b_group = group;
+  p.b_stages = stages;
+  p.b_stage_bytes = round_up((uint32_t)group * chunk, 128);
   const uint32_t smem_bytes = a_total + (uint32_t)p.b_stages * p.b_stage_bytes + tail;
   PBT_REQUIRE(smem_bytes <= 227 * 1024, "conv: configuration does not fit shared memory");
 
@@ -428,13 +486,10 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
   if (rc != PBT_OK) return rc;
 
   const int grid = p.n_img * p.tiles_x * p.tiles_y;
-  if (d->dtype == PBT_BF16) {
-    PBT_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    conv_igemm_kernel<0><<<grid, kThreads, smem_bytes, stream>>>(tmap, p);
-  } else {
-    PBT_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    conv_igemm_kernel<1><<<grid, kThreads, smem_bytes, stream>>>(tmap, p);
+  const int kb = d->blk_c / 16;
+  switch (T) {
+    case 1: return launch_conv_kb<1>(kb, tmap, p, grid, smem_bytes, stream);
+    case 2: return launch_conv_kb<2>(kb, tmap, p, grid, smem_bytes, stream);
+    default: return launch_conv_kb<3>(kb, tmap, p, grid, smem_bytes, stream);
   }
-  PBT_CUDA_CHECK(cudaGetLastError());
-  return PBT_OK;
 }

@@ -176,8 +176,42 @@ __global__ void mask_dilate7_kernel(const uint8_t* __restrict__ m, int h, int w,
 }
 
 // ------------------------------------------------------------------ norm finalize
-// one block per (image, 32-channel group) in instance mode; per 32-channel group in batch mode
-__global__ void norm_finalize_kernel(const float* __restrict__ partial, int n, int tiles, int c, long long count_per_image,
+// Stage 1 of the deterministic statistics reduction (large images have thousands of tiles): block
+// (32-channel group, chunk, image) sums the tiles of its chunk in a fixed order (double accumulation) and
+// overwrites the FIRST tile slot of its own chunk with the result, so stage 2 only visits tiles/chunk slots.
+__global__ void norm_reduce_partials_kernel(float* __restrict__ partial, int tiles, int c, int chunk) {
+  __shared__ double s_sum[8][32], s_sq[8][32];
+  const int cg = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int row = threadIdx.x >> 5;
+  const int t0 = blockIdx.y * chunk;
+  const int t1 = min(tiles, t0 + chunk);
+  float* base = partial + (long long)blockIdx.z * tiles * 2 * c;
+  double a = 0.0, b = 0.0;
+  if (cg < c) {
+    for (int t = t0 + row; t < t1; t += 8) {
+      const float* pp = base + (long long)t * 2 * c;
+      a += (double)pp[cg];
+      b += (double)pp[c + cg];
+    }
+  }
+  s_sum[row][threadIdx.x & 31] = a;
+  s_sq[row][threadIdx.x & 31] = b;
+  __syncthreads();  // every read of this chunk is done before its first slot is overwritten
+  if (row == 0 && cg < c) {
+    for (int r2 = 1; r2 < 8; ++r2) {
+      a += s_sum[r2][threadIdx.x];
+      b += s_sq[r2][threadIdx.x];
+    }
+    float* dst = base + (long long)t0 * 2 * c;
+    dst[cg] = (float)a;
+    dst[c + cg] = (float)b;
+  }
+}
+
+// one block per (image, 32-channel group) in instance mode; per 32-channel group in batch mode.
+// `tiles` slots are visited with stride `tile_stride` (= the stage-1 chunk, or 1).
+__global__ void norm_finalize_kernel(const float* __restrict__ partial, int n, int tiles, int tile_stride, int img_tiles, int c,
+                                     long long count_per_image,
                                      float eps, int batch_mode, const float* __restrict__ gamma,
                                      const float* __restrict__ beta, float* running_mean, float* running_var, float momentum,
                                      float* __restrict__ scale, float* __restrict__ shift, float* mean_out, float* rstd_out) {
@@ -190,7 +224,7 @@ __global__ void norm_finalize_kernel(const float* __restrict__ partial, int n, i
   if (cg < c) {
     for (int ni = n_lo; ni < n_hi; ++ni)
       for (int t = row; t < tiles; t += 8) {
-        const float* pp = partial + ((long long)ni * tiles + t) * 2 * c;
+        const float* pp = partial + ((long long)ni * img_tiles + (long long)t * tile_stride) * 2 * c;
         a += (double)pp[cg];
         b += (double)pp[c + cg];
       }
@@ -704,9 +738,20 @@ extern "C" int pbt_norm_finalize(const float* partial, int32_t n, int32_t tiles,
                                  float* rstd_out, void* stream_) {
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   PBT_REQUIRE(partial && scale && shift && n > 0 && tiles > 0 && c > 0 && count_per_image > 0, "norm_finalize: bad arguments");
+  // NOTE: `partial` is consumed (stage 1 folds chunks of tiles in place when there are many tiles)
+  int slots = tiles, stride = 1;
+  if (tiles > 64) {
+    int chunk = ceil_div(tiles, 64);
+    if (chunk < 16) chunk = 16;
+    slots = ceil_div(tiles, chunk);
+    stride = chunk;
+    dim3 g1(ceil_div(c, 32), slots, n);
+    norm_reduce_partials_kernel<<<g1, 256, 0, st>>>(const_cast<float*>(partial), tiles, c, chunk);
+    PBT_CUDA_CHECK(cudaGetLastError());
+  }
   dim3 grid(ceil_div(c, 32), batch_mode ? 1 : n);
-  norm_finalize_kernel<<<grid, 256, 0, st>>>(partial, n, tiles, c, count_per_image, eps, batch_mode, gamma, beta, running_mean,
-                                            running_var, momentum, scale, shift, mean_out, rstd_out);
+  norm_finalize_kernel<<<grid, 256, 0, st>>>(partial, n, slots, stride, tiles, c, count_per_image, eps, batch_mode, gamma, beta,
+                                            running_mean, running_var, momentum, scale, shift, mean_out, rstd_out);
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
 }
