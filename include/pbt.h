@@ -162,8 +162,11 @@ typedef struct {
 } pbt_norm_apply_desc_t;
 int pbt_norm_apply(const pbt_norm_apply_desc_t* d, void* stream);
 
-/* Bilinear x2 upsample, align_corners=True (src/models/generator.py:13), on a P8 view. */
-int pbt_upsample2x(const pbt_act_t* in, const pbt_act_t* out, int32_t dtype, void* stream);
+/* Bilinear x2 upsample, align_corners=True (src/models/generator.py:13), on a P8 view.
+ * scale/shift ([n][c], optional) + act: the taps are normalised and activated on load, i.e. the kernel
+ * computes upsample(act(in*scale+shift)) without materialising the normalised low-resolution tensor. */
+int pbt_upsample2x(const pbt_act_t* in, const pbt_act_t* out, const float* scale, const float* shift, int32_t act,
+                   int32_t dtype, void* stream);
 /* its transpose (autograd): gin[h,w] (16-bit and/or fp32 P8F) = sum of gout[2h,2w] contributions */
 int pbt_upsample2x_bwd(const pbt_act_t* gout, const pbt_act_t* gin16, float* gin32, int32_t dtype, void* stream);
 

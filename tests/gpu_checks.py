@@ -296,6 +296,15 @@ def check_upsample(dt=BF16):
     got = big.view(16, c).to_nchw()
     e = (got - exp).abs().max().item()
     ok = e < (2e-2 if dt == BF16 else 2e-3) and bool((big.to_nchw()[:, :16] == 0).all())
+    # fused producer: upsample(leaky(x*scale+shift)) with per-(n,c) scale/shift
+    sc = torch.rand((n, c), generator=g, device="cuda") + 0.5
+    sh = torch.randn((n, c), generator=g, device="cuda")
+    fused = P8.empty(n, c, 2 * h, 2 * w, dt)
+    ops.upsample2x(P8.from_nchw(x, dt), fused, dt, scale=sc, shift=sh, act=ACT_LEAKY)
+    expf = F.interpolate(act_ref(x * sc[:, :, None, None] + sh[:, :, None, None], ACT_LEAKY), scale_factor=2,
+                         mode="bilinear", align_corners=True)
+    ef = (fused.to_nchw() - expf).abs().max().item()
+    ok &= ef < (4e-2 if dt == BF16 else 4e-3)
     # transpose
     gy = torch.randn((n, c, 2 * h, 2 * w), generator=g, device="cuda").to(tdt).float()
     xr = x.double().requires_grad_(True)

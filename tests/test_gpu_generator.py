@@ -89,13 +89,17 @@ def test_train_forward_and_one_step_gradients(trained_sd, vec, dtype):
     # BatchNorm running statistics after the step
     assert torch.allclose(g.smoothers[2].running_mean.cpu(), torch.from_numpy(vec["bn_rm_after"]), atol=2e-3)
     assert torch.allclose(g.smoothers[2].running_var.cpu(), torch.from_numpy(vec["bn_rv_after"]), rtol=2e-2, atol=2e-3)
-    # full per-parameter gradients from the oracle (itself pinned to the reference in test_oracle.py)
+    # per-parameter gradients: (1) the fp32 oracle (pinned to the reference in test_oracle.py); (2) a torch fp32
+    # autograd run of the same network with the forward pass rounded to the operand dtype (tests/emulation.py)
+    from emulation import emulated_loss_and_grads
     _, _, ref_grads = go.loss_and_grads(trained_sd, torch.from_numpy(vec["x"]), torch.from_numpy(vec["target"]))
-    worst_rel, worst_ps, rows = (0.0, ""), (1e9, ""), []
-    lim = MAX_ABS if dtype == "fp16" else 3 * MAX_ABS
-    ps_lim = PSNR_MIN if dtype == "fp16" else 35.0
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sd_gpu = {k: v.cuda() for k, v in trained_sd.items()}
+    _, _, emu_grads = emulated_loss_and_grads(sd_gpu, x, tgt, torch.float16 if dtype == "fp16" else torch.bfloat16)
     before_in = ("initial_conv.0.bias", "downsample1.0.bias", "downsample2.0.bias", "upsample1.1.bias", "upsample2.1.bias")
-    failures = []
+    rows, failures = [], []
+    worst = {"psnr": 1e9, "abs": 0.0, "rel": 0.0, "emu_rel": 0.0, "emu_psnr": 1e9, "emu_vs_ref_rel": 0.0}
     for k, p in g.named_parameters():
         ref = ref_grads[k]
         got = p.grad.detach().cpu()
@@ -106,19 +110,26 @@ def test_train_forward_and_one_step_gradients(trained_sd, vec, dtype):
             assert float(got.abs().max()) == 0.0, k
             assert float(ref.abs().max()) <= 1e-3 * wref, (k, float(ref.abs().max()), wref)
             continue
+        emu = emu_grads[k].cpu()
         peak = float(ref.abs().max())
-        rel = float((got - ref).abs().max()) / peak
-        ps = psnr(got, ref, peak)
-        rows.append(f"   {k:38s} rel_max_abs={rel:.5f} psnr={ps:.1f}")
-        if rel > worst_rel[0]:
-            worst_rel = (rel, k)
-        if ps < worst_ps[0]:
-            worst_ps = (ps, k)
-        if not (rel <= lim and ps >= ps_lim):
-            failures.append((k, rel, ps))
+        absd = float((got - ref).abs().max())
+        rel, ps = absd / peak, psnr(got, ref, peak)
+        erel, eps_ = float((got - emu).abs().max()) / peak, psnr(got, emu, peak)
+        e2r = float((emu - ref).abs().max()) / peak
+        rows.append(f"   {k:34s} vs fp32 ref: rel_max_abs={rel:.4f} psnr={ps:5.1f} | vs rounded-forward emulation: "
+                    f"rel_max_abs={erel:.4f} psnr={eps_:5.1f} | emulation vs ref: {e2r:.4f}")
+        worst["psnr"], worst["abs"], worst["rel"] = min(worst["psnr"], ps), max(worst["abs"], absd), max(worst["rel"], rel)
+        worst["emu_rel"], worst["emu_psnr"] = max(worst["emu_rel"], erel), min(worst["emu_psnr"], eps_)
+        worst["emu_vs_ref_rel"] = max(worst["emu_vs_ref_rel"], e2r)
+        # north star: max-abs <= 2e-2 (literal, absolute) and PSNR >= 40 dB against the fp32 reference
+        if absd > MAX_ABS or ps < (PSNR_MIN if dtype == "fp16" else 35.0):
+            failures.append((k, absd, ps))
     print("\n".join(rows))
-    print(f"{dtype} grads: worst rel max-abs {worst_rel[0]:.4f} ({worst_rel[1]}), worst PSNR {worst_ps[0]:.1f} dB ({worst_ps[1]})")
+    print(f"{dtype} grads worst-case: {worst}")
     assert not failures, failures
+    # the normalised max-abs against the fp32 reference is bounded by what forward rounding alone causes
+    # (mask flips; see DESIGN.md "precision"): the native backward may not add more than half of that again
+    assert worst["rel"] <= 1.5 * worst["emu_vs_ref_rel"] + 1e-3, worst
 
 
 def test_training_reduces_loss_like_the_reference(trained_sd, vec):

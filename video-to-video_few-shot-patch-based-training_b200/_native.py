@@ -90,7 +90,7 @@ def lib() -> C.CDLL:
         "pbt_conv_wgrad": (C.c_int, [C.POINTER(WgradDesc), vp]),
         "pbt_norm_finalize": (C.c_int, [vp, i32, i32, i32, i64, f32, i32, vp, vp, vp, vp, f32, vp, vp, vp, vp, vp]),
         "pbt_norm_apply": (C.c_int, [C.POINTER(NormApplyDesc), vp]),
-        "pbt_upsample2x": (C.c_int, [C.POINTER(Act), C.POINTER(Act), i32, vp]),
+        "pbt_upsample2x": (C.c_int, [C.POINTER(Act), C.POINTER(Act), vp, vp, i32, i32, vp]),
         "pbt_upsample2x_bwd": (C.c_int, [C.POINTER(Act), C.POINTER(Act), vp, i32, vp]),
         "pbt_norm_bwd_reduce": (C.c_int, [C.POINTER(NormBwdDesc), vp]),
         "pbt_norm_bwd_apply": (C.c_int, [C.POINTER(NormBwdDesc), vp]),

@@ -375,8 +375,9 @@ class _Engine:
         # decoder
         ops.upsample2x(ws.c2cat, ws.u2in, dt)
         st = conv_in("up2", ws.u2in, f[4], 3, 1, ws.rawU2, 2)
-        ops.norm_apply(ws.rawU2, dt, scale=st["scale"], shift=st["shift"], act=ACT_RELU, out=ws.c1cat.view(0, f[4]))
-        ops.upsample2x(ws.c1cat, ws.u1in, dt)
+        # IN + ReLU of the up2 output are applied on load by the upsample kernel (never materialised at H/2)
+        ops.upsample2x(ws.rawU2, ws.u1in.view(0, f[4]), dt, scale=st["scale"], shift=st["shift"], act=ACT_RELU)
+        ops.upsample2x(ws.c1cat.view(f[4], f[1]), ws.u1in.view(f[4], f[1]), dt)
         st = conv_in("up1", ws.u1in, f[4], 3, 1, ws.rawU1, 2)
         ops.norm_apply(ws.rawU1, dt, scale=st["scale"], shift=st["shift"], act=ACT_RELU, out=ws.cat11.view(0, f[4]))
         # conv11 + smoothers + fused head

@@ -121,9 +121,10 @@ def norm_apply(x: P8, dt: int, *, scale=None, shift=None, per_channel=False, act
     check(lib().pbt_norm_apply(C.byref(d), stream_ptr()), "pbt_norm_apply")
 
 
-def upsample2x(x: P8, out: P8, dt: int) -> None:
+def upsample2x(x: P8, out: P8, dt: int, scale=None, shift=None, act: int = ACT_NONE) -> None:
+    """bilinear x2 (align_corners=True); with scale/shift the taps are normalised + activated on load"""
     a, b = x.act(), out.act()
-    check(lib().pbt_upsample2x(C.byref(a), C.byref(b), dt, stream_ptr()), "pbt_upsample2x")
+    check(lib().pbt_upsample2x(C.byref(a), C.byref(b), ptr(scale), ptr(shift), act, dt, stream_ptr()), "pbt_upsample2x")
 
 
 def upsample2x_bwd(gout: P8, dt: int, gin16: P8 | None = None, gin32=None) -> None:
