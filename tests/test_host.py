@@ -1,0 +1,152 @@
+"""CPU-side tests: C-ABI surface, host logic (sampler bookkeeping, weight packing, config), drop-in contracts."""
+import ctypes
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from pbt_b200 import _native
+    hdr = open(os.path.join(ROOT, "include", "pbt.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(pbt_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 25
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/pbt.h but not exported"
+    assert sorted(_native.EXPORTED_SYMBOLS) == declared
+    L = _native.lib()
+    assert L.pbt_abi_version() == 1
+    assert L.pbt_error_string(0) == b"ok" and b"argument" in L.pbt_error_string(-1)
+    assert L.pbt_conv_num_tiles(1080, 1920, 3) == 68 * 80
+    # no GPU here: a compute call must fail loudly, never fall back
+    if not torch.cuda.is_available():
+        d = _native.ConvDesc()
+        assert L.pbt_conv_fwd(ctypes.byref(d), None) != 0
+
+
+def test_ostree_equals_list_pop():
+    from pbt_b200.sampler import _OsTree
+    rnd = random.Random(5)
+    for n in (1, 2, 7, 64, 1000):
+        tree, ref = _OsTree(n), list(range(n))
+        for _ in range(2):                      # second pass exercises reset()
+            while ref:
+                k = rnd.randrange(len(ref))
+                assert len(tree) == len(ref)
+                assert tree.take(k) == ref.pop(k)
+            with pytest.raises(IndexError):
+                tree.take(0)
+            tree.reset()
+            ref = list(range(n))
+
+
+def test_pack_conv_weight_layout():
+    from pbt_b200 import ops
+    w = torch.randn(32, 20, 3, 3)
+    cin_pad, blk = 48, 32
+    flat = ops.pack_conv_weight(w, cin_pad, blk, 1).float()
+    off = 0
+    wq = w.half().float()
+    for c0 in range(0, cin_pad, blk):
+        kc = min(blk, cin_pad - c0)
+        blkt = flat[off:off + 9 * kc * 32].reshape(9, kc // 8, 32, 8)
+        off += 9 * kc * 32
+        for tap in range(9):
+            for k8 in range(kc // 8):
+                for k in range(8):
+                    ci = c0 + k8 * 8 + k
+                    exp = wq[:, ci, tap // 3, tap % 3] if ci < 20 else torch.zeros(32)
+                    assert torch.equal(blkt[tap, k8, :, k], exp)
+    assert off == flat.numel()
+
+
+def test_s2d_weight_is_the_stride2_conv():
+    from pbt_b200 import ops
+    torch.manual_seed(0)
+    x = torch.randn(2, 8, 12, 16)
+    w = torch.randn(5, 8, 3, 3)
+    ref = F.conv2d(x, w, stride=2, padding=1)
+    s2d = torch.cat([x[:, :, py::2, px::2] for py in range(2) for px in range(2)], 1)
+    got = F.conv2d(F.pad(s2d, (1, 0, 1, 0)), ops.s2d_weight(w))
+    assert torch.allclose(ref, got, atol=1e-5)
+    assert torch.equal(ops.s2d_weight_grad(ops.s2d_weight(w), 8), w)
+
+
+def test_dgrad_weight_is_the_input_gradient():
+    from pbt_b200 import ops
+    torch.manual_seed(1)
+    x = torch.randn(1, 6, 9, 11, requires_grad=True)
+    w = torch.randn(4, 6, 3, 3)
+    gy = torch.randn(1, 4, 9, 11)
+    F.conv2d(x, w, padding=1).backward(gy)
+    got = F.conv2d(gy, ops.dgrad_weight(w), padding=1)
+    assert torch.allclose(x.grad, got, atol=1e-5)
+
+
+def test_generator_state_dict_matches_reference_layout():
+    from pbt_b200.generator import GeneratorJ
+    z = np.load(os.path.join(ROOT, "tests", "golden", "gen_c3_trained.npz"))
+    torch.manual_seed(0)
+    g = GeneratorJ(input_channels=3, use_bias=True)
+    sd = g.state_dict()
+    assert list(sd.keys()) == list(z.files)
+    for k in z.files:
+        assert tuple(sd[k].shape) == z[k].shape, k
+    g.load_state_dict({k: torch.from_numpy(z[k]) for k in z.files}, strict=True)
+    assert sum(p.numel() for p in g.parameters()) == 3265027
+    assert sum(p.numel() for p in GeneratorJ(input_channels=9, use_bias=True).parameters()) == 3293251
+    no_bias = GeneratorJ(input_channels=3, use_bias=False).state_dict()
+    assert "initial_conv.0.bias" not in no_bias and "output.0.bias" in no_bias
+
+
+def test_generator_has_no_cpu_path_and_validates_input():
+    from pbt_b200.generator import GeneratorJ
+    g = GeneratorJ(input_channels=3)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        g(torch.zeros(1, 3, 32, 32))
+    with pytest.raises(NotImplementedError):
+        gg = GeneratorJ(input_channels=3, norm_layer="batch_norm")
+        gg._check_supported()
+
+
+def test_config_compose_and_overrides():
+    from pbt_b200.config import compose
+    cfg = compose(os.path.join(ROOT, "config"), "config", ["training.batch_size=40", "data.patch_size=32", "+training.max_steps=7"])
+    assert cfg.training.batch_size == 40 and cfg.data.patch_size == 32 and cfg.training.max_steps == 7
+    assert cfg.model.generator.args.input_channels == "auto"
+    assert cfg.model.generator.args.filters == [32, 64, 128, 128, 128, 64]
+    assert cfg.optimizer.generator.lr == 0.0004 and cfg.training.gradient_clip_val == 0.5
+    assert cfg.hydra.run.dir.startswith("outputs/20")
+    inf = compose(os.path.join(ROOT, "config"), "inference")
+    assert inf.data.dir_pre == inf.paths.input_dir and inf.data.patch_size == 80
+
+
+def test_style_transfer_model_auto_channels():
+    import lightning_model as lm
+    from pbt_b200.config import compose
+    cfg = compose(os.path.join(ROOT, "config"), "config")
+    m = lm.StyleTransferModel(cfg.model.generator, None, cfg.training, cfg.optimizer, cfg.data, None)
+    assert m.generator.input_channels == 6          # RGB + point_vector (depth 3)
+    (opt,) = m.configure_optimizers()
+    assert opt.defaults["lr"] == 0.0004 and opt.defaults["weight_decay"] == 1e-5 and opt.defaults["betas"] == (0.9, 0.999)
+
+
+def test_shard_range_partitions_exactly():
+    from pbt_b200.parallel import shard_range
+    for n in (0, 1, 7, 500, 2000):
+        for world in (1, 2, 3, 4, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(10, 4, 4)
