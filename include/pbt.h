@@ -102,7 +102,26 @@ typedef struct {
   float*       head_out;
   int32_t      head_tanh;    /* 1 = apply tanh */
   int32_t      debug_flags;  /* bring-up only; 0 in production */
+  void*        debug_buf;    /* bring-up only: int64[grid][8] per-CTA phase timestamps, NULL in production */
 } pbt_conv_desc_t;
+
+/* One launch packs every conv parameter (nn.Conv2d layout [co][ci][kh][kw], fp32 or fp16 master copy) into the
+ * operand layout above, optionally as the space-to-depth form of a stride-2 3x3 kernel (mode bit 0) and/or as
+ * the dgrad kernel: channels transposed, taps flipped (mode bit 1).  `jobs` is a DEVICE array. */
+typedef struct {
+  const void* w;        /* source parameter */
+  void*       dst;      /* packed 16-bit destination: taps * k_pad * n_out elements */
+  int32_t     co, ci, kh, kw;   /* source dims */
+  int32_t     mode;     /* bit 0: space-to-depth, bit 1: dgrad */
+  int32_t     k_pad;    /* destination K channels (multiple of 16) */
+  int32_t     n_out;    /* destination N rows (multiple of 16) */
+  int32_t     n_keep;   /* rows taken from the source, remaining rows are zero */
+  int32_t     blk_c;    /* channels per K block */
+  int32_t     dtype;    /* pbt_dtype of dst */
+  int32_t     src_is_half;
+  int32_t     reserved;
+} pbt_pack_job_t;
+int pbt_pack_weights(const pbt_pack_job_t* jobs_dev, int32_t n_jobs, int64_t max_elems, void* stream);
 
 /* number of stats tiles per image for a given geometry (tiles_x*tiles_y) */
 int pbt_conv_num_tiles(int32_t h, int32_t w, int32_t tiles_per_cta);

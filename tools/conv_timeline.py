@@ -1,0 +1,43 @@
+"""per-CTA phase timeline of the conv kernel (debug_buf instrumentation): where does a CTA's lifetime go?"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pbt_b200 import ops  # noqa: E402
+from pbt_b200._native import FP16, P8  # noqa: E402
+
+dt = FP16
+cases = [("res 128->128 3x3 @270x480 T2", 128, 128, 3, 270, 480, 2, 32, False),
+         ("smooth 64->64 3x3 @1080x1920 T3", 64, 64, 3, 1080, 1920, 3, 32, False),
+         ("initial 16->32 7x7 T3 +stats", 16, 32, 7, 1080, 1920, 3, 16, True),
+         ("conv11 176->64 7x7 T3", 176, 64, 7, 1080, 1920, 3, 32, False),
+         ("up1 192->128 3x3 T2", 192, 128, 3, 1080, 1920, 2, 32, False)]
+FLAGS = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+for name, cin, cout, k, h, w, T, blk, stats in cases:
+    x = P8.empty(1, cin, h, w, dt)
+    x.t.normal_()
+    wp = ops.pack_conv_weight(torch.randn((cout, cin, k, k), device="cuda") * 0.05, cin, blk, dt)
+    out = P8.empty(1, cout, h, w, dt)
+    tiles = ops.conv_num_tiles(h, w, T)
+    part = torch.empty((1, tiles, 2, cout), device="cuda") if stats else None
+    dbg = torch.zeros((tiles, 8), dtype=torch.int64, device="cuda")
+    for _ in range(2):
+        ops.conv_fwd(x, wp, cout, k, k, k // 2, k // 2, dt, blk_c=blk, tiles_per_cta=T, out=out, stats_partial=part, debug_buf=dbg, debug_flags=FLAGS)
+    torch.cuda.synchronize()
+    d = dbg.cpu().double()
+    t0 = d[:, 0:1]
+    rel = d[:, 1:7] - t0
+    med = rel.median(0).values
+    names = ["setup done", "first A landed", "MMA issue done", "acc ready (epi start)", "epilogue done", "exit"]
+    print(f"== {name}: {tiles} CTAs; median cycles since CTA start:")
+    for nm, v in zip(names, med.tolist()):
+        print(f"     {nm:24s} {v:10.0f}")
+    # per-SM occupancy of time: CTAs per SM and total span
+    sm = d[:, 7].long()
+    span = []
+    for s in sm.unique().tolist()[:8]:
+        m = sm == s
+        span.append((int(m.sum()), float(d[m, 6].max() - d[m, 0].min())))
+    print("     per-SM (n_ctas, span cycles) samples:", span)

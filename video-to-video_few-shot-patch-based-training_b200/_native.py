@@ -39,7 +39,7 @@ class ConvDesc(C.Structure):
         ("bias", C.c_void_p), ("act", C.c_int32), ("post_scale", C.c_void_p), ("post_shift", C.c_void_p),
         ("mask", Act), ("addend32", C.c_void_p), ("out32", C.c_void_p), ("out", Act),
         ("stats_partial", C.c_void_p), ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("head_out", C.c_void_p),
-        ("head_tanh", C.c_int32), ("debug_flags", C.c_int32),
+        ("head_tanh", C.c_int32), ("debug_flags", C.c_int32), ("debug_buf", C.c_void_p),
     ]
 
 
@@ -56,6 +56,14 @@ class NormApplyDesc(C.Structure):
         ("residual32", C.c_void_p), ("out", Act), ("out_relu", Act), ("out32", C.c_void_p), ("out_s2d", Act),
         ("dtype", C.c_int32),
     ]
+
+
+class PackJob(C.Structure):
+    """pbt_pack_job_t (64 bytes)"""
+
+    _fields_ = [("w", C.c_void_p), ("dst", C.c_void_p), ("co", C.c_int32), ("ci", C.c_int32), ("kh", C.c_int32),
+                ("kw", C.c_int32), ("mode", C.c_int32), ("k_pad", C.c_int32), ("n_out", C.c_int32), ("n_keep", C.c_int32),
+                ("blk_c", C.c_int32), ("dtype", C.c_int32), ("src_is_half", C.c_int32), ("reserved", C.c_int32)]
 
 
 class NormBwdDesc(C.Structure):
@@ -108,6 +116,7 @@ def lib() -> C.CDLL:
         "pbt_make_grad_scale": (C.c_int, [vp, f32, vp, vp]),
         "pbt_ostree_reset": (None, [vp, i32]),
         "pbt_ostree_take": (i32, [vp, i32, i32]),
+        "pbt_pack_weights": (C.c_int, [vp, i32, i64, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError here = header/library mismatch
@@ -125,7 +134,7 @@ EXPORTED_SYMBOLS = [
     "pbt_norm_bwd_reduce", "pbt_norm_bwd_apply", "pbt_head_bwd", "pbt_channel_sum", "pbt_nchw_to_p8",
     "pbt_p8_to_nchw_f32", "pbt_p8f_to_nchw_f32", "pbt_u8hwc_to_p8", "pbt_nchw_to_u8hwc", "pbt_u8hwc_to_norm_chw",
     "pbt_patch_gather", "pbt_mask_dilate7", "pbt_absmax_f32", "pbt_make_grad_scale", "pbt_ostree_reset",
-    "pbt_ostree_take",
+    "pbt_ostree_take", "pbt_pack_weights",
 ]
 
 

@@ -54,6 +54,7 @@ struct ConvKParams {
   float* head_out;
   int head_tanh;
   int debug_flags;
+  long long* debug_buf;  // bring-up: per-CTA phase timestamps (clock64), 8 slots per CTA
 };
 
 constexpr int kThreads = 192;
@@ -126,7 +127,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvKParams p
   const int ntaps = p.KH * p.KW;
   const int ngroups = (ntaps + p.b_group - 1) / p.b_group;
 
+#define PBT_STAMP(slot)                                                         \
+  do {                                                                           \
+    if (p.debug_buf) p.debug_buf[(long long)blockIdx.x * 8 + (slot)] = clock64(); \
+  } while (0)
   if (threadIdx.x == 0) {
+    PBT_STAMP(0);
     for (int i = 0; i < p.a_stages; ++i) {
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
@@ -144,6 +150,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvKParams p
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) {
+    PBT_STAMP(1);
+    if (p.debug_buf) {
+      uint32_t smid;
+      asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+      p.debug_buf[(long long)blockIdx.x * 8 + 7] = smid;
+    }
+  }
 
   if (warp == 0) {
     // ------------------------------------------------------------ producer
@@ -192,6 +206,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvKParams p
         const uint32_t pa = (uint32_t)(cb / p.a_stages) & 1u;
         mbar_wait(&a_full[sa], pa);
         tc_fence_after();
+        if (cb == 0) PBT_STAMP(2);
         const uint32_t a_base = (smem_u32(sA + (size_t)sa * p.a_stage_bytes) >> 4) | a_lo_const;
         const int pib = min(p.blk_p, p.Cp - cb * p.blk_p);
         const int k16n = pib >> 1;
@@ -207,11 +222,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvKParams p
           for (int j = 0; j < nt; ++j) {
             const uint32_t a_tap = a_base + (uint32_t)(dy * p.BW + dx);
             const uint32_t first = (cb == 0 && g == 0 && j == 0) ? 0u : 1u;
+            // k outer / t inner: consecutive MMAs target DIFFERENT accumulators, so the read-modify-write
+            // dependency on one TMEM tile is T instructions apart (measured: same-accumulator chains serialise)
 #pragma unroll
-            for (int t = 0; t < T; ++t) {
+            for (int k = 0; k < KB; ++k) {
+              if (k < k16n) {
 #pragma unroll
-              for (int k = 0; k < KB; ++k) {
-                if (k < k16n)
+                for (int t = 0; t < T; ++t)
                   umma_f16(tmem_base + (uint32_t)t * acc_stride, desc64(a_tap + (uint32_t)(t * 8) + (uint32_t)k * a_kstep, a_hi),
                            desc64(b_lo + (uint32_t)k * b_kstep, b_hi), idesc, (k == 0) ? first : 1u);
               }
@@ -224,6 +241,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvKParams p
         umma_commit(&a_empty[sa]);
       }
       umma_commit(acc_full);
+      PBT_STAMP(3);
     }
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..5)
@@ -244,6 +262,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvKParams p
 
     mbar_wait(acc_full, 0);
     tc_fence_after();
+    if (threadIdx.x == 64) PBT_STAMP(4);
 
     for (int t = 0; t < T; ++t) {
       const int x = x0 + 8 * t + tx;
@@ -362,9 +381,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvKParams p
     }
   }
 
+  if (threadIdx.x == 64) PBT_STAMP(5);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  if (threadIdx.x == 0) PBT_STAMP(6);
 }
 
 static int pow2_cols(int c) {
@@ -457,6 +478,7 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
   p.head_w = d->head_w; p.head_b = d->head_b; p.head_out = d->head_out; p.head_tanh = d->head_tanh;
   PBT_REQUIRE(!d->head_w || (d->head_b && d->head_out), "conv: head needs head_b and head_out");
   p.debug_flags = d->debug_flags;
+  p.debug_buf = static_cast<long long*>(d->debug_buf);
 
   // shared memory budget: A ring + B ring (groups of taps) + barriers + tmem slot + stats scratch.
   // Aim at two co-resident CTAs per SM (one CTA's epilogue/prologue overlaps the other's main loop).
@@ -478,7 +500,8 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
   p.b_group = group;
   p.b_stages = stages;
   p.b_stage_bytes = round_up((uint32_t)group * chunk, 128);
-  const uint32_t smem_bytes = a_total + (uint32_t)p.b_stages * p.b_stage_bytes + tail;
+  uint32_t smem_bytes = a_total + (uint32_t)p.b_stages * p.b_stage_bytes + tail;
+  if ((d->debug_flags & 8) && smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;  // bring-up: force one CTA per SM
   PBT_REQUIRE(smem_bytes <= 227 * 1024, "conv: configuration does not fit shared memory");
 
   CUtensorMap tmap;

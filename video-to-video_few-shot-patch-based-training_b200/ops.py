@@ -67,6 +67,38 @@ def s2d_weight_grad(dw2: torch.Tensor, c: int) -> torch.Tensor:
     return dw
 
 
+class WeightPacker:
+    """device-side job table for pbt_pack_weights: every conv parameter -> packed 16-bit operands in ONE launch"""
+
+    def __init__(self, device):
+        self.device = device
+        self.jobs = []
+        self.out = {}
+        self._table = None
+        self._max = 0
+
+    def add(self, name: str, param: torch.Tensor, *, s2d=False, dgrad=False, k_pad: int, n_out: int, n_keep: int, blk_c: int,
+            dt: int) -> torch.Tensor:
+        co, ci, kh, kw = param.shape
+        taps = 4 if s2d else kh * kw
+        dst = torch.empty(taps * k_pad * n_out, dtype=nv.torch_dtype(dt), device=self.device)
+        assert param.is_contiguous() and param.dtype in (torch.float32, torch.float16)
+        self.jobs.append(nv.PackJob(param.data_ptr(), dst.data_ptr(), co, ci, kh, kw, int(s2d) | (int(dgrad) << 1), k_pad, n_out,
+                                    n_keep, blk_c, dt, int(param.dtype == torch.float16), 0))
+        self._src = getattr(self, "_src", []) + [param]   # keep the parameters alive / pointers stable
+        self.out[name] = dst
+        self._max = max(self._max, dst.numel())
+        self._table = None
+        return dst
+
+    def run(self) -> None:
+        if self._table is None:
+            arr = (nv.PackJob * len(self.jobs))(*self.jobs)
+            raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+            self._table = raw.to(self.device)
+        check(lib().pbt_pack_weights(self._table.data_ptr(), len(self.jobs), self._max, stream_ptr()), "pbt_pack_weights")
+
+
 # ----------------------------------------------------------------------------- convolution
 def conv_num_tiles(h: int, w: int, tiles_per_cta: int) -> int:
     return lib().pbt_conv_num_tiles(h, w, tiles_per_cta)
@@ -75,7 +107,7 @@ def conv_num_tiles(h: int, w: int, tiles_per_cta: int) -> int:
 def conv_fwd(x: P8, wpack: torch.Tensor, cout: int, kh: int, kw: int, pad_t: int, pad_l: int, dt: int, *,
              blk_c: int = 32, tiles_per_cta: int = 2, bias=None, act: int = ACT_NONE, post_scale=None, post_shift=None,
              mask: P8 | None = None, addend32=None, out32=None, out: P8 | None = None, stats_partial=None,
-             head_w=None, head_b=None, head_out=None, head_tanh: bool = True, debug_flags: int = 0) -> None:
+             head_w=None, head_b=None, head_out=None, head_tanh: bool = True, debug_flags: int = 0, debug_buf=None) -> None:
     d = nv.ConvDesc()
     d.inp = x.act()
     d.wpack = wpack.data_ptr()
@@ -89,6 +121,7 @@ def conv_fwd(x: P8, wpack: torch.Tensor, cout: int, kh: int, kw: int, pad_t: int
     d.stats_partial = ptr(stats_partial)
     d.head_w, d.head_b, d.head_out, d.head_tanh = ptr(head_w), ptr(head_b), ptr(head_out), int(head_tanh)
     d.debug_flags = debug_flags
+    d.debug_buf = ptr(debug_buf)
     check(lib().pbt_conv_fwd(C.byref(d), stream_ptr()), "pbt_conv_fwd")
 
 
