@@ -234,7 +234,7 @@ def run_native(args):
         torch.manual_seed(0)
         tg = GeneratorJ(input_channels=9, use_bias=True).to(dev).train()
         tg.operand_dtype = operand
-        opt = torch.optim.Adam(tg.parameters(), lr=4e-4, betas=(0.9, 0.999), weight_decay=1e-5)
+        opt = torch.optim.Adam(tg.parameters(), lr=4e-4, betas=(0.9, 0.999), weight_decay=1e-5, capturable=True)
         B, P = 80, 80
         g = torch.Generator(device=dev).manual_seed(99 + rank)
         xs = torch.rand((B, 9, P, P), generator=g, device=dev) * 2 - 1
@@ -244,7 +244,7 @@ def run_native(args):
         if ar is not None:
             tg._engine.grad_hook = ar.grad_ready
 
-        def train_step():
+        def eager_step():
             opt.zero_grad(set_to_none=True)
             loss = torch.nn.functional.l1_loss(tg(xs), ts) * 4.0
             loss.backward()
@@ -252,7 +252,18 @@ def run_native(args):
                 ar.finish()
             torch.nn.utils.clip_grad_norm_(tg.parameters(), 0.5)
             opt.step()
-            return loss
+            return loss.detach()
+
+        mode = "cuda-graph replay of the whole step"
+        try:
+            from pbt_b200.graphs import GraphedGeneratorStep
+            gstep = GraphedGeneratorStep(tg, opt, (B, 9, P, P), grad_sync=ar)
+
+            def train_step():
+                return gstep(xs, ts)
+        except Exception as e:  # noqa: BLE001 - e.g. a collective that cannot be captured on this stack
+            mode = f"eager launches (graph capture failed: {type(e).__name__})"
+            train_step = eager_step
 
         tsteps = max(3, args.steps)
         for _ in range(3):
@@ -267,7 +278,7 @@ def run_native(args):
         pps = world * B * tsteps / (ms_t / 1e3)
         train = {"metric": "train patches/s", "value": pps, "unit": "patches/s", "ms_per_step": ms_t / tsteps,
                  "config": {"workload": "C3: G-only step (L1*4, clip 0.5, Adam) batch 80 x 80x80 patches, Cin 9 per GPU",
-                            "allreduce_bytes_per_step": (ar.nbytes if ar else 0)},
+                            "allreduce_bytes_per_step": (ar.nbytes if ar else 0), "launch_mode": mode},
                  "tflops_algorithmic": 3 * flops_per_pixel(9) * P * P * B * world / (ms_t / tsteps) / 1e9,
                  "final_loss": float(loss)}
 

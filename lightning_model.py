@@ -73,14 +73,17 @@ class StyleTransferModel(_Base):
             print("[StyleTransferModel] discriminator / perceptual branches are outside the B200 hot path "
                   "(SURVEY.md section 8f): running the generator-only step (L1 reconstruction loss)")
         self.reconstruction_criterion = getattr(nn, training_config["reconstruction_criterion"])()
-        self.trainer_ref = None
+        self.use_cuda_graph = bool(training_config.get("cuda_graph", True))
         self.grad_sync = None
         self._optimizers = None
+        self._graphed = None
 
     # ------------------------------------------------------------------ Lightning-shaped hooks
     def configure_optimizers(self):
         oc = to_container(dict(self.optimizer_config["generator"]))
         oc["betas"] = tuple(oc.get("betas", (0.9, 0.999)))
+        if self.use_cuda_graph and next(self.generator.parameters()).is_cuda:
+            oc["capturable"] = True   # the whole step is replayed as one CUDA graph (pbt_b200/graphs.py)
         return [torch.optim.Adam(self.generator.parameters(), **oc)]
 
     def setup(self, stage: Optional[str] = None):
@@ -122,6 +125,25 @@ class StyleTransferModel(_Base):
             torch.nn.utils.clip_grad_norm_(self.generator.parameters(), self.training_config["gradient_clip_val"])
         opt_g.step()
         return g_loss
+
+    def graphed_training_step(self, batch: Dict[str, torch.Tensor], batch_idx: int):
+        """the same generator step replayed as ONE CUDA graph (static shapes; falls back to training_step for the
+        ragged last batch of an epoch)"""
+        from pbt_b200.graphs import GraphedGeneratorStep
+        x = batch["combined_input"]
+        if self._graphed is None:
+            self._graphed = GraphedGeneratorStep(
+                self.generator, self.optimizers()[0], tuple(x.shape),
+                reconstruction_weight=float(self.training_config["reconstruction_weight"]),
+                clip=float(self.training_config["gradient_clip_val"]) if self.training_config.get("use_gradient_clipping", False) else None,
+                criterion=self.reconstruction_criterion, grad_sync=self.grad_sync)
+        if tuple(x.shape) != tuple(self._graphed.x.shape):
+            return self.training_step(batch, batch_idx)
+        loss = self._graphed(x, batch["post"])
+        tr = getattr(self, "trainer", None)
+        if tr is not None and getattr(tr, "global_step", 0) % max(1, int(self.training_config.get("log_every_n_steps", 10))) == 0:
+            self.log_dict({"g_image_loss": float(loss), "g_total_loss": float(loss)})
+        return {"loss": loss, "g_total_loss": loss}
 
     def _generator_step(self, combined_input, batch):
         generated = self.generator(combined_input)

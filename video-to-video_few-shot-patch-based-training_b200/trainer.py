@@ -59,7 +59,8 @@ class Trainer:
         for epoch in range(self.max_epochs):
             t0, losses = time.time(), []
             for batch_idx, batch in enumerate(loader):
-                out = model.training_step(batch, batch_idx)
+                graphed = getattr(model, "use_cuda_graph", False) and hasattr(model, "graphed_training_step")
+                out = model.graphed_training_step(batch, batch_idx) if graphed else model.training_step(batch, batch_idx)
                 self.global_step += 1
                 losses.append(float(out["loss"]) if self.global_step % self.log_every == 0 or batch_idx == 0 else None)
                 if self.rank == 0 and self.global_step % self.log_every == 0:
