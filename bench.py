@@ -141,14 +141,14 @@ def run_reference(args):
         dt = time.perf_counter() - t0
     fps = args.steps * frac / dt
     sample = f"{args.steps} x one {sh}x{sw} crop ({frac:.3f} of a 1080p frame) through the oracle port, scaled by pixel count"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "C4: 1920x1080 RGB full-frame GeneratorJ inference", "frame": [H, W, CIN]},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 # ------------------------------------------------------------------------------------------ native arm
@@ -339,10 +339,23 @@ def run_native(args):
         line["cpu_baseline"] = cpu
     if train is not None:
         line["train"] = train
-    print(json.dumps(line))
+    emit(line)
+
+
+def emit(line: dict) -> None:
+    """the ONE JSON line goes to the real stdout; everything else this process (or a C library such as NCCL's
+    version banner) prints to fd 1 was redirected to stderr in main()"""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
