@@ -57,7 +57,16 @@ struct ConvKParams {
   long long* debug_buf;  // bring-up: per-CTA phase timestamps (clock64), 8 slots per CTA
 };
 
-constexpr int kThreads = 192;
+// warps: 0 = producer, 1..NI = MMA issuers (one per accumulator when PBT_MULTI_ISSUE), then 4 epilogue warps
+// Measured on B200 (profiles/r1_issue_experiments.md): one CTA's MMAs execute back to back with ~40-70 cycles of
+// exposed operand-fetch latency each, regardless of how many warps issue them or how accumulators are
+// interleaved; streams of DIFFERENT co-resident CTAs overlap.  One issuer warp is therefore enough.
+#ifndef PBT_MULTI_ISSUE
+#define PBT_MULTI_ISSUE 0
+#endif
+constexpr int kMaxThreads = 256;
+__host__ __device__ constexpr int num_issuers(int T) { return PBT_MULTI_ISSUE ? T : 1; }
+__host__ __device__ constexpr int conv_threads(int T) { return 32 * (5 + num_issuers(T)); }
 
 // Sum over the 32 lanes of a warp of 16 per-lane values; afterwards every lane holds the total of
 // column  col = 8*b4 + 4*b3 + 2*b2 + b1  (b_i = bit i of the lane id); lanes differing only in bit 0 agree.
@@ -101,7 +110,7 @@ __device__ __forceinline__ uint4 pack8_rt(int dt, const float* f) { return dt ==
 __device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 
 template <int T, int KB>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kMaxThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvKParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sA = smem;
@@ -116,6 +125,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvKParams p
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  constexpr int NI = num_issuers(T);
+  constexpr int kEpi0 = 32 * (1 + NI);  // first epilogue thread
 
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const int n = blockIdx.x / tiles_per_img;
@@ -135,13 +146,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvKParams p
     PBT_STAMP(0);
     for (int i = 0; i < p.a_stages; ++i) {
       mbar_init(&a_full[i], 1);
-      mbar_init(&a_empty[i], 1);
+      mbar_init(&a_empty[i], NI);
     }
     for (int i = 0; i < p.b_stages; ++i) {
       mbar_init(&b_full[i], 1);
-      mbar_init(&b_empty[i], 1);
+      mbar_init(&b_empty[i], NI);
     }
-    mbar_init(acc_full, 1);
+    mbar_init(acc_full, NI);
     fence_barrier_init();
     prefetch_tmap(&tmapA);
   }
@@ -185,9 +196,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvKParams p
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (elect_one()) {
+  } else if (warp <= NI) {
+    // ------------------------------------------------------------ MMA issuer(s)
+    // With NI == T every accumulator has its own issuing warp: the MMA streams of different warps overlap their
+    // operand-fetch latency (a single stream executes MMAs back to back with the fetch latency exposed).
+    const int ti = warp - 1;
+    // The WHOLE warp runs the (warp-uniform) loops so that descriptor arithmetic and barrier waits live in the
+    // uniform datapath; only the tcgen05 instructions are predicated on one elected lane.  (With the loop inside
+    // `if (elect_one())` the compiler built every descriptor in vector registers and paid ~10 R2UR moves per
+    // group of MMAs, which made the issuing thread — not the tensor pipe — the bottleneck.)
+    const bool leader = elect_one();
+    {
       const uint32_t plane_bytes = (uint32_t)(p.BH * p.BW * 16);
       const uint32_t row_bytes = (uint32_t)(p.BW * 16);
       const uint32_t b_kstride = (uint32_t)(p.NC * 16);
@@ -206,7 +225,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvKParams p
         const uint32_t pa = (uint32_t)(cb / p.a_stages) & 1u;
         mbar_wait(&a_full[sa], pa);
         tc_fence_after();
-        if (cb == 0) PBT_STAMP(2);
+        if (cb == 0 && leader) PBT_STAMP(2);
         const uint32_t a_base = (smem_u32(sA + (size_t)sa * p.a_stage_bytes) >> 4) | a_lo_const;
         const int pib = min(p.blk_p, p.Cp - cb * p.blk_p);
         const int k16n = pib >> 1;
@@ -224,24 +243,33 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvKParams p
             const uint32_t first = (cb == 0 && g == 0 && j == 0) ? 0u : 1u;
             // k outer / t inner: consecutive MMAs target DIFFERENT accumulators, so the read-modify-write
             // dependency on one TMEM tile is T instructions apart (measured: same-accumulator chains serialise)
+            if (leader) {
 #pragma unroll
-            for (int k = 0; k < KB; ++k) {
-              if (k < k16n) {
+              for (int k = 0; k < KB; ++k) {
+                if (k < k16n) {
 #pragma unroll
-                for (int t = 0; t < T; ++t)
-                  umma_f16(tmem_base + (uint32_t)t * acc_stride, desc64(a_tap + (uint32_t)(t * 8) + (uint32_t)k * a_kstep, a_hi),
-                           desc64(b_lo + (uint32_t)k * b_kstep, b_hi), idesc, (k == 0) ? first : 1u);
+                  for (int t = 0; t < T; ++t)
+                    if (NI == 1 || t == ti)
+                      umma_f16(tmem_base + (uint32_t)t * acc_stride,
+                               desc64(a_tap + (uint32_t)(t * 8) + (uint32_t)k * a_kstep, a_hi),
+                               desc64(b_lo + (uint32_t)k * b_kstep, b_hi), idesc, (k == 0) ? first : 1u);
+                }
               }
             }
             b_lo += chunk16;
             if (++dx == p.KW) { dx = 0; ++dy; }
           }
-          umma_commit(&b_empty[sb]);
+          if (leader) umma_commit(&b_empty[sb]);
+          __syncwarp();
         }
-        umma_commit(&a_empty[sa]);
+        if (leader) umma_commit(&a_empty[sa]);
+        __syncwarp();
       }
-      umma_commit(acc_full);
-      PBT_STAMP(3);
+      if (leader) {
+        umma_commit(acc_full);
+        if (ti == 0) PBT_STAMP(3);
+      }
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..5)
@@ -262,7 +290,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvKParams p
 
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    if (threadIdx.x == 64) PBT_STAMP(4);
+    if (threadIdx.x == kEpi0) PBT_STAMP(4);
 
     for (int t = 0; t < T; ++t) {
       const int x = x0 + 8 * t + tx;
@@ -374,14 +402,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvKParams p
     }
     if (do_stats) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int e = threadIdx.x - 64;  // 0..127
+      const int e = threadIdx.x - kEpi0;  // 0..127
       float* dst = p.stats_partial + ((long long)n * tiles_per_img + rem) * 2 * NC;
       for (int i = e; i < 2 * NC; i += 128)
         dst[i] = s_stats[i] + s_stats[2 * NC + i] + s_stats[4 * NC + i] + s_stats[6 * NC + i];
     }
   }
 
-  if (threadIdx.x == 64) PBT_STAMP(5);
+  if (threadIdx.x == kEpi0) PBT_STAMP(5);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
@@ -397,7 +425,7 @@ static int pow2_cols(int c) {
 template <int T, int KB>
 static int launch_conv(const CUtensorMap& tmap, const ConvKParams& p, int grid, uint32_t smem_bytes, cudaStream_t stream) {
   PBT_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<T, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-  conv_igemm_kernel<T, KB><<<grid, kThreads, smem_bytes, stream>>>(tmap, p);
+  conv_igemm_kernel<T, KB><<<grid, conv_threads(T), smem_bytes, stream>>>(tmap, p);
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
 }

@@ -82,7 +82,9 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ 
         }
       }
     } else if (warp == 1) {
-      if (elect_one()) {
+      // whole warp runs the uniform loops; only the tcgen05 instructions are predicated on one elected lane
+      const bool leader = elect_one();
+      {
         // descriptor words (MN-major, SWIZZLE_NONE): lo = addr>>4 | (LBO>>4)<<16, hi = SBO>>4 | version<<14.
         // Only the low word changes per MMA: +dx (one pixel = 16 B) per tap, +2 tile rows per K=16 step.
         const uint32_t row16 = (uint32_t)p.BW;                                   // haloed row pitch in 16-byte units
@@ -101,18 +103,22 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ 
           const uint32_t x_lo = (smem_u32(sX + (size_t)st * p.x_stage_bytes) >> 4) | a_lo_const;
           const uint32_t dy_lo = (smem_u32(sDY + (size_t)st * p.dy_stage_bytes) >> 4) | b_lo_const;
           const uint32_t first = it == 0 ? 0u : 1u;
-          for (int dx = 0; dx < p.KW; ++dx) {
-            const uint32_t d_tmem = tmem_base + (uint32_t)dx * acc_stride;
+          if (leader) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {  // 8 x K=16 pixels (two 8-pixel tile rows each)
-              const uint64_t adesc = ((uint64_t)a_hi << 32) | (x_lo + (uint32_t)dx + (uint32_t)k * a_kstep);
               const uint64_t bdesc = ((uint64_t)b_hi << 32) | (dy_lo + (uint32_t)k * b_kstep);
-              umma_f16(d_tmem, adesc, bdesc, idesc, k == 0 ? first : 1u);
+              // taps inner: consecutive MMAs go to different accumulators (same-accumulator chains serialise)
+              for (int dx = 0; dx < p.KW; ++dx) {
+                const uint64_t adesc = ((uint64_t)a_hi << 32) | (x_lo + (uint32_t)dx + (uint32_t)k * a_kstep);
+                umma_f16(tmem_base + (uint32_t)dx * acc_stride, adesc, bdesc, idesc, k == 0 ? first : 1u);
+              }
             }
+            umma_commit(&empty[st]);
           }
-          umma_commit(&empty[st]);
+          __syncwarp();
         }
-        umma_commit(acc_full);
+        if (leader) umma_commit(acc_full);
+        __syncwarp();
       }
     } else {
       const int q = warp & 3;
