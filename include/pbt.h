@@ -101,6 +101,8 @@ typedef struct {
   const float* head_b;       /* [3] */
   float*       head_out;
   int32_t      head_tanh;    /* 1 = apply tanh */
+  int32_t      upsample2x;   /* 1: `in` is [n,cin,h/2,w/2]; the conv consumes its bilinear x2 (align_corners=True) upsample,
+                              * interpolated inside the kernel (src/models/generator.py:13 fused into :200); 3x3 pad 1 only */
   int32_t      debug_flags;  /* bring-up only; 0 in production */
   void*        debug_buf;    /* bring-up only: int64[grid][8] per-CTA phase timestamps, NULL in production */
 } pbt_conv_desc_t;

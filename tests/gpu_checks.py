@@ -453,3 +453,30 @@ def check_gather(patch=32, n_patches=37, seed=7):
         ok &= torch.equal(comb[b, 3:6], ref_cut_patch(imgs[1][i], y, x, patch))
         ok &= torch.equal(other[b], ref_cut_patch(imgs[2][i], y, x, patch))
     return bool(ok), 0.0, ""
+
+
+def check_conv_upsample(n=2, cin=64, cout=32, h=20, w=28, T=2, blk_c=32, dt=FP16, seed=11, stats=True):
+    """conv3x3(pad 1) over the bilinear x2 (align_corners=True) upsample of a low-res input, interpolated in-kernel"""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    tdt = torch_dtype(dt)
+    x = torch.randn((n, cin, h, w), generator=g, device="cuda").to(tdt).float()
+    wt = (torch.randn((cout, cin, 3, 3), generator=g, device="cuda") * 0.05).to(tdt).float()
+    up = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True).to(tdt).float()
+    exp = ref_conv(up, wt, 1, 1)
+    out = P8.empty(n, cout, 2 * h, 2 * w, dt)
+    tiles = ops.conv_num_tiles(2 * h, 2 * w, T)
+    part = torch.full((n, tiles, 2, cout), float("nan"), device="cuda") if stats else None
+    ops.conv_fwd(P8.from_nchw(x, dt), ops.pack_conv_weight(wt, cin, blk_c, dt), cout, 3, 3, 1, 1, dt, blk_c=blk_c,
+                 tiles_per_cta=T, out=out, stats_partial=part, upsample2x=True)
+    torch.cuda.synchronize()
+    got = out.to_nchw().double()
+    err = (got - exp).abs().max().item()
+    scale = max(1.0, exp.abs().max().item())
+    ok = err / scale < (3e-2 if dt == BF16 else 4e-3)
+    msg = f"err={err:.4g}"
+    if stats:
+        s_exp = torch.stack([got.sum((2, 3)), (got * got).sum((2, 3))], 1)
+        serr = ((part.double().sum(1) - s_exp).abs() / (1.0 + s_exp.abs())).max().item()
+        ok &= serr < 1e-4
+        msg += f" stats={serr:.3g}"
+    return ok, err, msg

@@ -43,6 +43,14 @@ def test_conv_fwd(case):
     assert ok, f"err={err} {msg}"
 
 
+@pytest.mark.parametrize("kw", [dict(), dict(cin=192, cout=128, h=16, w=16), dict(n=3, cin=256, cout=128, h=10, w=12),
+                                dict(cin=64, cout=64, h=24, w=24, T=3, dt=0), dict(cin=32, cout=16, h=5, w=7, T=1)],
+                         ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()) or "default")
+def test_conv_with_upsample_on_load(kw):
+    ok, err, msg = gc.check_conv_upsample(**kw)
+    assert ok, msg
+
+
 WGRAD_CASES = [
     dict(cin=16, cout=16),
     dict(cin=128, cout=16),

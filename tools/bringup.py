@@ -76,6 +76,20 @@ def g_conv_tiles():
         print(f"[conv_tiles] {name}: {'PASS' if ok else 'FAIL'} err={err:.4g} {msg}", flush=True)
 
 
+def g_conv_up():
+    import gpu_checks as gc
+    from pbt_b200._native import BF16, FP16
+    for name, kw in [("64->32 20x28 T2", dict()), ("192->128 16x16 T2", dict(cin=192, cout=128, h=16, w=16)),
+                     ("256->128 10x12 T2 n3", dict(n=3, cin=256, cout=128, h=10, w=12)),
+                     ("64->64 24x24 T3 bf16", dict(cin=64, cout=64, h=24, w=24, T=3, dt=BF16)),
+                     ("32->16 5x7 T1 (partial tiles)", dict(cin=32, cout=16, h=5, w=7, T=1))]:
+        try:
+            ok, err, msg = gc.check_conv_upsample(**kw)
+            print(f"[conv_up] {name}: {'PASS' if ok else 'FAIL'} {msg}", flush=True)
+        except Exception as e:  # noqa: BLE001
+            print(f"[conv_up] {name}: EXC {type(e).__name__}: {e}", flush=True)
+
+
 def g_wgrad():
     import gpu_checks as gc
     from pbt_b200._native import FP16
@@ -178,7 +192,7 @@ def g_conv_perf():
         print(f"[conv_perf] {name}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s (padded-K flops)", flush=True)
 
 
-GROUPS = {"conv_basic": g_conv_basic, "conv_tiles": g_conv_tiles, "wgrad": g_wgrad, "elementwise": g_elementwise,
+GROUPS = {"conv_up": g_conv_up, "conv_basic": g_conv_basic, "conv_tiles": g_conv_tiles, "wgrad": g_wgrad, "elementwise": g_elementwise,
           "norm": g_norm, "conv_perf": g_conv_perf}
 
 if __name__ == "__main__":

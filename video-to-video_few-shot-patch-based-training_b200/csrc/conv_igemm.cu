@@ -53,6 +53,8 @@ struct ConvKParams {
   const float* head_b;
   float* head_out;
   int head_tanh;
+  int up, LH, LW, LBH, LBW;   // upsample-on-load: low-res dims and staging box (pixels)
+  uint32_t l_stage_bytes;
   int debug_flags;
   long long* debug_buf;  // bring-up: per-CTA phase timestamps (clock64), 8 slots per CTA
 };
@@ -64,9 +66,10 @@ struct ConvKParams {
 #ifndef PBT_MULTI_ISSUE
 #define PBT_MULTI_ISSUE 0
 #endif
-constexpr int kMaxThreads = 256;
+constexpr int kMaxThreads = PBT_MULTI_ISSUE ? 384 : 320;
+constexpr int kEpiWarps = 8;  // two warps per TMEM lane quadrant: they split the accumulator columns
 __host__ __device__ constexpr int num_issuers(int T) { return PBT_MULTI_ISSUE ? T : 1; }
-__host__ __device__ constexpr int conv_threads(int T) { return 32 * (5 + num_issuers(T)); }
+__host__ __device__ constexpr int conv_threads(int T) { return 32 * (1 + num_issuers(T) + kEpiWarps); }
 
 // Sum over the 32 lanes of a warp of 16 per-lane values; afterwards every lane holds the total of
 // column  col = 8*b4 + 4*b3 + 2*b2 + b1  (b_i = bit i of the lane id); lanes differing only in bit 0 agree.
@@ -109,19 +112,42 @@ __device__ __forceinline__ uint4 pack8_rt(int dt, const float* f) { return dt ==
 
 __device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 
+// bilinear x2, align_corners=True: source index / weight of destination coordinate `dst` (same arithmetic as
+// upsample2x_kernel in elementwise.cu and as torch's area_pixel_compute_source_index)
+__device__ __forceinline__ void up_src_index(int dst, float scale, int in_size, int& i0, int& i1, float& l1) {
+  const float s = scale * (float)dst;
+  i0 = (int)s;
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  l1 = s - (float)i0;
+}
+// first low-res row/column touched by the haloed tile that starts at high-res coordinate `hr0` (may be negative)
+__device__ __forceinline__ int up_origin(int hr0, int hr_size, int lr_size) {
+  const float scale = hr_size > 1 ? (float)(lr_size - 1) / (float)(hr_size - 1) : 0.f;
+  const int h = hr0 < 0 ? 0 : hr0;
+  int i0 = (int)(scale * (float)h);
+  if (i0 > lr_size - 1) i0 = lr_size - 1;
+  return i0;
+}
+
 template <int T, int KB>
-__global__ void __launch_bounds__(kMaxThreads, 1)
+// two co-resident CTAs per SM are essential (their MMA streams overlap): cap registers accordingly
+__global__ void __launch_bounds__(kMaxThreads, PBT_MULTI_ISSUE ? 1 : 2)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvKParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sB = sA + (size_t)p.a_stages * p.a_stage_bytes;
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(sB + (size_t)p.b_stages * p.b_stage_bytes);
+  uint8_t* sL = sB + (size_t)p.b_stages * p.b_stage_bytes;  // low-res staging (upsample-on-load only), 2 stages
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sL + 2 * (size_t)p.l_stage_bytes);
   uint64_t* a_empty = a_full + p.a_stages;
   uint64_t* b_full = a_empty + p.a_stages;
   uint64_t* b_empty = b_full + p.b_stages;
   uint64_t* acc_full = b_empty + p.b_stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
-  float* s_stats = reinterpret_cast<float*>(tmem_slot + 2);  // [4 warps][2][NC]
+  uint64_t* l_full = acc_full + 1;
+  uint64_t* l_empty = l_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(l_empty + 2);
+  float* s_stats = reinterpret_cast<float*>(tmem_slot + 2);  // [8 warps][2][NC]
+  float* s_head = s_stats + kEpiWarps * 2 * p.NC;             // [T][4 quadrants][32 lanes][3]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -145,7 +171,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvKParams p
   if (threadIdx.x == 0) {
     PBT_STAMP(0);
     for (int i = 0; i < p.a_stages; ++i) {
-      mbar_init(&a_full[i], 1);
+      mbar_init(&a_full[i], p.up ? 32 * kEpiWarps : 1);  // upsample-on-load: every transform thread arrives
       mbar_init(&a_empty[i], NI);
     }
     for (int i = 0; i < p.b_stages; ++i) {
@@ -153,6 +179,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvKParams p
       mbar_init(&b_empty[i], NI);
     }
     mbar_init(acc_full, NI);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&l_full[i], 1);
+      mbar_init(&l_empty[i], 32 * kEpiWarps);
+    }
     fence_barrier_init();
     prefetch_tmap(&tmapA);
   }
@@ -177,10 +207,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvKParams p
       for (int cb = 0; cb < p.n_blk; ++cb) {
         const int sa = cb % p.a_stages;
         const uint32_t pa = (uint32_t)(cb / p.a_stages) & 1u;
-        mbar_wait(&a_empty[sa], pa ^ 1u);
-        mbar_arrive_expect_tx(&a_full[sa], (uint32_t)(p.blk_p * p.BH * p.BW * 16));
-        tma_load_4d(sA + (size_t)sa * p.a_stage_bytes, &tmapA, &a_full[sa], (x0 - p.pad_l) * 8, y0 - p.pad_t,
-                    cb * p.blk_p, n);
+        if (p.up) {
+          // low-res footprint of the haloed tile -> staging; the epilogue warps interpolate it into the A stage
+          const int sl = cb & 1;
+          const uint32_t pl = (uint32_t)(cb >> 1) & 1u;
+          mbar_wait(&l_empty[sl], pl ^ 1u);
+          mbar_arrive_expect_tx(&l_full[sl], (uint32_t)(p.blk_p * p.LBH * p.LBW * 16));
+          tma_load_4d(sL + (size_t)sl * p.l_stage_bytes, &tmapA, &l_full[sl], up_origin(x0 - p.pad_l, p.W, p.LW) * 8,
+                      up_origin(y0 - p.pad_t, p.H, p.LH), cb * p.blk_p, n);
+        } else {
+          mbar_wait(&a_empty[sa], pa ^ 1u);
+          mbar_arrive_expect_tx(&a_full[sa], (uint32_t)(p.blk_p * p.BH * p.BW * 16));
+          tma_load_4d(sA + (size_t)sa * p.a_stage_bytes, &tmapA, &a_full[sa], (x0 - p.pad_l) * 8, y0 - p.pad_t,
+                      cb * p.blk_p, n);
+        }
         const int pib = min(p.blk_p, p.Cp - cb * p.blk_p);
         const uint32_t chunk = (uint32_t)(pib * p.NC * 16);
         const uint8_t* wsrc = p.wpack + (size_t)cb * ntaps * ((size_t)p.blk_p * p.NC * 16);
@@ -272,12 +312,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvKParams p
       __syncwarp();
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------ epilogue (8 warps)
+    // TMEM lanes are reachable per warp quadrant (warp id % 4); the two warps of a quadrant take alternate
+    // 16-column chunks of the accumulators, which halves the epilogue latency of a tile.
     const int q = warp & 3;  // TMEM lane quadrant this warp may read
+    const int ew = warp - (1 + NI);
+    const int half = ew >> 2;
     const int NC = p.NC;
     const int dt = p.dt;
     const bool do_stats = p.stats_partial != nullptr;
-    float* my_stats = s_stats + (size_t)q * 2 * NC;
+    float* my_stats = s_stats + (size_t)ew * 2 * NC;
     if (do_stats) {
       for (int i = lane; i < 2 * NC; i += 32) my_stats[i] = 0.f;
       __syncwarp();
@@ -288,6 +332,92 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvKParams p
     const long long plane_px = (long long)p.H * p.W;
     const int col_of_lane = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 
+    if (p.up) {
+      // ---- upsample-on-load: while the MMAs run, these warps build the haloed A tiles of the 2x bilinear
+      // (align_corners=True, reference src/models/generator.py:13) upsampled input from the low-res staging copy.
+      const int et = threadIdx.x - kEpi0;  // 0..255
+      const float sy = p.H > 1 ? (float)(p.LH - 1) / (float)(p.H - 1) : 0.f;
+      const float sx = p.W > 1 ? (float)(p.LW - 1) / (float)(p.W - 1) : 0.f;
+      const int ly0 = up_origin(y0 - p.pad_t, p.H, p.LH), lx0 = up_origin(x0 - p.pad_l, p.W, p.LW);
+      const int npos = p.BH * p.BW;
+      // each thread owns up to two haloed-tile positions; their tap offsets / weights are fixed for the whole CTA
+      int tap00[2], tap01[2], tap10[2], tap11[2], dsto[2];
+      float w00[2], w01[2], w10[2], w11[2];
+      bool has[2], ins[2];
+#pragma unroll
+      for (int qq = 0; qq < 2; ++qq) {
+        const int pos = et + qq * 32 * kEpiWarps;
+        has[qq] = pos < npos;
+        const int r = pos / p.BW, c = pos - r * p.BW;
+        const int Y = y0 - p.pad_t + r, X = x0 - p.pad_l + c;
+        ins[qq] = has[qq] && Y >= 0 && Y < p.H && X >= 0 && X < p.W;
+        int i0 = 0, i1 = 0, j0 = 0, j1 = 0;
+        float wy = 0.f, wx = 0.f;
+        if (ins[qq]) {
+          up_src_index(Y, sy, p.LH, i0, i1, wy);
+          up_src_index(X, sx, p.LW, j0, j1, wx);
+          i0 -= ly0; i1 -= ly0; j0 -= lx0; j1 -= lx0;
+        }
+        tap00[qq] = (i0 * p.LBW + j0) * 16; tap01[qq] = (i0 * p.LBW + j1) * 16;
+        tap10[qq] = (i1 * p.LBW + j0) * 16; tap11[qq] = (i1 * p.LBW + j1) * 16;
+        w00[qq] = (1.f - wy) * (1.f - wx); w01[qq] = (1.f - wy) * wx;
+        w10[qq] = wy * (1.f - wx);         w11[qq] = wy * wx;
+        dsto[qq] = pos * 16;
+      }
+      const int l_plane = p.LBH * p.LBW * 16, a_plane = npos * 16;
+      for (int cb = 0; cb < p.n_blk; ++cb) {
+        const int sa = cb % p.a_stages, sl = cb & 1;
+        mbar_wait(&l_full[sl], (uint32_t)(cb >> 1) & 1u);
+        mbar_wait(&a_empty[sa], ((uint32_t)(cb / p.a_stages) & 1u) ^ 1u);
+        const uint8_t* src = sL + (size_t)sl * p.l_stage_bytes;
+        uint8_t* dstA = sA + (size_t)sa * p.a_stage_bytes;
+#pragma unroll
+        for (int qq = 0; qq < 2; ++qq) {
+          if (!has[qq]) continue;
+          if (!ins[qq]) {  // conv zero padding outside the (upsampled) image
+            for (int pln = 0; pln < p.blk_p; ++pln)
+              *reinterpret_cast<uint4*>(dstA + (size_t)pln * a_plane + dsto[qq]) = make_uint4(0u, 0u, 0u, 0u);
+            continue;
+          }
+#pragma unroll 2
+          for (int pln = 0; pln < p.blk_p; ++pln) {
+            const uint8_t* pb = src + (size_t)pln * l_plane;
+            const uint4 ua = *reinterpret_cast<const uint4*>(pb + tap00[qq]);
+            const uint4 ub = *reinterpret_cast<const uint4*>(pb + tap01[qq]);
+            const uint4 uc = *reinterpret_cast<const uint4*>(pb + tap10[qq]);
+            const uint4 ud = *reinterpret_cast<const uint4*>(pb + tap11[qq]);
+            if (dt == 1) {
+              // fp16 operands: blend with packed half2 FMAs (16 HFMA2 per chunk instead of ~75 fp32-path instructions;
+              // the extra half-precision roundings are ~2^-11 relative, far inside the forward tolerance)
+              const __half2 h00 = __float2half2_rn(w00[qq]), h01 = __float2half2_rn(w01[qq]);
+              const __half2 h10 = __float2half2_rn(w10[qq]), h11 = __float2half2_rn(w11[qq]);
+              const __half2* pa = reinterpret_cast<const __half2*>(&ua);
+              const __half2* pb2 = reinterpret_cast<const __half2*>(&ub);
+              const __half2* pc = reinterpret_cast<const __half2*>(&uc);
+              const __half2* pd = reinterpret_cast<const __half2*>(&ud);
+              uint4 o;
+              __half2* po = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                po[k] = __hfma2(h11, pd[k], __hfma2(h10, pc[k], __hfma2(h01, pb2[k], __hmul2(h00, pa[k]))));
+              *reinterpret_cast<uint4*>(dstA + (size_t)pln * a_plane + dsto[qq]) = o;
+            } else {
+              float a[8], b[8], cc[8], d[8], rr[8];
+              unpack8_rt(dt, ua, a);
+              unpack8_rt(dt, ub, b);
+              unpack8_rt(dt, uc, cc);
+              unpack8_rt(dt, ud, d);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) rr[k] = w00[qq] * a[k] + w01[qq] * b[k] + w10[qq] * cc[k] + w11[qq] * d[k];
+              *reinterpret_cast<uint4*>(dstA + (size_t)pln * a_plane + dsto[qq]) = pack8_rt(dt, rr);
+            }
+          }
+        }
+        fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        mbar_arrive(&a_full[sa]);
+        mbar_arrive(&l_empty[sl]);
+      }
+    }
     mbar_wait(acc_full, 0);
     tc_fence_after();
     if (threadIdx.x == kEpi0) PBT_STAMP(4);
@@ -297,7 +427,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvKParams p
       const bool valid = (y < p.H) && (x < p.W);
       const long long pix = (long long)y * p.W + x;
       float h0 = 0.f, h1 = 0.f, h2 = 0.f;
-      for (int c0 = 0; c0 < NC; c0 += 16) {
+      for (int c0 = half * 16; c0 < NC; c0 += 32) {
         uint32_t raw[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * p.acc_stride + c0), raw);
         tmem_ld_wait();
@@ -385,7 +515,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvKParams p
           }
         }
       }
-      if (p.head_w && valid) {
+      if (p.head_w) {  // combine the two column halves of the fused 1x1 head
+        float* hs = s_head + ((size_t)(t * 4 + q) * 32 + lane) * 3;
+        if (half == 1) {
+          hs[0] = h0;
+          hs[1] = h1;
+          hs[2] = h2;
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (half == 0) {
+          h0 += hs[0];
+          h1 += hs[1];
+          h2 += hs[2];
+        }
+      }
+      if (p.head_w && valid && half == 0) {
         h0 += __ldg(&p.head_b[0]);
         h1 += __ldg(&p.head_b[1]);
         h2 += __ldg(&p.head_b[2]);
@@ -401,11 +545,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvKParams p
       }
     }
     if (do_stats) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int e = threadIdx.x - kEpi0;  // 0..127
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int e = threadIdx.x - kEpi0;  // 0..255
       float* dst = p.stats_partial + ((long long)n * tiles_per_img + rem) * 2 * NC;
-      for (int i = e; i < 2 * NC; i += 128)
-        dst[i] = s_stats[i] + s_stats[2 * NC + i] + s_stats[4 * NC + i] + s_stats[6 * NC + i];
+      for (int i = e; i < 2 * NC; i += 256) {
+        float acc = 0.f;
+#pragma unroll
+        for (int w8 = 0; w8 < kEpiWarps; ++w8) acc += s_stats[w8 * 2 * NC + i];
+        dst[i] = acc;
+      }
     }
   }
 
@@ -452,6 +600,7 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PBT_REQUIRE(d != nullptr, "conv: null descriptor");
   const pbt_act_t& in = d->in;
+  const int up = d->upsample2x ? 1 : 0;  // input is the low-res tensor; the conv sees its bilinear x2 upsample
   PBT_REQUIRE(in.ptr && aligned16(in.ptr), "conv: input pointer null or not 16-byte aligned");
   PBT_REQUIRE(in.n > 0 && in.h > 0 && in.w > 0, "conv: empty input");
   PBT_REQUIRE(in.c > 0 && in.c % 16 == 0, "conv: cin must be a multiple of 16");
@@ -467,7 +616,8 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
 
   ConvKParams p;
   memset(&p, 0, sizeof(p));
-  p.n_img = in.n; p.H = in.h; p.W = in.w;
+  p.n_img = in.n; p.H = in.h << up; p.W = in.w << up;
+  p.up = up; p.LH = in.h; p.LW = in.w;
   p.Cp = in.c / 8;
   p.blk_p = d->blk_c / 8;
   p.n_blk = ceil_div(p.Cp, p.blk_p);
@@ -485,19 +635,23 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
   p.tiles_y = ceil_div(p.H, 16);
   p.idesc = make_idesc_f16(128, p.NC, d->dtype == PBT_BF16 ? 1 : 0, 0, 0);
   p.a_stage_bytes = round_up((uint32_t)(p.blk_p * p.BH * p.BW * 16), 128);
+  p.LBH = (p.BH + 1) / 2 + 2;
+  p.LBW = (p.BW + 1) / 2 + 2;
+  p.l_stage_bytes = up ? round_up((uint32_t)(p.blk_p * p.LBH * p.LBW * 16), 128) : 0;
+  PBT_REQUIRE(!up || (d->kh == 3 && d->kw == 3 && d->pad_t == 1 && d->pad_l == 1), "conv: upsample-on-load supports 3x3 pad 1");
   p.a_stages = p.n_blk > 1 ? 2 : 1;
   p.wpack = static_cast<const uint8_t*>(d->wpack);
   p.bias = d->bias; p.act = d->act; p.post_scale = d->post_scale; p.post_shift = d->post_shift;
   PBT_REQUIRE((d->post_scale == nullptr) == (d->post_shift == nullptr), "conv: post_scale/post_shift must come together");
   if (d->mask.ptr) {
-    PBT_REQUIRE(d->mask.c >= d->cout && d->mask.h == in.h && d->mask.w == in.w && d->mask.n == in.n && aligned16(d->mask.ptr),
+    PBT_REQUIRE(d->mask.c >= d->cout && d->mask.h == p.H && d->mask.w == p.W && d->mask.n == in.n && aligned16(d->mask.ptr),
                 "conv: mask shape mismatch");
     p.mask = static_cast<const uint8_t*>(d->mask.ptr);
     p.mask_img_stride = d->mask.img_stride;
   }
   p.addend32 = d->addend32; p.out32 = d->out32;
   if (d->out.ptr) {
-    PBT_REQUIRE(d->out.c >= d->cout && d->out.h == in.h && d->out.w == in.w && d->out.n == in.n && aligned16(d->out.ptr),
+    PBT_REQUIRE(d->out.c >= d->cout && d->out.h == p.H && d->out.w == p.W && d->out.n == in.n && aligned16(d->out.ptr),
                 "conv: output shape mismatch");
     p.out = static_cast<uint8_t*>(d->out.ptr);
     p.out_img_stride = d->out.img_stride;
@@ -510,8 +664,8 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
 
   // shared memory budget: A ring + B ring (groups of taps) + barriers + tmem slot + stats scratch.
   // Aim at two co-resident CTAs per SM (one CTA's epilogue/prologue overlaps the other's main loop).
-  const uint32_t tail = 8u * (2 * 2 + 2 * 8 + 1) + 16 + (uint32_t)(4 * 2 * p.NC * 4) + 128;
-  const uint32_t a_total = (uint32_t)p.a_stages * p.a_stage_bytes;
+  const uint32_t tail = 8u * (2 * 2 + 2 * 8 + 1) + 16 + (uint32_t)(kEpiWarps * 2 * p.NC * 4) + 3 * 4 * 32 * 3 * 4 + 8 * 4 + 128;
+  const uint32_t a_total = (uint32_t)p.a_stages * p.a_stage_bytes + 2 * p.l_stage_bytes;
   const uint32_t chunk = (uint32_t)(p.blk_p * p.NC * 16);  // one tap of one channel block
   const int ntaps = p.KH * p.KW;
   const uint32_t budget = 112 * 1024;
@@ -533,7 +687,7 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
   PBT_REQUIRE(smem_bytes <= 227 * 1024, "conv: configuration does not fit shared memory");
 
   CUtensorMap tmap;
-  int rc = make_p8_tmap(&tmap, in, p.BW, p.BH, p.blk_p);
+  int rc = up ? make_p8_tmap(&tmap, in, p.LBW, p.LBH, p.blk_p) : make_p8_tmap(&tmap, in, p.BW, p.BH, p.blk_p);
   if (rc != PBT_OK) return rc;
 
   const int grid = p.n_img * p.tiles_x * p.tiles_y;

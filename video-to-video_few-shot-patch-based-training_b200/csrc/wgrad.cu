@@ -8,31 +8,42 @@
 // P8 activation layout [c/8][y][x][8]: 8 channels are contiguous, so the channel dimension is the
 // "MN-major" dimension of a SWIZZLE_NONE UMMA operand (core matrix = 8 pixels x 8 channels = 128 B),
 // and the pixel shift of a tap is again a 16-byte shift of the descriptor start address.
-// One CTA owns (pixel split, tap row dy, ci block): it streams 8x16-pixel tiles (TMA, zero fill outside
-// the image = the conv padding), keeps kw accumulators [128 x co] in TMEM (kw*co <= 512 columns) over its
-// whole pixel range, and finally adds them to dW with fp32 reductions.
+//
+// Work decomposition (v2): one CTA owns a *unit* = (tap row dy, a run of <= GW taps in that row, a slice of
+// NCg output channels, a 128-channel ci block) over a strided subset of 8x8-pixel tiles.  Units are sized so
+// that a CTA needs <= 256 TMEM columns and ~100 KB of shared memory: TWO CTAs are co-resident per SM, which
+// matters because one CTA's MMA stream cannot hide its own operand-fetch latency (profiles/r1_issue_experiments.md).
+// Per tile: one TMA load of the haloed X rows (zero fill = conv padding) + one of the dY tile, 4 x ntaps MMAs
+// (K = 16 pixels each) with the taps innermost so that consecutive MMAs hit different accumulators.
+// The accumulators stay in TMEM over the CTA's whole pixel range and are finally added to dW with 128-bit
+// fp32 vector reductions.
 #include "internal.h"
 #include "ptx.cuh"
 
 namespace pbt {
 
+constexpr int kMaxUnits = 64;
+constexpr int kTileRows = 8;
+
 struct WgradKParams {
   int n_img, H, W;
-  int Cm, NC;
+  int Cm, NC, NCg;
   int KH, KW, pad_t, pad_l;
   int splits, tiles_x, tiles_y, n_tiles;
-  int BW;
+  int BW;  // haloed X width in pixels: 8 + GW - 1
   uint32_t idesc;
   int acc_stride, tmem_cols, stages;
   uint32_t x_stage_bytes, dy_stage_bytes, x_plane_bytes;
   float* dw;
   const float* inv_scale;
-  int debug_flags;
+  int n_units;
+  signed char u_dy[kMaxUnits], u_dx0[kMaxUnits], u_ntap[kMaxUnits];
+  short u_noff[kMaxUnits];
 };
 
 constexpr int kWgThreads = 192;
 
-__global__ void __launch_bounds__(kWgThreads, 1)
+__global__ void __launch_bounds__(kWgThreads, 2)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUtensorMap tmapDY, const WgradKParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sX = smem;
@@ -44,7 +55,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int split = blockIdx.x, dy = blockIdx.y, mb = blockIdx.z;
+  const int split = blockIdx.x, unit = blockIdx.y, mb = blockIdx.z;
+  const int dy = p.u_dy[unit], dx0 = p.u_dx0[unit], ntap = p.u_ntap[unit], noff = p.u_noff[unit];
   const int my_tiles = split < p.n_tiles ? (p.n_tiles - split + p.splits - 1) / p.splits : 0;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
 
@@ -67,70 +79,69 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ 
   if (my_tiles > 0) {
     if (warp == 0) {
       if (elect_one()) {
+        const uint32_t tx_bytes = (uint32_t)(16 * kTileRows * p.BW * 16) + (uint32_t)((p.NCg / 8) * kTileRows * 128);
         for (int it = 0; it < my_tiles; ++it) {
           const int tile = split + it * p.splits;
           const int n = tile / tiles_per_img;
           const int rem = tile - n * tiles_per_img;
           const int tyi = rem / p.tiles_x, txi = rem - tyi * p.tiles_x;
-          const int x0 = txi * 8, y0 = tyi * 16;
+          const int x0 = txi * 8, y0 = tyi * kTileRows;
           const int st = it % p.stages;
           const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
           mbar_wait(&empty[st], ph ^ 1u);
-          mbar_arrive_expect_tx(&full[st], (uint32_t)(16 * 16 * p.BW * 16) + (uint32_t)((p.NC / 8) * 2048));
-          tma_load_4d(sX + (size_t)st * p.x_stage_bytes, &tmapX, &full[st], (x0 - p.pad_l) * 8, y0 + dy - p.pad_t, mb * 16, n);
-          tma_load_4d(sDY + (size_t)st * p.dy_stage_bytes, &tmapDY, &full[st], x0 * 8, y0, 0, n);
+          mbar_arrive_expect_tx(&full[st], tx_bytes);
+          tma_load_4d(sX + (size_t)st * p.x_stage_bytes, &tmapX, &full[st], (x0 - p.pad_l + dx0) * 8, y0 + dy - p.pad_t,
+                      mb * 16, n);
+          tma_load_4d(sDY + (size_t)st * p.dy_stage_bytes, &tmapDY, &full[st], x0 * 8, y0, noff / 8, n);
         }
       }
     } else if (warp == 1) {
       // whole warp runs the uniform loops; only the tcgen05 instructions are predicated on one elected lane
       const bool leader = elect_one();
-      {
-        // descriptor words (MN-major, SWIZZLE_NONE): lo = addr>>4 | (LBO>>4)<<16, hi = SBO>>4 | version<<14.
-        // Only the low word changes per MMA: +dx (one pixel = 16 B) per tap, +2 tile rows per K=16 step.
-        const uint32_t row16 = (uint32_t)p.BW;                                   // haloed row pitch in 16-byte units
-        const uint32_t a_lo_const = (row16 & 0x3FFF) << 16;                      // LBO = next 8-pixel K group = next row
-        const uint32_t a_hi = ((p.x_plane_bytes >> 4) & 0x3FFF) | (1u << 14);    // SBO = next 8-channel group = next plane
-        const uint32_t b_lo_const = (128u >> 4) << 16;
-        const uint32_t b_hi = (2048u >> 4) | (1u << 14);
-        const uint32_t a_kstep = 2u * row16, b_kstep = 2u * 8u;
-        const uint32_t idesc = p.idesc;
-        const uint32_t acc_stride = (uint32_t)p.acc_stride;
-        for (int it = 0; it < my_tiles; ++it) {
-          const int st = it % p.stages;
-          const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-          mbar_wait(&full[st], ph);
-          tc_fence_after();
-          const uint32_t x_lo = (smem_u32(sX + (size_t)st * p.x_stage_bytes) >> 4) | a_lo_const;
-          const uint32_t dy_lo = (smem_u32(sDY + (size_t)st * p.dy_stage_bytes) >> 4) | b_lo_const;
-          const uint32_t first = it == 0 ? 0u : 1u;
-          if (leader) {
+      // descriptor words (MN-major, SWIZZLE_NONE): lo = addr>>4 | (LBO>>4)<<16, hi = SBO>>4 | version<<14.
+      // Only the low word changes per MMA: +1 (one pixel = 16 B) per tap, +2 tile rows per K=16 step.
+      const uint32_t row16 = (uint32_t)p.BW;                                   // haloed row pitch in 16-byte units
+      const uint32_t a_lo_const = (row16 & 0x3FFF) << 16;                      // LBO = next 8-pixel K group = next row
+      const uint32_t a_hi = ((p.x_plane_bytes >> 4) & 0x3FFF) | (1u << 14);    // SBO = next 8-channel group = next plane
+      const uint32_t b_lo_const = (128u >> 4) << 16;
+      const uint32_t b_hi = ((uint32_t)(kTileRows * 128) >> 4) | (1u << 14);
+      const uint32_t a_kstep = 2u * row16, b_kstep = 2u * 8u;
+      const uint32_t idesc = p.idesc;
+      const uint32_t acc_stride = (uint32_t)p.acc_stride;
+      for (int it = 0; it < my_tiles; ++it) {
+        const int st = it % p.stages;
+        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        mbar_wait(&full[st], ph);
+        tc_fence_after();
+        const uint32_t x_lo = (smem_u32(sX + (size_t)st * p.x_stage_bytes) >> 4) | a_lo_const;
+        const uint32_t dy_lo = (smem_u32(sDY + (size_t)st * p.dy_stage_bytes) >> 4) | b_lo_const;
+        const uint32_t first = it == 0 ? 0u : 1u;
+        if (leader) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {  // 8 x K=16 pixels (two 8-pixel tile rows each)
-              const uint64_t bdesc = ((uint64_t)b_hi << 32) | (dy_lo + (uint32_t)k * b_kstep);
-              // taps inner: consecutive MMAs go to different accumulators (same-accumulator chains serialise)
-              for (int dx = 0; dx < p.KW; ++dx) {
-                const uint64_t adesc = ((uint64_t)a_hi << 32) | (x_lo + (uint32_t)dx + (uint32_t)k * a_kstep);
-                umma_f16(tmem_base + (uint32_t)dx * acc_stride, adesc, bdesc, idesc, k == 0 ? first : 1u);
-              }
+          for (int k = 0; k < kTileRows / 2; ++k) {  // K = 16 pixels = two 8-pixel tile rows per MMA
+            const uint64_t bdesc = ((uint64_t)b_hi << 32) | (dy_lo + (uint32_t)k * b_kstep);
+            for (int j = 0; j < ntap; ++j) {
+              const uint64_t adesc = ((uint64_t)a_hi << 32) | (x_lo + (uint32_t)j + (uint32_t)k * a_kstep);
+              umma_f16(tmem_base + (uint32_t)j * acc_stride, adesc, bdesc, idesc, k == 0 ? first : 1u);
             }
-            umma_commit(&empty[st]);
           }
-          __syncwarp();
+          umma_commit(&empty[st]);
         }
-        if (leader) umma_commit(acc_full);
         __syncwarp();
       }
+      if (leader) umma_commit(acc_full);
+      __syncwarp();
     } else {
       const int q = warp & 3;
       const int ci = mb * 128 + q * 32 + lane;
       const float inv = p.inv_scale ? __ldg(p.inv_scale) : 1.f;
       mbar_wait(acc_full, 0);
       tc_fence_after();
-      for (int dx = 0; dx < p.KW; ++dx) {
-        float* dst = p.dw + ((long long)(dy * p.KW + dx) * p.Cm + ci) * p.NC;
-        for (int c0 = 0; c0 < p.NC; c0 += 16) {
+      for (int j = 0; j < ntap; ++j) {
+        float* dst = p.dw + ((long long)(dy * p.KW + dx0 + j) * p.Cm + ci) * p.NC + noff;
+        for (int c0 = 0; c0 < p.NCg; c0 += 16) {
           uint32_t raw[16];
-          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(dx * p.acc_stride + c0), raw);
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * p.acc_stride + c0), raw);
           tmem_ld_wait();
           if (ci < p.Cm) {
 #pragma unroll
@@ -173,25 +184,46 @@ extern "C" int pbt_conv_wgrad(const pbt_wgrad_desc_t* d, void* stream_) {
   p.n_img = x.n; p.H = x.h; p.W = x.w;
   p.Cm = x.c; p.NC = g.c;
   p.KH = d->kh; p.KW = d->kw; p.pad_t = d->pad_t; p.pad_l = d->pad_l;
-  p.BW = 8 + p.KW - 1;
+  // unit shape: <= 256 TMEM columns per CTA.  Narrow kernels split the output channels, wide ones the tap row.
+  int n_split = 1;
+  while (p.NC / n_split > 128 && (p.NC / n_split) % 32 == 0) n_split *= 2;
+  if (p.KW <= 3 && p.KW * (int)round_up((uint32_t)(p.NC / n_split), 32) > 256 && (p.NC / n_split) % 32 == 0) n_split *= 2;
+  p.NCg = p.NC / n_split;
+  p.acc_stride = (int)round_up((uint32_t)p.NCg, 32);
+  int gw = 256 / p.acc_stride;
+  if (gw > p.KW) gw = p.KW;
+  if (gw < 1) gw = 1;
+  const int groups_per_row = ceil_div(p.KW, gw);
+  gw = ceil_div(p.KW, groups_per_row);  // balance the runs (7 taps, limit 4 -> 4 + 3)
+  p.n_units = 0;
+  for (int dyi = 0; dyi < p.KH; ++dyi)
+    for (int gi = 0; gi < groups_per_row; ++gi)
+      for (int ns = 0; ns < n_split; ++ns) {
+        PBT_REQUIRE(p.n_units < kMaxUnits, "wgrad: too many work units");
+        const int dx0 = gi * gw;
+        p.u_dy[p.n_units] = (signed char)dyi;
+        p.u_dx0[p.n_units] = (signed char)dx0;
+        p.u_ntap[p.n_units] = (signed char)((dx0 + gw <= p.KW) ? gw : p.KW - dx0);
+        p.u_noff[p.n_units] = (short)(ns * p.NCg);
+        ++p.n_units;
+      }
+  p.BW = 8 + gw - 1;
   p.tiles_x = ceil_div(p.W, 8);
-  p.tiles_y = ceil_div(p.H, 16);
+  p.tiles_y = ceil_div(p.H, kTileRows);
   p.n_tiles = p.n_img * p.tiles_x * p.tiles_y;
-  p.acc_stride = (int)round_up((uint32_t)p.NC, 32);
   int cols = 32;
-  while (cols < p.KW * p.acc_stride) cols <<= 1;
-  PBT_REQUIRE(cols <= 512, "wgrad: kw*cout exceeds tensor memory (512 columns)");
+  while (cols < gw * p.acc_stride) cols <<= 1;
+  PBT_REQUIRE(cols <= 512, "wgrad: unit exceeds tensor memory (512 columns)");
   p.tmem_cols = cols;
-  p.idesc = make_idesc_f16(128, p.NC, d->dtype == PBT_BF16 ? 1 : 0, 1, 1);
-  p.x_plane_bytes = (uint32_t)(16 * p.BW * 16);
+  p.idesc = make_idesc_f16(128, p.NCg, d->dtype == PBT_BF16 ? 1 : 0, 1, 1);
+  p.x_plane_bytes = (uint32_t)(kTileRows * p.BW * 16);
   p.x_stage_bytes = round_up(16 * p.x_plane_bytes, 128);
-  p.dy_stage_bytes = (uint32_t)((p.NC / 8) * 2048);
-  p.stages = 2;
+  p.dy_stage_bytes = (uint32_t)((p.NCg / 8) * kTileRows * 128);
+  p.stages = 3;
   p.dw = d->dw;
   p.inv_scale = d->inv_scale;
-  p.debug_flags = d->debug_flags;
   const int m_blocks = ceil_div(p.Cm, 128);
-  int splits = (2 * num_sms()) / (m_blocks * p.KH);
+  int splits = (4 * num_sms()) / (m_blocks * p.n_units);
   if (splits < 1) splits = 1;
   if (splits > p.n_tiles) splits = p.n_tiles;
   p.splits = splits;
@@ -199,13 +231,13 @@ extern "C" int pbt_conv_wgrad(const pbt_wgrad_desc_t* d, void* stream_) {
   PBT_REQUIRE(smem_bytes <= 227 * 1024, "wgrad: configuration does not fit shared memory");
 
   CUtensorMap tx, tg;
-  int rc = make_p8_tmap(&tx, x, p.BW, 16, 16);
+  int rc = make_p8_tmap(&tx, x, p.BW, kTileRows, 16);
   if (rc != PBT_OK) return rc;
-  rc = make_p8_tmap(&tg, g, 8, 16, p.NC / 8);
+  rc = make_p8_tmap(&tg, g, 8, kTileRows, p.NCg / 8);
   if (rc != PBT_OK) return rc;
 
   PBT_CUDA_CHECK(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-  dim3 grid(p.splits, p.KH, m_blocks);
+  dim3 grid(p.splits, p.n_units, m_blocks);
   wgrad_kernel<<<grid, kWgThreads, smem_bytes, stream>>>(tx, tg, p);
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;

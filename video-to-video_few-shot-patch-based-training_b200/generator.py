@@ -198,9 +198,9 @@ class _Workspace:
         self.hmid = [E(f[2], h4, w4) for _ in range(k)]
         self.a = [E(f[2], h4, w4) for _ in range((nb + 1) if train else 2)]
         self.r = [torch.empty((n, f[2] // 8, h4, w4, 8), device=dev) for _ in range(2)]
-        self.u2in = E(2 * f[2], h2, w2)
+        self.u2in = E(2 * f[2], h2, w2) if train else None   # inference upsamples inside the conv kernel
         self.rawU2 = E(f[4], h2, w2)
-        self.u1in = E(f[4] + f[1], h, w)
+        self.u1in = E(f[4] + f[1], h, w) if train else None
         self.rawU1 = E(f[4], h, w)
         self.c11 = E(f[5], h, w)
         self.s0 = E(f[5], h, w)
@@ -337,13 +337,15 @@ class _Engine:
         if not u8_hwc and x.dtype not in (torch.float32, torch.float16):
             x = x.float()
 
-        def conv_in(name, xin, cout, k, pad, raw, T_pref):
-            """conv (bias skipped: a constant per channel is removed by the following InstanceNorm) + IN statistics"""
-            T = self._T(T_pref, xin.w)
-            st = ws.stat(name, cout, xin.h, xin.w, T, dev)
+        def conv_in(name, xin, cout, k, pad, raw, T_pref, up=False):
+            """conv (bias skipped: a constant per channel is removed by the following InstanceNorm) + IN statistics;
+            up=True: xin is the low-res tensor, the conv consumes its bilinear x2 upsample (interpolated in-kernel)"""
+            oh, ow = (2 * xin.h, 2 * xin.w) if up else (xin.h, xin.w)
+            T = self._T(T_pref, ow)
+            st = ws.stat(name, cout, oh, ow, T, dev)
             ops.conv_fwd(xin, W[name], cout, k, k, pad, pad, dt, blk_c=self._blk(xin.c), tiles_per_cta=T, out=raw,
-                         stats_partial=st["partial"])
-            ops.norm_finalize(st["partial"], n, st["tiles"], cout, xin.h * xin.w, st["scale"], st["shift"], eps=EPS)
+                         stats_partial=st["partial"], upsample2x=up)
+            ops.norm_finalize(st["partial"], n, st["tiles"], cout, oh * ow, st["scale"], st["shift"], eps=EPS)
             return st
 
         # input -> tail channels of cat11 (pad channels zeroed every call)
@@ -381,13 +383,19 @@ class _Engine:
                            out32=None if lastb else r_nxt, out=last16 if lastb else None,
                            out_relu=None if lastb else a_of(b + 1))
             r_cur, r_nxt = r_nxt, r_cur
-        # decoder
-        ops.upsample2x(ws.c2cat, ws.u2in, dt)
-        st = conv_in("up2", ws.u2in, f[4], 3, 1, ws.rawU2, 2)
-        # IN + ReLU of the up2 output are applied on load by the upsample kernel (never materialised at H/2)
-        ops.upsample2x(ws.rawU2, ws.u1in.view(0, f[4]), dt, scale=st["scale"], shift=st["shift"], act=ACT_RELU)
-        ops.upsample2x(ws.c1cat.view(f[4], f[1]), ws.u1in.view(f[4], f[1]), dt)
-        st = conv_in("up1", ws.u1in, f[4], 3, 1, ws.rawU1, 2)
+        # decoder.  Inference: the bilinear x2 upsample is interpolated inside the conv kernel's producer
+        # (upsample2x=True), the upsampled tensors are never written.  Training keeps them: wgrad reads them.
+        if save:
+            ops.upsample2x(ws.c2cat, ws.u2in, dt)
+            st = conv_in("up2", ws.u2in, f[4], 3, 1, ws.rawU2, 2)
+            # IN + ReLU of the up2 output are applied on load by the upsample kernel (never materialised at H/2)
+            ops.upsample2x(ws.rawU2, ws.u1in.view(0, f[4]), dt, scale=st["scale"], shift=st["shift"], act=ACT_RELU)
+            ops.upsample2x(ws.c1cat.view(f[4], f[1]), ws.u1in.view(f[4], f[1]), dt)
+            st = conv_in("up1", ws.u1in, f[4], 3, 1, ws.rawU1, 2)
+        else:
+            st = conv_in("up2", ws.c2cat, f[4], 3, 1, ws.rawU2, 2, up=True)
+            ops.norm_apply(ws.rawU2, dt, scale=st["scale"], shift=st["shift"], act=ACT_RELU, out=ws.c1cat.view(0, f[4]))
+            st = conv_in("up1", ws.c1cat, f[4], 3, 1, ws.rawU1, 2, up=True)
         ops.norm_apply(ws.rawU1, dt, scale=st["scale"], shift=st["shift"], act=ACT_RELU, out=ws.cat11.view(0, f[4]))
         # conv11 + smoothers + fused head
         ev = self.kernel_timer

@@ -107,7 +107,8 @@ def conv_num_tiles(h: int, w: int, tiles_per_cta: int) -> int:
 def conv_fwd(x: P8, wpack: torch.Tensor, cout: int, kh: int, kw: int, pad_t: int, pad_l: int, dt: int, *,
              blk_c: int = 32, tiles_per_cta: int = 2, bias=None, act: int = ACT_NONE, post_scale=None, post_shift=None,
              mask: P8 | None = None, addend32=None, out32=None, out: P8 | None = None, stats_partial=None,
-             head_w=None, head_b=None, head_out=None, head_tanh: bool = True, debug_flags: int = 0, debug_buf=None) -> None:
+             head_w=None, head_b=None, head_out=None, head_tanh: bool = True, upsample2x: bool = False, debug_flags: int = 0,
+             debug_buf=None) -> None:
     d = nv.ConvDesc()
     d.inp = x.act()
     d.wpack = wpack.data_ptr()
@@ -120,6 +121,7 @@ def conv_fwd(x: P8, wpack: torch.Tensor, cout: int, kh: int, kw: int, pad_t: int
     d.out = act_or_null(out)
     d.stats_partial = ptr(stats_partial)
     d.head_w, d.head_b, d.head_out, d.head_tanh = ptr(head_w), ptr(head_b), ptr(head_out), int(head_tanh)
+    d.upsample2x = int(upsample2x)
     d.debug_flags = debug_flags
     d.debug_buf = ptr(debug_buf)
     check(lib().pbt_conv_fwd(C.byref(d), stream_ptr()), "pbt_conv_fwd")
