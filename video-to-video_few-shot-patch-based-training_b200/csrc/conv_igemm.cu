@@ -203,24 +203,29 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvKParams p
   if (warp == 0) {
     // ------------------------------------------------------------ producer
     if (elect_one()) {
-      int bi = 0;  // running B-group counter
-      for (int cb = 0; cb < p.n_blk; ++cb) {
-        const int sa = cb % p.a_stages;
-        const uint32_t pa = (uint32_t)(cb / p.a_stages) & 1u;
+      // activation tile (or, with upsample-on-load, its low-res footprint) of channel block `cb`
+      auto issue_act = [&](int cb) {
         if (p.up) {
-          // low-res footprint of the haloed tile -> staging; the epilogue warps interpolate it into the A stage
           const int sl = cb & 1;
-          const uint32_t pl = (uint32_t)(cb >> 1) & 1u;
-          mbar_wait(&l_empty[sl], pl ^ 1u);
+          mbar_wait(&l_empty[sl], ((uint32_t)(cb >> 1) & 1u) ^ 1u);
           mbar_arrive_expect_tx(&l_full[sl], (uint32_t)(p.blk_p * p.LBH * p.LBW * 16));
           tma_load_4d(sL + (size_t)sl * p.l_stage_bytes, &tmapA, &l_full[sl], up_origin(x0 - p.pad_l, p.W, p.LW) * 8,
                       up_origin(y0 - p.pad_t, p.H, p.LH), cb * p.blk_p, n);
         } else {
-          mbar_wait(&a_empty[sa], pa ^ 1u);
+          const int sa = cb % p.a_stages;
+          mbar_wait(&a_empty[sa], ((uint32_t)(cb / p.a_stages) & 1u) ^ 1u);
           mbar_arrive_expect_tx(&a_full[sa], (uint32_t)(p.blk_p * p.BH * p.BW * 16));
           tma_load_4d(sA + (size_t)sa * p.a_stage_bytes, &tmapA, &a_full[sa], (x0 - p.pad_l) * 8, y0 - p.pad_t,
                       cb * p.blk_p, n);
         }
+      };
+      int bi = 0;  // running B-group counter
+      issue_act(0);
+      for (int cb = 0; cb < p.n_blk; ++cb) {
+        // Block cb+1 is requested once the weight ring of block cb is primed (b_stages groups in flight): by then
+        // the MMAs of block cb-1 have retired (its stage is free, no blocking wait here), and the load — plus the
+        // upsample transform — overlaps almost a whole block of MMAs instead of starting when the ring drains.
+        const int gpre = min(p.b_stages, ngroups - 1);
         const int pib = min(p.blk_p, p.Cp - cb * p.blk_p);
         const uint32_t chunk = (uint32_t)(pib * p.NC * 16);
         const uint8_t* wsrc = p.wpack + (size_t)cb * ntaps * ((size_t)p.blk_p * p.NC * 16);
@@ -233,6 +238,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvKParams p
           mbar_arrive_expect_tx(&b_full[sb], chunk * (uint32_t)nt);
           // the taps of a group are contiguous in the packed weights: one bulk copy per group
           bulk_load_1d(sB + (size_t)sb * p.b_stage_bytes, wsrc + (size_t)tap0 * chunk, chunk * (uint32_t)nt, &b_full[sb]);
+          if (g == gpre && cb + 1 < p.n_blk && p.a_stages > 1) issue_act(cb + 1);
         }
       }
     }
