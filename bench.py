@@ -311,14 +311,17 @@ def run_native(args):
         diff = (yn.cpu().int() - yc.int()).abs().max().item()
         cpu["max_abs_u8_diff_vs_native"] = int(diff)
 
-    conv11_flops = 2.0 * H * W * (49 * (160 + CIN)) * 64
+    frames_per_launch = min(F, max(1, int(sty.frames_per_pass)))
+    conv11_flops = 2.0 * H * W * (49 * (160 + CIN)) * 64 * frames_per_launch
     peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
     achieved = conv11_flops / (k_ms / 1e3) / 1e12 if k_ms > 0 else 0.0
     traffic = None
     tp = os.path.join(ROOT, "profiles", "conv11_traffic.json")
     if os.path.exists(tp):
         with open(tp) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            traffic = json.load(f).get("dram_bytes_per_launch")   # captured on a one-frame launch
+        if traffic is not None:
+            traffic *= frames_per_launch
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -332,7 +335,8 @@ def run_native(args):
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (conv11 7x7, 163->64)", "achieved": achieved, "peak": peak_tf,
                      "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None, "traffic": traffic,
-                     "peak_source": f"{peak_src} bf16_tflops_sustained", "launch_ms": k_ms, "launches_timed": len(kt)},
+                     "peak_source": f"{peak_src} bf16_tflops_sustained", "launch_ms": k_ms, "launches_timed": len(kt),
+                     "frames_per_launch": frames_per_launch},
         "clocks": clk,
     }
     if cpu is not None:

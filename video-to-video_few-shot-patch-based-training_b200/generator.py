@@ -439,6 +439,16 @@ class _Engine:
             self._saved = (ws, W)
         return y
 
+    def zero_pool_floats(self, n: int) -> int:
+        """upper bound (in floats) of all accumulate-into buffers of one backward sweep"""
+        g = self.gen
+        f, cp = g.filters, self.cin_p
+        nb = len(g.resnet_blocks)
+        wg = (49 * cp * f[0] + 4 * 4 * f[0] * f[1] + 4 * 4 * f[1] * f[2] + nb * 2 * 9 * f[2] * f[2] + 9 * 2 * f[2] * f[4]
+              + 9 * (f[4] + f[1]) * f[4] + 49 * (f[4] + f[0] + cp) * f[5] + 2 * 9 * f[5] * f[5])
+        sums = n * 2 * (f[0] + f[1] + f[2] * (1 + 2 * nb) + 2 * f[4]) + 16 * f[5] + 64
+        return wg + sums + 64 * 64   # slack for the 64-float alignment of each carve
+
     # -------------------------------------------------------------- backward
     def backward(self, gy: Tensor, y: Tensor):
         """returns gradients for `list(gen.parameters())` in order"""

@@ -39,7 +39,22 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor) -> List[torch.Ten
     if nb == 0:
         raise NotImplementedError("native backward needs at least one residual block")
     E = lambda c, hh, ww: P8.empty(n, c, hh, ww, dt, device=dev)  # noqa: E731
-    Z = lambda *shape: torch.zeros(shape, device=dev)  # noqa: E731
+
+    # every accumulate-into buffer of the sweep (wgrad outputs, reduction sums, bias gradients) is carved out of ONE
+    # zero-filled allocation: a single memset instead of ~70 fill launches per step
+    pool = torch.zeros(eng.zero_pool_floats(n), device=dev)
+    pool_off = [0]
+
+    def Z(*shape):
+        cnt = 1
+        for d_ in shape:
+            cnt *= d_
+        cnt_al = (cnt + 63) // 64 * 64          # keep every carve 256-byte aligned (vector reductions need 16 B)
+        lo = pool_off[0]
+        if lo + cnt_al > pool.numel():
+            return torch.zeros(shape, device=dev)
+        pool_off[0] = lo + cnt_al
+        return pool[lo:lo + cnt].view(shape)
 
     # ---- gradient scale (fp16 only): S = 2^k with max|gy|*S in (target/2, target]
     scale2 = None

@@ -18,6 +18,10 @@ from .generator import GeneratorJ, _Engine
 
 
 class FrameStylizer:
+    #: frames per generator pass.  Two frames per pass fill the GPU better on the 1/16-resolution layers (their
+    #: grids are ~1.7 waves at 1080p) and amortise the ~70 launches of a pass; InstanceNorm stays per frame.
+    frames_per_pass = 2
+
     def __init__(self, gen: GeneratorJ):
         if not next(gen.parameters()).is_cuda:
             raise RuntimeError("FrameStylizer needs the generator on a CUDA device (no CPU path)")
@@ -37,9 +41,10 @@ class FrameStylizer:
             raise ValueError(f"expected {self.gen.input_channels} channels, got {c}")
         if out_u8 is None:
             out_u8 = torch.empty((n, h, w, 3), dtype=torch.uint8, device=self.device)
-        for i in range(n):
-            y = self.eng.forward(frames_u8[i:i + 1], save=False, u8_hwc=True)
-            ops.nchw_to_u8hwc(y, out_u8[i:i + 1])
+        step = max(1, int(self.frames_per_pass))
+        for i in range(0, n, step):
+            y = self.eng.forward(frames_u8[i:i + step], save=False, u8_hwc=True)
+            ops.nchw_to_u8hwc(y, out_u8[i:i + step])
         return out_u8
 
     @torch.no_grad()
@@ -52,28 +57,30 @@ class FrameStylizer:
             self._streams = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
         copy_in, copy_out = self._streams
         main = torch.cuda.current_stream(self.device)
-        dev_in = [torch.empty((1, h, w, c), dtype=torch.uint8, device=self.device) for _ in range(2)]
-        dev_out = [torch.empty((1, h, w, 3), dtype=torch.uint8, device=self.device) for _ in range(2)]
+        step = max(1, int(self.frames_per_pass))
+        dev_in = [torch.empty((step, h, w, c), dtype=torch.uint8, device=self.device) for _ in range(2)]
+        dev_out = [torch.empty((step, h, w, 3), dtype=torch.uint8, device=self.device) for _ in range(2)]
         in_ready = [torch.cuda.Event() for _ in range(2)]
         in_free = [torch.cuda.Event() for _ in range(2)]
         out_ready = [torch.cuda.Event() for _ in range(2)]
         out_free = [torch.cuda.Event() for _ in range(2)]
         for e in in_free + out_free:
             e.record(main)
-        for i in range(n):
-            b = i & 1
+        for k, i in enumerate(range(0, n, step)):
+            b = k & 1
+            m = min(step, n - i)
             with torch.cuda.stream(copy_in):
                 copy_in.wait_event(in_free[b])
-                dev_in[b].copy_(frames_pinned[i:i + 1], non_blocking=True)
+                dev_in[b][:m].copy_(frames_pinned[i:i + m], non_blocking=True)
                 in_ready[b].record(copy_in)
             main.wait_event(in_ready[b])
             main.wait_event(out_free[b])
-            y = self.eng.forward(dev_in[b], save=False, u8_hwc=True)
-            ops.nchw_to_u8hwc(y, dev_out[b])
+            y = self.eng.forward(dev_in[b][:m], save=False, u8_hwc=True)
+            ops.nchw_to_u8hwc(y, dev_out[b][:m])
             in_free[b].record(main)
             out_ready[b].record(main)
             with torch.cuda.stream(copy_out):
                 copy_out.wait_event(out_ready[b])
-                out_pinned[i:i + 1].copy_(dev_out[b], non_blocking=True)
+                out_pinned[i:i + m].copy_(dev_out[b][:m], non_blocking=True)
                 out_free[b].record(copy_out)
         main.wait_stream(copy_out)
