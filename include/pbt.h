@@ -103,6 +103,15 @@ typedef struct {
   int32_t      head_tanh;    /* 1 = apply tanh */
   int32_t      upsample2x;   /* 1: `in` is [n,cin,h/2,w/2]; the conv consumes its bilinear x2 (align_corners=True) upsample,
                               * interpolated inside the kernel (src/models/generator.py:13 fused into :200); 3x3 pad 1 only */
+  /* normalise-on-load (inference): `pre` (optional, ptr NULL = absent) supplies the FIRST pre.c input channels as the RAW
+   * output of the previous conv; the kernel applies that layer's InstanceNorm + activation, act(x*pre_scale+pre_shift)
+   * with pre_scale/pre_shift fp32 [n][pre.c], inside shared memory before the tensor core reads the tile
+   * (src/models/generator.py:36-40 fused into the next conv).  `in` supplies the remaining channels (in.ptr NULL = none).
+   * pre.c must be a multiple of blk_c; not combinable with upsample2x. */
+  pbt_act_t    pre;
+  const float* pre_scale;
+  const float* pre_shift;
+  int32_t      pre_act;
   int32_t      debug_flags;  /* bring-up only; 0 in production */
   void*        debug_buf;    /* bring-up only: int64[grid][8] per-CTA phase timestamps, NULL in production */
 } pbt_conv_desc_t;

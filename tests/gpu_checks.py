@@ -455,6 +455,33 @@ def check_gather(patch=32, n_patches=37, seed=7):
     return bool(ok), 0.0, ""
 
 
+def check_conv_norm_on_load(n=2, cpre=64, cin=32, cout=32, h=37, w=45, T=2, blk_c=32, dt=FP16, act="relu", seed=13):
+    """conv3x3(pad 1) over cat(act(pre*scale+shift), x): the normalisation + activation of `pre` applied in-kernel"""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    tdt = torch_dtype(dt)
+    pre = torch.randn((n, cpre, h, w), generator=g, device="cuda").to(tdt).float()
+    sc = torch.rand((n, cpre), generator=g, device="cuda") + 0.5
+    sh = torch.randn((n, cpre), generator=g, device="cuda") * 0.3
+    y = pre * sc[:, :, None, None] + sh[:, :, None, None]
+    y = {"relu": F.relu, "leaky": lambda t: F.leaky_relu(t, 0.2), "none": lambda t: t}[act](y).to(tdt).float()
+    xs = [y]
+    x = None
+    if cin:
+        x = torch.randn((n, cin, h, w), generator=g, device="cuda").to(tdt).float()
+        xs.append(x)
+    wt = (torch.randn((cout, cpre + cin, 3, 3), generator=g, device="cuda") * 0.05).to(tdt).float()
+    exp = ref_conv(torch.cat(xs, 1), wt, 1, 1)
+    out = P8.empty(n, cout, h, w, dt)
+    ops.conv_fwd(P8.from_nchw(x, dt) if cin else None, ops.pack_conv_weight(wt, cpre + cin, blk_c, dt), cout, 3, 3, 1, 1, dt,
+                 blk_c=blk_c, tiles_per_cta=T, out=out, pre=P8.from_nchw(pre, dt), pre_scale=sc.contiguous(),
+                 pre_shift=sh.contiguous(), pre_act={"relu": ACT_RELU, "leaky": ACT_LEAKY, "none": ACT_NONE}[act])
+    torch.cuda.synchronize()
+    err = (out.to_nchw().double() - exp).abs().max().item()
+    scale = max(1.0, exp.abs().max().item())
+    ok = err / scale < (3e-2 if dt == BF16 else 4e-3)
+    return ok, err, f"err={err:.4g}"
+
+
 def check_conv_upsample(n=2, cin=64, cout=32, h=20, w=28, T=2, blk_c=32, dt=FP16, seed=11, stats=True):
     """conv3x3(pad 1) over the bilinear x2 (align_corners=True) upsample of a low-res input, interpolated in-kernel"""
     g = torch.Generator(device="cuda").manual_seed(seed)

@@ -51,6 +51,15 @@ def test_conv_with_upsample_on_load(kw):
     assert ok, msg
 
 
+@pytest.mark.parametrize("kw", [dict(), dict(cpre=128, cin=48, cout=64, h=40, w=50), dict(cpre=256, cin=0, cout=256, h=20, w=20, blk_c=64),
+                                dict(cpre=64, cin=0, cout=16, h=9, w=70, T=3, dt=0, act="leaky"),
+                                dict(n=3, cpre=16, cin=16, cout=16, h=5, w=7, T=1, blk_c=16, act="none")],
+                         ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()) or "default")
+def test_conv_with_norm_on_load(kw):
+    ok, err, msg = gc.check_conv_norm_on_load(**kw)
+    assert ok, msg
+
+
 WGRAD_CASES = [
     dict(cin=16, cout=16),
     dict(cin=128, cout=16),

@@ -90,6 +90,19 @@ def g_conv_up():
             print(f"[conv_up] {name}: EXC {type(e).__name__}: {e}", flush=True)
 
 
+def g_conv_nrm():
+    import gpu_checks as gc
+    for name, kw in [("64+32->32", dict()), ("128+48->64", dict(cpre=128, cin=48, cout=64, h=40, w=50)),
+                     ("256+0->256 blk64", dict(cpre=256, cin=0, cout=256, h=20, w=20, blk_c=64)),
+                     ("64+0->16 T3 bf16 leaky", dict(cpre=64, cin=0, cout=16, h=9, w=70, T=3, dt=0, act="leaky")),
+                     ("16+16->16 T1 blk16 none", dict(n=3, cpre=16, cin=16, cout=16, h=5, w=7, T=1, blk_c=16, act="none"))]:
+        try:
+            ok, err, msg = gc.check_conv_norm_on_load(**kw)
+            print(f"[conv_nrm] {name}: {'PASS' if ok else 'FAIL'} {msg}", flush=True)
+        except Exception as e:  # noqa: BLE001
+            print(f"[conv_nrm] {name}: EXC {type(e).__name__}: {e}", flush=True)
+
+
 def g_wgrad():
     import gpu_checks as gc
     from pbt_b200._native import FP16
@@ -192,7 +205,7 @@ def g_conv_perf():
         print(f"[conv_perf] {name}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s (padded-K flops)", flush=True)
 
 
-GROUPS = {"conv_up": g_conv_up, "conv_basic": g_conv_basic, "conv_tiles": g_conv_tiles, "wgrad": g_wgrad, "elementwise": g_elementwise,
+GROUPS = {"conv_nrm": g_conv_nrm, "conv_up": g_conv_up, "conv_basic": g_conv_basic, "conv_tiles": g_conv_tiles, "wgrad": g_wgrad, "elementwise": g_elementwise,
           "norm": g_norm, "conv_perf": g_conv_perf}
 
 if __name__ == "__main__":

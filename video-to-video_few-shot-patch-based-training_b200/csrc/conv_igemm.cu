@@ -54,6 +54,9 @@ struct ConvKParams {
   float* head_out;
   int head_tanh;
   int up, LH, LW, LBH, LBW;   // upsample-on-load: low-res dims and staging box (pixels)
+  int nrm, nblk0, pre_c, pre_act;  // normalise-on-load: the first nblk0 channel blocks come from `pre` and get act(x*s+t)
+  const float* pre_scale;
+  const float* pre_shift;
   uint32_t l_stage_bytes;
   int debug_flags;
   long long* debug_buf;  // bring-up: per-CTA phase timestamps (clock64), 8 slots per CTA
@@ -133,7 +136,7 @@ __device__ __forceinline__ int up_origin(int hr0, int hr_size, int lr_size) {
 template <int T, int KB>
 // two co-resident CTAs per SM are essential (their MMA streams overlap): cap registers accordingly
 __global__ void __launch_bounds__(kMaxThreads, PBT_MULTI_ISSUE ? 1 : 2)
-conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvKParams p) {
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapP, const ConvKParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sB = sA + (size_t)p.a_stages * p.a_stage_bytes;
@@ -145,9 +148,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvKParams p
   uint64_t* acc_full = b_empty + p.b_stages;
   uint64_t* l_full = acc_full + 1;
   uint64_t* l_empty = l_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(l_empty + 2);
+  uint64_t* a_land = l_empty + 2;  // normalise-on-load: raw tile landed (TMA), not yet normalised
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_land + 2);
   float* s_stats = reinterpret_cast<float*>(tmem_slot + 2);  // [8 warps][2][NC]
   float* s_head = s_stats + kEpiWarps * 2 * p.NC;             // [T][4 quadrants][32 lanes][3]
+  float* s_norm = s_head + 3 * 4 * 32 * 3;                    // [2][pre_c] scale / shift of this image
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -171,7 +176,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvKParams p
   if (threadIdx.x == 0) {
     PBT_STAMP(0);
     for (int i = 0; i < p.a_stages; ++i) {
-      mbar_init(&a_full[i], p.up ? 32 * kEpiWarps : 1);  // upsample-on-load: every transform thread arrives
+      mbar_init(&a_full[i], (p.up || p.nrm) ? 32 * kEpiWarps : 1);  // transform modes: every transform thread arrives
       mbar_init(&a_empty[i], NI);
     }
     for (int i = 0; i < p.b_stages; ++i) {
@@ -182,6 +187,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvKParams p
     for (int i = 0; i < 2; ++i) {
       mbar_init(&l_full[i], 1);
       mbar_init(&l_empty[i], 32 * kEpiWarps);
+      mbar_init(&a_land[i], 1);
     }
     fence_barrier_init();
     prefetch_tmap(&tmapA);
@@ -214,9 +220,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvKParams p
         } else {
           const int sa = cb % p.a_stages;
           mbar_wait(&a_empty[sa], ((uint32_t)(cb / p.a_stages) & 1u) ^ 1u);
-          mbar_arrive_expect_tx(&a_full[sa], (uint32_t)(p.blk_p * p.BH * p.BW * 16));
-          tma_load_4d(sA + (size_t)sa * p.a_stage_bytes, &tmapA, &a_full[sa], (x0 - p.pad_l) * 8, y0 - p.pad_t,
-                      cb * p.blk_p, n);
+          uint64_t* bar = p.nrm ? &a_land[sa] : &a_full[sa];
+          mbar_arrive_expect_tx(bar, (uint32_t)(p.blk_p * p.BH * p.BW * 16));
+          if (cb < p.nblk0)
+            tma_load_4d(sA + (size_t)sa * p.a_stage_bytes, &tmapP, bar, (x0 - p.pad_l) * 8, y0 - p.pad_t, cb * p.blk_p, n);
+          else
+            tma_load_4d(sA + (size_t)sa * p.a_stage_bytes, &tmapA, bar, (x0 - p.pad_l) * 8, y0 - p.pad_t,
+                        (cb - p.nblk0) * p.blk_p, n);
         }
       };
       int bi = 0;  // running B-group counter
@@ -424,6 +434,63 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvKParams p
         mbar_arrive(&l_empty[sl]);
       }
     }
+    if (p.nrm) {
+      // ---- normalise-on-load: the raw output of the previous conv lands in the A stage by TMA; these warps apply
+      // its InstanceNorm + activation in place (y = act(x*scale + shift), reference src/models/generator.py:36-40,
+      // 204-206) before the tensor core reads it, so the normalised tensor never round-trips HBM.  Pixels outside
+      // the image stay zero (the conv pads the NORMALISED tensor with zeros).
+      const int et = threadIdx.x - kEpi0;
+      for (int i = et; i < p.pre_c; i += 32 * kEpiWarps) {
+        s_norm[i] = __ldg(&p.pre_scale[(long long)n * p.pre_c + i]);
+        s_norm[p.pre_c + i] = __ldg(&p.pre_shift[(long long)n * p.pre_c + i]);
+      }
+      asm volatile("bar.sync 3, 256;" ::: "memory");
+      const int npos = p.BH * p.BW;
+      int dsto[3];
+      bool ins[3];
+#pragma unroll
+      for (int qq = 0; qq < 3; ++qq) {
+        const int pos = et + qq * 32 * kEpiWarps;
+        const int r = pos / p.BW, c = pos - r * p.BW;
+        const int Y = y0 - p.pad_t + r, X = x0 - p.pad_l + c;
+        ins[qq] = pos < npos && Y >= 0 && Y < p.H && X >= 0 && X < p.W;
+        dsto[qq] = pos * 16;
+      }
+      const int a_plane = npos * 16;
+      for (int cb = 0; cb < p.n_blk; ++cb) {
+        const int sa = cb % p.a_stages;
+        mbar_wait(&a_land[sa], (uint32_t)(cb / p.a_stages) & 1u);
+        if (cb < p.nblk0) {
+          uint8_t* tile = sA + (size_t)sa * p.a_stage_bytes;
+          for (int pln = 0; pln < p.blk_p; ++pln) {
+            const int ch = (cb * p.blk_p + pln) * 8;
+            float sc[8], sh[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              sc[k] = s_norm[ch + k];
+              sh[k] = s_norm[p.pre_c + ch + k];
+            }
+#pragma unroll
+            for (int qq = 0; qq < 3; ++qq) {
+              if (!ins[qq]) continue;
+              uint4* ptr = reinterpret_cast<uint4*>(tile + (size_t)pln * a_plane + dsto[qq]);
+              float v[8];
+              unpack8_rt(dt, *ptr, v);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                float t = fmaf(v[k], sc[k], sh[k]);
+                if (p.pre_act == PBT_ACT_RELU) t = fmaxf(t, 0.f);
+                else if (p.pre_act == PBT_ACT_LEAKY02) t = t > 0.f ? t : 0.2f * t;
+                v[k] = t;
+              }
+              *ptr = pack8_rt(dt, v);
+            }
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(&a_full[sa]);
+      }
+    }
     mbar_wait(acc_full, 0);
     tc_fence_after();
     if (threadIdx.x == kEpi0) PBT_STAMP(4);
@@ -577,19 +644,21 @@ static int pow2_cols(int c) {
 }
 
 template <int T, int KB>
-static int launch_conv(const CUtensorMap& tmap, const ConvKParams& p, int grid, uint32_t smem_bytes, cudaStream_t stream) {
+static int launch_conv(const CUtensorMap& tmap, const CUtensorMap& tmapP, const ConvKParams& p, int grid, uint32_t smem_bytes,
+                       cudaStream_t stream) {
   PBT_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<T, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-  conv_igemm_kernel<T, KB><<<grid, conv_threads(T), smem_bytes, stream>>>(tmap, p);
+  conv_igemm_kernel<T, KB><<<grid, conv_threads(T), smem_bytes, stream>>>(tmap, tmapP, p);
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
 }
 
 template <int T>
-static int launch_conv_kb(int kb, const CUtensorMap& tmap, const ConvKParams& p, int grid, uint32_t smem, cudaStream_t s) {
+static int launch_conv_kb(int kb, const CUtensorMap& tmap, const CUtensorMap& tmapP, const ConvKParams& p, int grid, uint32_t smem,
+                          cudaStream_t s) {
   switch (kb) {
-    case 1: return launch_conv<T, 1>(tmap, p, grid, smem, s);
-    case 2: return launch_conv<T, 2>(tmap, p, grid, smem, s);
-    default: return launch_conv<T, 4>(tmap, p, grid, smem, s);
+    case 1: return launch_conv<T, 1>(tmap, tmapP, p, grid, smem, s);
+    case 2: return launch_conv<T, 2>(tmap, tmapP, p, grid, smem, s);
+    default: return launch_conv<T, 4>(tmap, tmapP, p, grid, smem, s);
   }
 }
 
@@ -605,11 +674,25 @@ extern "C" int pbt_conv_num_tiles(int32_t h, int32_t w, int32_t tiles_per_cta) {
 extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PBT_REQUIRE(d != nullptr, "conv: null descriptor");
-  const pbt_act_t& in = d->in;
   const int up = d->upsample2x ? 1 : 0;  // input is the low-res tensor; the conv sees its bilinear x2 upsample
+  const int has_pre = d->pre.ptr != nullptr;
+  PBT_REQUIRE(d->in.ptr || has_pre, "conv: no input tensor");
+  // `pre` (optional) supplies the first pre.c input channels, normalised + activated on load; `in` the rest
+  pbt_act_t in = d->in;
+  if (!in.ptr) {  // all channels come from `pre`: keep the geometry, zero channels
+    in = d->pre;
+    in.c = 0;
+  }
   PBT_REQUIRE(in.ptr && aligned16(in.ptr), "conv: input pointer null or not 16-byte aligned");
   PBT_REQUIRE(in.n > 0 && in.h > 0 && in.w > 0, "conv: empty input");
-  PBT_REQUIRE(in.c > 0 && in.c % 16 == 0, "conv: cin must be a multiple of 16");
+  PBT_REQUIRE(in.c % 16 == 0 && (in.c > 0 || has_pre), "conv: cin must be a multiple of 16");
+  if (has_pre) {
+    PBT_REQUIRE(!up, "conv: normalise-on-load cannot be combined with upsample-on-load");
+    PBT_REQUIRE(aligned16(d->pre.ptr) && d->pre.n == in.n && d->pre.h == in.h && d->pre.w == in.w && d->pre.img_stride % 8 == 0,
+                "conv: `pre` tensor shape mismatch");
+    PBT_REQUIRE(d->pre.c > 0 && d->pre.c % d->blk_c == 0 && d->pre.c <= 256, "conv: pre.c must be a multiple of blk_c, <= 256");
+    PBT_REQUIRE(d->pre_scale && d->pre_shift, "conv: `pre` needs pre_scale / pre_shift");
+  }
   PBT_REQUIRE(d->cout >= 16 && d->cout <= 256 && d->cout % 16 == 0, "conv: cout must be a multiple of 16 in [16,256]");
   PBT_REQUIRE(d->blk_c == 16 || d->blk_c == 32 || d->blk_c == 64, "conv: blk_c must be 16, 32 or 64");
   PBT_REQUIRE(d->kh >= 1 && d->kh <= 7 && d->kw >= 1 && d->kw <= 7, "conv: kernel size must be in [1,7]");
@@ -624,8 +707,10 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
   memset(&p, 0, sizeof(p));
   p.n_img = in.n; p.H = in.h << up; p.W = in.w << up;
   p.up = up; p.LH = in.h; p.LW = in.w;
-  p.Cp = in.c / 8;
+  p.Cp = in.c / 8 + (has_pre ? d->pre.c / 8 : 0);
   p.blk_p = d->blk_c / 8;
+  p.nrm = has_pre; p.nblk0 = has_pre ? d->pre.c / d->blk_c : 0; p.pre_c = has_pre ? d->pre.c : 0;
+  p.pre_act = d->pre_act; p.pre_scale = d->pre_scale; p.pre_shift = d->pre_shift;
   p.n_blk = ceil_div(p.Cp, p.blk_p);
   p.KH = d->kh; p.KW = d->kw; p.pad_t = d->pad_t; p.pad_l = d->pad_l;
   const int T = d->tiles_per_cta;
@@ -670,7 +755,7 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
 
   // shared memory budget: A ring + B ring (groups of taps) + barriers + tmem slot + stats scratch.
   // Aim at two co-resident CTAs per SM (one CTA's epilogue/prologue overlaps the other's main loop).
-  const uint32_t tail = 8u * (2 * 2 + 2 * 8 + 1) + 16 + (uint32_t)(kEpiWarps * 2 * p.NC * 4) + 3 * 4 * 32 * 3 * 4 + 8 * 4 + 128;
+  const uint32_t tail = 8u * (2 * 2 + 2 * 8 + 1) + 16 + (uint32_t)(kEpiWarps * 2 * p.NC * 4) + 3 * 4 * 32 * 3 * 4 + 8 * 6 + (uint32_t)(2 * p.pre_c * 4) + 128;
   const uint32_t a_total = (uint32_t)p.a_stages * p.a_stage_bytes + 2 * p.l_stage_bytes;
   const uint32_t chunk = (uint32_t)(p.blk_p * p.NC * 16);  // one tap of one channel block
   const int ntaps = p.KH * p.KW;
@@ -692,15 +777,23 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
   if ((d->debug_flags & 8) && smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;  // bring-up: force one CTA per SM
   PBT_REQUIRE(smem_bytes <= 227 * 1024, "conv: configuration does not fit shared memory");
 
-  CUtensorMap tmap;
-  int rc = up ? make_p8_tmap(&tmap, in, p.LBW, p.LBH, p.blk_p) : make_p8_tmap(&tmap, in, p.BW, p.BH, p.blk_p);
+  CUtensorMap tmap, tmapP;
+  int rc = PBT_OK;
+  if (in.c > 0) rc = up ? make_p8_tmap(&tmap, in, p.LBW, p.LBH, p.blk_p) : make_p8_tmap(&tmap, in, p.BW, p.BH, p.blk_p);
   if (rc != PBT_OK) return rc;
+  if (has_pre) {
+    rc = make_p8_tmap(&tmapP, d->pre, p.BW, p.BH, p.blk_p);
+    if (rc != PBT_OK) return rc;
+    if (in.c == 0) tmap = tmapP;
+  } else {
+    tmapP = tmap;
+  }
 
   const int grid = p.n_img * p.tiles_x * p.tiles_y;
   const int kb = d->blk_c / 16;
   switch (T) {
-    case 1: return launch_conv_kb<1>(kb, tmap, p, grid, smem_bytes, stream);
-    case 2: return launch_conv_kb<2>(kb, tmap, p, grid, smem_bytes, stream);
-    default: return launch_conv_kb<3>(kb, tmap, p, grid, smem_bytes, stream);
+    case 1: return launch_conv_kb<1>(kb, tmap, tmapP, p, grid, smem_bytes, stream);
+    case 2: return launch_conv_kb<2>(kb, tmap, tmapP, p, grid, smem_bytes, stream);
+    default: return launch_conv_kb<3>(kb, tmap, tmapP, p, grid, smem_bytes, stream);
   }
 }

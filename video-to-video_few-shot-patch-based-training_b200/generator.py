@@ -337,14 +337,19 @@ class _Engine:
         if not u8_hwc and x.dtype not in (torch.float32, torch.float16):
             x = x.float()
 
-        def conv_in(name, xin, cout, k, pad, raw, T_pref, up=False):
+        def conv_in(name, xin, cout, k, pad, raw, T_pref, up=False, pre=None, pre_st=None, pre_act=ACT_NONE):
             """conv (bias skipped: a constant per channel is removed by the following InstanceNorm) + IN statistics;
-            up=True: xin is the low-res tensor, the conv consumes its bilinear x2 upsample (interpolated in-kernel)"""
-            oh, ow = (2 * xin.h, 2 * xin.w) if up else (xin.h, xin.w)
+            up=True: xin is the low-res tensor, the conv consumes its bilinear x2 upsample (interpolated in-kernel);
+            pre: raw output of the previous conv, its InstanceNorm (pre_st) + activation applied on load"""
+            src = xin if xin is not None else pre
+            oh, ow = (2 * src.h, 2 * src.w) if up else (src.h, src.w)
             T = self._T(T_pref, ow)
             st = ws.stat(name, cout, oh, ow, T, dev)
-            ops.conv_fwd(xin, W[name], cout, k, k, pad, pad, dt, blk_c=self._blk(xin.c), tiles_per_cta=T, out=raw,
-                         stats_partial=st["partial"], upsample2x=up)
+            cin = (xin.c if xin is not None else 0) + (pre.c if pre is not None else 0)
+            ops.conv_fwd(xin, W[name], cout, k, k, pad, pad, dt, blk_c=self._blk(cin), tiles_per_cta=T, out=raw,
+                         stats_partial=st["partial"], upsample2x=up, pre=pre,
+                         pre_scale=None if pre is None else pre_st["scale"], pre_shift=None if pre is None else pre_st["shift"],
+                         pre_act=pre_act)
             ops.norm_finalize(st["partial"], n, st["tiles"], cout, oh * ow, st["scale"], st["shift"], eps=EPS)
             return st
 
@@ -373,11 +378,18 @@ class _Engine:
             ops.norm_apply(ws.raw2, dt, scale=st["scale"], shift=st["shift"], act=ACT_LEAKY, out=ws.c2cat.view(f[2], f[2]),
                            out32=r_cur, out_relu=a_of(0))
         # residual blocks: r_{b+1} = r_b + IN(convB(relu(IN(convA(relu(r_b))))))
+        # inference: IN + ReLU of a conv's raw output are applied inside the NEXT conv's shared-memory tile
+        # (normalise-on-load), so hmid and the up1 half of cat11 are never written; training keeps them for wgrad
+        nol_res = not save and f[2] % self._blk(f[2]) == 0 and f[2] <= 256
+        nol_11 = not save and f[4] % 32 == 0 and f[4] <= 256
         for b in range(nb):
             k = b if save else 0
             st = conv_in(f"res{b}.a", a_of(b), f[2], 3, 1, ws.rawA[k], 2)
-            ops.norm_apply(ws.rawA[k], dt, scale=st["scale"], shift=st["shift"], act=ACT_RELU, out=ws.hmid[k])
-            st = conv_in(f"res{b}.b", ws.hmid[k], f[2], 3, 1, ws.rawB[k], 2)
+            if nol_res:
+                st = conv_in(f"res{b}.b", None, f[2], 3, 1, ws.rawB[k], 2, pre=ws.rawA[k], pre_st=st, pre_act=ACT_RELU)
+            else:
+                ops.norm_apply(ws.rawA[k], dt, scale=st["scale"], shift=st["shift"], act=ACT_RELU, out=ws.hmid[k])
+                st = conv_in(f"res{b}.b", ws.hmid[k], f[2], 3, 1, ws.rawB[k], 2)
             lastb = b == nb - 1
             ops.norm_apply(ws.rawB[k], dt, scale=st["scale"], shift=st["shift"], act=ACT_NONE, residual32=r_cur,
                            out32=None if lastb else r_nxt, out=last16 if lastb else None,
@@ -396,14 +408,20 @@ class _Engine:
             st = conv_in("up2", ws.c2cat, f[4], 3, 1, ws.rawU2, 2, up=True)
             ops.norm_apply(ws.rawU2, dt, scale=st["scale"], shift=st["shift"], act=ACT_RELU, out=ws.c1cat.view(0, f[4]))
             st = conv_in("up1", ws.c1cat, f[4], 3, 1, ws.rawU1, 2, up=True)
-        ops.norm_apply(ws.rawU1, dt, scale=st["scale"], shift=st["shift"], act=ACT_RELU, out=ws.cat11.view(0, f[4]))
+        if not nol_11:
+            ops.norm_apply(ws.rawU1, dt, scale=st["scale"], shift=st["shift"], act=ACT_RELU, out=ws.cat11.view(0, f[4]))
         # conv11 + smoothers + fused head
         ev = self.kernel_timer
         if ev is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        ops.conv_fwd(ws.cat11, W["conv11"], f[5], 7, 7, 3, 3, dt, blk_c=32, tiles_per_cta=self._T(3, w), bias=W["b11"],
-                     act=ACT_RELU, out=ws.c11)
+        if nol_11:
+            ops.conv_fwd(ws.cat11.view(f[4], f[0] + cp), W["conv11"], f[5], 7, 7, 3, 3, dt, blk_c=32,
+                         tiles_per_cta=self._T(3, w), bias=W["b11"], act=ACT_RELU, out=ws.c11, pre=ws.rawU1,
+                         pre_scale=st["scale"], pre_shift=st["shift"], pre_act=ACT_RELU)
+        else:
+            ops.conv_fwd(ws.cat11, W["conv11"], f[5], 7, 7, 3, 3, dt, blk_c=32, tiles_per_cta=self._T(3, w), bias=W["b11"],
+                         act=ACT_RELU, out=ws.c11)
         if ev is not None:
             e1.record()
             ev.append((e0, e1))
