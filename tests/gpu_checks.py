@@ -32,8 +32,8 @@ def act_ref(v, act):
 
 def check_conv(n=1, cin=16, cout=16, h=16, w=8, kh=1, kw=1, pad_t=0, pad_l=0, T=1, blk_c=16, dt=BF16, seed=0,
                debug_flags=0, in_off=0, in_extra=0, out_off=0, out_extra=0, bias=False, act=ACT_NONE, affine=False,
-               mask=False, addend=False, out32=False, stats=False, head=False, integer=True, store16=True):
-    """returns (ok, max_abs_err, message)"""
+               mask=False, addend=False, out32=False, stats=False, head=False, integer=True, store16=True, cps=0):
+    """returns (ok, max_abs_err, message); cps = ctas_per_sm configuration of the kernel"""
     g = torch.Generator(device="cuda").manual_seed(seed)
     if integer:
         x = _ints((n, cin, h, w), -3, 3, g)
@@ -90,7 +90,8 @@ def check_conv(n=1, cin=16, cout=16, h=16, w=8, kh=1, kw=1, pad_t=0, pad_l=0, T=
         hb = torch.randn((3,), generator=g, device="cuda") * 0.1
         hout = torch.full((n, 3, h, w), float("nan"), device="cuda")
         kwargs.update(head_w=hw_, head_b=hb, head_out=hout, head_tanh=True)
-    ops.conv_fwd(xin, wp, cout, kh, kw, pad_t, pad_l, dt, blk_c=blk_c, tiles_per_cta=T, debug_flags=debug_flags, **kwargs)
+    ops.conv_fwd(xin, wp, cout, kh, kw, pad_t, pad_l, dt, blk_c=blk_c, tiles_per_cta=T, debug_flags=debug_flags, ctas_per_sm=cps,
+                 **kwargs)
     torch.cuda.synchronize()
     msgs, ok, worst = [], True, 0.0
     tol16 = 0.0 if integer else (2e-2 if dt == BF16 else 3e-3)

@@ -34,6 +34,13 @@ CONV_CASES = [
     dict(n=2, cin=64, cout=64, h=16, w=24, kh=3, kw=3, pad_t=1, pad_l=1, T=2, blk_c=32, bias=True, act=1, head=True,
          integer=False),
     dict(cin=128, cout=128, h=32, w=32, kh=3, kw=3, pad_t=1, pad_l=1, T=2, blk_c=32, integer=False, dt=1),
+    # small-footprint configuration (four co-resident CTAs per SM, one epilogue warp per TMEM quadrant)
+    dict(n=2, cin=64, cout=64, h=40, w=56, kh=3, kw=3, pad_t=1, pad_l=1, T=2, blk_c=32, bias=True, act=1, head=True,
+         integer=False, cps=4),
+    dict(n=2, cin=64, cout=64, h=24, w=40, kh=3, kw=3, pad_t=1, pad_l=1, T=2, blk_c=32, bias=True, act=1, affine=True, cps=4),
+    dict(n=2, cin=16, cout=32, h=33, w=50, kh=7, kw=7, pad_t=3, pad_l=3, T=3, blk_c=16, stats=True, cps=4),
+    dict(n=3, cin=128, cout=128, h=20, w=20, kh=3, kw=3, pad_t=1, pad_l=1, T=1, blk_c=32, stats=True, integer=False, cps=4),
+    dict(n=2, cin=32, cout=16, h=16, w=24, kh=2, kw=2, pad_t=1, pad_l=1, T=3, blk_c=32, mask=True, addend=True, out32=True, cps=4),
 ]
 
 

@@ -21,6 +21,8 @@
 //  * the issuing thread is the critical resource (one tcgen05.mma per 16..64 tensor cycles): the kernel is
 //    templated on T and on the K steps per channel block so that the issue loop is fully unrolled and each MMA
 //    costs two 32-bit adds on the low descriptor words.
+#include <type_traits>
+
 #include "internal.h"
 #include "ptx.cuh"
 
@@ -70,9 +72,11 @@ struct ConvKParams {
 #define PBT_MULTI_ISSUE 0
 #endif
 constexpr int kMaxThreads = PBT_MULTI_ISSUE ? 384 : 320;
-constexpr int kEpiWarps = 8;  // two warps per TMEM lane quadrant: they split the accumulator columns
+constexpr int kEpiWarps = 8;  // default: two warps per TMEM lane quadrant, they split the accumulator columns.
+// EW = 4 (one warp per quadrant, 192 threads) is the small-footprint configuration: four co-resident CTAs per SM for
+// the layers whose CTAs are short (cout <= 64 or tiny maps) - more MMA streams in flight hide the per-CTA phases.
 __host__ __device__ constexpr int num_issuers(int T) { return PBT_MULTI_ISSUE ? T : 1; }
-__host__ __device__ constexpr int conv_threads(int T) { return 32 * (1 + num_issuers(T) + kEpiWarps); }
+__host__ __device__ constexpr int conv_threads(int T, int EW) { return 32 * (1 + num_issuers(T) + EW); }
 
 // Sum over the 32 lanes of a warp of 16 per-lane values; afterwards every lane holds the total of
 // column  col = 8*b4 + 4*b3 + 2*b2 + b1  (b_i = bit i of the lane id); lanes differing only in bit 0 agree.
@@ -133,9 +137,9 @@ __device__ __forceinline__ int up_origin(int hr0, int hr_size, int lr_size) {
   return i0;
 }
 
-template <int T, int KB>
-// two co-resident CTAs per SM are essential (their MMA streams overlap): cap registers accordingly
-__global__ void __launch_bounds__(kMaxThreads, PBT_MULTI_ISSUE ? 1 : 2)
+template <int T, int KB, int EW>
+// two (EW = 8) or four (EW = 4) co-resident CTAs per SM are essential (their MMA streams overlap): cap registers accordingly
+__global__ void __launch_bounds__(EW == 8 ? kMaxThreads : 192, PBT_MULTI_ISSUE ? 1 : (EW == 8 ? 2 : 4))
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapP, const ConvKParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sA = smem;
@@ -151,7 +155,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   uint64_t* a_land = l_empty + 2;  // normalise-on-load: raw tile landed (TMA), not yet normalised
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_land + 2);
   float* s_stats = reinterpret_cast<float*>(tmem_slot + 2);  // [8 warps][2][NC]
-  float* s_head = s_stats + kEpiWarps * 2 * p.NC;             // [T][4 quadrants][32 lanes][3]
+  float* s_head = s_stats + EW * 2 * p.NC;             // [T][4 quadrants][32 lanes][3]
   float* s_norm = s_head + 3 * 4 * 32 * 3;                    // [2][pre_c] scale / shift of this image
 
   const int warp = threadIdx.x >> 5;
@@ -176,7 +180,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   if (threadIdx.x == 0) {
     PBT_STAMP(0);
     for (int i = 0; i < p.a_stages; ++i) {
-      mbar_init(&a_full[i], (p.up || p.nrm) ? 32 * kEpiWarps : 1);  // transform modes: every transform thread arrives
+      mbar_init(&a_full[i], (p.up || p.nrm) ? 32 * EW : 1);  // transform modes: every transform thread arrives
       mbar_init(&a_empty[i], NI);
     }
     for (int i = 0; i < p.b_stages; ++i) {
@@ -186,7 +190,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     mbar_init(acc_full, NI);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&l_full[i], 1);
-      mbar_init(&l_empty[i], 32 * kEpiWarps);
+      mbar_init(&l_empty[i], 32 * EW);
       mbar_init(&a_land[i], 1);
     }
     fence_barrier_init();
@@ -362,7 +366,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       bool has[2], ins[2];
 #pragma unroll
       for (int qq = 0; qq < 2; ++qq) {
-        const int pos = et + qq * 32 * kEpiWarps;
+        const int pos = et + qq * 32 * EW;
         has[qq] = pos < npos;
         const int r = pos / p.BW, c = pos - r * p.BW;
         const int Y = y0 - p.pad_t + r, X = x0 - p.pad_l + c;
@@ -440,17 +444,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       // 204-206) before the tensor core reads it, so the normalised tensor never round-trips HBM.  Pixels outside
       // the image stay zero (the conv pads the NORMALISED tensor with zeros).
       const int et = threadIdx.x - kEpi0;
-      for (int i = et; i < p.pre_c; i += 32 * kEpiWarps) {
+      for (int i = et; i < p.pre_c; i += 32 * EW) {
         s_norm[i] = __ldg(&p.pre_scale[(long long)n * p.pre_c + i]);
         s_norm[p.pre_c + i] = __ldg(&p.pre_shift[(long long)n * p.pre_c + i]);
       }
-      asm volatile("bar.sync 3, 256;" ::: "memory");
+      asm volatile("bar.sync 3, %0;" ::"r"(32 * EW) : "memory");
       const int npos = p.BH * p.BW;
       int dsto[3];
       bool ins[3];
 #pragma unroll
       for (int qq = 0; qq < 3; ++qq) {
-        const int pos = et + qq * 32 * kEpiWarps;
+        const int pos = et + qq * 32 * EW;
         const int r = pos / p.BW, c = pos - r * p.BW;
         const int Y = y0 - p.pad_t + r, X = x0 - p.pad_l + c;
         ins[qq] = pos < npos && Y >= 0 && Y < p.H && X >= 0 && X < p.W;
@@ -491,39 +495,55 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         mbar_arrive(&a_full[sa]);
       }
     }
-    mbar_wait(acc_full, 0);
+    if (p.debug_flags & 64) mbar_wait(acc_full, 0);
+    else mbar_wait_backoff(acc_full, 0, 256);
     tc_fence_after();
     if (threadIdx.x == kEpi0) PBT_STAMP(4);
 
-    for (int t = 0; t < T; ++t) {
-      const int x = x0 + 8 * t + tx;
-      const bool valid = (y < p.H) && (x < p.W);
-      const long long pix = (long long)y * p.W + x;
-      float h0 = 0.f, h1 = 0.f, h2 = 0.f;
-      for (int c0 = half * 16; c0 < NC; c0 += 32) {
+    // Feature bits live in a register: testing `p.<field>` inside the column loop costs one dependent constant-bank load
+    // + uniform branch per feature per iteration (measured ~1000 cycles per 16-column chunk, 360 without them).
+    enum : uint32_t { kFBias = 1, kFRelu = 2, kFLeaky = 4, kFAffine = 8, kFMask = 16, kFAddend = 32, kFOut32 = 64,
+                      kFOut16 = 128, kFHead = 256, kFStats = 512, kFGeneric = 0x80000000u };
+    uint32_t feat = (p.bias ? kFBias : 0u) | (p.act == PBT_ACT_RELU ? kFRelu : 0u) | (p.act == PBT_ACT_LEAKY02 ? kFLeaky : 0u) |
+                    (p.post_scale ? kFAffine : 0u) | (p.mask ? kFMask : 0u) | (p.addend32 ? kFAddend : 0u) |
+                    (p.out32 ? kFOut32 : 0u) | (p.out ? kFOut16 : 0u) | (p.head_w ? kFHead : 0u) | (do_stats ? kFStats : 0u);
+    asm volatile("" : "+r"(feat));  // keep it a register value, not re-derived constant loads
+    // The column loop is instantiated once per common feature set (compile-time mask) plus a generic copy (run-time
+    // mask): the fully generic body is ~13 KB of mostly skipped code and ran at ~1000 cycles per 16-column chunk
+    // (instruction fetch across the skipped regions), a specialised body at ~400.
+    auto epi_loop = [&](auto cf) {
+      constexpr uint32_t CF = decltype(cf)::value;
+      const uint32_t fm = CF == kFGeneric ? feat : CF;
+      // statistics variants run the tile loop innermost: one cross-lane column reduction per 16-column chunk, not per tile
+      constexpr bool kColOuter = CF != kFGeneric && (CF & kFStats) != 0 && (CF & kFHead) == 0;
+      // one 16-column chunk of tile t: accumulator -> registers -> fused pointwise work -> stores
+      auto chunk = [&](int t, int c0, float (&hd)[3], float* sacc) {
+        const int x = x0 + 8 * t + tx;
+        const bool valid = (y < p.H) && (x < p.W);
+        const long long pix = (long long)y * p.W + x;
         uint32_t raw[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * p.acc_stride + c0), raw);
         tmem_ld_wait();
         float v[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]);
-        if (p.bias) {
+        if (fm & kFBias) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] += __ldg(&p.bias[c0 + i]);
         }
-        if (p.act == PBT_ACT_RELU) {
+        if (fm & kFRelu) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-        } else if (p.act == PBT_ACT_LEAKY02) {
+        } else if (fm & kFLeaky) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : 0.2f * v[i];
         }
-        if (p.post_scale) {
+        if (fm & kFAffine) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], __ldg(&p.post_scale[c0 + i]), __ldg(&p.post_shift[c0 + i]));
         }
         if (valid) {
-          if (p.mask) {
+          if (fm & kFMask) {
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
               const uint4 m = *reinterpret_cast<const uint4*>(
@@ -534,7 +554,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
               for (int i = 0; i < 8; ++i) v[hh * 8 + i] = mf[i] > 0.f ? v[hh * 8 + i] : 0.f;
             }
           }
-          if (p.addend32) {
+          if (fm & kFAddend) {
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
               const float4* ap = reinterpret_cast<const float4*>(
@@ -544,17 +564,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
               v[hh * 8 + 4] += a1.x; v[hh * 8 + 5] += a1.y; v[hh * 8 + 6] += a1.z; v[hh * 8 + 7] += a1.w;
             }
           }
-          if (p.out32) {
+          if (fm & kFOut32) {
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
-              float4* op =
-                  reinterpret_cast<float4*>(p.out32 + (((long long)n * (NC / 8) + (c0 / 8 + hh)) * plane_px + pix) * 8);
+              float4* op = reinterpret_cast<float4*>(p.out32 + (((long long)n * (NC / 8) + (c0 / 8 + hh)) * plane_px + pix) * 8);
               op[0] = make_float4(v[hh * 8 + 0], v[hh * 8 + 1], v[hh * 8 + 2], v[hh * 8 + 3]);
               op[1] = make_float4(v[hh * 8 + 4], v[hh * 8 + 5], v[hh * 8 + 6], v[hh * 8 + 7]);
             }
           }
         }
-        if (p.out) {
+        if (fm & kFOut16) {
           // round to the storage type; statistics and the head see the rounded values
           const uint4 u0 = pack8_rt(dt, v), u1 = pack8_rt(dt, v + 8);
           if (valid) {
@@ -565,66 +584,106 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
           unpack8_rt(dt, u0, v);
           unpack8_rt(dt, u1, v + 8);
         }
-        if (p.head_w) {
+        if (fm & kFHead) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            h0 = fmaf(v[i], __ldg(&p.head_w[c0 + i]), h0);
-            h1 = fmaf(v[i], __ldg(&p.head_w[NC + c0 + i]), h1);
-            h2 = fmaf(v[i], __ldg(&p.head_w[2 * NC + c0 + i]), h2);
+            hd[0] = fmaf(v[i], __ldg(&p.head_w[c0 + i]), hd[0]);
+            hd[1] = fmaf(v[i], __ldg(&p.head_w[NC + c0 + i]), hd[1]);
+            hd[2] = fmaf(v[i], __ldg(&p.head_w[2 * NC + c0 + i]), hd[2]);
           }
         }
-        if (do_stats) {
-          float s[16], s2[16];
+        if (fm & kFStats) {
+          if (kColOuter) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            s[i] = valid ? v[i] : 0.f;
-            s2[i] = s[i] * s[i];
+            for (int i = 0; i < 16; ++i) {
+              const float sv = valid ? v[i] : 0.f;
+              sacc[i] += sv;
+              sacc[16 + i] = fmaf(sv, sv, sacc[16 + i]);
+            }
+          } else {
+            float s[16], s2[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              s[i] = valid ? v[i] : 0.f;
+              s2[i] = s[i] * s[i];
+            }
+            const float cs = warp_colsum16(s, lane);
+            const float cs2 = warp_colsum16(s2, lane);
+            if ((lane & 1) == 0) {
+              my_stats[c0 + col_of_lane] += cs;
+              my_stats[NC + c0 + col_of_lane] += cs2;
+            }
           }
-          const float cs = warp_colsum16(s, lane);
-          const float cs2 = warp_colsum16(s2, lane);
+        }
+      };
+      if constexpr (kColOuter) {
+        for (int c0 = half * 16; c0 < NC; c0 += 4 * EW) {
+          float sacc[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sacc[i] = 0.f;
+          float hd[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+          for (int t = 0; t < T; ++t) chunk(t, c0, hd, sacc);
+          const float cs = warp_colsum16(sacc, lane);
+          const float cs2 = warp_colsum16(sacc + 16, lane);
           if ((lane & 1) == 0) {
             my_stats[c0 + col_of_lane] += cs;
             my_stats[NC + c0 + col_of_lane] += cs2;
           }
         }
-      }
-      if (p.head_w) {  // combine the two column halves of the fused 1x1 head
-        float* hs = s_head + ((size_t)(t * 4 + q) * 32 + lane) * 3;
-        if (half == 1) {
-          hs[0] = h0;
-          hs[1] = h1;
-          hs[2] = h2;
+      } else {
+        for (int t = 0; t < T; ++t) {
+          float hd[3] = {0.f, 0.f, 0.f};
+          for (int c0 = half * 16; c0 < NC; c0 += 4 * EW) chunk(t, c0, hd, nullptr);
+          if (!(fm & kFHead)) continue;
+          if (EW == 8) {  // combine the two column halves of the fused 1x1 head
+            float* hs = s_head + ((size_t)(t * 4 + q) * 32 + lane) * 3;
+            if (half == 1) {
+              hs[0] = hd[0];
+              hs[1] = hd[1];
+              hs[2] = hd[2];
+            }
+            asm volatile("bar.sync 2, %0;" ::"r"(32 * EW) : "memory");
+            if (half == 0) {
+              hd[0] += hs[0];
+              hd[1] += hs[1];
+              hd[2] += hs[2];
+            }
+          }
+          const int x = x0 + 8 * t + tx;
+          if (y < p.H && x < p.W && half == 0) {
+            float h0 = hd[0] + __ldg(&p.head_b[0]), h1 = hd[1] + __ldg(&p.head_b[1]), h2 = hd[2] + __ldg(&p.head_b[2]);
+            if (p.head_tanh) {
+              h0 = tanhf(h0);
+              h1 = tanhf(h1);
+              h2 = tanhf(h2);
+            }
+            float* ho = p.head_out + (long long)n * 3 * plane_px + (long long)y * p.W + x;
+            ho[0] = h0;
+            ho[plane_px] = h1;
+            ho[2 * plane_px] = h2;
+          }
         }
-        asm volatile("bar.sync 2, 256;" ::: "memory");
-        if (half == 0) {
-          h0 += hs[0];
-          h1 += hs[1];
-          h2 += hs[2];
-        }
       }
-      if (p.head_w && valid && half == 0) {
-        h0 += __ldg(&p.head_b[0]);
-        h1 += __ldg(&p.head_b[1]);
-        h2 += __ldg(&p.head_b[2]);
-        if (p.head_tanh) {
-          h0 = tanhf(h0);
-          h1 = tanhf(h1);
-          h2 = tanhf(h2);
-        }
-        float* ho = p.head_out + (long long)n * 3 * plane_px + pix;
-        ho[0] = h0;
-        ho[plane_px] = h1;
-        ho[2 * plane_px] = h2;
-      }
+    };
+    switch (feat) {
+      case kFOut16 | kFStats: epi_loop(std::integral_constant<uint32_t, kFOut16 | kFStats>{}); break;
+      case kFBias | kFRelu | kFOut16: epi_loop(std::integral_constant<uint32_t, kFBias | kFRelu | kFOut16>{}); break;
+      case kFBias | kFRelu | kFAffine | kFOut16: epi_loop(std::integral_constant<uint32_t, kFBias | kFRelu | kFAffine | kFOut16>{}); break;
+      case kFBias | kFRelu | kFHead: epi_loop(std::integral_constant<uint32_t, kFBias | kFRelu | kFHead>{}); break;
+      case kFBias | kFRelu | kFHead | kFOut16: epi_loop(std::integral_constant<uint32_t, kFBias | kFRelu | kFHead | kFOut16>{}); break;
+      case kFBias | kFRelu | kFOut16 | kFStats: epi_loop(std::integral_constant<uint32_t, kFBias | kFRelu | kFOut16 | kFStats>{}); break;
+      case kFOut16: epi_loop(std::integral_constant<uint32_t, kFOut16>{}); break;
+      default: epi_loop(std::integral_constant<uint32_t, kFGeneric>{}); break;
     }
     if (do_stats) {
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"r"(32 * EW) : "memory");
       const int e = threadIdx.x - kEpi0;  // 0..255
       float* dst = p.stats_partial + ((long long)n * tiles_per_img + rem) * 2 * NC;
-      for (int i = e; i < 2 * NC; i += 256) {
+      for (int i = e; i < 2 * NC; i += 32 * EW) {
         float acc = 0.f;
 #pragma unroll
-        for (int w8 = 0; w8 < kEpiWarps; ++w8) acc += s_stats[w8 * 2 * NC + i];
+        for (int w8 = 0; w8 < EW; ++w8) acc += s_stats[w8 * 2 * NC + i];
         dst[i] = acc;
       }
     }
@@ -643,22 +702,22 @@ static int pow2_cols(int c) {
   return v;
 }
 
-template <int T, int KB>
+template <int T, int KB, int EW>
 static int launch_conv(const CUtensorMap& tmap, const CUtensorMap& tmapP, const ConvKParams& p, int grid, uint32_t smem_bytes,
                        cudaStream_t stream) {
-  PBT_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<T, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-  conv_igemm_kernel<T, KB><<<grid, conv_threads(T), smem_bytes, stream>>>(tmap, tmapP, p);
+  PBT_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<T, KB, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  conv_igemm_kernel<T, KB, EW><<<grid, conv_threads(T, EW), smem_bytes, stream>>>(tmap, tmapP, p);
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
 }
 
 template <int T>
-static int launch_conv_kb(int kb, const CUtensorMap& tmap, const CUtensorMap& tmapP, const ConvKParams& p, int grid, uint32_t smem,
+static int launch_conv_kb(int kb, int ew, const CUtensorMap& tmap, const CUtensorMap& tmapP, const ConvKParams& p, int grid, uint32_t smem,
                           cudaStream_t s) {
   switch (kb) {
-    case 1: return launch_conv<T, 1>(tmap, tmapP, p, grid, smem, s);
-    case 2: return launch_conv<T, 2>(tmap, tmapP, p, grid, smem, s);
-    default: return launch_conv<T, 4>(tmap, tmapP, p, grid, smem, s);
+    case 1: return ew == 4 ? launch_conv<T, 1, 4>(tmap, tmapP, p, grid, smem, s) : launch_conv<T, 1, 8>(tmap, tmapP, p, grid, smem, s);
+    case 2: return ew == 4 ? launch_conv<T, 2, 4>(tmap, tmapP, p, grid, smem, s) : launch_conv<T, 2, 8>(tmap, tmapP, p, grid, smem, s);
+    default: return ew == 4 ? launch_conv<T, 4, 4>(tmap, tmapP, p, grid, smem, s) : launch_conv<T, 4, 8>(tmap, tmapP, p, grid, smem, s);
   }
 }
 
@@ -755,12 +814,19 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
 
   // shared memory budget: A ring + B ring (groups of taps) + barriers + tmem slot + stats scratch.
   // Aim at two co-resident CTAs per SM (one CTA's epilogue/prologue overlaps the other's main loop).
-  const uint32_t tail = 8u * (2 * 2 + 2 * 8 + 1) + 16 + (uint32_t)(kEpiWarps * 2 * p.NC * 4) + 3 * 4 * 32 * 3 * 4 + 8 * 6 + (uint32_t)(2 * p.pre_c * 4) + 128;
+  const int ew = d->ctas_per_sm == 4 ? 4 : 8;  // epilogue warps
+  const uint32_t tail = 8u * (2 * 2 + 2 * 8 + 1) + 16 + (uint32_t)(ew * 2 * p.NC * 4) + (ew == 8 ? 3 * 4 * 32 * 3 * 4 : 0) + 8 * 6 + (uint32_t)(2 * p.pre_c * 4) + 128;
   const uint32_t a_total = (uint32_t)p.a_stages * p.a_stage_bytes + 2 * p.l_stage_bytes;
   const uint32_t chunk = (uint32_t)(p.blk_p * p.NC * 16);  // one tap of one channel block
   const int ntaps = p.KH * p.KW;
-  const uint32_t budget = 112 * 1024;
-  int group = (int)(16384u / chunk);
+  // ctas_per_sm = 4: small-footprint configuration (4 epilogue warps, <= 128 TMEM columns, <= 55 KB shared memory)
+  PBT_REQUIRE(d->ctas_per_sm == 0 || d->ctas_per_sm == 2 || d->ctas_per_sm == 4, "conv: ctas_per_sm must be 0, 2 or 4");
+  if (ew == 4) {
+    PBT_REQUIRE(!up && !has_pre, "conv: ctas_per_sm=4 does not support upsample/normalise-on-load");
+    PBT_REQUIRE(p.tmem_cols <= 128, "conv: ctas_per_sm=4 needs tiles_per_cta*cout <= 128 accumulator columns");
+  }
+  const uint32_t budget = ew == 4 ? 55 * 1024 : 112 * 1024;
+  int group = (int)((ew == 4 ? 8192u : 16384u) / chunk);
   if (group < 1) group = 1;
   if (group > ntaps) group = ntaps;
   int stages = 4;
@@ -776,6 +842,7 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
   uint32_t smem_bytes = a_total + (uint32_t)p.b_stages * p.b_stage_bytes + tail;
   if ((d->debug_flags & 8) && smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;  // bring-up: force one CTA per SM
   PBT_REQUIRE(smem_bytes <= 227 * 1024, "conv: configuration does not fit shared memory");
+  PBT_REQUIRE(ew == 8 || smem_bytes <= 56 * 1024, "conv: ctas_per_sm=4 configuration exceeds 56 KB of shared memory");
 
   CUtensorMap tmap, tmapP;
   int rc = PBT_OK;
@@ -792,8 +859,8 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
   const int grid = p.n_img * p.tiles_x * p.tiles_y;
   const int kb = d->blk_c / 16;
   switch (T) {
-    case 1: return launch_conv_kb<1>(kb, tmap, tmapP, p, grid, smem_bytes, stream);
-    case 2: return launch_conv_kb<2>(kb, tmap, tmapP, p, grid, smem_bytes, stream);
-    default: return launch_conv_kb<3>(kb, tmap, tmapP, p, grid, smem_bytes, stream);
+    case 1: return launch_conv_kb<1>(kb, ew, tmap, tmapP, p, grid, smem_bytes, stream);
+    case 2: return launch_conv_kb<2>(kb, ew, tmap, tmapP, p, grid, smem_bytes, stream);
+    default: return launch_conv_kb<3>(kb, ew, tmap, tmapP, p, grid, smem_bytes, stream);
   }
 }

@@ -72,6 +72,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #endif
 }
 
+// Long waits (an epilogue warp waiting for its CTA's whole main loop): back off between polls so the waiting warps do not
+// take issue slots from the co-resident CTA's working warps.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+#if PBT_WATCHDOG
+    if (clock64() - t0 > 4000000000ll) {
+      printf("pbt: mbarrier watchdog block %d thread %d bar %u parity %u\n", (int)blockIdx.x, (int)threadIdx.x, smem_u32(bar),
+             parity);
+      __trap();
+    }
+#endif
+  }
+}
+
 // ---------------------------------------------------------------- TMA
 // 4-D tiled tensor load: global (tensor map) -> shared, completion on mbarrier.
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2,
