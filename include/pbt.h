@@ -112,8 +112,9 @@ typedef struct {
   const float* pre_scale;
   const float* pre_shift;
   int32_t      pre_act;
-  int32_t      ctas_per_sm;  /* 0 or 2: default configuration (8 epilogue warps, two co-resident CTAs per SM); 4: small-footprint
-                              * configuration for short CTAs (4 epilogue warps, tiles_per_cta*cout <= 128, <= 56 KB smem) */
+  int32_t      ctas_per_sm;  /* 0 or 2: default configuration (8 epilogue warps, two co-resident CTAs per SM); 4: request the
+                              * small-footprint configuration for short CTAs (4 epilogue warps, four co-resident CTAs); used when
+                              * tiles_per_cta*cout <= 128, the rings fit 56 KB and no on-load transform is active, else default */
   int32_t      debug_flags;  /* bring-up only; 0 in production */
   void*        debug_buf;    /* bring-up only: int64[grid][8] per-CTA phase timestamps, NULL in production */
 } pbt_conv_desc_t;

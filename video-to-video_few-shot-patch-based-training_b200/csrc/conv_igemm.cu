@@ -814,35 +814,40 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
 
   // shared memory budget: A ring + B ring (groups of taps) + barriers + tmem slot + stats scratch.
   // Aim at two co-resident CTAs per SM (one CTA's epilogue/prologue overlaps the other's main loop).
-  const int ew = d->ctas_per_sm == 4 ? 4 : 8;  // epilogue warps
-  const uint32_t tail = 8u * (2 * 2 + 2 * 8 + 1) + 16 + (uint32_t)(ew * 2 * p.NC * 4) + (ew == 8 ? 3 * 4 * 32 * 3 * 4 : 0) + 8 * 6 + (uint32_t)(2 * p.pre_c * 4) + 128;
+  // ctas_per_sm = 4 requests the small-footprint configuration (4 epilogue warps, <= 128 TMEM columns, <= 56 KB of
+  // shared memory -> four co-resident CTAs); shapes that do not fit it run the default configuration.
+  PBT_REQUIRE(d->ctas_per_sm == 0 || d->ctas_per_sm == 2 || d->ctas_per_sm == 4, "conv: ctas_per_sm must be 0, 2 or 4");
   const uint32_t a_total = (uint32_t)p.a_stages * p.a_stage_bytes + 2 * p.l_stage_bytes;
   const uint32_t chunk = (uint32_t)(p.blk_p * p.NC * 16);  // one tap of one channel block
   const int ntaps = p.KH * p.KW;
-  // ctas_per_sm = 4: small-footprint configuration (4 epilogue warps, <= 128 TMEM columns, <= 55 KB shared memory)
-  PBT_REQUIRE(d->ctas_per_sm == 0 || d->ctas_per_sm == 2 || d->ctas_per_sm == 4, "conv: ctas_per_sm must be 0, 2 or 4");
-  if (ew == 4) {
-    PBT_REQUIRE(!up && !has_pre, "conv: ctas_per_sm=4 does not support upsample/normalise-on-load");
-    PBT_REQUIRE(p.tmem_cols <= 128, "conv: ctas_per_sm=4 needs tiles_per_cta*cout <= 128 accumulator columns");
+  int ew = (d->ctas_per_sm == 4 && !up && !has_pre && p.tmem_cols <= 128) ? 4 : 8;  // epilogue warps
+  uint32_t smem_bytes = 0;
+  for (;;) {
+    const uint32_t tail = 8u * (2 * 2 + 2 * 8 + 1) + 16 + (uint32_t)(ew * 2 * p.NC * 4) + (ew == 8 ? 3 * 4 * 32 * 3 * 4 : 0) +
+                          8 * 6 + (uint32_t)(2 * p.pre_c * 4) + 128;
+    const uint32_t budget = ew == 4 ? 55 * 1024 : 112 * 1024;
+    int group = (int)((ew == 4 ? 8192u : 16384u) / chunk);
+    if (group < 1) group = 1;
+    if (group > ntaps) group = ntaps;
+    int stages = 4;
+    auto fits = [&](int g, int s) { return a_total + (uint32_t)s * round_up((uint32_t)g * chunk, 128) + tail <= budget; };
+    while (!fits(group, stages) && (stages > 2 || group > 1)) {
+      if (stages > 2) --stages;
+      else --group;
+    }
+    if (d->debug_flags & 4) group = 1;  // bring-up: one tap per stage
+    p.b_group = group;
+    p.b_stages = stages;
+    p.b_stage_bytes = round_up((uint32_t)group * chunk, 128);
+    smem_bytes = a_total + (uint32_t)p.b_stages * p.b_stage_bytes + tail;
+    if (ew == 4 && smem_bytes > 56 * 1024) {
+      ew = 8;
+      continue;
+    }
+    break;
   }
-  const uint32_t budget = ew == 4 ? 55 * 1024 : 112 * 1024;
-  int group = (int)((ew == 4 ? 8192u : 16384u) / chunk);
-  if (group < 1) group = 1;
-  if (group > ntaps) group = ntaps;
-  int stages = 4;
-  auto fits = [&](int g, int s) { return a_total + (uint32_t)s * round_up((uint32_t)g * chunk, 128) + tail <= budget; };
-  while (!fits(group, stages) && (stages > 2 || group > 1)) {
-    if (stages > 2) --stages;
-    else --group;
-  }
-  if (d->debug_flags & 4) group = 1;  // bring-up: one tap per stage
-  p.b_group = group;
-  p.b_stages = stages;
-  p.b_stage_bytes = round_up((uint32_t)group * chunk, 128);
-  uint32_t smem_bytes = a_total + (uint32_t)p.b_stages * p.b_stage_bytes + tail;
   if ((d->debug_flags & 8) && smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;  // bring-up: force one CTA per SM
   PBT_REQUIRE(smem_bytes <= 227 * 1024, "conv: configuration does not fit shared memory");
-  PBT_REQUIRE(ew == 8 || smem_bytes <= 56 * 1024, "conv: ctas_per_sm=4 configuration exceeds 56 KB of shared memory");
 
   CUtensorMap tmap, tmapP;
   int rc = PBT_OK;

@@ -253,6 +253,11 @@ class _Engine:
                 best, best_pad = t, pad
         return best
 
+    # The short-CTA layers (initial conv, first strided conv, smoothers: cout <= 64) request the kernel's small-footprint
+    # configuration: four co-resident CTAs per SM hide the per-CTA load / epilogue phases (tools/conv_occ.py: 10-25 %).
+    SMOOTH_BLK = 16
+    SMOOTH_T = 2
+
     def _blk(self, cin: int) -> int:
         return 32 if cin % 32 == 0 or cin > 32 else 16
 
@@ -274,9 +279,9 @@ class _Engine:
         f = g.filters
         pk = ops.WeightPacker(self.device)
 
-        def fwd(name, conv, k_pad, s2d=False):
+        def fwd(name, conv, k_pad, s2d=False, blk=None):
             co = conv.weight.shape[0]
-            pk.add(name, conv.weight.detach(), s2d=s2d, k_pad=k_pad, n_out=co, n_keep=co, blk_c=self._blk(k_pad), dt=dt)
+            pk.add(name, conv.weight.detach(), s2d=s2d, k_pad=k_pad, n_out=co, n_keep=co, blk_c=blk or self._blk(k_pad), dt=dt)
 
         def dgr(name, conv, s2d=False, keep=None):
             co, ci = conv.weight.shape[0], conv.weight.shape[1]
@@ -298,8 +303,8 @@ class _Engine:
         fwd("up1", g.upsample1[1], f[4] + f[1])
         # conv11 input order = [out(f4), conv0(f0), x(cin)] — identical to the reference cat (:230), zero padded
         fwd("conv11", g.conv11[0], f[4] + f[0] + cp)
-        fwd("smooth0", g.smoothers[0], f[5])
-        fwd("smooth3", g.smoothers[3], f[5])
+        fwd("smooth0", g.smoothers[0], f[5], blk=self.SMOOTH_BLK)
+        fwd("smooth3", g.smoothers[3], f[5], blk=self.SMOOTH_BLK)
         if with_dgrad:
             dgr("down1", g.downsample1[0], s2d=True)
             dgr("down2", g.downsample2[0], s2d=True)
@@ -337,7 +342,7 @@ class _Engine:
         if not u8_hwc and x.dtype not in (torch.float32, torch.float16):
             x = x.float()
 
-        def conv_in(name, xin, cout, k, pad, raw, T_pref, up=False, pre=None, pre_st=None, pre_act=ACT_NONE):
+        def conv_in(name, xin, cout, k, pad, raw, T_pref, up=False, pre=None, pre_st=None, pre_act=ACT_NONE, cps=0):
             """conv (bias skipped: a constant per channel is removed by the following InstanceNorm) + IN statistics;
             up=True: xin is the low-res tensor, the conv consumes its bilinear x2 upsample (interpolated in-kernel);
             pre: raw output of the previous conv, its InstanceNorm (pre_st) + activation applied on load"""
@@ -349,7 +354,7 @@ class _Engine:
             ops.conv_fwd(xin, W[name], cout, k, k, pad, pad, dt, blk_c=self._blk(cin), tiles_per_cta=T, out=raw,
                          stats_partial=st["partial"], upsample2x=up, pre=pre,
                          pre_scale=None if pre is None else pre_st["scale"], pre_shift=None if pre is None else pre_st["shift"],
-                         pre_act=pre_act)
+                         pre_act=pre_act, ctas_per_sm=cps)
             ops.norm_finalize(st["partial"], n, st["tiles"], cout, oh * ow, st["scale"], st["shift"], eps=EPS)
             return st
 
@@ -360,10 +365,10 @@ class _Engine:
         else:
             ops.nchw_to_p8(x, xin, dt)
         # encoder
-        st = conv_in("initial", xin, f[0], 7, 3, ws.raw0, 3)
+        st = conv_in("initial", xin, f[0], 7, 3, ws.raw0, 3, cps=4)
         ops.norm_apply(ws.raw0, dt, scale=st["scale"], shift=st["shift"], act=ACT_LEAKY, out=ws.cat11.view(f[4], f[0]),
                        out_s2d=ws.s2d0)
-        st = conv_in("down1", ws.s2d0, f[1], 2, 1, ws.raw1, 2)
+        st = conv_in("down1", ws.s2d0, f[1], 2, 1, ws.raw1, 2, cps=4)
         ops.norm_apply(ws.raw1, dt, scale=st["scale"], shift=st["shift"], act=ACT_LEAKY, out=ws.c1cat.view(f[4], f[1]),
                        out_s2d=ws.s2d1)
         st = conv_in("down2", ws.s2d1, f[2], 2, 1, ws.raw2, 2)
@@ -426,11 +431,11 @@ class _Engine:
             e1.record()
             ev.append((e0, e1))
         bn = g.smoothers[2]
-        T3 = self._T(3, w)
+        T3, sblk = self._T(self.SMOOTH_T, w), self.SMOOTH_BLK
         if train_bn:
             st = ws.stat("bn", f[5], h, w, T3, dev)
-            ops.conv_fwd(ws.c11, W["smooth0"], f[5], 3, 3, 1, 1, dt, blk_c=32, tiles_per_cta=T3, bias=W["bs0"], act=ACT_RELU,
-                         out=ws.s0, stats_partial=st["partial"])
+            ops.conv_fwd(ws.c11, W["smooth0"], f[5], 3, 3, 1, 1, dt, blk_c=sblk, tiles_per_cta=T3, bias=W["bs0"], act=ACT_RELU,
+                         out=ws.s0, stats_partial=st["partial"], ctas_per_sm=4)
             if "mean" not in st:
                 st["mean"] = torch.empty((f[5],), device=dev)
                 st["rstd"] = torch.empty((f[5],), device=dev)
@@ -446,13 +451,14 @@ class _Engine:
             rstd = torch.rsqrt(bn.running_var.float() + bn.eps)
             sc = (bn.weight.detach().float() * rstd).contiguous()
             sh = (bn.bias.detach().float() - bn.running_mean.float() * sc).contiguous()
-            ops.conv_fwd(ws.c11, W["smooth0"], f[5], 3, 3, 1, 1, dt, blk_c=32, tiles_per_cta=T3, bias=W["bs0"], act=ACT_RELU,
-                         post_scale=sc, post_shift=sh, out=ws.s0n)
+            ops.conv_fwd(ws.c11, W["smooth0"], f[5], 3, 3, 1, 1, dt, blk_c=sblk, tiles_per_cta=T3, bias=W["bs0"], act=ACT_RELU,
+                         post_scale=sc, post_shift=sh, out=ws.s0n, ctas_per_sm=4)
             if save:
                 raise RuntimeError("autograd through GeneratorJ in eval() mode is not supported by the native path")
         y = torch.empty((n, 3, h, w), device=dev)  # fresh result tensor: callers may keep it across calls
-        ops.conv_fwd(ws.s0n, W["smooth3"], f[5], 3, 3, 1, 1, dt, blk_c=32, tiles_per_cta=T3, bias=W["bs3"], act=ACT_RELU,
-                     out=ws.s3 if save else None, head_w=W["head_w"], head_b=W["head_b"], head_out=y, head_tanh=g.use_tanh)
+        ops.conv_fwd(ws.s0n, W["smooth3"], f[5], 3, 3, 1, 1, dt, blk_c=sblk, tiles_per_cta=T3, bias=W["bs3"], act=ACT_RELU,
+                     out=ws.s3 if save else None, head_w=W["head_w"], head_b=W["head_b"], head_out=y, head_tanh=g.use_tanh,
+                     ctas_per_sm=4)
         if save:
             self._saved = (ws, W)
         return y
