@@ -15,6 +15,21 @@ cases = [("smooth 64->64 3x3 @1080p", 64, 64, 3, 1080, 1920, 32, [(3, 0), (2, 4)
          ("down1 s2d 128->64 2x2 @540p", 128, 64, 2, 540, 960, 32, [(2, 0), (2, 4), (3, 0)]),
          ("res 128->128 3x3 @270x480", 128, 128, 3, 270, 480, 32, [(2, 0), (1, 0), (1, 4)]),
          ("conv11 176->64 7x7 @1080p", 176, 64, 7, 1080, 1920, 32, [(3, 0), (2, 0), (2, 4)])]
+if len(sys.argv) > 2 and sys.argv[2] == "train":   # C3 training shapes: 80 patches of 80x80 (N = batch)
+    N = 80
+    cases = [("res 128->128 3x3 @20x20", 128, 128, 3, 20, 20, 32, [(1, 0), (1, 4), (2, 0)]),
+             ("down2 s2d 256->128 2x2 @20x20", 256, 128, 2, 20, 20, 32, [(1, 0), (1, 4), (2, 0)]),
+             ("up2 256->128 3x3 @40x40", 256, 128, 3, 40, 40, 32, [(2, 0), (1, 0), (1, 4)]),
+             ("up1 192->128 3x3 @80x80", 192, 128, 3, 80, 80, 32, [(2, 0), (1, 0), (1, 4)]),
+             ("conv11 176->64 7x7 @80x80", 176, 64, 7, 80, 80, 32, [(2, 0), (2, 4), (1, 4)]),
+             ("conv11 dgrad 64->160 7x7 @80x80", 64, 160, 7, 80, 80, 32, [(2, 0), (1, 0)]),
+             ("up1 dgrad 128->192 3x3 @80x80", 128, 192, 3, 80, 80, 32, [(2, 0), (1, 0)]),
+             ("up2 dgrad 128->256 3x3 @40x40", 128, 256, 3, 40, 40, 32, [(1, 0), (2, 0)]),
+             ("smooth 64->64 3x3 @80x80", 64, 64, 3, 80, 80, 32, [(2, 0), (2, 4), (2, 4.16), (1, 4)]),
+             ("initial 16->32 7x7 @80x80", 16, 32, 7, 80, 80, 16, [(2, 0), (2, 4), (3, 4)]),
+             ("down1 s2d 128->64 2x2 @40x40", 128, 64, 2, 40, 40, 32, [(2, 0), (2, 4), (1, 4)]),
+             ("down1 dgrad 64->128 2x2 @40x40", 64, 128, 2, 40, 40, 32, [(2, 0), (1, 4), (1, 0)]),
+             ("down2 dgrad 128->256 2x2 @20x20", 128, 256, 2, 20, 20, 32, [(1, 0), (2, 0)])]
 for name, cin, cout, k, h, w, blk, cfgs in cases:
     x = P8.empty(N, cin, h, w, dt)
     x.t.normal_()
@@ -45,6 +60,6 @@ for name, cin, cout, k, h, w, blk, cfgs in cases:
             if ref is None:
                 ref = out.t.float().clone()
             tf = 2.0 * N * h * w * k * k * cin * cout / ms / 1e9
-            print(f"{name}: T={T} cps={cps or 2} blk={b}: {ms * 1e3 / N:8.1f} us/frame  {tf:7.1f} TFLOP/s  maxdiff vs first {diff:.3g}", flush=True)
+            print(f"{name}: T={T} cps={cps or 2} blk={b}: {ms * 1e3:8.1f} us ({ms * 1e3 / N:8.1f} us/frame)  {tf:7.1f} TFLOP/s  maxdiff vs first {diff:.3g}", flush=True)
         except Exception as e:  # noqa: BLE001
             print(f"{name}: T={T} cps={cps}: EXC {e}", flush=True)

@@ -674,6 +674,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       case kFBias | kFRelu | kFHead | kFOut16: epi_loop(std::integral_constant<uint32_t, kFBias | kFRelu | kFHead | kFOut16>{}); break;
       case kFBias | kFRelu | kFOut16 | kFStats: epi_loop(std::integral_constant<uint32_t, kFBias | kFRelu | kFOut16 | kFStats>{}); break;
       case kFOut16: epi_loop(std::integral_constant<uint32_t, kFOut16>{}); break;
+      case kFMask | kFOut16: epi_loop(std::integral_constant<uint32_t, kFMask | kFOut16>{}); break;
+      case kFMask | kFAddend | kFOut32: epi_loop(std::integral_constant<uint32_t, kFMask | kFAddend | kFOut32>{}); break;
       default: epi_loop(std::integral_constant<uint32_t, kFGeneric>{}); break;
     }
     if (do_stats) {

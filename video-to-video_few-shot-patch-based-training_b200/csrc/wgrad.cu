@@ -223,7 +223,12 @@ extern "C" int pbt_conv_wgrad(const pbt_wgrad_desc_t* d, void* stream_) {
   p.dw = d->dw;
   p.inv_scale = d->inv_scale;
   const int m_blocks = ceil_div(p.Cm, 128);
-  int splits = (4 * num_sms()) / (m_blocks * p.n_units);
+  // Pixel split: one wave of CTAs (two per SM), but at least ~24 tiles per CTA - every CTA ends with a flush of its
+  // accumulators into dW by fp32 reductions, and on small maps those reductions, not the MMAs, set the time
+  // (tools/wgrad_occ.py: 128->128 3x3 on 80 x 20x20 maps: 46 us with 4 CTAs/SM worth of splits, 27 us with one wave).
+  const int ovr = (d->debug_flags >> 8) & 0xff;  // (bring-up: bits 8-15 override the CTA budget multiplier)
+  int splits = ((ovr ? ovr : 2) * num_sms()) / (m_blocks * p.n_units);
+  if (!ovr && splits > p.n_tiles / 24) splits = p.n_tiles / 24;
   if (splits < 1) splits = 1;
   if (splits > p.n_tiles) splits = p.n_tiles;
   p.splits = splits;

@@ -371,7 +371,7 @@ class _Engine:
         st = conv_in("down1", ws.s2d0, f[1], 2, 1, ws.raw1, 2, cps=4)
         ops.norm_apply(ws.raw1, dt, scale=st["scale"], shift=st["shift"], act=ACT_LEAKY, out=ws.c1cat.view(f[4], f[1]),
                        out_s2d=ws.s2d1)
-        st = conv_in("down2", ws.s2d1, f[2], 2, 1, ws.raw2, 2)
+        st = conv_in("down2", ws.s2d1, f[2], 2, 1, ws.raw2, 2, cps=4)
         nb = len(g.resnet_blocks)
         r_cur, r_nxt = ws.r[0], ws.r[1]
         a_of = (lambda i: ws.a[i]) if save else (lambda i: ws.a[i % 2])
@@ -389,12 +389,12 @@ class _Engine:
         nol_11 = not save and f[4] % 32 == 0 and f[4] <= 256
         for b in range(nb):
             k = b if save else 0
-            st = conv_in(f"res{b}.a", a_of(b), f[2], 3, 1, ws.rawA[k], 2)
+            st = conv_in(f"res{b}.a", a_of(b), f[2], 3, 1, ws.rawA[k], 2, cps=4)
             if nol_res:
                 st = conv_in(f"res{b}.b", None, f[2], 3, 1, ws.rawB[k], 2, pre=ws.rawA[k], pre_st=st, pre_act=ACT_RELU)
             else:
                 ops.norm_apply(ws.rawA[k], dt, scale=st["scale"], shift=st["shift"], act=ACT_RELU, out=ws.hmid[k])
-                st = conv_in(f"res{b}.b", ws.hmid[k], f[2], 3, 1, ws.rawB[k], 2)
+                st = conv_in(f"res{b}.b", ws.hmid[k], f[2], 3, 1, ws.rawB[k], 2, cps=4)
             lastb = b == nb - 1
             ops.norm_apply(ws.rawB[k], dt, scale=st["scale"], shift=st["shift"], act=ACT_NONE, residual32=r_cur,
                            out32=None if lastb else r_nxt, out=last16 if lastb else None,

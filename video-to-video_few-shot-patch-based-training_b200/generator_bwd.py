@@ -75,8 +75,9 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor) -> List[torch.Ten
         T = T_of(T_pref, gin.w)
         while T > 1 and T * acc_stride > 512:
             T -= 1
+        # small maps / narrow outputs get the small-footprint configuration (the kernel falls back when it does not fit)
         ops.conv_fwd(gin, W[name + ".d"], cout, k, k, k - 1 - pad, k - 1 - pad, dt, blk_c=eng._blk(gin.c), tiles_per_cta=T,
-                     out=out, **kw)
+                     out=out, ctas_per_sm=4, **kw)
 
     def wgrad(x: P8, dy: P8, k, pad):
         dw = Z(k * k, x.c, dy.c)
