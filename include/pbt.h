@@ -230,6 +230,10 @@ typedef struct {
 } pbt_norm_bwd_desc_t;
 int pbt_norm_bwd_reduce(const pbt_norm_bwd_desc_t* d, void* stream);
 int pbt_norm_bwd_apply(const pbt_norm_bwd_desc_t* d, void* stream);
+/* reduce + apply in ONE launch for per-image statistics (batch_mode = 0): a CTA per (image, 8-channel plane) sums its
+ * slice and re-reads it from L2 for the apply.  Meant for patch-sized maps with n * c/8 >= the SM count; writes (not
+ * accumulates) d->sums. */
+int pbt_norm_bwd_fused(const pbt_norm_bwd_desc_t* d, void* stream);
 
 /* Backward of the fused head (tanh(1x1 conv), src/models/generator.py:141-144) and of the
  * ReLU in front of it:  gz = gy*(1-y^2)*gscale ; dW[3][c] += gz (x) s ; db += gz ;

@@ -107,7 +107,9 @@ def test_upsample_and_transpose(dt):
     assert ok, msg
 
 
-@pytest.mark.parametrize("kw", [dict(dt=1), dict(dt=1, s2d=True), dict(dt=1, batch_mode=True), dict(dt=0)])
+@pytest.mark.parametrize("kw", [dict(dt=1), dict(dt=1, s2d=True), dict(dt=1, batch_mode=True), dict(dt=0),
+                                dict(dt=1, n=40, c=32), dict(dt=1, n=40, c=32, s2d=True), dict(dt=0, n=33, c=32)],
+                         ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
 def test_norm_backward(kw):
     ok, err, msg = gc.check_norm_bwd(**kw)
     assert ok, msg

@@ -591,6 +591,73 @@ __global__ void norm_bwd_apply_kernel(NormBwdK p) {
   }
 }
 
+// Fused reduce + apply for per-image statistics on small maps (patch training): one CTA owns one (image, plane) slice,
+// sums it, then re-reads it (L2 hits: the slice was just read by this CTA) and writes dx.  No atomics, one launch,
+// half the DRAM traffic of the two-kernel path.  grid: (planes, n).
+template <int DT>
+__global__ void norm_bwd_fused_kernel(NormBwdK p) {
+  const int hw = p.x.h * p.x.w;
+  const int planes = p.x.c / 8;
+  const int pl = blockIdx.x, ni = blockIdx.y;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s1[k] = s2[k] = 0.f;
+  for (int pix = threadIdx.x; pix < hw; pix += blockDim.x) {
+    float gact[8], xhat[8], xr[8];
+    load_gact<DT>(p, ni, pl, pix, planes, hw, gact, xhat, xr);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      s1[k] += gact[k];
+      s2[k] = fmaf(gact[k], xhat[k], s2[k]);
+    }
+  }
+  __shared__ float red[kEwThreads / 32][16];
+  __shared__ float tot[16];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], o);
+      s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], o);
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      red[wid][k] = s1[k];
+      red[wid][8 + k] = s2[k];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    float t = 0.f;
+    for (int w2 = 0; w2 < kEwThreads / 32; ++w2) t += red[w2][threadIdx.x];
+    tot[threadIdx.x] = t;
+    const int which = threadIdx.x >> 3, k = threadIdx.x & 7;
+    p.sums[(long long)ni * 2 * p.x.c + (long long)which * p.x.c + pl * 8 + k] = t;
+  }
+  __syncthreads();
+  float m1[8], m2[8], km[8];
+  const long long ko = (p.per_channel ? 0 : (long long)ni * p.x.c) + pl * 8;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    m1[k] = tot[k] * p.inv_count;
+    m2[k] = tot[8 + k] * p.inv_count;
+    km[k] = __ldg(&p.kmul[ko + k]);
+  }
+  for (int pix = threadIdx.x; pix < hw; pix += blockDim.x) {
+    float gact[8], xhat[8], r[8], xr[8];
+    load_gact<DT>(p, ni, pl, pix, planes, hw, gact, xhat, xr);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      r[k] = km[k] * (gact[k] - m1[k] - xhat[k] * m2[k]);
+      if (p.relu_mask_x && !(xr[k] > 0.f)) r[k] = 0.f;
+    }
+    *chunk_ptr(p.dx, ni, pl, pix) = pack8<DT>(r);
+  }
+}
+
 // ------------------------------------------------------------------ head backward
 // grid: (chunks, planes of s); block reduces dW[3][8], dbias_prev[8] (+ db[3] on plane 0)
 template <int DT>
@@ -921,6 +988,22 @@ extern "C" int pbt_norm_bwd_apply(const pbt_norm_bwd_desc_t* d, void* stream_) {
               "norm_bwd_apply: dx shape mismatch");
   p.dx = view(d->dx);
   DISPATCH_DT(d->dtype, norm_bwd_apply_kernel<DT><<<ew_grid3(d->x.h * d->x.w, d->x.c / 8, d->x.n), kEwThreads, 0, st>>>(p));
+  PBT_CUDA_CHECK(cudaGetLastError());
+  return PBT_OK;
+}
+
+extern "C" int pbt_norm_bwd_fused(const pbt_norm_bwd_desc_t* d, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  NormBwdK p;
+  int rc = fill_norm_bwd(d, p);
+  if (rc) return rc;
+  PBT_REQUIRE(!d->batch_mode, "norm_bwd_fused: per-image statistics only (use reduce + apply for batch statistics)");
+  PBT_REQUIRE((long long)d->x.h * d->x.w <= (1 << 20), "norm_bwd_fused: map too large");
+  PBT_REQUIRE(d->kmul && act_ok(d->dx) && d->dx.h == d->x.h && d->dx.w == d->x.w && d->dx.c >= d->x.c && d->dx.n == d->x.n,
+              "norm_bwd_fused: dx shape mismatch");
+  p.dx = view(d->dx);
+  dim3 grid(d->x.c / 8, d->x.n);
+  DISPATCH_DT(d->dtype, norm_bwd_fused_kernel<DT><<<grid, kEwThreads, 0, st>>>(p));
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
 }

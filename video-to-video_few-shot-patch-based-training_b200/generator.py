@@ -463,6 +463,12 @@ class _Engine:
             self._saved = (ws, W)
         return y
 
+    def side_stream(self) -> "torch.cuda.Stream":
+        """second stream of the backward sweep (weight gradients overlap the data-gradient chain)"""
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(self.device)
+        return self._side
+
     def zero_pool_floats(self, n: int) -> int:
         """upper bound (in floats) of all accumulate-into buffers of one backward sweep"""
         g = self.gen

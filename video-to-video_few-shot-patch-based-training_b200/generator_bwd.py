@@ -79,10 +79,41 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor) -> List[torch.Ten
         ops.conv_fwd(gin, W[name + ".d"], cout, k, k, k - 1 - pad, k - 1 - pad, dt, blk_c=eng._blk(gin.c), tiles_per_cta=T,
                      out=out, ctas_per_sm=4, **kw)
 
-    def wgrad(x: P8, dy: P8, k, pad):
+    # Weight gradients run on a side stream: a conv's wgrad and dgrad are independent, and on patch-sized maps neither
+    # fills the GPU (a 128->128 3x3 wgrad is ~180 CTAs, its dgrad ~480 of 592 slots).  Their parameter gradients are
+    # published (grad hook -> all-reduce bucket) at the join points, on the main stream.
+    main = torch.cuda.current_stream(dev)
+    side = eng.side_stream()
+    capturing = torch.cuda.is_current_stream_capturing()
+    pending, keep = [], []
+
+    def wgrad_side(name, x: P8, dy: P8, k, pad, convert):
+        """enqueue wgrad(x, dy) + `convert(dw)` on the side stream after everything enqueued so far on the main stream;
+        returns the event that marks the side job's completion (wait for it before overwriting x or dy)"""
         dw = Z(k * k, x.c, dy.c)
-        ops.conv_wgrad(x, dy, k, k, pad, pad, dt, dw, inv_scale=inv)
-        return dw
+        fork = torch.cuda.Event()
+        fork.record(main)
+        side.wait_event(fork)
+        with torch.cuda.stream(side):
+            ops.conv_wgrad(x, dy, k, k, pad, pad, dt, dw, inv_scale=inv)
+            gr = convert(dw)
+            if not capturing:
+                gr.record_stream(main)
+            pending.append((name, gr))
+            done = torch.cuda.Event()
+            done.record(side)
+        keep.append((x, dy))
+        return done
+
+    def join():
+        """main stream waits for the side stream; publish the finished parameter gradients"""
+        ev = torch.cuda.Event()
+        ev.record(side)
+        main.wait_event(ev)
+        for name, gr in pending:
+            grads[name] = gr
+        pending.clear()
+        keep.clear()
 
     def in_bwd(x: P8, st, act, dx: P8, count, **kw):
         sums = Z(n, 2, x.c)
@@ -112,7 +143,7 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor) -> List[torch.Ten
     grads["output.0.weight"] = dw_out.reshape(3, f[5], 1, 1)
     grads["output.0.bias"] = db_out
     # ---- smoothers.3
-    grads["smoothers.3.weight"] = _wgrad_to_param(wgrad(ws.s0n, g_s3, 3, 1), f[5], f[5], 3, 3)
+    wgrad_side("smoothers.3.weight", ws.s0n, g_s3, 3, 1, lambda dw: _wgrad_to_param(dw, f[5], f[5], 3, 3))
     grads["smoothers.3.bias"] = db_s3
     g_s0n = E(f[5], h, w)
     dgrad("smooth3", g_s3, f[5], 3, 1, out=g_s0n, T_pref=3)
@@ -130,7 +161,7 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor) -> List[torch.Ten
     db_s0 = Z(f[5])
     ops.channel_sum(g_s0, db_s0, dt, inv_scale=inv)
     # ---- smoothers.0
-    grads["smoothers.0.weight"] = _wgrad_to_param(wgrad(ws.c11, g_s0, 3, 1), f[5], f[5], 3, 3)
+    wgrad_side("smoothers.0.weight", ws.c11, g_s0, 3, 1, lambda dw: _wgrad_to_param(dw, f[5], f[5], 3, 3))
     grads["smoothers.0.bias"] = db_s0
     g_c11 = E(f[5], h, w)
     dgrad("smooth0", g_s0, f[5], 3, 1, out=g_c11, T_pref=3, mask=ws.c11)
@@ -138,15 +169,16 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor) -> List[torch.Ten
     ops.channel_sum(g_c11, db_11, dt, inv_scale=inv)
     # ---- conv11 (input = cat11 = [up1 | conv0 | x])
     cin11 = f[4] + f[0] + g.input_channels
-    grads["conv11.0.weight"] = _wgrad_to_param(wgrad(ws.cat11, g_c11, 7, 3), f[5], cin11, 7, 7)
+    wgrad_side("conv11.0.weight", ws.cat11, g_c11, 7, 3, lambda dw: _wgrad_to_param(dw, f[5], cin11, 7, 7))
     grads["conv11.0.bias"] = db_11
     g_cat = E(f[4] + f[0], h, w)
     dgrad("conv11", g_c11, f[4] + f[0], 7, 3, out=g_cat, T_pref=3)
+    join()   # tail group complete (output head, smoothers, conv11)
     del g_c11, g_s0, g_s0n, g_s3
     # ---- upsample1 block
     g_rawU1 = E(f[4], h, w)
     in_bwd(ws.rawU1, ws.stats["up1"], ACT_RELU, g_rawU1, h * w, ga=g_cat.view(0, f[4]))
-    grads["upsample1.1.weight"] = _wgrad_to_param(wgrad(ws.u1in, g_rawU1, 3, 1), f[4], f[4] + f[1], 3, 3)
+    wgrad_side("upsample1.1.weight", ws.u1in, g_rawU1, 3, 1, lambda dw: _wgrad_to_param(dw, f[4], f[4] + f[1], 3, 3))
     g_u1in = E(f[4] + f[1], h, w)
     dgrad("up1", g_rawU1, f[4] + f[1], 3, 1, out=g_u1in)
     del g_rawU1
@@ -156,44 +188,54 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor) -> List[torch.Ten
     # ---- upsample2 block
     g_rawU2 = E(f[4], h2, w2)
     in_bwd(ws.rawU2, ws.stats["up2"], ACT_RELU, g_rawU2, h2 * w2, ga=g_c1cat.view(0, f[4]))
-    grads["upsample2.1.weight"] = _wgrad_to_param(wgrad(ws.u2in, g_rawU2, 3, 1), f[4], 2 * f[2], 3, 3)
+    wgrad_side("upsample2.1.weight", ws.u2in, g_rawU2, 3, 1, lambda dw: _wgrad_to_param(dw, f[4], 2 * f[2], 3, 3))
     g_u2in = E(2 * f[2], h2, w2)
     dgrad("up2", g_rawU2, 2 * f[2], 3, 1, out=g_u2in)
     g_r = torch.empty((n, f[2] // 8, h4, w4, 8), device=dev)          # fp32 gradient of the residual stream
     g_c2skip = E(f[2], h4, w4)
     ops.upsample2x_bwd(g_u2in.view(0, f[2]), dt, gin32=g_r)
     ops.upsample2x_bwd(g_u2in.view(f[2], f[2]), dt, gin16=g_c2skip)
+    join()   # decoder group complete
     del g_u2in, g_rawU2
-    # ---- residual blocks, last to first
-    g_raw = E(f[2], h4, w4)
+    # ---- residual blocks, last to first.  Two gradient buffers (one per conv of a block): the side-stream wgrad of
+    # block b still reads g_rawB / g_rawA while the main stream moves on; a buffer is rewritten only after the wgrad
+    # that read it has finished (event wait - normally already satisfied).
+    g_rawB, g_rawA = E(f[2], h4, w4), E(f[2], h4, w4)
     g_h = E(f[2], h4, w4)
+    evB = evA = None
+    res_cv = lambda dw: _wgrad_to_param(dw, f[2], f[2], 3, 3)  # noqa: E731
     for b in range(nb - 1, -1, -1):
-        in_bwd(ws.rawB[b], ws.stats[f"res{b}.b"], ACT_NONE, g_raw, h4 * w4, gb32=g_r)
-        grads[f"resnet_blocks.{b}.block.4.weight"] = _wgrad_to_param(wgrad(ws.hmid[b], g_raw, 3, 1), f[2], f[2], 3, 3)
-        dgrad(f"res{b}.b", g_raw, f[2], 3, 1, out=g_h)
-        in_bwd(ws.rawA[b], ws.stats[f"res{b}.a"], ACT_RELU, g_raw, h4 * w4, ga=g_h)
-        grads[f"resnet_blocks.{b}.block.1.weight"] = _wgrad_to_param(wgrad(ws.a[b], g_raw, 3, 1), f[2], f[2], 3, 3)
+        if evB is not None:
+            main.wait_event(evB)
+        in_bwd(ws.rawB[b], ws.stats[f"res{b}.b"], ACT_NONE, g_rawB, h4 * w4, gb32=g_r)
+        evB = wgrad_side(f"resnet_blocks.{b}.block.4.weight", ws.hmid[b], g_rawB, 3, 1, res_cv)
+        dgrad(f"res{b}.b", g_rawB, f[2], 3, 1, out=g_h)
+        if evA is not None:
+            main.wait_event(evA)
+        in_bwd(ws.rawA[b], ws.stats[f"res{b}.a"], ACT_RELU, g_rawA, h4 * w4, ga=g_h)
+        evA = wgrad_side(f"resnet_blocks.{b}.block.1.weight", ws.a[b], g_rawA, 3, 1, res_cv)
         # g_r <- g_r + relu'(r_b) * dgrad   (in place: every element is read then written by the same thread)
-        dgrad(f"res{b}.a", g_raw, f[2], 3, 1, out=None, mask=ws.a[b], addend32=g_r, out32=g_r)
+        dgrad(f"res{b}.a", g_rawA, f[2], 3, 1, out=None, mask=ws.a[b], addend32=g_r, out32=g_r)
     # ---- downsample2 (conv2 feeds the residual stream and the decoder skip)
     g_raw2 = E(f[2], h4, w4)
     in_bwd(ws.raw2, ws.stats["down2"], ACT_LEAKY, g_raw2, h4 * w4, gb16=g_c2skip, gb32=g_r)
-    dw2 = wgrad(ws.s2d1, g_raw2, 2, 1)                                   # [4, 4*f1, f2]
-    grads["downsample2.0.weight"] = ops.s2d_weight_grad(dw2.permute(2, 1, 0).reshape(f[2], 4 * f[1], 2, 2), f[1])
+    wgrad_side("downsample2.0.weight", ws.s2d1, g_raw2, 2, 1,                # dw: [4, 4*f1, f2]
+               lambda dw: ops.s2d_weight_grad(dw.permute(2, 1, 0).reshape(f[2], 4 * f[1], 2, 2), f[1]))
     g_s2d1 = E(4 * f[1], h4, w4)
     dgrad("down2", g_raw2, 4 * f[1], 2, 1, out=g_s2d1)
     # ---- downsample1
     g_raw1 = E(f[1], h2, w2)
     in_bwd(ws.raw1, ws.stats["down1"], ACT_LEAKY, g_raw1, h2 * w2, ga=g_s2d1, ga_is_s2d=True, gb16=g_c1cat.view(f[4], f[1]))
-    dw1 = wgrad(ws.s2d0, g_raw1, 2, 1)
-    grads["downsample1.0.weight"] = ops.s2d_weight_grad(dw1.permute(2, 1, 0).reshape(f[1], 4 * f[0], 2, 2), f[0])
+    wgrad_side("downsample1.0.weight", ws.s2d0, g_raw1, 2, 1,
+               lambda dw: ops.s2d_weight_grad(dw.permute(2, 1, 0).reshape(f[1], 4 * f[0], 2, 2), f[0]))
     g_s2d0 = E(4 * f[0], h2, w2)
     dgrad("down1", g_raw1, 4 * f[0], 2, 1, out=g_s2d0)
     # ---- initial conv
     g_raw0 = E(f[0], h, w)
     in_bwd(ws.raw0, ws.stats["initial"], ACT_LEAKY, g_raw0, h * w, ga=g_s2d0, ga_is_s2d=True, gb16=g_cat.view(f[4], f[0]))
-    dw0 = wgrad(ws.cat11.view(f[4] + f[0], cp), g_raw0, 7, 3)
-    grads["initial_conv.0.weight"] = _wgrad_to_param(dw0, f[0], g.input_channels, 7, 7)
+    wgrad_side("initial_conv.0.weight", ws.cat11.view(f[4] + f[0], cp), g_raw0, 7, 3,
+               lambda dw: _wgrad_to_param(dw, f[0], g.input_channels, 7, 7))
+    join()   # trunk group complete
 
     # ---- assemble in parameter order
     out: List[torch.Tensor] = []

@@ -182,6 +182,10 @@ def norm_bwd(x: P8, dt: int, *, scale, shift, per_channel=False, act=ACT_NONE, g
     d.ga, d.ga_is_s2d, d.gb16, d.gb32 = act_or_null(ga), int(ga_is_s2d), act_or_null(gb16), ptr(gb32)
     d.sums, d.kmul, d.count, d.batch_mode = sums.data_ptr(), kmul.data_ptr(), count, int(batch_mode)
     d.dx, d.dtype, d.relu_mask_x = dx.act(), dt, int(relu_mask_x)
+    if not batch_mode and x.h * x.w <= 16384 and x.n * (x.c // 8) >= 128:
+        # patch-sized maps: one launch, a CTA per (image, plane) slice (second pass hits L2)
+        check(lib().pbt_norm_bwd_fused(C.byref(d), stream_ptr()), "pbt_norm_bwd_fused")
+        return
     check(lib().pbt_norm_bwd_reduce(C.byref(d), stream_ptr()), "pbt_norm_bwd_reduce")
     check(lib().pbt_norm_bwd_apply(C.byref(d), stream_ptr()), "pbt_norm_bwd_apply")
 
