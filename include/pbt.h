@@ -115,6 +115,9 @@ typedef struct {
   int32_t      ctas_per_sm;  /* 0 or 2: default configuration (8 epilogue warps, two co-resident CTAs per SM); 4: request the
                               * small-footprint configuration for short CTAs (4 epilogue warps, four co-resident CTAs); used when
                               * tiles_per_cta*cout <= 128, the rings fit 56 KB and no on-load transform is active, else default */
+  int32_t      cta_pair;     /* 1: CTA-pair configuration (clusters of two CTAs run one M=256 cta_group::2 MMA stream, each CTA
+                              * stages half of the weight columns); `wpack` must be in the pair layout (pack mode bit 2).
+                              * Needs blk_c 32, tiles_per_cta 2 or 3, cout % 32 == 0; not combinable with upsample2x */
   int32_t      debug_flags;  /* bring-up only; 0 in production */
   void*        debug_buf;    /* bring-up only: int64[grid][8] per-CTA phase timestamps, NULL in production */
 } pbt_conv_desc_t;
@@ -126,7 +129,7 @@ typedef struct {
   const void* w;        /* source parameter */
   void*       dst;      /* packed 16-bit destination: taps * k_pad * n_out elements */
   int32_t     co, ci, kh, kw;   /* source dims */
-  int32_t     mode;     /* bit 0: space-to-depth, bit 1: dgrad */
+  int32_t     mode;     /* bit 0: space-to-depth, bit 1: dgrad, bit 2: CTA-pair layout [cb][half][tap][k/8][n/2][8] */
   int32_t     k_pad;    /* destination K channels (multiple of 16) */
   int32_t     n_out;    /* destination N rows (multiple of 16) */
   int32_t     n_keep;   /* rows taken from the source, remaining rows are zero */

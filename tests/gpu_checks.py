@@ -32,7 +32,7 @@ def act_ref(v, act):
 
 def check_conv(n=1, cin=16, cout=16, h=16, w=8, kh=1, kw=1, pad_t=0, pad_l=0, T=1, blk_c=16, dt=BF16, seed=0,
                debug_flags=0, in_off=0, in_extra=0, out_off=0, out_extra=0, bias=False, act=ACT_NONE, affine=False,
-               mask=False, addend=False, out32=False, stats=False, head=False, integer=True, store16=True, cps=0):
+               mask=False, addend=False, out32=False, stats=False, head=False, integer=True, store16=True, cps=0, pair=False):
     """returns (ok, max_abs_err, message); cps = ctas_per_sm configuration of the kernel"""
     g = torch.Generator(device="cuda").manual_seed(seed)
     if integer:
@@ -49,8 +49,8 @@ def check_conv(n=1, cin=16, cout=16, h=16, w=8, kh=1, kw=1, pad_t=0, pad_l=0, T=
     xfull.t.copy_(P8.from_nchw(torch.cat([torch.full((n, in_off, h, w), 7.0, device="cuda"), x,
                                           torch.full((n, in_extra, h, w), -5.0, device="cuda")], 1), dt).t)
     xin = xfull.view(in_off, cin)
-    wp = ops.pack_conv_weight(wt, cin, blk_c, dt)
-    kwargs = {}
+    wp = ops.pack_conv_weight(wt, cin, blk_c, dt, pair=pair)   # pair: CTA-pair (cta_group::2) configuration
+    kwargs = {"cta_pair": pair}
     exp = ref_conv(x, wt, pad_t, pad_l)
     if bias:
         b = _ints((cout,), -4, 4, g)
@@ -457,7 +457,7 @@ def check_gather(patch=32, n_patches=37, seed=7):
     return bool(ok), 0.0, ""
 
 
-def check_conv_norm_on_load(n=2, cpre=64, cin=32, cout=32, h=37, w=45, T=2, blk_c=32, dt=FP16, act="relu", seed=13):
+def check_conv_norm_on_load(n=2, cpre=64, cin=32, cout=32, h=37, w=45, T=2, blk_c=32, dt=FP16, act="relu", seed=13, pair=False, cps=0):
     """conv3x3(pad 1) over cat(act(pre*scale+shift), x): the normalisation + activation of `pre` applied in-kernel"""
     g = torch.Generator(device="cuda").manual_seed(seed)
     tdt = torch_dtype(dt)
@@ -474,8 +474,8 @@ def check_conv_norm_on_load(n=2, cpre=64, cin=32, cout=32, h=37, w=45, T=2, blk_
     wt = (torch.randn((cout, cpre + cin, 3, 3), generator=g, device="cuda") * 0.05).to(tdt).float()
     exp = ref_conv(torch.cat(xs, 1), wt, 1, 1)
     out = P8.empty(n, cout, h, w, dt)
-    ops.conv_fwd(P8.from_nchw(x, dt) if cin else None, ops.pack_conv_weight(wt, cpre + cin, blk_c, dt), cout, 3, 3, 1, 1, dt,
-                 blk_c=blk_c, tiles_per_cta=T, out=out, pre=P8.from_nchw(pre, dt), pre_scale=sc.contiguous(),
+    ops.conv_fwd(P8.from_nchw(x, dt) if cin else None, ops.pack_conv_weight(wt, cpre + cin, blk_c, dt, pair=pair), cout, 3, 3, 1, 1,
+                 dt, blk_c=blk_c, tiles_per_cta=T, out=out, cta_pair=pair, ctas_per_sm=cps, pre=P8.from_nchw(pre, dt), pre_scale=sc.contiguous(),
                  pre_shift=sh.contiguous(), pre_act={"relu": ACT_RELU, "leaky": ACT_LEAKY, "none": ACT_NONE}[act])
     torch.cuda.synchronize()
     err = (out.to_nchw().double() - exp).abs().max().item()

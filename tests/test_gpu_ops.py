@@ -41,6 +41,16 @@ CONV_CASES = [
     dict(n=2, cin=16, cout=32, h=33, w=50, kh=7, kw=7, pad_t=3, pad_l=3, T=3, blk_c=16, stats=True, cps=4),
     dict(n=3, cin=128, cout=128, h=20, w=20, kh=3, kw=3, pad_t=1, pad_l=1, T=1, blk_c=32, stats=True, integer=False, cps=4),
     dict(n=2, cin=32, cout=16, h=16, w=24, kh=2, kw=2, pad_t=1, pad_l=1, T=3, blk_c=32, mask=True, addend=True, out32=True, cps=4),
+    # CTA-pair configuration (cta_group::2, M = 256 across two CTAs, each staging half of the weight columns)
+    dict(n=2, cin=64, cout=64, h=40, w=56, kh=3, kw=3, pad_t=1, pad_l=1, T=2, blk_c=32, pair=True),
+    dict(n=1, cin=32, cout=32, h=16, w=40, kh=3, kw=3, pad_t=1, pad_l=1, T=2, blk_c=32, bias=True, act=1, pair=True),  # odd grid
+    dict(n=2, cin=176, cout=64, h=48, w=72, kh=7, kw=7, pad_t=3, pad_l=3, T=3, blk_c=32, bias=True, act=1, integer=False, pair=True),
+    dict(n=3, cin=128, cout=128, h=36, w=36, kh=3, kw=3, pad_t=1, pad_l=1, T=2, blk_c=32, stats=True, integer=False, pair=True),
+    dict(n=2, cin=64, cout=64, h=24, w=48, kh=3, kw=3, pad_t=1, pad_l=1, T=3, blk_c=32, bias=True, act=1, head=True,
+         integer=False, pair=True),
+    dict(n=2, cin=64, cout=64, h=40, w=56, kh=3, kw=3, pad_t=1, pad_l=1, T=2, blk_c=16, bias=True, act=1, pair=True, cps=4),
+    dict(n=1, cin=48, cout=64, h=33, w=40, kh=7, kw=7, pad_t=3, pad_l=3, T=2, blk_c=16, stats=True, integer=False, pair=True,
+         cps=4),
 ]
 
 
@@ -60,7 +70,10 @@ def test_conv_with_upsample_on_load(kw):
 
 @pytest.mark.parametrize("kw", [dict(), dict(cpre=128, cin=48, cout=64, h=40, w=50), dict(cpre=256, cin=0, cout=256, h=20, w=20, blk_c=64),
                                 dict(cpre=64, cin=0, cout=16, h=9, w=70, T=3, dt=0, act="leaky"),
-                                dict(n=3, cpre=16, cin=16, cout=16, h=5, w=7, T=1, blk_c=16, act="none")],
+                                dict(n=3, cpre=16, cin=16, cout=16, h=5, w=7, T=1, blk_c=16, act="none"),
+                                dict(cpre=128, cin=48, cout=64, h=40, w=50, T=3, pair=True), dict(cpre=64, cin=0, cout=128, h=33, w=40, pair=True),
+                                dict(cpre=64, cin=32, cout=64, h=40, w=50, blk_c=16, cps=4),
+                                dict(cpre=128, cin=48, cout=64, h=40, w=50, blk_c=16, cps=4, pair=True)],
                          ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()) or "default")
 def test_conv_with_norm_on_load(kw):
     ok, err, msg = gc.check_conv_norm_on_load(**kw)

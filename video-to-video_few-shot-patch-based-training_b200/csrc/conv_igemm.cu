@@ -137,7 +137,7 @@ __device__ __forceinline__ int up_origin(int hr0, int hr_size, int lr_size) {
   return i0;
 }
 
-template <int T, int KB, int EW>
+template <int T, int KB, int EW, bool PAIR>
 // two (EW = 8) or four (EW = 4) co-resident CTAs per SM are essential (their MMA streams overlap): cap registers accordingly
 __global__ void __launch_bounds__(EW == 8 ? kMaxThreads : 192, PBT_MULTI_ISSUE ? 1 : (EW == 8 ? 2 : 4))
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapP, const ConvKParams p) {
@@ -153,16 +153,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   uint64_t* l_full = acc_full + 1;
   uint64_t* l_empty = l_full + 2;
   uint64_t* a_land = l_empty + 2;  // normalise-on-load: raw tile landed (TMA), not yet normalised
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_land + 2);
+  uint64_t* a_peer = a_land + 2;   // CTA-pair mode, leader only: the peer CTA's A stage / weight stage is ready
+  uint64_t* b_peer = a_peer + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_peer + 4);
   float* s_stats = reinterpret_cast<float*>(tmem_slot + 2);  // [8 warps][2][NC]
   float* s_head = s_stats + EW * 2 * p.NC;             // [T][4 quadrants][32 lanes][3]
-  float* s_norm = s_head + 3 * 4 * 32 * 3;                    // [2][pre_c] scale / shift of this image
+  float* s_norm = s_head + (EW == 8 ? 3 * 4 * 32 * 3 : 0);                    // [2][pre_c] scale / shift of this image
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   constexpr int NI = num_issuers(T);
   constexpr int kEpi0 = 32 * (1 + NI);  // first epilogue thread
 
+  // CTA-pair mode (PAIR): this CTA and its cluster peer (x-adjacent unit) run ONE M=256 cta_group::2 MMA stream issued
+  // by the leader (rank 0).  Each CTA loads its own activation tile and HALF of the weight columns, so an SM reads
+  // 4096 + 16*N bytes of operands per MMA instead of 4096 + 32*N (the shared-memory bound of the N = 64 layers).
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+  const int NCb = PAIR ? p.NC / 2 : p.NC;  // weight columns staged by this CTA
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const int n = blockIdx.x / tiles_per_img;
   const int rem = blockIdx.x - n * tiles_per_img;
@@ -192,13 +199,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       mbar_init(&l_full[i], 1);
       mbar_init(&l_empty[i], 32 * EW);
       mbar_init(&a_land[i], 1);
+      mbar_init(&a_peer[i], 1);
     }
+    for (int i = 0; i < 4; ++i) mbar_init(&b_peer[i], 1);
     fence_barrier_init();
     prefetch_tmap(&tmapA);
   }
-  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_pair(tmem_slot, (uint32_t)p.tmem_cols);
+    else tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer's barriers are initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) {
@@ -241,8 +254,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         // upsample transform — overlaps almost a whole block of MMAs instead of starting when the ring drains.
         const int gpre = min(p.b_stages, ngroups - 1);
         const int pib = min(p.blk_p, p.Cp - cb * p.blk_p);
-        const uint32_t chunk = (uint32_t)(pib * p.NC * 16);
-        const uint8_t* wsrc = p.wpack + (size_t)cb * ntaps * ((size_t)p.blk_p * p.NC * 16);
+        const uint32_t chunk = (uint32_t)(pib * NCb * 16);
+        const uint8_t* wsrc = p.wpack + (size_t)cb * ntaps * ((size_t)p.blk_p * p.NC * 16) + (size_t)crank * ntaps * chunk;
         for (int g = 0; g < ngroups; ++g, ++bi) {
           const int sb = bi % p.b_stages;
           const uint32_t pb = (uint32_t)(bi / p.b_stages) & 1u;
@@ -266,10 +279,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     // `if (elect_one())` the compiler built every descriptor in vector registers and paid ~10 R2UR moves per
     // group of MMAs, which made the issuing thread — not the tensor pipe — the bottleneck.)
     const bool leader = elect_one();
-    {
+    if (PAIR && crank != 0) {
+      // peer CTA of a pair: no MMAs here - forward "my stage is ready" to the leader's barriers, in the order the
+      // leader consumes them
+      int bi = 0;
+      for (int cb = 0; cb < p.n_blk; ++cb) {
+        const int sa = cb % p.a_stages;
+        mbar_wait(&a_full[sa], (uint32_t)(cb / p.a_stages) & 1u);
+        if (leader) mbar_arrive_remote(&a_peer[sa], 0);
+        for (int g = 0; g < ngroups; ++g, ++bi) {
+          const int sb = bi % p.b_stages;
+          mbar_wait(&b_full[sb], (uint32_t)(bi / p.b_stages) & 1u);
+          if (leader) mbar_arrive_remote(&b_peer[sb], 0);
+        }
+        __syncwarp();
+      }
+    } else {
       const uint32_t plane_bytes = (uint32_t)(p.BH * p.BW * 16);
       const uint32_t row_bytes = (uint32_t)(p.BW * 16);
-      const uint32_t b_kstride = (uint32_t)(p.NC * 16);
+      const uint32_t b_kstride = (uint32_t)(NCb * 16);
       // descriptor words: lo = addr>>4 | (LBO>>4)<<16 ; hi = SBO>>4 | version(1)<<14
       const uint32_t a_lo_const = ((plane_bytes >> 4) & 0x3FFF) << 16;
       const uint32_t a_hi = ((row_bytes >> 4) & 0x3FFF) | (1u << 14);
@@ -284,18 +312,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         const int sa = cb % p.a_stages;
         const uint32_t pa = (uint32_t)(cb / p.a_stages) & 1u;
         mbar_wait(&a_full[sa], pa);
+        if (PAIR) mbar_wait_cluster(&a_peer[sa], pa);
         tc_fence_after();
         if (cb == 0 && leader) PBT_STAMP(2);
         const uint32_t a_base = (smem_u32(sA + (size_t)sa * p.a_stage_bytes) >> 4) | a_lo_const;
         const int pib = min(p.blk_p, p.Cp - cb * p.blk_p);
         const int k16n = pib >> 1;
-        const uint32_t chunk16 = (uint32_t)(pib * p.NC);  // bytes/16 of one tap's weights
+        const uint32_t chunk16 = (uint32_t)(pib * NCb);  // bytes/16 of one tap's weights (this CTA's columns)
         int dy = 0, dx = 0;
         for (int g = 0; g < ngroups; ++g, ++bi) {
           const int sb = bi % p.b_stages;
           const uint32_t pb = (uint32_t)(bi / p.b_stages) & 1u;
           const int nt = min(p.b_group, ntaps - g * p.b_group);
           mbar_wait(&b_full[sb], pb);
+          if (PAIR) mbar_wait_cluster(&b_peer[sb], pb);
           tc_fence_after();
           uint32_t b_lo = (smem_u32(sB + (size_t)sb * p.b_stage_bytes) >> 4) | b_lo_const;
           for (int j = 0; j < nt; ++j) {
@@ -309,24 +339,37 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
                 if (k < k16n) {
 #pragma unroll
                   for (int t = 0; t < T; ++t)
-                    if (NI == 1 || t == ti)
-                      umma_f16(tmem_base + (uint32_t)t * acc_stride,
-                               desc64(a_tap + (uint32_t)(t * 8) + (uint32_t)k * a_kstep, a_hi),
-                               desc64(b_lo + (uint32_t)k * b_kstep, b_hi), idesc, (k == 0) ? first : 1u);
+                    if (NI == 1 || t == ti) {
+                      if (PAIR)
+                        umma_f16_pair(tmem_base + (uint32_t)t * acc_stride,
+                                      desc64(a_tap + (uint32_t)(t * 8) + (uint32_t)k * a_kstep, a_hi),
+                                      desc64(b_lo + (uint32_t)k * b_kstep, b_hi), idesc, (k == 0) ? first : 1u);
+                      else
+                        umma_f16(tmem_base + (uint32_t)t * acc_stride,
+                                 desc64(a_tap + (uint32_t)(t * 8) + (uint32_t)k * a_kstep, a_hi),
+                                 desc64(b_lo + (uint32_t)k * b_kstep, b_hi), idesc, (k == 0) ? first : 1u);
+                    }
                 }
               }
             }
             b_lo += chunk16;
             if (++dx == p.KW) { dx = 0; ++dy; }
           }
-          if (leader) umma_commit(&b_empty[sb]);
+          if (leader) {
+            if (PAIR) umma_commit_pair(&b_empty[sb]);
+            else umma_commit(&b_empty[sb]);
+          }
           __syncwarp();
         }
-        if (leader) umma_commit(&a_empty[sa]);
+        if (leader) {
+          if (PAIR) umma_commit_pair(&a_empty[sa]);
+          else umma_commit(&a_empty[sa]);
+        }
         __syncwarp();
       }
       if (leader) {
-        umma_commit(acc_full);
+        if (PAIR) umma_commit_pair(acc_full);
+        else umma_commit(acc_full);
         if (ti == 0) PBT_STAMP(3);
       }
       __syncwarp();
@@ -445,15 +488,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       // the image stay zero (the conv pads the NORMALISED tensor with zeros).
       const int et = threadIdx.x - kEpi0;
       for (int i = et; i < p.pre_c; i += 32 * EW) {
-        s_norm[i] = __ldg(&p.pre_scale[(long long)n * p.pre_c + i]);
-        s_norm[p.pre_c + i] = __ldg(&p.pre_shift[(long long)n * p.pre_c + i]);
+        const int nn = min(n, p.n_img - 1);  // (a pair's padding CTA past the last unit loads zeros and stores nothing)
+        s_norm[i] = __ldg(&p.pre_scale[(long long)nn * p.pre_c + i]);
+        s_norm[p.pre_c + i] = __ldg(&p.pre_shift[(long long)nn * p.pre_c + i]);
       }
       asm volatile("bar.sync 3, %0;" ::"r"(32 * EW) : "memory");
       const int npos = p.BH * p.BW;
-      int dsto[3];
-      bool ins[3];
+      constexpr int NQ = EW == 8 ? 3 : 4;  // tile positions per thread: BH*BW <= NQ * 32 * EW (host-checked)
+      int dsto[NQ];
+      bool ins[NQ];
 #pragma unroll
-      for (int qq = 0; qq < 3; ++qq) {
+      for (int qq = 0; qq < NQ; ++qq) {
         const int pos = et + qq * 32 * EW;
         const int r = pos / p.BW, c = pos - r * p.BW;
         const int Y = y0 - p.pad_t + r, X = x0 - p.pad_l + c;
@@ -485,7 +530,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
               }
               const __half2 zero2 = __float2half2_rn(0.f), leak2 = __float2half2_rn(0.2f);
 #pragma unroll
-              for (int qq = 0; qq < 3; ++qq) {
+              for (int qq = 0; qq < NQ; ++qq) {
                 if (!ins[qq]) continue;
                 uint4* ptr = reinterpret_cast<uint4*>(tile + (size_t)pln * a_plane + dsto[qq]);
                 uint4 u = *ptr;
@@ -502,7 +547,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
               continue;
             }
 #pragma unroll
-            for (int qq = 0; qq < 3; ++qq) {
+            for (int qq = 0; qq < NQ; ++qq) {
               if (!ins[qq]) continue;
               uint4* ptr = reinterpret_cast<uint4*>(tile + (size_t)pln * a_plane + dsto[qq]);
               float v[8];
@@ -546,7 +591,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       // one 16-column chunk of tile t: accumulator -> registers -> fused pointwise work -> stores
       auto chunk = [&](int t, int c0, float (&hd)[3], float* sacc) {
         const int x = x0 + 8 * t + tx;
-        const bool valid = (y < p.H) && (x < p.W);
+        const bool valid = (y < p.H) && (x < p.W) && (n < p.n_img);
         const long long pix = (long long)y * p.W + x;
         uint32_t raw[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * p.acc_stride + c0), raw);
@@ -678,7 +723,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
             }
           }
           const int x = x0 + 8 * t + tx;
-          if (y < p.H && x < p.W && half == 0) {
+          if (y < p.H && x < p.W && half == 0 && n < p.n_img) {
             float h0 = hd[0] + __ldg(&p.head_b[0]), h1 = hd[1] + __ldg(&p.head_b[1]), h2 = hd[2] + __ldg(&p.head_b[2]);
             if (p.head_tanh) {
               h0 = tanhf(h0);
@@ -709,7 +754,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       asm volatile("bar.sync 1, %0;" ::"r"(32 * EW) : "memory");
       const int e = threadIdx.x - kEpi0;  // 0..255
       float* dst = p.stats_partial + ((long long)n * tiles_per_img + rem) * 2 * NC;
-      for (int i = e; i < 2 * NC; i += 32 * EW) {
+      for (int i = e; i < 2 * NC && n < p.n_img; i += 32 * EW) {
         float acc = 0.f;
 #pragma unroll
         for (int w8 = 0; w8 < EW; ++w8) acc += s_stats[w8 * 2 * NC + i];
@@ -721,7 +766,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   if (threadIdx.x == kEpi0) PBT_STAMP(5);
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  if (PAIR) cluster_sync_all();  // both CTAs are done with each other's shared memory and barriers
+  if (warp == 1) {
+    if (PAIR) tmem_dealloc_pair(tmem_base, (uint32_t)p.tmem_cols);
+    else tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
   if (threadIdx.x == 0) PBT_STAMP(6);
 }
 
@@ -734,9 +783,32 @@ static int pow2_cols(int c) {
 template <int T, int KB, int EW>
 static int launch_conv(const CUtensorMap& tmap, const CUtensorMap& tmapP, const ConvKParams& p, int grid, uint32_t smem_bytes,
                        cudaStream_t stream) {
-  PBT_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<T, KB, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-  conv_igemm_kernel<T, KB, EW><<<grid, conv_threads(T, EW), smem_bytes, stream>>>(tmap, tmapP, p);
+  PBT_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<T, KB, EW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  conv_igemm_kernel<T, KB, EW, false><<<grid, conv_threads(T, EW), smem_bytes, stream>>>(tmap, tmapP, p);
   PBT_CUDA_CHECK(cudaGetLastError());
+  return PBT_OK;
+}
+
+// CTA-pair configuration: clusters of two x-adjacent units (grid rounded up to even; a padding CTA loads zeros).
+template <int T, int KB, int EW>
+static int launch_conv_pair(const CUtensorMap& tmap, const CUtensorMap& tmapP, const ConvKParams& p, int grid, uint32_t smem_bytes,
+                            cudaStream_t stream) {
+  auto kfn = conv_igemm_kernel<T, KB, EW, true>;
+  PBT_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)((grid + 1) & ~1), 1, 1);
+  cfg.blockDim = dim3((unsigned)conv_threads(T, EW), 1, 1);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PBT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kfn, tmap, tmapP, p));
   return PBT_OK;
 }
 
@@ -812,7 +884,16 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
   PBT_REQUIRE(p.BW <= 32, "conv: haloed tile wider than 32 pixels (reduce tiles_per_cta)");
   p.tiles_x = ceil_div(p.W, 8 * T);
   p.tiles_y = ceil_div(p.H, 16);
-  p.idesc = make_idesc_f16(128, p.NC, d->dtype == PBT_BF16 ? 1 : 0, 0, 0);
+  const int pair = d->cta_pair ? 1 : 0;
+  if (pair) {
+    // instantiated pair configurations: default footprint (blk_c 32, T 2|3) and small footprint (blk_c 16, T 2)
+    PBT_REQUIRE(!up && p.NC % 32 == 0, "conv: cta_pair needs cout % 32 == 0 and no upsample-on-load");
+    if (d->ctas_per_sm == 4)
+      PBT_REQUIRE(d->blk_c == 16 && T == 2 && p.NC <= 64, "conv: cta_pair + ctas_per_sm=4 needs blk_c 16, tiles_per_cta 2, cout <= 64");
+    else
+      PBT_REQUIRE(d->blk_c == 32 && (T == 2 || T == 3), "conv: cta_pair needs blk_c 32 and tiles_per_cta 2 or 3");
+  }
+  p.idesc = make_idesc_f16(pair ? 256 : 128, p.NC, d->dtype == PBT_BF16 ? 1 : 0, 0, 0);
   p.a_stage_bytes = round_up((uint32_t)(p.blk_p * p.BH * p.BW * 16), 128);
   p.LBH = (p.BH + 1) / 2 + 2;
   p.LBW = (p.BW + 1) / 2 + 2;
@@ -847,13 +928,13 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
   // shared memory -> four co-resident CTAs); shapes that do not fit it run the default configuration.
   PBT_REQUIRE(d->ctas_per_sm == 0 || d->ctas_per_sm == 2 || d->ctas_per_sm == 4, "conv: ctas_per_sm must be 0, 2 or 4");
   const uint32_t a_total = (uint32_t)p.a_stages * p.a_stage_bytes + 2 * p.l_stage_bytes;
-  const uint32_t chunk = (uint32_t)(p.blk_p * p.NC * 16);  // one tap of one channel block
+  const uint32_t chunk = (uint32_t)(p.blk_p * (pair ? p.NC / 2 : p.NC) * 16);  // one tap of one channel block (this CTA's columns)
   const int ntaps = p.KH * p.KW;
-  int ew = (d->ctas_per_sm == 4 && !up && !has_pre && p.tmem_cols <= 128) ? 4 : 8;  // epilogue warps
+  int ew = (d->ctas_per_sm == 4 && !up && (!has_pre || p.BH * p.BW <= 4 * 128) && p.tmem_cols <= 128) ? 4 : 8;  // epilogue warps
   uint32_t smem_bytes = 0;
   for (;;) {
     const uint32_t tail = 8u * (2 * 2 + 2 * 8 + 1) + 16 + (uint32_t)(ew * 2 * p.NC * 4) + (ew == 8 ? 3 * 4 * 32 * 3 * 4 : 0) +
-                          8 * 6 + (uint32_t)(2 * p.pre_c * 4) + 128;
+                          8 * 12 + (uint32_t)(2 * p.pre_c * 4) + 128;
     const uint32_t budget = ew == 4 ? 55 * 1024 : 112 * 1024;
     int group = (int)((ew == 4 ? 8192u : 16384u) / chunk);
     if (group < 1) group = 1;
@@ -870,6 +951,7 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
     p.b_stage_bytes = round_up((uint32_t)group * chunk, 128);
     smem_bytes = a_total + (uint32_t)p.b_stages * p.b_stage_bytes + tail;
     if (ew == 4 && smem_bytes > 56 * 1024) {
+      PBT_REQUIRE(!pair, "conv: cta_pair with ctas_per_sm=4 does not fit 56 KB of shared memory");
       ew = 8;
       continue;
     }
@@ -892,6 +974,12 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
 
   const int grid = p.n_img * p.tiles_x * p.tiles_y;
   const int kb = d->blk_c / 16;
+  if (pair) {
+    PBT_REQUIRE((ew == 4) == (d->ctas_per_sm == 4), "conv: cta_pair + ctas_per_sm=4 shape does not fit the small footprint");
+    if (ew == 4) return launch_conv_pair<2, 1, 4>(tmap, tmapP, p, grid, smem_bytes, stream);
+    return T == 2 ? launch_conv_pair<2, 2, 8>(tmap, tmapP, p, grid, smem_bytes, stream)
+                  : launch_conv_pair<3, 2, 8>(tmap, tmapP, p, grid, smem_bytes, stream);
+  }
   switch (T) {
     case 1: return launch_conv_kb<1>(kb, ew, tmap, tmapP, p, grid, smem_bytes, stream);
     case 2: return launch_conv_kb<2>(kb, ew, tmap, tmapP, p, grid, smem_bytes, stream);

@@ -4,6 +4,7 @@
 // including the two re-indexings the native path needs:
 //   * space-to-depth form of the stride-2 3x3 convs (2x2 stride-1 kernel over 4*ci channels)
 //   * dgrad form (input/output channels transposed, taps flipped) of the (possibly space-to-depth) kernel
+//   * CTA-pair form (mode bit 2): w[cin_block][half][tap][k/8][n/2][k%8] for the cta_group::2 conv configuration
 // Training re-packs after every optimiser step, so this replaces ~250 tiny tensor-library launches per step.
 #include "internal.h"
 #include "ptx.cuh"
@@ -53,7 +54,14 @@ __global__ void pack_weights_kernel(const pbt_pack_job_t* __restrict__ jobs) {
     const int ty = tap / vkw, tx = tap - ty * vkw;
     float v = 0.f;
     if (n < n_lim && k < pi) v = dgrad ? virt(j, k, n, vkh - 1 - ty, vkw - 1 - tx) : virt(j, n, k, ty, tx);
-    const long long off = (long long)cb * full + (long long)tap * per_tap + (long long)k8 * j.n_out * 8 + n * 8 + kk;
+    long long off;
+    if (j.mode & 4) {
+      // CTA-pair layout [cb][half][tap][k8][n/2][8]: each CTA of a pair streams the taps of ITS half of the output columns
+      const int nh = j.n_out >> 1, half = n / nh, nn = n - half * nh;
+      off = (long long)cb * full + (long long)half * taps * kc * nh + (long long)tap * kc * nh + (long long)k8 * nh * 8 + nn * 8 + kk;
+    } else {
+      off = (long long)cb * full + (long long)tap * per_tap + (long long)k8 * j.n_out * 8 + n * 8 + kk;
+    }
     if (j.dtype == PBT_BF16) static_cast<__nv_bfloat16*>(j.dst)[off] = __float2bfloat16_rn(v);
     else static_cast<__half*>(j.dst)[off] = __float2half_rn(v);
   }

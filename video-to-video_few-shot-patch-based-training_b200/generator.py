@@ -258,6 +258,15 @@ class _Engine:
     SMOOTH_BLK = 16
     SMOOTH_T = 2
 
+    def _T11(self, w: int) -> int:
+        t = self._T(3, w)
+        return 2 if (t == 1 and self.pair11()) else t   # the pair configuration is built for 2 or 3 tiles per CTA
+
+    def pair11(self) -> bool:
+        """conv11 (the dominant layer, cout 64) runs in the CTA-pair configuration: one M=256 cta_group::2 MMA stream per
+        two CTAs, each staging half of the weight columns (+3-5 % on that layer, tools/conv_occ.py)"""
+        return self.gen.filters[5] % 32 == 0
+
     def _blk(self, cin: int) -> int:
         return 32 if cin % 32 == 0 or cin > 32 else 16
 
@@ -279,9 +288,10 @@ class _Engine:
         f = g.filters
         pk = ops.WeightPacker(self.device)
 
-        def fwd(name, conv, k_pad, s2d=False, blk=None):
+        def fwd(name, conv, k_pad, s2d=False, blk=None, pair=False):
             co = conv.weight.shape[0]
-            pk.add(name, conv.weight.detach(), s2d=s2d, k_pad=k_pad, n_out=co, n_keep=co, blk_c=blk or self._blk(k_pad), dt=dt)
+            pk.add(name, conv.weight.detach(), s2d=s2d, k_pad=k_pad, n_out=co, n_keep=co, blk_c=blk or self._blk(k_pad), dt=dt,
+                   pair=pair)
 
         def dgr(name, conv, s2d=False, keep=None):
             co, ci = conv.weight.shape[0], conv.weight.shape[1]
@@ -302,7 +312,7 @@ class _Engine:
         fwd("up2", g.upsample2[1], 2 * f[2])
         fwd("up1", g.upsample1[1], f[4] + f[1])
         # conv11 input order = [out(f4), conv0(f0), x(cin)] — identical to the reference cat (:230), zero padded
-        fwd("conv11", g.conv11[0], f[4] + f[0] + cp)
+        fwd("conv11", g.conv11[0], f[4] + f[0] + cp, pair=self.pair11())
         fwd("smooth0", g.smoothers[0], f[5], blk=self.SMOOTH_BLK)
         fwd("smooth3", g.smoothers[3], f[5], blk=self.SMOOTH_BLK)
         if with_dgrad:
@@ -422,11 +432,11 @@ class _Engine:
             e0.record()
         if nol_11:
             ops.conv_fwd(ws.cat11.view(f[4], f[0] + cp), W["conv11"], f[5], 7, 7, 3, 3, dt, blk_c=32,
-                         tiles_per_cta=self._T(3, w), bias=W["b11"], act=ACT_RELU, out=ws.c11, pre=ws.rawU1,
-                         pre_scale=st["scale"], pre_shift=st["shift"], pre_act=ACT_RELU)
+                         tiles_per_cta=self._T11(w), bias=W["b11"], act=ACT_RELU, out=ws.c11, pre=ws.rawU1,
+                         pre_scale=st["scale"], pre_shift=st["shift"], pre_act=ACT_RELU, cta_pair=self.pair11())
         else:
-            ops.conv_fwd(ws.cat11, W["conv11"], f[5], 7, 7, 3, 3, dt, blk_c=32, tiles_per_cta=self._T(3, w), bias=W["b11"],
-                         act=ACT_RELU, out=ws.c11)
+            ops.conv_fwd(ws.cat11, W["conv11"], f[5], 7, 7, 3, 3, dt, blk_c=32, tiles_per_cta=self._T11(w), bias=W["b11"],
+                         act=ACT_RELU, out=ws.c11, cta_pair=self.pair11())
         if ev is not None:
             e1.record()
             ev.append((e0, e1))

@@ -21,8 +21,9 @@ __all__ = [
 
 
 # ----------------------------------------------------------------------------- weights
-def pack_conv_weight(w: torch.Tensor, cin_pad: int, blk_c: int, dt: int) -> torch.Tensor:
-    """[cout, cin, kh, kw] fp32 -> flat 16-bit buffer  w[cb][tap][k/8][cout][k%8]  (see include/pbt.h)."""
+def pack_conv_weight(w: torch.Tensor, cin_pad: int, blk_c: int, dt: int, pair: bool = False) -> torch.Tensor:
+    """[cout, cin, kh, kw] fp32 -> flat 16-bit buffer  w[cb][tap][k/8][cout][k%8]  (see include/pbt.h);
+    pair=True: the CTA-pair layout w[cb][half][tap][k/8][cout/2][k%8]."""
     cout, cin, kh, kw = w.shape
     assert cin_pad % 16 == 0 and cin_pad >= cin and cout % 16 == 0
     wp = w.new_zeros((cout, cin_pad, kh, kw))
@@ -32,6 +33,8 @@ def pack_conv_weight(w: torch.Tensor, cin_pad: int, blk_c: int, dt: int) -> torc
     for c0 in range(0, cin_pad, blk_c):
         c1 = min(c0 + blk_c, cin_pad)
         blk = t[:, c0:c1].reshape(kh * kw, (c1 - c0) // 8, 8, cout).permute(0, 1, 3, 2)  # [tap][k8][co][8]
+        if pair:
+            blk = blk.reshape(kh * kw, (c1 - c0) // 8, 2, cout // 2, 8).permute(2, 0, 1, 3, 4)  # [half][tap][k8][co/2][8]
         chunks.append(blk.reshape(-1))
     return torch.cat(chunks).to(nv.torch_dtype(dt)).contiguous()
 
@@ -78,12 +81,12 @@ class WeightPacker:
         self._max = 0
 
     def add(self, name: str, param: torch.Tensor, *, s2d=False, dgrad=False, k_pad: int, n_out: int, n_keep: int, blk_c: int,
-            dt: int) -> torch.Tensor:
+            dt: int, pair: bool = False) -> torch.Tensor:
         co, ci, kh, kw = param.shape
         taps = 4 if s2d else kh * kw
         dst = torch.empty(taps * k_pad * n_out, dtype=nv.torch_dtype(dt), device=self.device)
         assert param.is_contiguous() and param.dtype in (torch.float32, torch.float16)
-        self.jobs.append(nv.PackJob(param.data_ptr(), dst.data_ptr(), co, ci, kh, kw, int(s2d) | (int(dgrad) << 1), k_pad, n_out,
+        self.jobs.append(nv.PackJob(param.data_ptr(), dst.data_ptr(), co, ci, kh, kw, int(s2d) | (int(dgrad) << 1) | (int(pair) << 2), k_pad, n_out,
                                     n_keep, blk_c, dt, int(param.dtype == torch.float16), 0))
         self._src = getattr(self, "_src", []) + [param]   # keep the parameters alive / pointers stable
         self.out[name] = dst
@@ -108,7 +111,7 @@ def conv_fwd(x: P8, wpack: torch.Tensor, cout: int, kh: int, kw: int, pad_t: int
              blk_c: int = 32, tiles_per_cta: int = 2, bias=None, act: int = ACT_NONE, post_scale=None, post_shift=None,
              mask: P8 | None = None, addend32=None, out32=None, out: P8 | None = None, stats_partial=None,
              head_w=None, head_b=None, head_out=None, head_tanh: bool = True, upsample2x: bool = False, debug_flags: int = 0,
-             debug_buf=None, pre: P8 | None = None, pre_scale=None, pre_shift=None, pre_act: int = ACT_NONE, ctas_per_sm: int = 0) -> None:
+             debug_buf=None, pre: P8 | None = None, pre_scale=None, pre_shift=None, pre_act: int = ACT_NONE, ctas_per_sm: int = 0, cta_pair: bool = False) -> None:
     """`pre` (raw output of the previous conv) supplies the first channels, normalised + activated on load; `x` (may be
     None then) the remaining ones."""
     d = nv.ConvDesc()
@@ -116,6 +119,7 @@ def conv_fwd(x: P8, wpack: torch.Tensor, cout: int, kh: int, kw: int, pad_t: int
     d.pre = act_or_null(pre)
     d.pre_scale, d.pre_shift, d.pre_act = ptr(pre_scale), ptr(pre_shift), pre_act
     d.ctas_per_sm = ctas_per_sm
+    d.cta_pair = int(cta_pair)
     d.wpack = wpack.data_ptr()
     d.cout, d.kh, d.kw, d.pad_t, d.pad_l = cout, kh, kw, pad_t, pad_l
     d.blk_c, d.tiles_per_cta, d.dtype = blk_c, tiles_per_cta, dt
