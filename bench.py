@@ -319,9 +319,10 @@ def run_native(args):
     tp = os.path.join(ROOT, "profiles", "conv11_traffic.json")
     if os.path.exists(tp):
         with open(tp) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")   # captured on a one-frame launch
+            tj = json.load(f)
+        traffic = tj.get("dram_bytes_per_launch")   # ncu capture of one conv11 launch (tj["frames_per_launch"] frames)
         if traffic is not None:
-            traffic *= frames_per_launch
+            traffic = int(traffic * frames_per_launch / max(1, int(tj.get("frames_per_launch", 1))))
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -333,7 +334,7 @@ def run_native(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": F * H * W * CIN, "d2h_bytes_per_step": F * H * W * 3,
                 "ms_per_step": ms_e2e / args.steps, "host_checksum": checksum},
         "gpu_launches": launches,
-        "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (conv11 7x7, 163->64)", "achieved": achieved, "peak": peak_tf,
+        "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (conv11 7x7, 163->64, CTA-pair configuration, norm+ReLU of up1 on load)", "achieved": achieved, "peak": peak_tf,
                      "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None, "traffic": traffic,
                      "peak_source": f"{peak_src} bf16_tflops_sustained", "launch_ms": k_ms, "launches_timed": len(kt),
                      "frames_per_launch": frames_per_launch},
