@@ -118,6 +118,8 @@ typedef struct {
   int32_t      cta_pair;     /* 1: CTA-pair configuration (clusters of two CTAs run one M=256 cta_group::2 MMA stream, each CTA
                               * stages half of the weight columns); `wpack` must be in the pair layout (pack mode bit 2).
                               * Needs blk_c 32, tiles_per_cta 2 or 3, cout % 32 == 0; not combinable with upsample2x */
+  int32_t      concurrent;   /* 1: kernels of other streams are expected to run next to this launch: never use persistent CTAs
+                              * (they would hold every SM slot / tensor-memory column until the launch ends) */
   int32_t      debug_flags;  /* bring-up only; 0 in production */
   void*        debug_buf;    /* bring-up only: int64[grid][8] per-CTA phase timestamps, NULL in production */
 } pbt_conv_desc_t;

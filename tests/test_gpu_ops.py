@@ -51,6 +51,15 @@ CONV_CASES = [
     dict(n=2, cin=64, cout=64, h=40, w=56, kh=3, kw=3, pad_t=1, pad_l=1, T=2, blk_c=16, bias=True, act=1, pair=True, cps=4),
     dict(n=1, cin=48, cout=64, h=33, w=40, kh=7, kw=7, pad_t=3, pad_l=3, T=2, blk_c=16, stats=True, integer=False, pair=True,
          cps=4),
+    # more units than one wave of CTAs: every CTA walks several units (persistent loop, barrier phases carried over)
+    dict(n=2, cin=64, cout=128, h=272, w=480, kh=3, kw=3, pad_t=1, pad_l=1, T=2, blk_c=32, stats=True, integer=False),
+    dict(n=3, cin=32, cout=64, h=200, w=330, kh=3, kw=3, pad_t=1, pad_l=1, T=2, blk_c=16, bias=True, act=1, head=True,
+         integer=False, cps=4),
+    dict(n=2, cin=16, cout=32, h=300, w=500, kh=7, kw=7, pad_t=3, pad_l=3, T=3, blk_c=16, stats=True, cps=4),
+    dict(n=2, cin=48, cout=64, h=250, w=410, kh=7, kw=7, pad_t=3, pad_l=3, T=3, blk_c=32, bias=True, act=1, integer=False,
+         pair=True),
+    dict(n=2, cin=32, cout=32, h=260, w=400, kh=3, kw=3, pad_t=1, pad_l=1, T=2, blk_c=32, mask=True, addend=True, out32=True,
+         store16=False),
 ]
 
 
@@ -61,7 +70,8 @@ def test_conv_fwd(case):
 
 
 @pytest.mark.parametrize("kw", [dict(), dict(cin=192, cout=128, h=16, w=16), dict(n=3, cin=256, cout=128, h=10, w=12),
-                                dict(cin=64, cout=64, h=24, w=24, T=3, dt=0), dict(cin=32, cout=16, h=5, w=7, T=1)],
+                                dict(cin=64, cout=64, h=24, w=24, T=3, dt=0), dict(cin=32, cout=16, h=5, w=7, T=1),
+                                dict(n=2, cin=64, cout=64, h=136, w=200, T=2)],
                          ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()) or "default")
 def test_conv_with_upsample_on_load(kw):
     ok, err, msg = gc.check_conv_upsample(**kw)
@@ -73,7 +83,8 @@ def test_conv_with_upsample_on_load(kw):
                                 dict(n=3, cpre=16, cin=16, cout=16, h=5, w=7, T=1, blk_c=16, act="none"),
                                 dict(cpre=128, cin=48, cout=64, h=40, w=50, T=3, pair=True), dict(cpre=64, cin=0, cout=128, h=33, w=40, pair=True),
                                 dict(cpre=64, cin=32, cout=64, h=40, w=50, blk_c=16, cps=4),
-                                dict(cpre=128, cin=48, cout=64, h=40, w=50, blk_c=16, cps=4, pair=True)],
+                                dict(cpre=128, cin=48, cout=64, h=40, w=50, blk_c=16, cps=4, pair=True),
+                                dict(n=2, cpre=64, cin=32, cout=64, h=270, w=470, T=3, pair=True), dict(n=3, cpre=64, cin=0, cout=64, h=240, w=400)],
                          ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()) or "default")
 def test_conv_with_norm_on_load(kw):
     ok, err, msg = gc.check_conv_norm_on_load(**kw)

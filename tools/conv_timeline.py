@@ -49,3 +49,9 @@ for name, cin, cout, k, h, w, T, blk, stats, *rest in cases:
         m = sm == s
         span.append((int(m.sum()), float(d[m, 6].max() - d[m, 0].min())))
     print("     per-SM (n_ctas, span cycles) samples:", span)
+    # average number of co-resident CTAs per SM = sum of CTA lifetimes / busy span (block-launch gaps show up here)
+    conc = []
+    for s_ in sm.unique().tolist():
+        m = sm == s_
+        conc.append(float((d[m, 6] - d[m, 0]).sum() / (d[m, 6].max() - d[m, 0].min())))
+    print(f"     mean co-resident CTAs per SM: {sum(conc) / len(conc):.2f}; median CTA lifetime {float((d[:, 6] - d[:, 0]).median()):.0f} cycles")

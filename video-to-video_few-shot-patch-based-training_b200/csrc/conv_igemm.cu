@@ -56,6 +56,7 @@ struct ConvKParams {
   float* head_out;
   int head_tanh;
   int up, LH, LW, LBH, LBW;   // upsample-on-load: low-res dims and staging box (pixels)
+  int n_units;                // work units (CTA tiles of T sub-tiles) of the launch; CTAs are persistent over them
   int nrm, nblk0, pre_c, pre_act;  // normalise-on-load: the first nblk0 channel blocks come from `pre` and get act(x*s+t)
   const float* pre_scale;
   const float* pre_shift;
@@ -155,7 +156,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   uint64_t* a_land = l_empty + 2;  // normalise-on-load: raw tile landed (TMA), not yet normalised
   uint64_t* a_peer = a_land + 2;   // CTA-pair mode, leader only: the peer CTA's A stage / weight stage is ready
   uint64_t* b_peer = a_peer + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_peer + 4);
+  uint64_t* acc_empty = b_peer + 4;  // persistent CTAs: the epilogue has drained the accumulators of the previous unit
+  uint64_t* acc_peer = acc_empty + 1;  // CTA-pair mode, leader only: the peer's accumulators are drained too
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_peer + 1);
   float* s_stats = reinterpret_cast<float*>(tmem_slot + 2);  // [8 warps][2][NC]
   float* s_head = s_stats + EW * 2 * p.NC;             // [T][4 quadrants][32 lanes][3]
   float* s_norm = s_head + (EW == 8 ? 3 * 4 * 32 * 3 : 0);                    // [2][pre_c] scale / shift of this image
@@ -171,11 +174,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
   const int NCb = PAIR ? p.NC / 2 : p.NC;  // weight columns staged by this CTA
   const int tiles_per_img = p.tiles_x * p.tiles_y;
-  const int n = blockIdx.x / tiles_per_img;
-  const int rem = blockIdx.x - n * tiles_per_img;
-  const int tyi = rem / p.tiles_x;
-  const int txi = rem - tyi * p.tiles_x;
-  const int x0 = txi * 8 * T;
+  // Persistent CTAs: the grid is one wave (SMs x co-resident CTAs) and every CTA walks the units
+  // blockIdx.x, blockIdx.x + gridDim.x, ...  Barrier stages / parities run on counters that continue across units, so the
+  // producer prefetches the next unit's first tiles while the current unit's last MMAs and epilogue run, and the
+  // per-CTA launch gap + setup (~10-25 % of a short CTA's life, tools/conv_timeline.py) is paid once.
+#define PBT_UNIT_GEOM(unit)                      \
+  const int n = (unit) / tiles_per_img;          \
+  const int rem = (unit) - n * tiles_per_img;    \
+  const int tyi = rem / p.tiles_x;               \
+  const int txi = rem - tyi * p.tiles_x;         \
+  const int x0 = txi * 8 * T;                    \
   const int y0 = tyi * 16;
   const int ntaps = p.KH * p.KW;
   const int ngroups = (ntaps + p.b_group - 1) / p.b_group;
@@ -202,6 +210,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       mbar_init(&a_peer[i], 1);
     }
     for (int i = 0; i < 4; ++i) mbar_init(&b_peer[i], 1);
+    mbar_init(acc_empty, 32 * EW);
+    mbar_init(acc_peer, 1);
     fence_barrier_init();
     prefetch_tmap(&tmapA);
   }
@@ -226,17 +236,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   if (warp == 0) {
     // ------------------------------------------------------------ producer
     if (elect_one()) {
+     int bi = 0;   // running B-group counter (continues across units)
+     int cbt = 0;  // running channel-block counter at the start of the unit
+     for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x, cbt += p.n_blk) {
+      PBT_UNIT_GEOM(unit)
+      (void)rem;
       // activation tile (or, with upsample-on-load, its low-res footprint) of channel block `cb`
       auto issue_act = [&](int cb) {
+        const int c = cbt + cb;
         if (p.up) {
-          const int sl = cb & 1;
-          mbar_wait(&l_empty[sl], ((uint32_t)(cb >> 1) & 1u) ^ 1u);
+          const int sl = c & 1;
+          mbar_wait(&l_empty[sl], ((uint32_t)(c >> 1) & 1u) ^ 1u);
           mbar_arrive_expect_tx(&l_full[sl], (uint32_t)(p.blk_p * p.LBH * p.LBW * 16));
           tma_load_4d(sL + (size_t)sl * p.l_stage_bytes, &tmapA, &l_full[sl], up_origin(x0 - p.pad_l, p.W, p.LW) * 8,
                       up_origin(y0 - p.pad_t, p.H, p.LH), cb * p.blk_p, n);
         } else {
-          const int sa = cb % p.a_stages;
-          mbar_wait(&a_empty[sa], ((uint32_t)(cb / p.a_stages) & 1u) ^ 1u);
+          const int sa = c % p.a_stages;
+          mbar_wait(&a_empty[sa], ((uint32_t)(c / p.a_stages) & 1u) ^ 1u);
           uint64_t* bar = p.nrm ? &a_land[sa] : &a_full[sa];
           mbar_arrive_expect_tx(bar, (uint32_t)(p.blk_p * p.BH * p.BW * 16));
           if (cb < p.nblk0)
@@ -246,7 +262,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
                         (cb - p.nblk0) * p.blk_p, n);
         }
       };
-      int bi = 0;  // running B-group counter
       issue_act(0);
       for (int cb = 0; cb < p.n_blk; ++cb) {
         // Block cb+1 is requested once the weight ring of block cb is primed (b_stages groups in flight): by then
@@ -268,6 +283,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
           if (g == gpre && cb + 1 < p.n_blk && p.a_stages > 1) issue_act(cb + 1);
         }
       }
+     }
     }
   } else if (warp <= NI) {
     // ------------------------------------------------------------ MMA issuer(s)
@@ -282,17 +298,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     if (PAIR && crank != 0) {
       // peer CTA of a pair: no MMAs here - forward "my stage is ready" to the leader's barriers, in the order the
       // leader consumes them
-      int bi = 0;
-      for (int cb = 0; cb < p.n_blk; ++cb) {
-        const int sa = cb % p.a_stages;
-        mbar_wait(&a_full[sa], (uint32_t)(cb / p.a_stages) & 1u);
-        if (leader) mbar_arrive_remote(&a_peer[sa], 0);
-        for (int g = 0; g < ngroups; ++g, ++bi) {
-          const int sb = bi % p.b_stages;
-          mbar_wait(&b_full[sb], (uint32_t)(bi / p.b_stages) & 1u);
-          if (leader) mbar_arrive_remote(&b_peer[sb], 0);
+      int bi = 0, cbt = 0, it = 0;
+      for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x, cbt += p.n_blk, ++it) {
+        if (it > 0) {  // this CTA's accumulators of the previous unit are drained -> tell the leader
+          mbar_wait(acc_empty, (uint32_t)(it - 1) & 1u);
+          if (leader) mbar_arrive_remote(acc_peer, 0);
         }
-        __syncwarp();
+        for (int cb = 0; cb < p.n_blk; ++cb) {
+          const int c = cbt + cb;
+          const int sa = c % p.a_stages;
+          mbar_wait(&a_full[sa], (uint32_t)(c / p.a_stages) & 1u);
+          if (leader) mbar_arrive_remote(&a_peer[sa], 0);
+          for (int g = 0; g < ngroups; ++g, ++bi) {
+            const int sb = bi % p.b_stages;
+            mbar_wait(&b_full[sb], (uint32_t)(bi / p.b_stages) & 1u);
+            if (leader) mbar_arrive_remote(&b_peer[sb], 0);
+          }
+          __syncwarp();
+        }
       }
     } else {
       const uint32_t plane_bytes = (uint32_t)(p.BH * p.BW * 16);
@@ -307,10 +330,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       const uint32_t b_kstep = (2u * b_kstride) >> 4;
       const uint32_t acc_stride = (uint32_t)p.acc_stride;
       const uint32_t idesc = p.idesc;
-      int bi = 0;
+      int bi = 0, cbt = 0, it = 0;
+      for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x, cbt += p.n_blk, ++it) {
+      if (it > 0) {  // the accumulators are overwritten: wait until the epilogue has read the previous unit's
+        mbar_wait(acc_empty, (uint32_t)(it - 1) & 1u);
+        if (PAIR) mbar_wait_cluster(acc_peer, (uint32_t)(it - 1) & 1u);
+        tc_fence_after();
+      }
       for (int cb = 0; cb < p.n_blk; ++cb) {
-        const int sa = cb % p.a_stages;
-        const uint32_t pa = (uint32_t)(cb / p.a_stages) & 1u;
+        const int sa = (cbt + cb) % p.a_stages;
+        const uint32_t pa = (uint32_t)((cbt + cb) / p.a_stages) & 1u;
         mbar_wait(&a_full[sa], pa);
         if (PAIR) mbar_wait_cluster(&a_peer[sa], pa);
         tc_fence_after();
@@ -373,6 +402,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         if (ti == 0) PBT_STAMP(3);
       }
       __syncwarp();
+      }
     }
   } else {
     // ------------------------------------------------------------ epilogue (8 warps)
@@ -385,6 +415,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     const int dt = p.dt;
     const bool do_stats = p.stats_partial != nullptr;
     float* my_stats = s_stats + (size_t)ew * 2 * NC;
+    int cbt = 0, it = 0;
+    for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x, cbt += p.n_blk, ++it) {
+    PBT_UNIT_GEOM(unit)
     if (do_stats) {
       for (int i = lane; i < 2 * NC; i += 32) my_stats[i] = 0.f;
       __syncwarp();
@@ -429,9 +462,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       }
       const int l_plane = p.LBH * p.LBW * 16, a_plane = npos * 16;
       for (int cb = 0; cb < p.n_blk; ++cb) {
-        const int sa = cb % p.a_stages, sl = cb & 1;
-        mbar_wait(&l_full[sl], (uint32_t)(cb >> 1) & 1u);
-        mbar_wait(&a_empty[sa], ((uint32_t)(cb / p.a_stages) & 1u) ^ 1u);
+        const int c = cbt + cb;
+        const int sa = c % p.a_stages, sl = c & 1;
+        mbar_wait(&l_full[sl], (uint32_t)(c >> 1) & 1u);
+        mbar_wait(&a_empty[sa], ((uint32_t)(c / p.a_stages) & 1u) ^ 1u);
         const uint8_t* src = sL + (size_t)sl * p.l_stage_bytes;
         uint8_t* dstA = sA + (size_t)sa * p.a_stage_bytes;
 #pragma unroll
@@ -507,8 +541,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       }
       const int a_plane = npos * 16;
       for (int cb = 0; cb < p.n_blk; ++cb) {
-        const int sa = cb % p.a_stages;
-        mbar_wait(&a_land[sa], (uint32_t)(cb / p.a_stages) & 1u);
+        const int sa = (cbt + cb) % p.a_stages;
+        mbar_wait(&a_land[sa], (uint32_t)((cbt + cb) / p.a_stages) & 1u);
         if (cb < p.nblk0) {
           uint8_t* tile = sA + (size_t)sa * p.a_stage_bytes;
           for (int pln = 0; pln < p.blk_p; ++pln) {
@@ -567,8 +601,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         mbar_arrive(&a_full[sa]);
       }
     }
-    if (p.debug_flags & 64) mbar_wait(acc_full, 0);
-    else mbar_wait_backoff(acc_full, 0, 256);
+    mbar_wait_backoff(acc_full, (uint32_t)it & 1u, 256);
     tc_fence_after();
     if (threadIdx.x == kEpi0) PBT_STAMP(4);
 
@@ -750,6 +783,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       case kFMask | kFAddend | kFOut32: epi_loop(std::integral_constant<uint32_t, kFMask | kFAddend | kFOut32>{}); break;
       default: epi_loop(std::integral_constant<uint32_t, kFGeneric>{}); break;
     }
+    // this thread's accumulator reads are complete: the MMA warp may start the next unit
+    tc_fence_before();
+    mbar_arrive(acc_empty);
     if (do_stats) {
       asm volatile("bar.sync 1, %0;" ::"r"(32 * EW) : "memory");
       const int e = threadIdx.x - kEpi0;  // 0..255
@@ -760,7 +796,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         for (int w8 = 0; w8 < EW; ++w8) acc += s_stats[w8 * 2 * NC + i];
         dst[i] = acc;
       }
+      if (unit + (int)gridDim.x < p.n_units)  // the scratch is zeroed again for the next unit: everyone has read it
+        asm volatile("bar.sync 1, %0;" ::"r"(32 * EW) : "memory");
     }
+    }  // unit loop
   }
 
   if (threadIdx.x == kEpi0) PBT_STAMP(5);
@@ -797,7 +836,7 @@ static int launch_conv_pair(const CUtensorMap& tmap, const CUtensorMap& tmapP, c
   PBT_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((unsigned)((grid + 1) & ~1), 1, 1);
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);   // even: the unit count and the SM count are
   cfg.blockDim = dim3((unsigned)conv_threads(T, EW), 1, 1);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
@@ -934,7 +973,7 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
   uint32_t smem_bytes = 0;
   for (;;) {
     const uint32_t tail = 8u * (2 * 2 + 2 * 8 + 1) + 16 + (uint32_t)(ew * 2 * p.NC * 4) + (ew == 8 ? 3 * 4 * 32 * 3 * 4 : 0) +
-                          8 * 12 + (uint32_t)(2 * p.pre_c * 4) + 128;
+                          8 * 14 + (uint32_t)(2 * p.pre_c * 4) + 128;
     const uint32_t budget = ew == 4 ? 55 * 1024 : 112 * 1024;
     int group = (int)((ew == 4 ? 8192u : 16384u) / chunk);
     if (group < 1) group = 1;
@@ -972,7 +1011,19 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
     tmapP = tmap;
   }
 
-  const int grid = p.n_img * p.tiles_x * p.tiles_y;
+  // one wave of persistent CTAs: SMs x co-resident CTAs (registers: 2 or 4; tensor memory; shared memory)
+  int grid = p.n_img * p.tiles_x * p.tiles_y;
+  if (pair) grid = (grid + 1) & ~1;   // a pair's padding unit loads zeros and stores nothing
+  p.n_units = grid;
+  int occ = ew == 4 ? 4 : 2;
+  if (512 / p.tmem_cols < occ) occ = 512 / p.tmem_cols;
+  if ((int)(233472u / (smem_bytes + 1024u)) < occ) occ = (int)(233472u / (smem_bytes + 1024u));
+  if (occ < 1) occ = 1;
+  // Persistent only for long queues (>= 8 units per CTA slot): the static round-robin then balances to a few percent and
+  // the kernel owns the GPU long enough.  Shorter launches, and launches flagged `concurrent` (the backward sweep, where
+  // side-stream wgrad kernels must be able to take SM slots and tensor memory in between), keep one unit per CTA and the
+  // hardware's dynamic block scheduling.
+  if (!(d->debug_flags & 128) && !d->concurrent && grid >= 8 * occ * num_sms()) grid = occ * num_sms();  // (bring-up: bit 7 = one unit per CTA)
   const int kb = d->blk_c / 16;
   if (pair) {
     PBT_REQUIRE((ew == 4) == (d->ctas_per_sm == 4), "conv: cta_pair + ctas_per_sm=4 shape does not fit the small footprint");

@@ -77,7 +77,7 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor) -> List[torch.Ten
             T -= 1
         # small maps / narrow outputs get the small-footprint configuration (the kernel falls back when it does not fit)
         ops.conv_fwd(gin, W[name + ".d"], cout, k, k, k - 1 - pad, k - 1 - pad, dt, blk_c=eng._blk(gin.c), tiles_per_cta=T,
-                     out=out, ctas_per_sm=4, **kw)
+                     out=out, ctas_per_sm=4, concurrent=True, **kw)
 
     # Weight gradients run on a side stream: a conv's wgrad and dgrad are independent, and on patch-sized maps neither
     # fills the GPU (a 128->128 3x3 wgrad is ~180 CTAs, its dgrad ~480 of 592 slots).  Their parameter gradients are
