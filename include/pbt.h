@@ -142,6 +142,23 @@ typedef struct {
 } pbt_pack_job_t;
 int pbt_pack_weights(const pbt_pack_job_t* jobs_dev, int32_t n_jobs, int64_t max_elems, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Fused optimiser tail of the G-only step: clip_grad_norm_ (lightning_model.py:245-248) + Adam with L2 weight decay
+ * (torch.optim.Adam semantics; lightning_model.py:326-329, config/optimizer/default.yaml:2-10) over a DEVICE table
+ * of fp32 tensors in two launches.  state = device float[2]: [0] scratch (sum of squares), [1] step count (advanced
+ * by one per call, so the call is CUDA-graph capturable).  max_norm <= 0 disables clipping.  norm_out (optional)
+ * receives the un-clipped total gradient norm.
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  void*       param;       /* fp32 [count], updated in place */
+  const void* grad;        /* fp32 [count] */
+  float*      exp_avg;     /* fp32 [count] first moment */
+  float*      exp_avg_sq;  /* fp32 [count] second moment */
+  int64_t     count;
+} pbt_optim_job_t;
+int pbt_clip_adam_step(const pbt_optim_job_t* jobs_dev, int32_t n_jobs, int64_t max_elems, float* state, double max_norm,
+                       double lr, double beta1, double beta2, double eps, double weight_decay, float* norm_out, void* stream);
+
 /* number of stats tiles per image for a given geometry (tiles_x*tiles_y) */
 int pbt_conv_num_tiles(int32_t h, int32_t w, int32_t tiles_per_cta);
 int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream);

@@ -82,6 +82,11 @@ class StyleTransferModel(_Base):
     def configure_optimizers(self):
         oc = to_container(dict(self.optimizer_config["generator"]))
         oc["betas"] = tuple(oc.get("betas", (0.9, 0.999)))
+        fused = bool(oc.pop("fused", True))
+        if fused and next(self.generator.parameters()).is_cuda:
+            # clip_grad_norm_ + Adam as two native launches over all 48 tensors (pbt_b200/optim.py); same state layout
+            from pbt_b200.optim import FusedClipAdam
+            return [FusedClipAdam(self.generator.parameters(), **oc)]
         if self.use_cuda_graph and next(self.generator.parameters()).is_cuda:
             oc["capturable"] = True   # the whole step is replayed as one CUDA graph (pbt_b200/graphs.py)
         return [torch.optim.Adam(self.generator.parameters(), **oc)]
@@ -121,9 +126,13 @@ class StyleTransferModel(_Base):
         g_loss["loss"].backward()
         if self.grad_sync is not None:
             self.grad_sync.finish()          # mean over ranks, before the clip (DDP semantics of the reference)
-        if self.training_config.get("use_gradient_clipping", False):
-            torch.nn.utils.clip_grad_norm_(self.generator.parameters(), self.training_config["gradient_clip_val"])
-        opt_g.step()
+        clip = self.training_config["gradient_clip_val"] if self.training_config.get("use_gradient_clipping", False) else None
+        if hasattr(opt_g, "last_grad_norm"):     # FusedClipAdam: the clip is part of the optimiser launch
+            opt_g.step(max_grad_norm=clip)
+        else:
+            if clip is not None:
+                torch.nn.utils.clip_grad_norm_(self.generator.parameters(), clip)
+            opt_g.step()
         return g_loss
 
     def graphed_training_step(self, batch: Dict[str, torch.Tensor], batch_idx: int):

@@ -509,3 +509,34 @@ def check_conv_upsample(n=2, cin=64, cout=32, h=20, w=28, T=2, blk_c=32, dt=FP16
         ok &= serr < 1e-4
         msg += f" stats={serr:.3g}"
     return ok, err, msg
+
+
+def check_fused_clip_adam(steps=5, clip=0.5, wd=1e-5, seed=3):
+    """FusedClipAdam vs clip_grad_norm_ + torch.optim.Adam on the same gradients (reference lightning_model.py:245-250)"""
+    from pbt_b200.optim import FusedClipAdam
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    shapes = [(32, 3, 7, 7), (32,), (64, 32, 3, 3), (128, 128, 3, 3), (3, 64, 1, 1), (3,), (5,)]
+    pa = [torch.nn.Parameter(torch.randn(s, generator=g, device="cuda") * 0.05) for s in shapes]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    oa = torch.optim.Adam(pa, lr=4e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=wd)
+    ob = FusedClipAdam(pb, lr=4e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=wd, max_grad_norm=clip)
+    worst, norm_err = 0.0, 0.0
+    for it in range(steps):
+        scale = 10.0 if it % 2 == 0 else 0.01      # alternate between clipped and un-clipped steps
+        grads = [torch.randn(s, generator=g, device="cuda") * scale for s in shapes]
+        for p, q, gr in zip(pa, pb, grads):
+            p.grad = gr.clone()
+            q.grad = gr.clone()
+        tn = torch.nn.utils.clip_grad_norm_(pa, clip) if clip else None
+        oa.step()
+        ob.step()
+        torch.cuda.synchronize()
+        if tn is not None:
+            norm_err = max(norm_err, abs(float(tn) - float(ob.last_grad_norm)) / float(tn))
+        for p, q in zip(pa, pb):
+            worst = max(worst, ((p - q).abs().max() / (p.abs().max() + 1e-12)).item())
+    sa, sb = oa.state[pa[3]], ob.state[pb[3]]
+    m_err = ((sa["exp_avg"] - sb["exp_avg"]).abs().max() / (sa["exp_avg"].abs().max() + 1e-20)).item()
+    v_err = ((sa["exp_avg_sq"] - sb["exp_avg_sq"]).abs().max() / (sa["exp_avg_sq"].abs().max() + 1e-30)).item()
+    ok = worst < 2e-6 and norm_err < 1e-5 and m_err < 2e-6 and v_err < 2e-6 and float(sb["step"]) == steps
+    return ok, worst, f"param rel err={worst:.3g} norm rel err={norm_err:.3g} m={m_err:.3g} v={v_err:.3g} step={float(sb['step'])}"

@@ -171,3 +171,9 @@ def test_bad_arguments_raise():
     w = torch.zeros(16 * 24 * 2, device="cuda", dtype=torch.bfloat16)
     with pytest.raises(RuntimeError, match="cin must be a multiple of 16"):
         ops.conv_fwd(x, w, 16, 1, 1, 0, 0, 0, blk_c=16, tiles_per_cta=1, out=P8.empty(1, 16, 16, 16, 0))
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(clip=None), dict(wd=0.0, steps=3)], ids=["clip", "noclip", "nowd"])
+def test_fused_clip_adam_matches_torch(kw):
+    ok, err, msg = gc.check_fused_clip_adam(**kw)
+    assert ok, msg

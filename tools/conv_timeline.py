@@ -9,7 +9,8 @@ from pbt_b200 import ops  # noqa: E402
 from pbt_b200._native import FP16, P8  # noqa: E402
 
 dt = FP16
-cases = [("conv11 176->64 7x7 T3 PAIR", 176, 64, 7, 1080, 1920, 3, 32, False, 0, True),
+cases = [("up1 192->128 3x3 T2 UPSAMPLE-ON-LOAD", 192, 128, 3, 1080, 1920, 2, 32, True, 0, False, True),
+         ("conv11 176->64 7x7 T3 PAIR", 176, 64, 7, 1080, 1920, 3, 32, False, 0, True),
          ("conv11 176->64 7x7 T2 blk16 PAIR cps4", 176, 64, 7, 1080, 1920, 2, 16, False, 4, True),
          ("conv11 176->64 7x7 T2 blk16 cps4", 176, 64, 7, 1080, 1920, 2, 16, False, 4, False),
          ("smooth 64->64 3x3 T2 blk16 cps4", 64, 64, 3, 1080, 1920, 2, 16, False, 4),
@@ -23,7 +24,8 @@ FLAGS = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 for name, cin, cout, k, h, w, T, blk, stats, *rest in cases:
     cps = rest[0] if rest else 0
     pair = rest[1] if len(rest) > 1 else False
-    x = P8.empty(1, cin, h, w, dt)
+    up = rest[2] if len(rest) > 2 else False
+    x = P8.empty(1, cin, h // 2 if up else h, w // 2 if up else w, dt)
     x.t.normal_()
     wp = ops.pack_conv_weight(torch.randn((cout, cin, k, k), device="cuda") * 0.05, cin, blk, dt, pair=pair)
     out = P8.empty(1, cout, h, w, dt)
@@ -31,7 +33,7 @@ for name, cin, cout, k, h, w, T, blk, stats, *rest in cases:
     part = torch.empty((1, tiles, 2, cout), device="cuda") if stats else None
     dbg = torch.zeros((tiles, 8), dtype=torch.int64, device="cuda")
     for _ in range(2):
-        ops.conv_fwd(x, wp, cout, k, k, k // 2, k // 2, dt, blk_c=blk, tiles_per_cta=T, out=out, stats_partial=part, debug_buf=dbg, debug_flags=FLAGS,
+        ops.conv_fwd(x, wp, cout, k, k, k // 2, k // 2, dt, blk_c=blk, tiles_per_cta=T, out=out, stats_partial=part, debug_buf=dbg, debug_flags=FLAGS | 128, upsample2x=up,
                      ctas_per_sm=cps, cta_pair=pair)
     torch.cuda.synchronize()
     d = dbg.cpu().double()

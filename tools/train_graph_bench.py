@@ -33,17 +33,17 @@ for i in range(6):
     losses1.append(float(loss))
 # graphed run: 3 warm-up steps happen inside the constructor, then replays
 g2 = make()
-o2 = torch.optim.Adam(g2.parameters(), lr=4e-4, weight_decay=1e-5, capturable=True)
-step = GraphedGeneratorStep(g2, o2, (n, cin, p, p))
+from pbt_b200.optim import FusedClipAdam  # noqa: E402
+o2 = FusedClipAdam(g2.parameters(), lr=4e-4, weight_decay=1e-5, max_grad_norm=0.5)
+step = GraphedGeneratorStep(g2, o2, (n, cin, p, p), clip=0.5)
 step.x.copy_(x)
 step.target.copy_(t)
 losses2 = []
 # the constructor ran warm-up + capture on zero inputs; restart from identical weights for the comparison
 g2.load_state_dict(make().state_dict())
-for st in o2.state.values():
-    for k, v in st.items():
-        if torch.is_tensor(v):
-            v.zero_()
+o2._m.zero_()
+o2._v.zero_()
+o2._state.zero_()
 for i in range(6):
     losses2.append(float(step(x, t)))
 print("eager  losses", [round(v, 5) for v in losses1])

@@ -12,6 +12,8 @@ from typing import Callable, Optional
 
 import torch
 
+from .optim import FusedClipAdam
+
 
 class GraphedGeneratorStep:
     def __init__(self, generator, optimizer: torch.optim.Optimizer, batch_shape, *, reconstruction_weight: float = 4.0,
@@ -46,9 +48,12 @@ class GraphedGeneratorStep:
         loss.backward()
         if self.grad_sync is not None:
             self.grad_sync.finish()
-        if self.clip is not None:
-            torch.nn.utils.clip_grad_norm_(self.gen.parameters(), self.clip)
-        self.opt.step()
+        if isinstance(self.opt, FusedClipAdam):       # clip + Adam in two native launches (pbt_clip_adam_step)
+            self.opt.step(max_grad_norm=self.clip)
+        else:
+            if self.clip is not None:
+                torch.nn.utils.clip_grad_norm_(self.gen.parameters(), self.clip)
+            self.opt.step()
         self.loss.copy_(loss.detach())
 
     def __call__(self, x: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
