@@ -232,12 +232,14 @@ __global__ void norm_finalize_kernel(const float* __restrict__ partial, int n, i
   const int n_lo = batch_mode ? 0 : img, n_hi = batch_mode ? n : img + 1;
   double a = 0.0, b = 0.0;
   if (cg < c) {
-    for (int ni = n_lo; ni < n_hi; ++ni)
-      for (int t = row; t < tiles; t += 8) {
-        const float* pp = partial + ((long long)ni * img_tiles + (long long)t * tile_stride) * 2 * c;
-        a += (double)pp[cg];
-        b += (double)pp[c + cg];
-      }
+    // (image, slot) pairs are walked flat so that all 8 rows stay busy in batch mode (n images x few slots)
+    const int total = (n_hi - n_lo) * tiles;
+    for (int idx = row; idx < total; idx += 8) {
+      const int ni = n_lo + idx / tiles, t = idx % tiles;
+      const float* pp = partial + ((long long)ni * img_tiles + (long long)t * tile_stride) * 2 * c;
+      a += (double)pp[cg];
+      b += (double)pp[c + cg];
+    }
   }
   s_sum[row][threadIdx.x & 31] = a;
   s_sq[row][threadIdx.x & 31] = b;
@@ -351,7 +353,7 @@ __device__ __forceinline__ void src_index(int dst, float scale, int in_size, int
   l1 = s - (float)i0;
 }
 
-// One thread = a 2x2 block of output pixels of one (image, plane); block (32, 8) = 64 x 16 output pixels.
+// One thread = a 2x2 block of output pixels of one (image, plane).
 // The 2x2 outputs read at most 3x3 input pixels (align_corners ratio ~0.5), so every input chunk is loaded,
 // normalised and activated once per thread instead of four times.
 // Optional fused producer: taps are normalised + activated on load (x*scale+shift, act), so the
@@ -361,9 +363,14 @@ __global__ void upsample2x_kernel(ActView in, ActView out, const float* __restri
                                   int act) {
   const int oh = out.h, ow = out.w;
   const int planes = in.c / 8;
-  const int X0 = (blockIdx.x * 32 + threadIdx.x) * 2, Y0 = (blockIdx.y * 8 + threadIdx.y) * 2;
-  if (X0 >= ow || Y0 >= oh) return;
-  const int ni = blockIdx.z / planes, pl = blockIdx.z - ni * planes;
+  // flat index over the 2x2 output blocks of one (image, plane): no idle threads on patch-sized maps (a 64x16-pixel
+  // thread block covered an 80-pixel-wide map at 62 %)
+  const int bw = (ow + 1) >> 1, bh = (oh + 1) >> 1;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= bw * bh) return;
+  const int by = t / bw;
+  const int X0 = (t - by * bw) * 2, Y0 = by * 2;
+  const int pl = blockIdx.y, ni = blockIdx.z;
   const float sy = oh > 1 ? (float)(in.h - 1) / (float)(oh - 1) : 0.f;
   const float sx = ow > 1 ? (float)(in.w - 1) / (float)(ow - 1) : 0.f;
   int ya[2], yb[2], xa[2], xb[2];
@@ -444,25 +451,33 @@ __global__ void upsample2x_bwd_kernel(ActView gout, ActView gin16, float* gin32,
     for (int k = 0; k < 8; ++k) acc[k] = 0.f;
     const int Ylo = max(0, 2 * y - 3), Yhi = min(oh - 1, 2 * y + 4);
     const int Xlo = max(0, 2 * x - 3), Xhi = min(ow - 1, 2 * x + 4);
-    for (int Y = Ylo; Y <= Yhi; ++Y) {
-      int y0, y1;
-      float ly;
-      src_index(Y, sy, ih, y0, y1, ly);
-      float wy = 0.f;
-      if (y0 == y) wy += 1.f - ly;
-      if (y1 == y) wy += ly;
-      if (wy == 0.f) continue;
-      for (int X = Xlo; X <= Xhi; ++X) {
-        int x0, x1;
-        float lx;
-        src_index(X, sx, iw, x0, x1, lx);
-        float wx = 0.f;
-        if (x0 == x) wx += 1.f - lx;
-        if (x1 == x) wx += lx;
-        if (wx == 0.f) continue;
+    // separable weights of the (at most 8 x 8) high-res window: 16 index computations instead of 8 + 64
+    float wys[8], wxs[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int a0, a1;
+      float l;
+      wys[j] = wxs[j] = 0.f;
+      if (Ylo + j <= Yhi) {
+        src_index(Ylo + j, sy, ih, a0, a1, l);
+        if (a0 == y) wys[j] += 1.f - l;
+        if (a1 == y) wys[j] += l;
+      }
+      if (Xlo + j <= Xhi) {
+        src_index(Xlo + j, sx, iw, a0, a1, l);
+        if (a0 == x) wxs[j] += 1.f - l;
+        if (a1 == x) wxs[j] += l;
+      }
+    }
+#pragma unroll
+    for (int jy = 0; jy < 8; ++jy) {
+      if (wys[jy] == 0.f) continue;
+#pragma unroll
+      for (int jx = 0; jx < 8; ++jx) {
+        if (wxs[jx] == 0.f) continue;
         float g[8];
-        unpack8<DT>(*chunk_ptr(gout, ni, pl, (long long)Y * ow + X), g);
-        const float wgt = wy * wx;
+        unpack8<DT>(*chunk_ptr(gout, ni, pl, (long long)(Ylo + jy) * ow + Xlo + jx), g);
+        const float wgt = wys[jy] * wxs[jx];
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[k] = fmaf(wgt, g[k], acc[k]);
       }
@@ -869,9 +884,13 @@ extern "C" int pbt_norm_finalize(const float* partial, int32_t n, int32_t tiles,
   PBT_REQUIRE(partial && scale && shift && n > 0 && tiles > 0 && c > 0 && count_per_image > 0, "norm_finalize: bad arguments");
   // NOTE: `partial` is consumed (stage 1 folds chunks of tiles in place when there are many tiles)
   int slots = tiles, stride = 1;
-  if (tiles > 64) {  // measured: one block walking >64 tiles is latency bound (25 us at 510 tiles vs 3+3.5 us in two stages)
+  // measured: one block walking >64 tiles is latency bound (25 us at 510 tiles vs 3+3.5 us in two stages); batch
+  // statistics walk n * tiles slots in ONE block per channel group (101 us at 80 x 25), so fold every image first
+  const bool fold_batch = batch_mode && tiles > 1 && (long long)n * tiles > 64;
+  if (tiles > 64 || fold_batch) {
     int chunk = ceil_div(tiles, 64);
     if (chunk < 16) chunk = 16;
+    if (fold_batch && tiles <= 64) chunk = tiles;
     slots = ceil_div(tiles, chunk);
     stride = chunk;
     dim3 g1(ceil_div(c, 32), slots, n);
@@ -915,9 +934,9 @@ extern "C" int pbt_upsample2x(const pbt_act_t* in, const pbt_act_t* out, const f
   PBT_REQUIRE(in && out && act_ok(*in) && act_ok(*out), "upsample2x: bad tensors");
   PBT_REQUIRE(out->h == 2 * in->h && out->w == 2 * in->w && out->n == in->n && out->c >= in->c, "upsample2x: shape mismatch");
   PBT_REQUIRE((scale == nullptr) == (shift == nullptr), "upsample2x: scale/shift must come together");
-  PBT_REQUIRE((long long)in->n * (in->c / 8) <= 65535, "upsample2x: too many (image, plane) pairs for one launch");
-  dim3 grid(ceil_div(out->w, 64), ceil_div(out->h, 16), in->n * (in->c / 8));
-  DISPATCH_DT(dtype, upsample2x_kernel<DT><<<grid, dim3(32, 8), 0, st>>>(view(*in), view(*out), scale, shift, act));
+  PBT_REQUIRE(in->n <= 65535 && in->c / 8 <= 65535, "upsample2x: too many images / planes for one launch");
+  dim3 grid(ceil_div(((out->w + 1) / 2) * ((out->h + 1) / 2), kEwThreads), in->c / 8, in->n);
+  DISPATCH_DT(dtype, upsample2x_kernel<DT><<<grid, kEwThreads, 0, st>>>(view(*in), view(*out), scale, shift, act));
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
 }
