@@ -1,8 +1,10 @@
 """Drop-in for the reference's generator.py (inference driver): ``StyleTransferInference(cfg).process_directory()``.
 
-North-star semantics: every frame goes through ONE full-frame ``GeneratorJ.forward`` on the GPU (the reference
-tiles the frame into patch_size windows and blends them, generator.py:427-565 — that tiled mode is a "next"
-item).  Pre/post-processing follows the reference: RGB + RGB-converted guide images
+Default (north-star semantics): every frame goes through ONE full-frame ``GeneratorJ.forward`` on the GPU.
+``inference.tiled=true`` selects the reference's own behaviour instead: the frame is cut into patch_size windows around
+sampled mask pixels, every window is stylised separately (per-window InstanceNorm statistics) and the outputs are
+blended with Gaussian weights (reference generator.py:327-565, native path in pbt_b200/tiled.py; fixtures from the
+unmodified reference methods in tests/golden/tiled_golden.npz).  Pre/post-processing follows the reference: RGB + RGB-converted guide images
 normalised to [-1,1] (:584-616), mask thresholded at 128 and eroded 7x7 (:327-351,627-631), composite
 ``rgb*(1-m) + out*m`` (:562-563), clamp / (x+1)*127.5 / round to uint8 (:643-647).
 """
@@ -16,7 +18,7 @@ import torch
 import torch.nn.functional as F
 from PIL import Image
 
-from pbt_b200 import ops
+from pbt_b200 import ops, tiled
 from pbt_b200.config import compose, to_container
 from pbt_b200.inference import FrameStylizer
 from src.models.generator import GeneratorJ
@@ -34,6 +36,8 @@ class StyleTransferInference:
         self.device = torch.device("cuda")
         self.additional_channels = to_container(dict(cfg.paths.get("additional_channels", {}) or {}))
         self.patch_size = cfg.data.patch_size
+        self.tiled = bool(cfg.inference.get("tiled", False))
+        self.overlap_percent = float(cfg.inference.get("overlap_percent", 30.0))   # reference default (:431)
         self._setup_model()
 
     def _setup_model(self):
@@ -78,6 +82,8 @@ class StyleTransferInference:
             imgs.append(Image.open(p).convert("RGB"))
         u8 = torch.from_numpy(np.concatenate([np.asarray(i, dtype=np.uint8) for i in imgs], axis=2)).to(self.device)
         h, w = u8.shape[0], u8.shape[1]
+        if self.tiled:
+            return self._process_image_tiled(u8, mask_path, save_path)
         ph, pw = (-h) % 4, (-w) % 4
         if ph or pw:  # GeneratorJ needs multiples of 4: replicate the border, crop afterwards
             u8 = F.pad(u8.permute(2, 0, 1)[None].float(), (0, pw, 0, ph), mode="replicate")[0].permute(1, 2, 0).to(torch.uint8)
@@ -90,6 +96,22 @@ class StyleTransferInference:
         out = (rgb * (1 - m) + y * m).contiguous()
         res = torch.empty((1, h, w, 3), dtype=torch.uint8, device=self.device)
         ops.nchw_to_u8hwc(out, res)
+        os.makedirs(os.path.dirname(save_path) or ".", exist_ok=True)
+        Image.fromarray(res[0].cpu().numpy()).save(save_path)
+
+    def _process_image_tiled(self, u8, mask_path, save_path):
+        """reference behaviour (generator.py:567-652): windows -> generator -> Gaussian blend -> mask composite"""
+        h, w = u8.shape[0], u8.shape[1]
+        x = ((u8.permute(2, 0, 1)[None].float() / 255.0) - 0.5) / 0.5          # ToTensor + Normalize(0.5, 0.5) (:91-95)
+        mask_file = self._find_corresponding_image(os.path.dirname(mask_path), mask_path)
+        if not os.path.exists(mask_file):
+            raise FileNotFoundError(f"Mask file not found: {mask_file}")
+        m = Image.open(mask_file).point(lambda p: p > 128 and 255).convert("L")  # (:629-631, GrayscaleConvert + ToTensor)
+        mt = torch.from_numpy(np.asarray(m, dtype=np.uint8).copy()).to(self.device).float().div_(255.0)[None]
+        mt = tiled.process_mask(mt)[:, :h, :w].unsqueeze(0)
+        out = tiled.process_large_image(self.generator, x, mt, int(self.patch_size), self.overlap_percent)
+        res = torch.empty((1, h, w, 3), dtype=torch.uint8, device=self.device)
+        ops.nchw_to_u8hwc(out.contiguous(), res)                                 # clamp, (x+1)*127.5, round (:643-647)
         os.makedirs(os.path.dirname(save_path) or ".", exist_ok=True)
         Image.fromarray(res[0].cpu().numpy()).save(save_path)
 

@@ -159,6 +159,22 @@ typedef struct {
 int pbt_clip_adam_step(const pbt_optim_job_t* jobs_dev, int32_t n_jobs, int64_t max_elems, float* state, double max_norm,
                        double lr, double beta1, double beta2, double eps, double weight_decay, float* norm_out, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Tiled inference mode (generator.py:427-565 `process_large_image`).  All tensors fp32, one frame at a time.
+ * boxes_dev: int32 [n_tiles][4] = (y_start, y_end, x_start, x_end) as built by `_get_valid_patch_positions` (:359-398).
+ * ---------------------------------------------------------------------- */
+/* out[b] = frame window b, centred in a zero patch when the window is smaller than `patch` (:470-497) */
+int pbt_tile_gather(const float* src /*[c][h][w]*/, int32_t channels, int32_t h, int32_t w, const int32_t* boxes_dev,
+                    int32_t n_tiles, int32_t patch, float* out /*[n_tiles][c][patch][patch]*/, void* stream);
+/* acc[:, y0+i, x0+j] += proc[b, :, i, j] * wt ; wsum[y0+i, x0+j] += wt, wt = weight_table[weight_index[b]][i][j] (:536-541);
+ * accumulation by fp32 atomics (the order of overlapping tiles is not fixed) */
+int pbt_tile_blend(const float* proc /*[n_tiles][3][patch][patch]*/, const int32_t* boxes_dev, const int32_t* weight_index_dev,
+                   const float* weight_table /*[n_shapes][patch][patch]*/, int32_t n_tiles, int32_t patch, int32_t h, int32_t w,
+                   float* acc /*[3][h][w]*/, float* wsum /*[h][w]*/, void* stream);
+/* out = rgb*(1-mask) + (acc / (wsum > 1e-8 ? wsum : 1))*mask   (:553-560) */
+int pbt_tile_finish(const float* acc, const float* wsum, const float* rgb /*[3][h][w]*/, const float* mask /*[h][w]*/,
+                    int32_t h, int32_t w, float* out /*[3][h][w]*/, void* stream);
+
 /* number of stats tiles per image for a given geometry (tiles_x*tiles_y) */
 int pbt_conv_num_tiles(int32_t h, int32_t w, int32_t tiles_per_cta);
 int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream);

@@ -60,6 +60,16 @@ def test_fit_checkpoint_and_directory_inference(tmp_path, graph):
     m = np.asarray(Image.open(os.path.join(MINI, "mask", outs[0])).convert("L")) > 128
     assert np.array_equal(img[~m], src[~m])
     assert not np.array_equal(img[m], src[m])
+    # the reference's own windowed mode (inference.tiled=true): same driver, same files, windows + Gaussian blend
+    out_t = os.path.join(str(tmp_path), "stylised_tiled")
+    tcfg = compose(os.path.join(ROOT, "config"), "inference",
+                   [f"paths.checkpoint={ckpt}", f"paths.input_dir={MINI}/input", f"paths.mask_dir={MINI}/mask",
+                    f"paths.output_dir={out_t}", f"paths.additional_channels.point_vector.path={MINI}/guide",
+                    "inference.tiled=true", "data.patch_size=32"])
+    infer_driver.StyleTransferInference(tcfg).process_directory()
+    assert sorted(os.listdir(out_t)) == outs
+    img_t = np.asarray(Image.open(os.path.join(out_t, outs[0])))
+    assert img_t.shape == src.shape and np.array_equal(img_t[~m], src[~m]) and not np.array_equal(img_t[m], src[m])
 
 
 def test_frame_stylizer_host_path_matches_device_path():
