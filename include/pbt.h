@@ -145,9 +145,10 @@ int pbt_pack_weights(const pbt_pack_job_t* jobs_dev, int32_t n_jobs, int64_t max
 /* ------------------------------------------------------------------------
  * Fused optimiser tail of the G-only step: clip_grad_norm_ (lightning_model.py:245-248) + Adam with L2 weight decay
  * (torch.optim.Adam semantics; lightning_model.py:326-329, config/optimizer/default.yaml:2-10) over a DEVICE table
- * of fp32 tensors in two launches.  state = device float[2]: [0] scratch (sum of squares), [1] step count (advanced
- * by one per call, so the call is CUDA-graph capturable).  max_norm <= 0 disables clipping.  norm_out (optional)
- * receives the un-clipped total gradient norm.
+ * of fp32 tensors in two launches.  state = device float[3]: [0] scratch (sum of squares), [1] step count (advanced
+ * by one per call, so the call is CUDA-graph capturable), [2] skipped steps: when the gradient norm is inf/nan (fp16
+ * overflow in the backward sweep) nothing is updated and the step does not count (AMP semantics).  max_norm <= 0
+ * disables clipping.  norm_out (optional) receives the un-clipped total gradient norm.
  * ---------------------------------------------------------------------- */
 typedef struct {
   void*       param;       /* fp32 [count], updated in place */
@@ -333,8 +334,13 @@ int pbt_mask_dilate7(const uint8_t* mask, int32_t h, int32_t w, uint8_t* out, vo
  * ---------------------------------------------------------------------- */
 /* max |g| over count fp32 values -> *out (device); used for dynamic fp16 gradient scaling */
 int pbt_absmax_f32(const float* g, int64_t count, float* out, void* stream);
-/* scale[0] = 2^k with amax*2^k in [target/2, target], scale[1] = 1/scale[0] (scale[0]=1 when amax==0) */
-int pbt_make_grad_scale(const float* amax, float target, float* scale2, void* stream);
+/* scale[0] = 2^k with amax*2^k in [target/2, target], scale[1] = 1/scale[0] (scale[0]=1 when amax==0);
+ * adjust (optional device float) multiplies the target: the overflow back-off maintained by pbt_grad_scale_feedback */
+int pbt_make_grad_scale(const float* amax, float target, float* scale2, const float* adjust, void* stream);
+/* AMP-style feedback for the fp16 gradient scale, device-side (graph capturable).  probe = the most downstream fp32
+ * gradient of the sweep; adjust = device float[3]: [0] target multiplier for the next sweep (/16 when the probe holds
+ * inf/nan, x2 after 256 clean sweeps, within [2^-20, 1]), [1] clean sweeps since the last change, [2] overflow count */
+int pbt_grad_scale_feedback(const float* probe, int64_t count, float* adjust, void* stream);
 
 /* ------------------------------------------------------------------------
  * Host-side sampler bookkeeping (no CUDA): order-statistics tree that replaces

@@ -783,8 +783,9 @@ __global__ void absmax_kernel(const float* __restrict__ g, long long count, floa
   if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));  // m >= 0: int order == float order
 }
 
-__global__ void make_grad_scale_kernel(const float* amax, float target, float* scale2) {
+__global__ void make_grad_scale_kernel(const float* amax, float target, float* scale2, const float* adjust) {
   const float a = *amax;
+  if (adjust) target *= *adjust;
   float s = 1.f;
   if (a > 0.f && isfinite(a)) {
     int e;
@@ -793,6 +794,33 @@ __global__ void make_grad_scale_kernel(const float* amax, float target, float* s
   }
   scale2[0] = s;
   scale2[1] = 1.f / s;
+}
+
+// Overflow feedback for the fp16 gradient scale (the AMP recipe, device-side so that it lives inside a CUDA graph):
+// `probe` is the most downstream gradient of the sweep (the first conv's weight gradient) - an fp16 overflow anywhere
+// upstream reaches it as inf/nan.  adjust[0] is the multiplier applied to the scale target of the NEXT sweep:
+// /16 on overflow (floor 2^-20), x2 after 256 clean sweeps (cap 1).  adjust[1] counts clean sweeps, adjust[2] overflows.
+__global__ void grad_scale_feedback_kernel(const float* __restrict__ probe, long long count, float* adjust) {
+  __shared__ int bad;
+  if (threadIdx.x == 0) bad = 0;
+  __syncthreads();
+  int b = 0;
+  for (long long i = threadIdx.x; i < count; i += blockDim.x) b |= !isfinite(probe[i]);
+  if (b) bad = 1;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (bad) {
+      adjust[0] = fmaxf(adjust[0] * 0.0625f, 9.5367431640625e-07f);
+      adjust[1] = 0.f;
+      adjust[2] += 1.f;
+    } else {
+      adjust[1] += 1.f;
+      if (adjust[1] >= 256.f) {
+        adjust[1] = 0.f;
+        adjust[0] = fminf(adjust[0] * 2.f, 1.f);
+      }
+    }
+  }
 }
 
 }  // namespace pbt
@@ -1066,10 +1094,18 @@ extern "C" int pbt_absmax_f32(const float* g, int64_t count, float* out, void* s
   return PBT_OK;
 }
 
-extern "C" int pbt_make_grad_scale(const float* amax, float target, float* scale2, void* stream_) {
+extern "C" int pbt_grad_scale_feedback(const float* probe, int64_t count, float* adjust, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  PBT_REQUIRE(probe && adjust && count > 0, "grad_scale_feedback: bad arguments");
+  grad_scale_feedback_kernel<<<1, 1024, 0, st>>>(probe, count, adjust);
+  PBT_CUDA_CHECK(cudaGetLastError());
+  return PBT_OK;
+}
+
+extern "C" int pbt_make_grad_scale(const float* amax, float target, float* scale2, const float* adjust, void* stream_) {
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   PBT_REQUIRE(amax && scale2 && target > 0.f, "make_grad_scale: bad arguments");
-  make_grad_scale_kernel<<<1, 1, 0, st>>>(amax, target, scale2);
+  make_grad_scale_kernel<<<1, 1, 0, st>>>(amax, target, scale2, adjust);
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
 }

@@ -25,7 +25,7 @@ __device__ __forceinline__ float block_sum(float v) {
   return v;  // valid in thread 0
 }
 
-// grid: (chunks, jobs).  state[0] += sum g^2 ; state[1] (step count) += 1 once per launch.
+// grid: (chunks, jobs).  state[0] += sum g^2 ; state[1] (step count) += 1 once per launch.  state = float[3].
 __global__ void grad_sqnorm_kernel(const pbt_optim_job_t* __restrict__ jobs, float* __restrict__ state) {
   const pbt_optim_job_t j = jobs[blockIdx.y];
   const float* g = static_cast<const float*>(j.grad);
@@ -59,10 +59,11 @@ __global__ void clip_adam_kernel(const pbt_optim_job_t* __restrict__ jobs, const
                                  float* __restrict__ norm_out) {
   const pbt_optim_job_t j = jobs[blockIdx.y];
   const float total = sqrtf(state[0]);
+  if (norm_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *norm_out = total;
+  if (!isfinite(total)) return;  // inf/nan gradients (fp16 overflow): the step is skipped, AMP-style (see clip_adam_skip_kernel)
   const float t = state[1];
   float coef = 1.f;
   if (k.max_norm > 0.f) coef = fminf(1.f, k.max_norm / (total + 1e-6f));
-  if (norm_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *norm_out = total;
   const float bc1 = 1.f - powf(k.b1, t);
   const float bc2 = 1.f - powf(k.b2, t);
   const float step_size = k.lr / bc1;
@@ -80,6 +81,14 @@ __global__ void clip_adam_kernel(const pbt_optim_job_t* __restrict__ jobs, const
     v[i] = vv;
     const float denom = fmaf(sqrtf(vv), inv_sqrt_bc2, k.eps);
     p[i] = pv - step_size * (mv / denom);
+  }
+}
+
+// a skipped step does not count: take back the increment of grad_sqnorm_kernel, count the skip in state[2]
+__global__ void clip_adam_skip_kernel(float* state) {
+  if (!isfinite(state[0])) {
+    state[1] -= 1.f;
+    state[2] += 1.f;
   }
 }
 
@@ -104,6 +113,8 @@ extern "C" int pbt_clip_adam_step(const pbt_optim_job_t* jobs_dev, int32_t n_job
   AdamK k{(float)max_norm, (float)lr, (float)beta1, (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps,
           (float)weight_decay};
   clip_adam_kernel<<<grid, 256, 0, st>>>(jobs_dev, state, k, norm_out);
+  PBT_CUDA_CHECK(cudaGetLastError());
+  clip_adam_skip_kernel<<<1, 1, 0, st>>>(state);
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
 }

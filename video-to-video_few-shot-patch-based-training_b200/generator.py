@@ -228,7 +228,7 @@ class _Engine:
         self.device = next(gen.parameters()).device
         self._ws: Dict[Any, _Workspace] = {}
         self._wslots: Dict[bool, Any] = {}
-        self.grad_scale_target = 1024.0 if self.dt == FP16 else 0.0  # dynamic power-of-two gradient scaling (fp16 only)
+        self.grad_scale_target = 32.0 if self.dt == FP16 else 0.0  # dynamic power-of-two gradient scaling (fp16 only), see backward()
         self.grad_hook = None     # callable(name, grad) fired as each parameter gradient is produced (data parallel)
         self.kernel_timer = None  # bench.py: list collecting CUDA-event pairs around the dominant kernel (conv11)
 
@@ -472,6 +472,13 @@ class _Engine:
         if save:
             self._saved = (ws, W)
         return y
+
+    def grad_scale_adjust(self) -> Tensor:
+        """device float[3]: multiplier of the fp16 gradient-scale target (overflow back-off), clean-sweep and overflow
+        counters - maintained by pbt_grad_scale_feedback at the end of every backward sweep"""
+        if getattr(self, "_gs_adjust", None) is None:
+            self._gs_adjust = torch.tensor([1.0, 0.0, 0.0], device=self.device)
+        return self._gs_adjust
 
     def side_stream(self) -> "torch.cuda.Stream":
         """second stream of the backward sweep (weight gradients overlap the data-gradient chain)"""

@@ -63,7 +63,7 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor) -> List[torch.Ten
         amax = torch.empty(1, device=dev)
         scale2 = torch.empty(2, device=dev)
         ops.absmax(gy, amax)
-        ops.make_grad_scale(amax, eng.grad_scale_target, scale2)
+        ops.make_grad_scale(amax, eng.grad_scale_target, scale2, adjust=eng.grad_scale_adjust())
         gscale, inv = scale2[0:1], scale2[1:2]
 
     def T_of(pref, ww):
@@ -236,6 +236,10 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor) -> List[torch.Ten
     wgrad_side("initial_conv.0.weight", ws.cat11.view(f[4] + f[0], cp), g_raw0, 7, 3,
                lambda dw: _wgrad_to_param(dw, f[0], g.input_channels, 7, 7))
     join()   # trunk group complete
+    if eng.grad_scale_target > 0:
+        # an fp16 overflow anywhere in the sweep ends up as inf/nan in this most-downstream gradient: shrink the scale
+        # of the next sweep (the optimiser skips a non-finite step - FusedClipAdam does; AMP semantics)
+        ops.grad_scale_feedback(grads["initial_conv.0.weight"], eng.grad_scale_adjust())
 
     # ---- assemble in parameter order
     out: List[torch.Tensor] = []

@@ -16,7 +16,7 @@ __all__ = [
     "pack_conv_weight", "s2d_weight", "s2d_weight_grad", "dgrad_weight", "conv_fwd", "conv_wgrad", "conv_num_tiles",
     "norm_finalize", "norm_apply", "upsample2x", "upsample2x_bwd", "norm_bwd", "head_bwd", "channel_sum", "nchw_to_p8",
     "p8_to_nchw", "p8f_to_nchw", "u8hwc_to_p8", "nchw_to_u8hwc", "u8hwc_to_norm_chw", "patch_gather", "mask_dilate7",
-    "absmax", "make_grad_scale",
+    "absmax", "make_grad_scale", "grad_scale_feedback",
 ]
 
 
@@ -263,5 +263,10 @@ def absmax(g: torch.Tensor, out: torch.Tensor) -> None:
     check(lib().pbt_absmax_f32(g.data_ptr(), g.numel(), out.data_ptr(), stream_ptr()), "pbt_absmax_f32")
 
 
-def make_grad_scale(amax: torch.Tensor, target: float, scale2: torch.Tensor) -> None:
-    check(lib().pbt_make_grad_scale(amax.data_ptr(), target, scale2.data_ptr(), stream_ptr()), "pbt_make_grad_scale")
+def make_grad_scale(amax: torch.Tensor, target: float, scale2: torch.Tensor, adjust=None) -> None:
+    check(lib().pbt_make_grad_scale(amax.data_ptr(), target, scale2.data_ptr(), ptr(adjust), stream_ptr()), "pbt_make_grad_scale")
+
+
+def grad_scale_feedback(probe: torch.Tensor, adjust: torch.Tensor) -> None:
+    """overflow back-off of the fp16 gradient scale (see include/pbt.h); probe: fp32, contiguous"""
+    check(lib().pbt_grad_scale_feedback(probe.data_ptr(), probe.numel(), adjust.data_ptr(), stream_ptr()), "pbt_grad_scale_feedback")

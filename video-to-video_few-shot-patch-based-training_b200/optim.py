@@ -37,7 +37,7 @@ class FusedClipAdam(torch.optim.Optimizer):
         dev = ps[0].device
         self._dev = dev
         # device state: [0] sum of squares scratch, [1] step count; total norm of the last step
-        self._state = torch.zeros(2, device=dev)
+        self._state = torch.zeros(3, device=dev)      # [sum of squares, step count, skipped (non-finite) steps]
         self.last_grad_norm = torch.zeros((), device=dev)
         total = sum(p.numel() for p in ps)
         self._m = torch.zeros(total, device=dev)
@@ -52,6 +52,11 @@ class FusedClipAdam(torch.optim.Optimizer):
         self._table = None
         self._table_key = None
         self._pinned = []   # host tables referenced by captured graphs must stay alive
+
+    @property
+    def skipped_steps(self) -> int:
+        """steps skipped because the gradients were not finite (fp16 overflow in the backward sweep)"""
+        return int(self._state[2].item())
 
     # torch.optim.Optimizer.load_state_dict re-creates the per-parameter tensors: copy them back into the flat buffers
     def load_state_dict(self, state_dict):
