@@ -168,6 +168,28 @@ def test_guide_channels_forward_matches_oracle():
     assert (y - ref).abs().max().item() <= MAX_ABS and psnr(y, ref, 2.0) >= PSNR_MIN
 
 
+@pytest.mark.parametrize("cin,h,w,n", [(3, 100, 140, 2), (6, 960, 540, 1), (5, 68, 52, 3)],
+                         ids=["100x140", "C2-960x540-cin6", "68x52-cin5"])
+def test_forward_at_sizes_that_are_not_multiples_of_the_tile(cin, h, w, n):
+    """H, W multiples of 4 only (module contract): partial conv tiles at every resolution level, odd tile counts for
+    the CTA-pair layer, partial stride-2 / upsample borders.  Includes the C2 frame size of BASELINE.json."""
+    from oracle import generator_oracle as go
+    torch.manual_seed(11)
+    g = load_gen("fp16", cin=cin)
+    sd = {k: v.detach().cpu().clone() for k, v in g.state_dict().items()}
+    x = (torch.rand(n, cin, h, w) * 2 - 1)
+    x[:, :, : h // 3] *= 0.2                       # non-stationary content: per-frame statistics matter
+    g.eval()
+    with torch.no_grad():
+        y = g(x.cuda()).cpu()
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        ref = go.generator_forward(sd, x, training=False)
+    err, p = (y - ref).abs().max().item(), psnr(y, ref, 2.0)
+    print(f"{cin}x{h}x{w}: max_abs={err:.5f} psnr={p:.1f} dB")
+    assert err <= MAX_ABS and p >= PSNR_MIN, (err, p)
+
+
 def test_sampler_bit_exact_vs_reference_golden():
     from pbt_b200.sampler import StyleTransferDataset
     z = np.load(os.path.join(GOLD, "sampler_golden.npz"))
