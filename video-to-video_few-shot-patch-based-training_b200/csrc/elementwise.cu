@@ -607,10 +607,12 @@ __global__ void norm_bwd_apply_kernel(NormBwdK p) {
 }
 
 // Fused reduce + apply for per-image statistics on small maps (patch training): one CTA owns one (image, plane) slice,
-// sums it, then re-reads it (L2 hits: the slice was just read by this CTA) and writes dx.  No atomics, one launch,
-// half the DRAM traffic of the two-kernel path.  grid: (planes, n).
-template <int DT>
-__global__ void norm_bwd_fused_kernel(NormBwdK p) {
+// sums it, then applies.  No atomics, one launch.  STAGE: the slice (x and the activated gradient, 32 B per pixel) is
+// kept in shared memory between the two passes, so DRAM is read once; without it the second pass re-reads global memory
+// (L2 hits only while the resident CTAs' slices fit L2 - at 80 x 128 x 80x80 they do not).  grid: (planes, n).
+template <int DT, bool STAGE>
+__global__ void __launch_bounds__(512) norm_bwd_fused_kernel(NormBwdK p) {
+  extern __shared__ __align__(16) uint4 s_slice[];  // STAGE: [hw][2] = (x chunk, gact chunk)
   const int hw = p.x.h * p.x.w;
   const int planes = p.x.c / 8;
   const int pl = blockIdx.x, ni = blockIdx.y;
@@ -620,13 +622,19 @@ __global__ void norm_bwd_fused_kernel(NormBwdK p) {
   for (int pix = threadIdx.x; pix < hw; pix += blockDim.x) {
     float gact[8], xhat[8], xr[8];
     load_gact<DT>(p, ni, pl, pix, planes, hw, gact, xhat, xr);
+    if (STAGE) {
+      const uint4 gq = pack8<DT>(gact);
+      s_slice[2 * pix] = pack8<DT>(xr);   // exact: xr came out of the same 16-bit chunk
+      s_slice[2 * pix + 1] = gq;
+      unpack8<DT>(gq, gact);              // the sums see what the second pass will see
+    }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       s1[k] += gact[k];
       s2[k] = fmaf(gact[k], xhat[k], s2[k]);
     }
   }
-  __shared__ float red[kEwThreads / 32][16];
+  __shared__ float red[32][16];
   __shared__ float tot[16];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
@@ -647,23 +655,32 @@ __global__ void norm_bwd_fused_kernel(NormBwdK p) {
   __syncthreads();
   if (threadIdx.x < 16) {
     float t = 0.f;
-    for (int w2 = 0; w2 < kEwThreads / 32; ++w2) t += red[w2][threadIdx.x];
+    for (int w2 = 0; w2 < (int)(blockDim.x >> 5); ++w2) t += red[w2][threadIdx.x];
     tot[threadIdx.x] = t;
     const int which = threadIdx.x >> 3, k = threadIdx.x & 7;
     p.sums[(long long)ni * 2 * p.x.c + (long long)which * p.x.c + pl * 8 + k] = t;
   }
   __syncthreads();
-  float m1[8], m2[8], km[8];
+  float m1[8], m2[8], km[8], mu[8], sh[8];
   const long long ko = (p.per_channel ? 0 : (long long)ni * p.x.c) + pl * 8;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     m1[k] = tot[k] * p.inv_count;
     m2[k] = tot[8 + k] * p.inv_count;
     km[k] = __ldg(&p.kmul[ko + k]);
+    mu[k] = __ldg(&p.mean[ko + k]);
+    sh[k] = __ldg(&p.shift[ko + k]);
   }
   for (int pix = threadIdx.x; pix < hw; pix += blockDim.x) {
     float gact[8], xhat[8], r[8], xr[8];
-    load_gact<DT>(p, ni, pl, pix, planes, hw, gact, xhat, xr);
+    if (STAGE) {
+      unpack8<DT>(s_slice[2 * pix], xr);
+      unpack8<DT>(s_slice[2 * pix + 1], gact);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) xhat[k] = fmaf(xr[k], mu[k], sh[k]);
+    } else {
+      load_gact<DT>(p, ni, pl, pix, planes, hw, gact, xhat, xr);
+    }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       r[k] = km[k] * (gact[k] - m1[k] - xhat[k] * m2[k]);
@@ -1050,7 +1067,23 @@ extern "C" int pbt_norm_bwd_fused(const pbt_norm_bwd_desc_t* d, void* stream_) {
               "norm_bwd_fused: dx shape mismatch");
   p.dx = view(d->dx);
   dim3 grid(d->x.c / 8, d->x.n);
-  DISPATCH_DT(d->dtype, norm_bwd_fused_kernel<DT><<<grid, kEwThreads, 0, st>>>(p));
+  const long long hw = (long long)d->x.h * d->x.w;
+  const size_t slice = (size_t)hw * 32;            // x chunk + activated-gradient chunk per pixel
+  const int threads = hw >= 4096 ? 512 : kEwThreads;   // one big CTA per SM when the slice fills shared memory
+  if (slice <= 200 * 1024) {
+    if (d->dtype == PBT_BF16) {
+      PBT_CUDA_CHECK(cudaFuncSetAttribute(norm_bwd_fused_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slice));
+      norm_bwd_fused_kernel<0, true><<<grid, threads, slice, st>>>(p);
+    } else if (d->dtype == PBT_FP16) {
+      PBT_CUDA_CHECK(cudaFuncSetAttribute(norm_bwd_fused_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slice));
+      norm_bwd_fused_kernel<1, true><<<grid, threads, slice, st>>>(p);
+    } else {
+      pbt::set_last_error("bad dtype");
+      return PBT_ERR_ARG;
+    }
+  } else {
+    DISPATCH_DT(d->dtype, norm_bwd_fused_kernel<DT, false><<<grid, kEwThreads, 0, st>>>(p));
+  }
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
 }
