@@ -180,6 +180,8 @@ def run_native(args):
     gen, weights = trained_like_generator(CIN, dev)
     gen.operand_dtype = operand
     sty = FrameStylizer(gen)
+    if os.environ.get("PBT_FRAMES_PER_PASS"):   # experiment knob; the default is the library's
+        sty.frames_per_pass = int(os.environ["PBT_FRAMES_PER_PASS"])
     F = FRAMES_PER_STEP
     n_frames = F * (args.steps + args.warmup)
     frames = synthetic_frames(min(n_frames, 16), H, W, CIN, 1234 + rank, dev)   # cycled; >> L2 per frame anyway

@@ -176,6 +176,10 @@ int pbt_tile_blend(const float* proc /*[n_tiles][3][patch][patch]*/, const int32
 int pbt_tile_finish(const float* acc, const float* wsum, const float* rgb /*[3][h][w]*/, const float* mask /*[h][w]*/,
                     int32_t h, int32_t w, float* out /*[3][h][w]*/, void* stream);
 
+/* L1 reconstruction loss of the G-only step (lightning_model.py:267-268), value and gradient in one launch:
+ * *loss = weight * mean|y - target| ;  gy = weight / count * sign(y - target).  All fp32, `count` elements. */
+int pbt_l1_loss_fwd_bwd(const float* y, const float* target, int64_t count, float weight, float* loss, float* gy, void* stream);
+
 /* number of stats tiles per image for a given geometry (tiles_x*tiles_y) */
 int pbt_conv_num_tiles(int32_t h, int32_t w, int32_t tiles_per_cta);
 int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream);

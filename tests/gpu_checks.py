@@ -540,3 +540,19 @@ def check_fused_clip_adam(steps=5, clip=0.5, wd=1e-5, seed=3):
     v_err = ((sa["exp_avg_sq"] - sb["exp_avg_sq"]).abs().max() / (sa["exp_avg_sq"].abs().max() + 1e-30)).item()
     ok = worst < 2e-6 and norm_err < 1e-5 and m_err < 2e-6 and v_err < 2e-6 and float(sb["step"]) == steps
     return ok, worst, f"param rel err={worst:.3g} norm rel err={norm_err:.3g} m={m_err:.3g} v={v_err:.3g} step={float(sb['step'])}"
+
+
+def check_fused_l1(seed=4, weight=4.0):
+    from pbt_b200.optim import fused_l1_loss
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    y = (torch.rand((7, 3, 20, 24), generator=g, device="cuda") * 2 - 1).requires_grad_(True)
+    t = torch.rand((7, 3, 20, 24), generator=g, device="cuda") * 2 - 1
+    t[0, 0, 0, :4] = y.detach()[0, 0, 0, :4]          # exact ties: sign(0) = 0 like torch
+    y2 = y.detach().clone().requires_grad_(True)
+    la = fused_l1_loss(y, t, weight)
+    (la * 1.5).backward()
+    lb = torch.nn.functional.l1_loss(y2, t) * weight
+    (lb * 1.5).backward()
+    e1 = abs(float(la) - float(lb)) / abs(float(lb))
+    e2 = (y.grad - y2.grad).abs().max().item() / y2.grad.abs().max().item()
+    return e1 < 1e-5 and e2 < 1e-6, e1, f"loss rel err={e1:.3g} grad rel err={e2:.3g}"

@@ -177,3 +177,8 @@ def test_bad_arguments_raise():
 def test_fused_clip_adam_matches_torch(kw):
     ok, err, msg = gc.check_fused_clip_adam(**kw)
     assert ok, msg
+
+
+def test_fused_l1_loss_matches_torch():
+    ok, err, msg = gc.check_fused_l1()
+    assert ok, msg

@@ -84,6 +84,20 @@ __global__ void clip_adam_kernel(const pbt_optim_job_t* __restrict__ jobs, const
   }
 }
 
+// L1 reconstruction loss of the G-only step, value and gradient in one pass (reference lightning_model.py:267-268:
+// L1Loss(G(x), post) * reconstruction_weight):  loss += weight/count * sum|y - t| ;  gy = weight/count * sign(y - t).
+__global__ void l1_loss_kernel(const float* __restrict__ y, const float* __restrict__ t, long long count, float scale,
+                               float* __restrict__ loss, float* __restrict__ gy) {
+  float acc = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+    const float d = y[i] - t[i];
+    acc += fabsf(d);
+    gy[i] = d > 0.f ? scale : (d < 0.f ? -scale : 0.f);
+  }
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) atomicAdd(loss, acc * scale);
+}
+
 // a skipped step does not count: take back the increment of grad_sqnorm_kernel, count the skip in state[2]
 __global__ void clip_adam_skip_kernel(float* state) {
   if (!isfinite(state[0])) {
@@ -115,6 +129,18 @@ extern "C" int pbt_clip_adam_step(const pbt_optim_job_t* jobs_dev, int32_t n_job
   clip_adam_kernel<<<grid, 256, 0, st>>>(jobs_dev, state, k, norm_out);
   PBT_CUDA_CHECK(cudaGetLastError());
   clip_adam_skip_kernel<<<1, 1, 0, st>>>(state);
+  PBT_CUDA_CHECK(cudaGetLastError());
+  return PBT_OK;
+}
+
+extern "C" int pbt_l1_loss_fwd_bwd(const float* y, const float* target, int64_t count, float weight, float* loss, float* gy,
+                                   void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  PBT_REQUIRE(y && target && loss && gy && count > 0, "l1_loss: bad arguments");
+  PBT_CUDA_CHECK(cudaMemsetAsync(loss, 0, sizeof(float), st));
+  long long blocks = (count + 256 * 8 - 1) / (256 * 8);
+  if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
+  l1_loss_kernel<<<(unsigned)blocks, 256, 0, st>>>(y, target, count, (float)((double)weight / (double)count), loss, gy);
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
 }

@@ -12,7 +12,7 @@ from typing import Callable, Optional
 
 import torch
 
-from .optim import FusedClipAdam
+from .optim import FusedClipAdam, fused_l1_loss
 
 
 class GraphedGeneratorStep:
@@ -23,6 +23,8 @@ class GraphedGeneratorStep:
         n, cin, ph, pw = batch_shape
         self.gen, self.opt, self.clip, self.weight = generator, optimizer, clip, reconstruction_weight
         self.criterion = criterion or torch.nn.functional.l1_loss
+        self._l1 = criterion is None or criterion is torch.nn.functional.l1_loss or (
+            isinstance(criterion, torch.nn.L1Loss) and criterion.reduction == "mean")
         self.grad_sync = grad_sync
         self.x = torch.zeros((n, cin, ph, pw), device=dev)
         self.target = torch.zeros((n, 3, ph, pw), device=dev)
@@ -44,7 +46,10 @@ class GraphedGeneratorStep:
     def _step(self):
         self.opt.zero_grad(set_to_none=True)
         y = self.gen(self.x)
-        loss = self.criterion(y, self.target) * self.weight
+        if self._l1:      # value + gradient of L1 * weight in one native launch
+            loss = fused_l1_loss(y, self.target, self.weight)
+        else:
+            loss = self.criterion(y, self.target) * self.weight
         loss.backward()
         if self.grad_sync is not None:
             self.grad_sync.finish()

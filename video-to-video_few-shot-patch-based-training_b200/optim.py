@@ -114,3 +114,28 @@ class FusedClipAdam(torch.optim.Optimizer):
         # the kernel wrote the parameters behind autograd's back: bump their version counters so that consumers keyed on
         # them (the generator's packed 16-bit weight cache) see the update
         torch.autograd.graph.increment_version(ps)
+
+
+class _FusedL1(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, target, weight):
+        if not (y.is_cuda and y.dtype == torch.float32 and target.dtype == torch.float32 and y.shape == target.shape):
+            raise RuntimeError("fused_l1_loss needs fp32 CUDA tensors of equal shape")
+        y, target = y.contiguous(), target.contiguous()
+        loss = torch.empty((), device=y.device)
+        gy = torch.empty_like(y)
+        check(lib().pbt_l1_loss_fwd_bwd(y.data_ptr(), target.data_ptr(), y.numel(), float(weight), loss.data_ptr(), gy.data_ptr(),
+                                        stream_ptr()), "pbt_l1_loss_fwd_bwd")
+        ctx.save_for_backward(gy)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (gy,) = ctx.saved_tensors
+        return gy * grad_out, None, None
+
+
+def fused_l1_loss(y: torch.Tensor, target: torch.Tensor, weight: float = 1.0) -> torch.Tensor:
+    """``torch.nn.functional.l1_loss(y, target) * weight`` (reference lightning_model.py:267-268) with the value and the
+    gradient w.r.t. ``y`` produced by one native launch"""
+    return _FusedL1.apply(y, target, weight)
