@@ -155,3 +155,29 @@ def test_fp16_gradient_overflow_backs_off_and_skips_the_step(trained_sd):
     assert all(torch.isfinite(p).all() for p in g.parameters())
     assert not torch.equal(w0, g.conv11[0].weight.detach())       # it recovered and trained
     assert all(math.isfinite(v) for v in losses) and losses[-1] < losses[0]
+
+
+def test_4k_frame_matches_oracle_and_is_batch_invariant():
+    """C5 of BASELINE.json: 3840x2160, Cin 5.  One frame against the fp32 oracle on the host cores (about a minute), plus
+    determinism / batch invariance - 4x the units of full HD, every conv layer runs persistent CTAs here."""
+    from oracle import generator_oracle as go
+    from pbt_b200.generator import GeneratorJ
+    torch.manual_seed(21)
+    g = GeneratorJ(input_channels=5, use_bias=True).cuda().eval()
+    sd = {k: v.detach().cpu().clone() for k, v in g.state_dict().items()}
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    low = torch.rand((2, 5, 135, 240), generator=gen, device="cuda") * 2 - 1
+    x = torch.nn.functional.interpolate(low, size=(2160, 3840), mode="bilinear", align_corners=False)
+    x = (x + (torch.rand(x.shape, generator=gen, device="cuda") - 0.5) * 0.1).clamp_(-1, 1)
+    with torch.no_grad():
+        y2 = g(x)                      # two frames in one pass
+        y0 = g(x[:1])
+        y0b = g(x[:1])
+    assert torch.equal(y0, y0b)
+    assert torch.equal(y2[:1], y0), "a frame's result depends on its batch neighbours"
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        ref = go.generator_forward(sd, x[:1].cpu())
+    err, p = (y0.cpu() - ref).abs().max().item(), psnr(y0.cpu(), ref, 2.0)
+    print(f"4K frame vs oracle: max_abs={err:.5f} psnr={p:.1f} dB")
+    assert err <= 2e-2 and p >= 40.0, (err, p)
