@@ -117,7 +117,7 @@ typedef struct {
                               * tiles_per_cta*cout <= 128, the rings fit 56 KB and no on-load transform is active, else default */
   int32_t      cta_pair;     /* 1: CTA-pair configuration (clusters of two CTAs run one M=256 cta_group::2 MMA stream, each CTA
                               * stages half of the weight columns); `wpack` must be in the pair layout (pack mode bit 2).
-                              * Needs blk_c 32, tiles_per_cta 2 or 3, cout % 32 == 0; not combinable with upsample2x */
+                              * Needs blk_c 32 and cout % 32 == 0 (or blk_c 16, tiles_per_cta 2 with ctas_per_sm = 4); no upsample2x */
   int32_t      concurrent;   /* 1: kernels of other streams are expected to run next to this launch: never use persistent CTAs
                               * (they would hold every SM slot / tensor-memory column until the launch ends) */
   int32_t      debug_flags;  /* bring-up only; 0 in production */

@@ -21,16 +21,16 @@ if len(sys.argv) > 2 and sys.argv[2] == "train":   # C3 training shapes: 80 patc
     cases = [("res 128->128 3x3 @20x20", 128, 128, 3, 20, 20, 32, [(1, 0), (1, 4), (2, 0)]),
              ("down2 s2d 256->128 2x2 @20x20", 256, 128, 2, 20, 20, 32, [(1, 0), (1, 4), (2, 0)]),
              ("up2 256->128 3x3 @40x40", 256, 128, 3, 40, 40, 32, [(2, 0), (1, 0), (1, 4)]),
-             ("up1 192->128 3x3 @80x80", 192, 128, 3, 80, 80, 32, [(2, 0), (1, 0), (1, 4)]),
+             ("up1 192->128 3x3 @80x80", 192, 128, 3, 80, 80, 32, [(2, 0), (2, "pair"), (1, "pair")]),
              ("conv11 176->64 7x7 @80x80", 176, 64, 7, 80, 80, 32, [(2, 0), (2, 4), (1, 4)]),
-             ("conv11 dgrad 64->160 7x7 @80x80", 64, 160, 7, 80, 80, 32, [(2, 0), (1, 0)]),
-             ("up1 dgrad 128->192 3x3 @80x80", 128, 192, 3, 80, 80, 32, [(2, 0), (1, 0)]),
-             ("up2 dgrad 128->256 3x3 @40x40", 128, 256, 3, 40, 40, 32, [(1, 0), (2, 0)]),
+             ("conv11 dgrad 64->160 7x7 @80x80", 64, 160, 7, 80, 80, 32, [(2, 0), (1, 0), (1, "pair")]),
+             ("up1 dgrad 128->192 3x3 @80x80", 128, 192, 3, 80, 80, 32, [(2, 0), (1, 0), (1, "pair")]),
+             ("up2 dgrad 128->256 3x3 @40x40", 128, 256, 3, 40, 40, 32, [(1, 0), (2, 0), (1, "pair")]),
              ("smooth 64->64 3x3 @80x80", 64, 64, 3, 80, 80, 32, [(2, 0), (2, 4), (2, 4.16), (1, 4)]),
              ("initial 16->32 7x7 @80x80", 16, 32, 7, 80, 80, 16, [(2, 0), (2, 4), (3, 4)]),
              ("down1 s2d 128->64 2x2 @40x40", 128, 64, 2, 40, 40, 32, [(2, 0), (2, 4), (1, 4)]),
              ("down1 dgrad 64->128 2x2 @40x40", 64, 128, 2, 40, 40, 32, [(2, 0), (1, 4), (1, 0)]),
-             ("down2 dgrad 128->256 2x2 @20x20", 128, 256, 2, 20, 20, 32, [(1, 0), (2, 0)])]
+             ("down2 dgrad 128->256 2x2 @20x20", 128, 256, 2, 20, 20, 32, [(1, 0), (2, 0), (1, "pair")])]
 for name, cin, cout, k, h, w, blk, cfgs in cases:
     x = P8.empty(N, cin, h, w, dt)
     x.t.normal_()

@@ -925,12 +925,12 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
   p.tiles_y = ceil_div(p.H, 16);
   const int pair = d->cta_pair ? 1 : 0;
   if (pair) {
-    // instantiated pair configurations: default footprint (blk_c 32, T 2|3) and small footprint (blk_c 16, T 2)
+    // instantiated pair configurations: default footprint (blk_c 32, T 1|2|3) and small footprint (blk_c 16, T 2)
     PBT_REQUIRE(!up && p.NC % 32 == 0, "conv: cta_pair needs cout % 32 == 0 and no upsample-on-load");
     if (d->ctas_per_sm == 4)
       PBT_REQUIRE(d->blk_c == 16 && T == 2 && p.NC <= 64, "conv: cta_pair + ctas_per_sm=4 needs blk_c 16, tiles_per_cta 2, cout <= 64");
     else
-      PBT_REQUIRE(d->blk_c == 32 && (T == 2 || T == 3), "conv: cta_pair needs blk_c 32 and tiles_per_cta 2 or 3");
+      PBT_REQUIRE(d->blk_c == 32 && T >= 1 && T <= 3, "conv: cta_pair needs blk_c 32");
   }
   p.idesc = make_idesc_f16(pair ? 256 : 128, p.NC, d->dtype == PBT_BF16 ? 1 : 0, 0, 0);
   p.a_stage_bytes = round_up((uint32_t)(p.blk_p * p.BH * p.BW * 16), 128);
@@ -1028,6 +1028,7 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
   if (pair) {
     PBT_REQUIRE((ew == 4) == (d->ctas_per_sm == 4), "conv: cta_pair + ctas_per_sm=4 shape does not fit the small footprint");
     if (ew == 4) return launch_conv_pair<2, 1, 4>(tmap, tmapP, p, grid, smem_bytes, stream);
+    if (T == 1) return launch_conv_pair<1, 2, 8>(tmap, tmapP, p, grid, smem_bytes, stream);
     return T == 2 ? launch_conv_pair<2, 2, 8>(tmap, tmapP, p, grid, smem_bytes, stream)
                   : launch_conv_pair<3, 2, 8>(tmap, tmapP, p, grid, smem_bytes, stream);
   }

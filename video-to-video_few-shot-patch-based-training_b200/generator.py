@@ -267,6 +267,13 @@ class _Engine:
         two CTAs, each staging half of the weight columns (+3-5 % on that layer, tools/conv_occ.py)"""
         return self.gen.filters[5] % 32 == 0
 
+    def pair11_dgrad(self) -> bool:
+        """conv11's data gradient (64 -> 160 channels, 7x7): 160 accumulator columns per tile leave room for one tile per
+        CTA at two CTAs per SM, and then every CTA streams the whole 1 MB of weights for 128 pixels (L2-bound).  In the
+        CTA-pair configuration the two CTAs of a cluster share the weight stream: 624 -> 434 us at the C3 shape."""
+        f = self.gen.filters
+        return _pad16(f[4] + f[0]) % 32 == 0 and self._blk(f[5]) == 32
+
     def _blk(self, cin: int) -> int:
         return 32 if cin % 32 == 0 or cin > 32 else 16
 
@@ -293,12 +300,12 @@ class _Engine:
             pk.add(name, conv.weight.detach(), s2d=s2d, k_pad=k_pad, n_out=co, n_keep=co, blk_c=blk or self._blk(k_pad), dt=dt,
                    pair=pair)
 
-        def dgr(name, conv, s2d=False, keep=None):
+        def dgr(name, conv, s2d=False, keep=None, pair=False):
             co, ci = conv.weight.shape[0], conv.weight.shape[1]
             vi = 4 * ci if s2d else ci
             n_keep = vi if keep is None else keep
             pk.add(name + ".d", conv.weight.detach(), s2d=s2d, dgrad=True, k_pad=co, n_out=_pad16(n_keep), n_keep=n_keep,
-                   blk_c=self._blk(co), dt=dt)
+                   blk_c=self._blk(co), dt=dt, pair=pair)
 
         fwd("initial", g.initial_conv[0], cp)
         fwd("down1", g.downsample1[0], 4 * f[0], s2d=True)
@@ -320,7 +327,7 @@ class _Engine:
             dgr("down2", g.downsample2[0], s2d=True)
             dgr("up2", g.upsample2[1])
             dgr("up1", g.upsample1[1])
-            dgr("conv11", g.conv11[0], keep=f[4] + f[0])
+            dgr("conv11", g.conv11[0], keep=f[4] + f[0], pair=self.pair11_dgrad())
             dgr("smooth0", g.smoothers[0])
             dgr("smooth3", g.smoothers[3])
         W: Dict[str, Any] = dict(pk.out)

@@ -73,11 +73,14 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor) -> List[torch.Ten
         """conv of the output gradient with the transposed/flipped kernel -> gradient of the conv input"""
         acc_stride = (cout + 31) // 32 * 32
         T = T_of(T_pref, gin.w)
-        while T > 1 and T * acc_stride > 512:
+        # two co-resident CTAs per SM need <= 256 tensor-memory columns each (allocations are powers of two)
+        while T > 1 and T * acc_stride > 256:
             T -= 1
+        if kw.get("cta_pair"):
+            T = 1
         # small maps / narrow outputs get the small-footprint configuration (the kernel falls back when it does not fit)
         ops.conv_fwd(gin, W[name + ".d"], cout, k, k, k - 1 - pad, k - 1 - pad, dt, blk_c=eng._blk(gin.c), tiles_per_cta=T,
-                     out=out, ctas_per_sm=4, concurrent=True, **kw)
+                     out=out, ctas_per_sm=0 if kw.get("cta_pair") else 4, concurrent=True, **kw)
 
     # Weight gradients run on a side stream: a conv's wgrad and dgrad are independent, and on patch-sized maps neither
     # fills the GPU (a 128->128 3x3 wgrad is ~180 CTAs, its dgrad ~480 of 592 slots).  Their parameter gradients are
@@ -172,7 +175,7 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor) -> List[torch.Ten
     wgrad_side("conv11.0.weight", ws.cat11, g_c11, 7, 3, lambda dw: _wgrad_to_param(dw, f[5], cin11, 7, 7))
     grads["conv11.0.bias"] = db_11
     g_cat = E(f[4] + f[0], h, w)
-    dgrad("conv11", g_c11, f[4] + f[0], 7, 3, out=g_cat, T_pref=3)
+    dgrad("conv11", g_c11, f[4] + f[0], 7, 3, out=g_cat, T_pref=3, cta_pair=eng.pair11_dgrad())
     join()   # tail group complete (output head, smoothers, conv11)
     del g_c11, g_s0, g_s0n, g_s3
     # ---- upsample1 block
