@@ -22,7 +22,7 @@ if len(sys.argv) > 2 and sys.argv[2] == "train":   # C3 training shapes: 80 patc
              ("down2 s2d 256->128 2x2 @20x20", 256, 128, 2, 20, 20, 32, [(1, 0), (1, 4), (2, 0)]),
              ("up2 256->128 3x3 @40x40", 256, 128, 3, 40, 40, 32, [(2, 0), (1, 0), (1, 4)]),
              ("up1 192->128 3x3 @80x80", 192, 128, 3, 80, 80, 32, [(2, 0), (2, "pair"), (1, "pair")]),
-             ("conv11 176->64 7x7 @80x80", 176, 64, 7, 80, 80, 32, [(2, 0), (2, 4), (1, 4)]),
+             ("conv11 176->64 7x7 @80x80", 176, 64, 7, 80, 80, 32, [(2, 0), (2, "pair"), (1, "pair"), (2, "pair4")]),
              ("conv11 dgrad 64->160 7x7 @80x80", 64, 160, 7, 80, 80, 32, [(2, 0), (1, 0), (1, "pair")]),
              ("up1 dgrad 128->192 3x3 @80x80", 128, 192, 3, 80, 80, 32, [(2, 0), (1, 0), (1, "pair")]),
              ("up2 dgrad 128->256 3x3 @40x40", 128, 256, 3, 40, 40, 32, [(1, 0), (2, 0), (1, "pair")]),
