@@ -100,6 +100,11 @@ WGRAD_CASES = [
     dict(cin=176, cout=64, h=32, w=32, kh=7, kw=7, pad_t=3, pad_l=3),
     dict(n=3, cin=256, cout=128, h=20, w=20, kh=2, kw=2, pad_t=1, pad_l=1),
     dict(cin=192, cout=128, h=24, w=24, kh=3, kw=3, pad_t=1, pad_l=1, dt=1, integer=False, inv_scale=0.25),
+    # few input channels + wide kernel: the taps-in-M kernel (M = 8 horizontal taps x 8 channels)
+    dict(n=2, cin=16, cout=32, h=40, w=56, kh=7, kw=7, pad_t=3, pad_l=3),
+    dict(n=3, cin=8, cout=64, h=21, w=30, kh=7, kw=7, pad_t=3, pad_l=3, dt=1, integer=False),
+    dict(n=2, cin=32, cout=32, h=24, w=24, kh=5, kw=5, pad_t=2, pad_l=2),
+    dict(n=1, cin=16, cout=128, h=16, w=24, kh=4, kw=4, pad_t=1, pad_l=2),
 ]
 
 
