@@ -17,10 +17,15 @@
 //    stages hold a GROUP of taps (one full/empty barrier round trip per group, not per tap).
 //  * fp32 accumulators in TMEM (T accumulators of `cout` columns); M=128, N=cout, K=16 per instruction.
 //  * warp roles: warp 0 = TMA/bulk producer, warp 1 = TMEM owner + single-thread MMA issuer,
-//    warps 2..5 = epilogue (TMEM -> registers -> fused bias/act/affine/mask/residual/stats/1x1-head -> global).
-//  * the issuing thread is the critical resource (one tcgen05.mma per 16..64 tensor cycles): the kernel is
-//    templated on T and on the K steps per channel block so that the issue loop is fully unrolled and each MMA
-//    costs two 32-bit adds on the low descriptor words.
+//    EW epilogue warps (8: two per TMEM lane quarter; 4 in the small-footprint configuration):
+//    TMEM -> registers -> fused bias/act/affine/mask/residual/stats/1x1-head -> global.  In the on-load modes the same
+//    warps first build the A tiles: bilinear x2 interpolation of a low-res staging tile (upsample-on-load) or
+//    InstanceNorm + activation of the landed raw tile in place (normalise-on-load).
+//  * the kernel is templated on T and on the K steps per channel block so that the issue loop is fully unrolled and
+//    each MMA costs two 32-bit adds on the low descriptor words; on EW; and on PAIR (cta_group::2: a cluster of two
+//    CTAs runs one M=256 MMA stream and each CTA stages half of the weight columns).
+//  * CTAs are persistent over the units of long launches (barrier phases continue across units).
+//  Measurements behind these choices: profiles/r1_issue_experiments.md, tools/conv_timeline.py, tools/conv_occ.py.
 #include <type_traits>
 
 #include "internal.h"

@@ -4,11 +4,14 @@ fires inside ``manual_backward`` at lightning_model.py:241).
 Hand-scheduled reverse sweep over the buffers the forward pass saved:
   per conv   : wgrad (tcgen05, K = pixels) + dgrad (the forward implicit-GEMM kernel with tap-flipped,
                channel-transposed weights; ReLU masks / residual fan-in fused into its epilogue)
-  per norm   : two-kernel InstanceNorm/BatchNorm backward (reduce, apply) with the activation derivative,
-               skip-connection fan-in and the space-to-depth indexing of the stride-2 layers folded in
+  per norm   : InstanceNorm/BatchNorm backward with the activation derivative, skip-connection fan-in and the
+               space-to-depth indexing of the stride-2 layers folded in: one fused launch per norm on patch-sized
+               maps, reduce + apply kernels for batch statistics and large maps
   upsample   : gather form of the transposed bilinear x2
-All 16-bit gradient tensors carry a power-of-two scale S chosen from max|dL/dy| (fp16 operands only); the
-fp32 parameter gradients are unscaled inside the producing kernels.
+Weight gradients run on a side stream next to the data-gradient chain; parameter gradients are published at three
+join points (all-reduce groups).  All 16-bit gradient tensors carry a power-of-two scale S chosen from max|dL/dy|
+(fp16 operands only, with a device-side overflow back-off); the fp32 parameter gradients are unscaled inside the
+producing kernels.
 """
 from __future__ import annotations
 
