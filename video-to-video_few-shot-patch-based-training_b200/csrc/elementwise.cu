@@ -362,7 +362,6 @@ template <int DT>
 __global__ void upsample2x_kernel(ActView in, ActView out, const float* __restrict__ scale, const float* __restrict__ shift,
                                   int act) {
   const int oh = out.h, ow = out.w;
-  const int planes = in.c / 8;
   // flat index over the 2x2 output blocks of one (image, plane): no idle threads on patch-sized maps (a 64x16-pixel
   // thread block covered an 80-pixel-wide map at 62 %)
   const int bw = (ow + 1) >> 1, bh = (oh + 1) >> 1;
@@ -381,6 +380,74 @@ __global__ void upsample2x_kernel(ActView in, ActView out, const float* __restri
     src_index(min(X0 + j, ow - 1), sx, in.w, xa[j], xb[j], lx[j]);
   }
   const int ylo = ya[0], xlo = xa[0];
+  if constexpr (DT == 1) {
+    // fp16 tensors: packed half2 arithmetic end to end (the fp32 path below needs 128 registers - two 256-thread blocks
+    // per SM - and ran at a quarter of the HBM roofline on patch-sized maps).  Weights rounded to fp16 add ~2^-11
+    // relative error per blend, the same order as the fp16 rounding of the result.
+    __half2 sc2[4], sh2[4];
+    if (scale) {
+      const long long so = (long long)ni * in.c + pl * 8;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        sc2[k] = __floats2half2_rn(__ldg(&scale[so + 2 * k]), __ldg(&scale[so + 2 * k + 1]));
+        sh2[k] = __floats2half2_rn(__ldg(&shift[so + 2 * k]), __ldg(&shift[so + 2 * k + 1]));
+      }
+    }
+    const __half2 zero2 = __float2half2_rn(0.f), leak2 = __float2half2_rn(0.2f);
+    uint4 hv[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int yy = min(ylo + r, in.h - 1);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int xx = min(xlo + c, in.w - 1);
+        hv[r][c] = *chunk_ptr(in, ni, pl, (long long)yy * in.w + xx);
+        if (scale) {
+          __half2* h = reinterpret_cast<__half2*>(&hv[r][c]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            __half2 t = __hfma2(h[k], sc2[k], sh2[k]);
+            if (act == PBT_ACT_RELU) t = __hmax2(t, zero2);
+            else if (act == PBT_ACT_LEAKY02) t = __hmax2(t, __hmul2(t, leak2));
+            h[k] = t;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (Y0 + j >= oh) break;
+      const int ra = ya[j] - ylo, rb = yb[j] - ylo;   // 0..1 and 0..2
+      const __half2 hy = __float2half2_rn(1.f - ly[j]), wy = __float2half2_rn(ly[j]);
+      uint4 row[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const uint4 top = ra == 0 ? hv[0][c] : hv[1][c];
+        const uint4 bot = rb == 0 ? hv[0][c] : (rb == 1 ? hv[1][c] : hv[2][c]);
+        const __half2* tp = reinterpret_cast<const __half2*>(&top);
+        const __half2* bp = reinterpret_cast<const __half2*>(&bot);
+        __half2* rp = reinterpret_cast<__half2*>(&row[c]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) rp[k] = __hfma2(wy, bp[k], __hmul2(hy, tp[k]));
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        if (X0 + i >= ow) break;
+        const int ca = xa[i] - xlo, cb = xb[i] - xlo;
+        const __half2 hx = __float2half2_rn(1.f - lx[i]), wx = __float2half2_rn(lx[i]);
+        const uint4 l = ca == 0 ? row[0] : row[1];
+        const uint4 rr = cb == 0 ? row[0] : (cb == 1 ? row[1] : row[2]);
+        const __half2* lp = reinterpret_cast<const __half2*>(&l);
+        const __half2* rp = reinterpret_cast<const __half2*>(&rr);
+        uint4 o;
+        __half2* op = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) op[k] = __hfma2(wx, rp[k], __hmul2(hx, lp[k]));
+        *chunk_ptr(out, ni, pl, (long long)(Y0 + j) * ow + X0 + i) = o;
+      }
+    }
+    return;
+  }
   float sc[8], sh[8];
   if (scale) {
     const long long so = (long long)ni * in.c + pl * 8;
@@ -449,6 +516,60 @@ __global__ void upsample2x_bwd_kernel(ActView gout, ActView gin16, float* gin32,
     float acc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    if constexpr (DT == 1) {
+      // fp16 gradients: the pixels that read low-res (y, x) lie in rows 2y-2..2y+3 and columns 2x-2..2x+3
+      // ((x-1)/r >= 2x-2 and (x+1)/r <= 2x+3 for r = (iw-1)/(2iw-1)).  Columns are walked branch-free with packed half2
+      // FMAs (a zero weight for the pixels that do not contribute): no divergence between the lanes of a warp, a
+      // quarter of the fp32 path's instructions.  Rows are skipped warp-uniformly.
+      const int Yb = 2 * y - 2, Xb = 2 * x - 2;
+      __half2 wx2[6];
+      float wyf[6];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        int a0, a1;
+        float l, wv = 0.f;
+        wyf[j] = 0.f;
+        if (Yb + j >= 0 && Yb + j < oh) {
+          src_index(Yb + j, sy, ih, a0, a1, l);
+          if (a0 == y) wyf[j] += 1.f - l;
+          if (a1 == y) wyf[j] += l;
+        }
+        if (Xb + j >= 0 && Xb + j < ow) {
+          src_index(Xb + j, sx, iw, a0, a1, l);
+          if (a0 == x) wv += 1.f - l;
+          if (a1 == x) wv += l;
+        }
+        wx2[j] = __float2half2_rn(wv);
+      }
+      const __half2 zero2 = __float2half2_rn(0.f);
+#pragma unroll
+      for (int jy = 0; jy < 6; ++jy) {
+        if (wyf[jy] == 0.f) continue;
+        __half2 r2[4] = {zero2, zero2, zero2, zero2};
+        const long long rowbase = (long long)(Yb + jy) * ow;
+#pragma unroll
+        for (int jx = 0; jx < 6; ++jx) {
+          const int X = min(max(Xb + jx, 0), ow - 1);       // clamped address, zero weight outside the image
+          const uint4 u = *chunk_ptr(gout, ni, pl, rowbase + X);
+          const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) r2[k] = __hfma2(wx2[jx], h[k], r2[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __half22float2(r2[k]);
+          acc[2 * k] = fmaf(wyf[jy], f.x, acc[2 * k]);
+          acc[2 * k + 1] = fmaf(wyf[jy], f.y, acc[2 * k + 1]);
+        }
+      }
+      if (gin16.ptr) *chunk_ptr(gin16, ni, pl, pix) = pack8<DT>(acc);
+      if (gin32) {
+        float* dst = gin32 + (((long long)ni * planes + pl) * ihw + pix) * 8;
+        *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      }
+      continue;
+    }
     const int Ylo = max(0, 2 * y - 3), Yhi = min(oh - 1, 2 * y + 4);
     const int Xlo = max(0, 2 * x - 3), Xhi = min(ow - 1, 2 * x + 4);
     // separable weights of the (at most 8 x 8) high-res window: 16 index computations instead of 8 + 64
