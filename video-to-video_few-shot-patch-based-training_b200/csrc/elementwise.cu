@@ -3,6 +3,8 @@
 // transpose, normalisation backward (reduce + apply), fused head backward, small reductions.
 // All kernels move one P8 pixel chunk (8 channels = 16 B) per thread access: coalesced 128-bit
 // loads/stores, grid-stride loops sized to a multiple of the SM count.
+#include <cooperative_groups.h>
+
 #include "internal.h"
 #include "ptx.cuh"
 
@@ -811,6 +813,98 @@ __global__ void __launch_bounds__(512) norm_bwd_fused_kernel(NormBwdK p) {
   }
 }
 
+// Cluster variant for large slices (hw >= 4096): the (image, plane) slice is split over a cluster of kNbCluster CTAs, each
+// staging its quarter in shared memory (51 KB at 80x80 -> four CTAs per SM instead of one 205 KB CTA, whose 16 warps could
+// not keep enough loads in flight: 190 us for 393 MB).  The 16 partial sums are exchanged through distributed shared
+// memory and added in rank order (deterministic).  grid: (planes * kNbCluster, n), cluster (kNbCluster, 1, 1).
+constexpr int kNbCluster = 4;
+template <int DT>
+__global__ void __launch_bounds__(kEwThreads) norm_bwd_fused_cluster_kernel(NormBwdK p) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) uint4 s_slice[];  // [pixels of this CTA][2] = (x chunk, gact chunk)
+  __shared__ float red[kEwThreads / 32][16];
+  __shared__ float part[16];
+  __shared__ float tot[16];
+  const int hw = p.x.h * p.x.w;
+  const int planes = p.x.c / 8;
+  const int rank = (int)cluster.block_rank();
+  const int pl = blockIdx.x / kNbCluster, ni = blockIdx.y;
+  const int per = (hw + kNbCluster - 1) / kNbCluster;
+  const int p0 = rank * per, p1 = min(hw, p0 + per);
+  float s1[8], s2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s1[k] = s2[k] = 0.f;
+  for (int pix = p0 + threadIdx.x; pix < p1; pix += blockDim.x) {
+    float gact[8], xhat[8], xr[8];
+    load_gact<DT>(p, ni, pl, pix, planes, hw, gact, xhat, xr);
+    const uint4 gq = pack8<DT>(gact);
+    s_slice[2 * (pix - p0)] = pack8<DT>(xr);
+    s_slice[2 * (pix - p0) + 1] = gq;
+    unpack8<DT>(gq, gact);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      s1[k] += gact[k];
+      s2[k] = fmaf(gact[k], xhat[k], s2[k]);
+    }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], o);
+      s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], o);
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      red[wid][k] = s1[k];
+      red[wid][8 + k] = s2[k];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    float t = 0.f;
+    for (int w2 = 0; w2 < kEwThreads / 32; ++w2) t += red[w2][threadIdx.x];
+    part[threadIdx.x] = t;
+  }
+  cluster.sync();                                   // every CTA's partial sums are visible cluster-wide
+  if (threadIdx.x < 16) {
+    float t = 0.f;
+    for (int r = 0; r < kNbCluster; ++r) t += *cluster.map_shared_rank(&part[threadIdx.x], r);
+    tot[threadIdx.x] = t;
+    if (rank == 0) {
+      const int which = threadIdx.x >> 3, k = threadIdx.x & 7;
+      p.sums[(long long)ni * 2 * p.x.c + (long long)which * p.x.c + pl * 8 + k] = t;
+    }
+  }
+  cluster.sync();                                   // nobody exits while a peer may still read its `part`
+  float m1[8], m2[8], km[8], mu[8], sh[8];
+  const long long ko = (p.per_channel ? 0 : (long long)ni * p.x.c) + pl * 8;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    m1[k] = tot[k] * p.inv_count;
+    m2[k] = tot[8 + k] * p.inv_count;
+    km[k] = __ldg(&p.kmul[ko + k]);
+    mu[k] = __ldg(&p.mean[ko + k]);
+    sh[k] = __ldg(&p.shift[ko + k]);
+  }
+  for (int pix = p0 + threadIdx.x; pix < p1; pix += blockDim.x) {
+    float gact[8], xhat[8], r[8], xr[8];
+    unpack8<DT>(s_slice[2 * (pix - p0)], xr);
+    unpack8<DT>(s_slice[2 * (pix - p0) + 1], gact);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      xhat[k] = fmaf(xr[k], mu[k], sh[k]);
+      r[k] = km[k] * (gact[k] - m1[k] - xhat[k] * m2[k]);
+      if (p.relu_mask_x && !(xr[k] > 0.f)) r[k] = 0.f;
+    }
+    *chunk_ptr(p.dx, ni, pl, pix) = pack8<DT>(r);
+  }
+}
+
 // ------------------------------------------------------------------ head backward
 // grid: (chunks, planes of s); block reduces dW[3][8], dbias_prev[8] (+ db[3] on plane 0)
 template <int DT>
@@ -1191,7 +1285,33 @@ extern "C" int pbt_norm_bwd_fused(const pbt_norm_bwd_desc_t* d, void* stream_) {
   const long long hw = (long long)d->x.h * d->x.w;
   const size_t slice = (size_t)hw * 32;            // x chunk + activated-gradient chunk per pixel
   const int threads = hw >= 4096 ? 512 : kEwThreads;   // one big CTA per SM when the slice fills shared memory
-  if (slice <= 200 * 1024) {
+  if (hw >= 4096 && slice / kNbCluster + 64 <= 56 * 1024) {
+    // large slices: a cluster of CTAs per slice (see norm_bwd_fused_cluster_kernel)
+    const size_t part_bytes = (size_t)((hw + kNbCluster - 1) / kNbCluster) * 32;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(d->x.c / 8 * kNbCluster), (unsigned)d->x.n, 1);
+    cfg.blockDim = dim3(kEwThreads, 1, 1);
+    cfg.dynamicSmemBytes = part_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kNbCluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (d->dtype == PBT_BF16) {
+      PBT_CUDA_CHECK(cudaFuncSetAttribute(norm_bwd_fused_cluster_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_bytes));
+      PBT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, norm_bwd_fused_cluster_kernel<0>, p));
+    } else if (d->dtype == PBT_FP16) {
+      PBT_CUDA_CHECK(cudaFuncSetAttribute(norm_bwd_fused_cluster_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_bytes));
+      PBT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, norm_bwd_fused_cluster_kernel<1>, p));
+    } else {
+      pbt::set_last_error("bad dtype");
+      return PBT_ERR_ARG;
+    }
+  } else if (slice <= 200 * 1024) {
     if (d->dtype == PBT_BF16) {
       PBT_CUDA_CHECK(cudaFuncSetAttribute(norm_bwd_fused_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slice));
       norm_bwd_fused_kernel<0, true><<<grid, threads, slice, st>>>(p);
