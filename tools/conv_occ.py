@@ -18,9 +18,9 @@ cases = [("smooth 64->64 3x3 @1080p", 64, 64, 3, 1080, 1920, 32, [(3, 0), (2, 4.
          ("conv11 176->64 7x7 @1080p", 176, 64, 7, 1080, 1920, 32, [(3, 0), (3, "pair"), (2, "pair4")])]
 if len(sys.argv) > 2 and sys.argv[2] == "train":   # C3 training shapes: 80 patches of 80x80 (N = batch)
     N = 80
-    cases = [("res 128->128 3x3 @20x20", 128, 128, 3, 20, 20, 32, [(1, 0), (1, 4), (2, 0)]),
-             ("down2 s2d 256->128 2x2 @20x20", 256, 128, 2, 20, 20, 32, [(1, 0), (1, 4), (2, 0)]),
-             ("up2 256->128 3x3 @40x40", 256, 128, 3, 40, 40, 32, [(2, 0), (1, 0), (1, 4)]),
+    cases = [("res 128->128 3x3 @20x20", 128, 128, 3, 20, 20, 32, [(1, 0), (1, 4), (1, "pair"), (2, "pair")]),
+             ("down2 s2d 256->128 2x2 @20x20", 256, 128, 2, 20, 20, 32, [(1, 0), (1, 4), (1, "pair")]),
+             ("up2 256->128 3x3 @40x40", 256, 128, 3, 40, 40, 32, [(2, 0), (1, 4), (1, "pair"), (2, "pair")]),
              ("up1 192->128 3x3 @80x80", 192, 128, 3, 80, 80, 32, [(2, 0), (2, "pair"), (1, "pair")]),
              ("conv11 176->64 7x7 @80x80", 176, 64, 7, 80, 80, 32, [(2, 0), (2, "pair"), (1, "pair"), (2, "pair4")]),
              ("conv11 dgrad 64->160 7x7 @80x80", 64, 160, 7, 80, 80, 32, [(2, 0), (1, 0), (1, "pair")]),
