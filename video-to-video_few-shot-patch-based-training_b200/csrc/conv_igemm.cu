@@ -26,6 +26,7 @@
 //    CTAs runs one M=256 MMA stream and each CTA stages half of the weight columns).
 //  * CTAs are persistent over the units of long launches (barrier phases continue across units).
 //  Measurements behind these choices: profiles/r1_issue_experiments.md, tools/conv_timeline.py, tools/conv_occ.py.
+#include <cstdlib>
 #include <type_traits>
 
 #include "internal.h"
@@ -1024,11 +1025,13 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
   if (512 / p.tmem_cols < occ) occ = 512 / p.tmem_cols;
   if ((int)(233472u / (smem_bytes + 1024u)) < occ) occ = (int)(233472u / (smem_bytes + 1024u));
   if (occ < 1) occ = 1;
-  // Persistent only for long queues (>= 8 units per CTA slot): the static round-robin then balances to a few percent and
+  // Persistent only for queues of >= 3 units per CTA slot (measured: 2..8 are within 1 %, 3 is best at 960x540): the
+  // static round-robin then balances well enough and
   // the kernel owns the GPU long enough.  Shorter launches, and launches flagged `concurrent` (the backward sweep, where
   // side-stream wgrad kernels must be able to take SM slots and tensor memory in between), keep one unit per CTA and the
   // hardware's dynamic block scheduling.
-  if (!(d->debug_flags & 128) && !d->concurrent && grid >= 8 * occ * num_sms()) grid = occ * num_sms();  // (bring-up: bit 7 = one unit per CTA)
+  static const int persist_min = getenv("PBT_PERSIST_MIN") ? atoi(getenv("PBT_PERSIST_MIN")) : 3;  // (tuning knob)
+  if (!(d->debug_flags & 128) && !d->concurrent && grid >= persist_min * occ * num_sms()) grid = occ * num_sms();  // (bring-up: bit 7 = one unit per CTA)
   const int kb = d->blk_c / 16;
   if (pair) {
     PBT_REQUIRE((ew == 4) == (d->ctas_per_sm == 4), "conv: cta_pair + ctas_per_sm=4 shape does not fit the small footprint");
