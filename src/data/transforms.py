@@ -1,17 +1,18 @@
-"""PIL mode helpers with the reference's names (src/data/transforms.py)."""
+"""Mode-normalising callables for torchvision-style pipelines, exported under the names the reference's loaders import
+(``RGBConvert``, ``GrayscaleConvert``): every frame / guide image becomes 3-channel RGB, every mask single-channel L."""
 
 
-class RGBConvert:
-    def __call__(self, img):
-        return img if img.mode == "RGB" else img.convert("RGB")
+class _ToMode:
+    mode = None
 
-    def __repr__(self):
-        return type(self).__name__
-
-
-class GrayscaleConvert:
-    def __call__(self, img):
-        return img if img.mode == "L" else img.convert("L")
+    def __call__(self, image):
+        if image.mode != self.mode:
+            image = image.convert(self.mode)
+        return image
 
     def __repr__(self):
-        return type(self).__name__
+        return f"{type(self).__name__}()"
+
+
+RGBConvert = type("RGBConvert", (_ToMode,), {"mode": "RGB", "__doc__": "any PIL image -> RGB"})
+GrayscaleConvert = type("GrayscaleConvert", (_ToMode,), {"mode": "L", "__doc__": "any PIL image -> 8-bit grey"})
