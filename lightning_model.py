@@ -3,9 +3,13 @@
 
 Scope: the generator half of ``training_step`` is the accelerated path — batched device
 sampler -> native GeneratorJ forward/backward -> L1*reconstruction_weight -> (data-parallel mean all-reduce)
--> clip_grad_norm_ -> Adam.  The PatchGAN discriminator and the VGG19 perceptual branch are outside that path
-(section 8f) and are not built here: configs that carry them load unchanged, the two loss terms are reported
-as disabled once, and the step runs generator-only (the G-only step is also what BASELINE.md times).
+-> clip_grad_norm_ -> Adam; the G-only step is what BASELINE.md times.
+The adversarial and perceptual branches (section 8f rank 4; reference lightning_model.py:224-236,270-283,294-319) are
+available behind ``training.use_adversarial_loss`` / ``training.use_perception_loss`` (default off = the G-only step):
+the PatchGAN critic (3->12->24->48->1 channels in the shipped config, 0.2 % of the generator's FLOPs) and the VGG taps
+run on the tensor library, the generator passes inside them — the no-grad pass of the critic step, the forward and the
+backward that receives dL/dy from both loss terms — run on the native kernels, and both Adam steps use the fused
+clip+Adam launches.  The whole two-network step replays as one CUDA graph (pbt_b200/graphs.py::GraphedGanStep).
 Uses pytorch_lightning.LightningModule as base when it is importable, else a plain nn.Module driven by
 pbt_b200.trainer.Trainer.
 """
@@ -69,27 +73,50 @@ class StyleTransferModel(_Base):
         self.generator = GeneratorJ(**args)
         self.discriminator = None
         self.perception_loss_model = None
-        if discriminator_config is not None or perception_loss_config:
-            print("[StyleTransferModel] discriminator / perceptual branches are outside the B200 hot path "
-                  "(SURVEY.md section 8f): running the generator-only step (L1 reconstruction loss)")
+        self.perception_loss_weight = 0.0
+        # The reference builds both branches whenever their config blocks exist (lightning_model.py:37-60).  Here the
+        # shipped config keeps the blocks (schema compatibility) and two switches turn the branches on; passing the
+        # blocks programmatically with the switches absent enables them, like the reference does.
+        want_d = discriminator_config is not None and bool(training_config.get("use_adversarial_loss", True))
+        want_p = bool(perception_loss_config) and bool(training_config.get("use_perception_loss", True))
+        if want_d:
+            from src.models.discriminator import DiscriminatorN_IN
+            d_args = to_container(dict(discriminator_config.get("args", {})))
+            if d_args.get("input_channels") in ("auto", None):
+                d_args["input_channels"] = 3          # the critic sees RGB patches (post / generated) only
+            self.discriminator = DiscriminatorN_IN(**d_args)
+        if want_p:
+            from src.models.perception import PerceptualVGG19
+            pm = perception_loss_config["perception_model"]
+            self.perception_loss_model = PerceptualVGG19(**to_container(dict(pm.get("args", {}))))
+            self.perception_loss_weight = float(perception_loss_config["weight"])
         self.reconstruction_criterion = getattr(nn, training_config["reconstruction_criterion"])()
+        self.adversarial_criterion = getattr(nn, training_config.get("adversarial_criterion", "MSELoss"))()
+        self.d_grad_sync = None
         self.use_cuda_graph = bool(training_config.get("cuda_graph", True))
         self.grad_sync = None
         self._optimizers = None
         self._graphed = None
 
     # ------------------------------------------------------------------ Lightning-shaped hooks
-    def configure_optimizers(self):
-        oc = to_container(dict(self.optimizer_config["generator"]))
+    def _adam(self, module: nn.Module, key: str):
+        oc = to_container(dict(self.optimizer_config[key]))
         oc["betas"] = tuple(oc.get("betas", (0.9, 0.999)))
         fused = bool(oc.pop("fused", True))
-        if fused and next(self.generator.parameters()).is_cuda:
-            # clip_grad_norm_ + Adam as two native launches over all 48 tensors (pbt_b200/optim.py); same state layout
+        if fused and next(module.parameters()).is_cuda:
+            # clip_grad_norm_ + Adam as two native launches over all tensors (pbt_b200/optim.py); same state layout
             from pbt_b200.optim import FusedClipAdam
-            return [FusedClipAdam(self.generator.parameters(), **oc)]
-        if self.use_cuda_graph and next(self.generator.parameters()).is_cuda:
+            return FusedClipAdam(module.parameters(), **oc)
+        if self.use_cuda_graph and next(module.parameters()).is_cuda:
             oc["capturable"] = True   # the whole step is replayed as one CUDA graph (pbt_b200/graphs.py)
-        return [torch.optim.Adam(self.generator.parameters(), **oc)]
+        return torch.optim.Adam(module.parameters(), **oc)
+
+    def configure_optimizers(self):
+        """[opt_g] or [opt_g, opt_d] (reference lightning_model.py:323-341)"""
+        opts = [self._adam(self.generator, "generator")]
+        if self.discriminator is not None:
+            opts.append(self._adam(self.discriminator, "discriminator"))
+        return opts
 
     def setup(self, stage: Optional[str] = None):
         if stage in ("fit", None):
@@ -121,25 +148,76 @@ class StyleTransferModel(_Base):
                     raise ValueError(f"Channel {name} not found in batch")
                 tensors.append(batch[key])
             combined_input = torch.cat(tensors, dim=1)
+        out = self.full_step(combined_input, batch["post"])
+        self._log_losses(out)
+        return out
+
+    def full_step(self, combined_input: torch.Tensor, post: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """critic update (when enabled), then generator update — reference training_step, lightning_model.py:224-250.
+        No host synchronisation inside: the same body is captured by the CUDA-graph steps."""
+        opts = self.optimizers()
+        opt_g = opts[0]
+        out: Dict[str, torch.Tensor] = {}
+        if self.discriminator is not None:
+            opt_d = opts[1]
+            opt_d.zero_grad(set_to_none=True)
+            d_loss = self._discriminator_step(combined_input, post)
+            d_loss["loss"].backward()
+            if self.d_grad_sync is not None:
+                self.d_grad_sync.collect_from_params()
+                self.d_grad_sync.finish()
+            self._clip_and_step(opt_d, self.discriminator)
+            out.update({k: v.detach() for k, v in d_loss.items() if k != "loss"})
         opt_g.zero_grad(set_to_none=True)
-        g_loss = self._generator_step(combined_input, batch)
+        g_loss = self._generator_step(combined_input, {"post": post})
         g_loss["loss"].backward()
         if self.grad_sync is not None:
             self.grad_sync.finish()          # mean over ranks, before the clip (DDP semantics of the reference)
+        self._clip_and_step(opt_g, self.generator)
+        out.update({k: v.detach() for k, v in g_loss.items()})
+        return out
+
+    def _clip_and_step(self, opt, module: nn.Module) -> None:
         clip = self.training_config["gradient_clip_val"] if self.training_config.get("use_gradient_clipping", False) else None
-        if hasattr(opt_g, "last_grad_norm"):     # FusedClipAdam: the clip is part of the optimiser launch
-            opt_g.step(max_grad_norm=clip)
+        if hasattr(opt, "last_grad_norm"):       # FusedClipAdam: the clip is part of the optimiser launch
+            opt.step(max_grad_norm=clip)
         else:
             if clip is not None:
-                torch.nn.utils.clip_grad_norm_(self.generator.parameters(), clip)
-            opt_g.step()
-        return g_loss
+                torch.nn.utils.clip_grad_norm_(module.parameters(), clip)
+            opt.step()
+
+    def _log_losses(self, out: Dict[str, torch.Tensor]) -> None:
+        tr = getattr(self, "trainer", None)
+        if tr is not None and getattr(tr, "global_step", 0) % max(1, int(self.training_config.get("log_every_n_steps", 10))) == 0:
+            names = {"margin_loss": "g_image_loss"}      # metric names of the reference's _log_metrics
+            self.log_dict({names.get(k, k): float(v) for k, v in out.items() if k != "loss"})
+
+    def _discriminator_step(self, combined_input: torch.Tensor, post: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """reference lightning_model.py:294-319; the generator pass is the native no-grad path in train() mode (its
+        BatchNorm running statistics advance, as they do in the reference)"""
+        with torch.no_grad():
+            generated = self.generator(combined_input)
+        real_labels, _ = self.discriminator(post)
+        real_loss = self.adversarial_criterion(real_labels, torch.ones_like(real_labels))
+        fake_labels, _ = self.discriminator(generated)
+        fake_loss = self.adversarial_criterion(fake_labels, torch.zeros_like(fake_labels))
+        d_loss = (real_loss + fake_loss) * 0.5
+        return {"loss": d_loss, "d_real_loss": real_loss, "d_fake_loss": fake_loss, "d_total_loss": d_loss}
 
     def graphed_training_step(self, batch: Dict[str, torch.Tensor], batch_idx: int):
         """the same generator step replayed as ONE CUDA graph (static shapes; falls back to training_step for the
         ragged last batch of an epoch)"""
         from pbt_b200.graphs import GraphedGeneratorStep
         x = batch["combined_input"]
+        if self.discriminator is not None or self.perception_loss_model is not None:
+            from pbt_b200.graphs import GraphedGanStep
+            if self._graphed is None:
+                self._graphed = GraphedGanStep(self, tuple(x.shape))
+            if tuple(x.shape) != tuple(self._graphed.x.shape):
+                return self.training_step(batch, batch_idx)
+            out = self._graphed(x, batch["post"])
+            self._log_losses(out)
+            return out
         if self._graphed is None:
             self._graphed = GraphedGeneratorStep(
                 self.generator, self.optimizers()[0], tuple(x.shape),
@@ -160,9 +238,14 @@ class StyleTransferModel(_Base):
         if self.training_config["use_image_loss"]:
             losses["margin_loss"] = self.reconstruction_criterion(generated, batch["post"]) * \
                 self.training_config["reconstruction_weight"]
+        if self.perception_loss_model is not None:      # reference lightning_model.py:270-275
+            _, fake_features = self.perception_loss_model(generated)
+            _, target_features = self.perception_loss_model(batch["post"].detach())
+            losses["g_perception_loss"] = ((fake_features - target_features) ** 2).mean() * self.perception_loss_weight
+        if self.discriminator is not None:              # reference lightning_model.py:277-283
+            fake_labels, _ = self.discriminator(generated)
+            losses["g_adversarial_loss"] = self.adversarial_criterion(fake_labels, torch.ones_like(fake_labels)) * \
+                self.training_config["adversarial_weight"]
         total = sum(losses.values())
         losses["g_total_loss"] = total
-        tr = getattr(self, "trainer", None)
-        if tr is not None and getattr(tr, "global_step", 0) % max(1, int(self.training_config.get("log_every_n_steps", 10))) == 0:
-            self.log_dict({"g_image_loss": float(losses.get("margin_loss", 0.0)), "g_total_loss": float(total)})
         return {"loss": total, **losses}

@@ -1,0 +1,62 @@
+"""``PerceptualVGG19`` under the reference's import path (reference src/models/perception.py:9-143): frozen VGG19
+feature taps for the perceptual term of the generator loss (reference lightning_model.py:270-275).
+
+Library module by design: the taps the shipped configuration uses (``feature_layers: [0, 3, 5]``) are the first three
+VGG convolutions on patch-sized inputs, evaluated by torchvision / cuDNN.  The ImageNet weights cannot be downloaded on
+an offline box, so ``path=None`` raises a clear error unless torchvision finds them in its local cache; ``path=<file>``
+loads a custom checkpoint exactly like the reference does (8x8 classifier head with ``num_classes`` outputs).
+"""
+from typing import List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch import Tensor
+
+
+class PerceptualVGG19(nn.Module):
+    def __init__(self, feature_layers: List[int], use_normalization: bool = True, path: Optional[str] = None,
+                 num_classes: int = 40, requires_grad: bool = False):
+        super().__init__()
+        from torchvision import models
+        if path is None:
+            try:
+                net = models.vgg19(weights=models.VGG19_Weights.IMAGENET1K_V1)
+            except Exception as e:  # noqa: BLE001 - no network / no cached weights
+                raise RuntimeError("PerceptualVGG19: the ImageNet VGG19 weights are not available offline; pass "
+                                   "perception_model.args.path=<state_dict file> or disable model.perception_loss") from e
+        else:
+            net = models.vgg19(weights=None)
+            head = [nn.Linear(512 * 8 * 8, 4096), nn.ReLU(True), nn.Dropout(), nn.Linear(4096, 4096), nn.ReLU(True),
+                    nn.Dropout(), nn.Linear(4096, num_classes)]
+            net.classifier = nn.Sequential(*head)
+            net.load_state_dict(torch.load(path, map_location="cpu"))
+        self.model = net.float().eval()
+        self.feature_layers = sorted(int(i) for i in feature_layers)
+        self.use_normalization = bool(use_normalization)
+        self.register_buffer("mean", torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1))
+        self.register_buffer("std", torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1))
+        if not requires_grad:
+            for p in self.parameters():
+                p.requires_grad = False
+
+    def normalize(self, x: Tensor) -> Tensor:
+        """[-1, 1] images -> ImageNet-normalised (identity when use_normalization is off)"""
+        return (0.5 * (x + 1.0) - self.mean) / self.std if self.use_normalization else x
+
+    def get_features(self, x: Tensor) -> Tensor:
+        """flattened taps after the listed ``features`` indices, concatenated per sample.  The taps are VIEWS of the
+        running activation, as in the reference (perception.py:106-110): an in-place ReLU that follows a tapped conv
+        therefore also rectifies the tap."""
+        taps, h = [], x
+        for i, layer in enumerate(self.model.features[: self.feature_layers[-1] + 1]):
+            h = layer(h)
+            if i in self.feature_layers:
+                taps.append(h.view(h.size(0), -1))
+        return torch.cat(taps, dim=1)
+
+    def forward(self, x: Tensor) -> Tuple[None, Tensor]:
+        return None, self.get_features(self.normalize(x))
+
+    def perceptual_loss(self, y_pred: Tensor, y_true: Tensor) -> Tensor:
+        return F.mse_loss(self(y_pred)[1], self(y_true)[1])

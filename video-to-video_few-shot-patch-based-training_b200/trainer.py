@@ -53,6 +53,8 @@ class Trainer:
             gen(torch.zeros(1, gen.input_channels, 16, 16, device=torch.device("cuda", self.local)))  # builds the engine
             model.grad_sync = GradAllReduce(list(gen.named_parameters()), world=self.world)
             gen._engine.grad_hook = model.grad_sync.grad_ready
+            if getattr(model, "discriminator", None) is not None:     # the critic's 98 kB of gradients: one exchange per step
+                model.d_grad_sync = GradAllReduce(list(model.discriminator.named_parameters()), world=self.world)
         loader = model.train_dataloader()
         bad_epochs, best_epoch_loss = 0, float("inf")
         model.train()
