@@ -93,6 +93,10 @@ class StyleTransferModel(_Base):
         self.reconstruction_criterion = getattr(nn, training_config["reconstruction_criterion"])()
         self.adversarial_criterion = getattr(nn, training_config.get("adversarial_criterion", "MSELoss"))()
         self.d_grad_sync = None
+        # one generator forward per adversarial step instead of the reference's two identical ones (see
+        # _shared_generator_pass); training.share_generator_pass=false restores the literal two-pass order
+        self.share_generator_pass = bool(training_config.get("share_generator_pass", True)) and \
+            all(bn.momentum is not None for bn in self.generator.modules() if isinstance(bn, nn.BatchNorm2d))
         self.use_cuda_graph = bool(training_config.get("cuda_graph", True))
         self.grad_sync = None
         self._optimizers = None
@@ -158,10 +162,13 @@ class StyleTransferModel(_Base):
         opts = self.optimizers()
         opt_g = opts[0]
         out: Dict[str, torch.Tensor] = {}
+        generated = None
         if self.discriminator is not None:
             opt_d = opts[1]
             opt_d.zero_grad(set_to_none=True)
-            d_loss = self._discriminator_step(combined_input, post)
+            if self.share_generator_pass:
+                generated = self._shared_generator_pass(combined_input)
+            d_loss = self._discriminator_step(combined_input, post, generated)
             d_loss["loss"].backward()
             if self.d_grad_sync is not None:
                 self.d_grad_sync.collect_from_params()
@@ -169,7 +176,7 @@ class StyleTransferModel(_Base):
             self._clip_and_step(opt_d, self.discriminator)
             out.update({k: v.detach() for k, v in d_loss.items() if k != "loss"})
         opt_g.zero_grad(set_to_none=True)
-        g_loss = self._generator_step(combined_input, {"post": post})
+        g_loss = self._generator_step(combined_input, {"post": post}, generated)
         g_loss["loss"].backward()
         if self.grad_sync is not None:
             self.grad_sync.finish()          # mean over ranks, before the clip (DDP semantics of the reference)
@@ -192,14 +199,42 @@ class StyleTransferModel(_Base):
             names = {"margin_loss": "g_image_loss"}      # metric names of the reference's _log_metrics
             self.log_dict({names.get(k, k): float(v) for k, v in out.items() if k != "loss"})
 
-    def _discriminator_step(self, combined_input: torch.Tensor, post: torch.Tensor) -> Dict[str, torch.Tensor]:
-        """reference lightning_model.py:294-319; the generator pass is the native no-grad path in train() mode (its
-        BatchNorm running statistics advance, as they do in the reference)"""
+    def _shared_generator_pass(self, combined_input: torch.Tensor) -> torch.Tensor:
+        """ONE generator forward for both halves of the step.  The reference runs the generator twice per step on the
+        same input with the same weights (no-grad for the critic, lightning_model.py:296-297, then with autograd, :262;
+        opt_g steps only afterwards), so the two outputs are identical: the pass with autograd serves both, its
+        detached result feeds the critic.  The only side effect of the second train()-mode pass — another momentum
+        update of the BatchNorm running statistics with the same batch moments — is applied in closed form:
+        r1 = (1-mu) r0 + mu m,  r2 = (1-mu) r1 + mu m  =>  r2 = (2-mu) r1 - (1-mu) r0."""
+        bns = [m for m in self.generator.modules() if isinstance(m, nn.BatchNorm2d)] if self.generator.training else []
+        before = [(bn.running_mean.clone(), bn.running_var.clone()) for bn in bns]
+        generated = self.generator(combined_input)
         with torch.no_grad():
-            generated = self.generator(combined_input)
-        real_labels, _ = self.discriminator(post)
+            for bn, (m0, v0) in zip(bns, before):
+                mu = bn.momentum
+                bn.running_mean.mul_(2.0 - mu).sub_(m0, alpha=1.0 - mu)
+                bn.running_var.mul_(2.0 - mu).sub_(v0, alpha=1.0 - mu)
+                bn.num_batches_tracked += 1
+        return generated
+
+    def _discriminator_step(self, combined_input: torch.Tensor, post: torch.Tensor,
+                            generated: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """reference lightning_model.py:294-319.  Without a shared pass the generator runs the native no-grad path in
+        train() mode (its BatchNorm running statistics advance, as they do in the reference).  Real and generated
+        patches go through the critic as ONE batch: its convolutions and InstanceNorms are per sample, so the logits
+        are those of two separate calls (BatchNorm critics, whose statistics would mix, keep the two calls)."""
+        if generated is None:
+            with torch.no_grad():
+                generated = self.generator(combined_input)
+        generated = generated.detach()
+        per_sample = not any(isinstance(m, nn.BatchNorm2d) for m in self.discriminator.modules()) and \
+            not (self.discriminator.use_noise and self.discriminator.training)
+        if per_sample and generated.shape == post.shape:
+            real_labels, fake_labels = self.discriminator(torch.cat([post, generated], dim=0))[0].chunk(2, dim=0)
+        else:
+            real_labels, _ = self.discriminator(post)
+            fake_labels, _ = self.discriminator(generated)
         real_loss = self.adversarial_criterion(real_labels, torch.ones_like(real_labels))
-        fake_labels, _ = self.discriminator(generated)
         fake_loss = self.adversarial_criterion(fake_labels, torch.zeros_like(fake_labels))
         d_loss = (real_loss + fake_loss) * 0.5
         return {"loss": d_loss, "d_real_loss": real_loss, "d_fake_loss": fake_loss, "d_total_loss": d_loss}
@@ -232,8 +267,9 @@ class StyleTransferModel(_Base):
             self.log_dict({"g_image_loss": float(loss), "g_total_loss": float(loss)})
         return {"loss": loss, "g_total_loss": loss}
 
-    def _generator_step(self, combined_input, batch):
-        generated = self.generator(combined_input)
+    def _generator_step(self, combined_input, batch, generated: Optional[torch.Tensor] = None):
+        if generated is None:
+            generated = self.generator(combined_input)
         losses = {}
         if self.training_config["use_image_loss"]:
             losses["margin_loss"] = self.reconstruction_criterion(generated, batch["post"]) * \

@@ -118,8 +118,10 @@ def test_gan_training_step_matches_oracle(gold):
                  "reconstruction_criterion": "L1Loss", "adversarial_criterion": "MSELoss", "use_gradient_clipping": True,
                  "gradient_clip_val": 0.5, "cuda_graph": False}
     adam = {"lr": 0.0004, "betas": [0.9, 0.999], "weight_decay": 0.00001}
-    for graphed in (False, True):
-        m = StyleTransferModel(gen_cfg, {"type": "DiscriminatorN_IN", "args": dict(D_ARGS)}, dict(train_cfg, cuda_graph=graphed),
+    # literal two-pass order of the reference (eager), then the shared-pass step eager and as one CUDA graph
+    for graphed, shared in ((False, False), (False, True), (True, True)):
+        m = StyleTransferModel(gen_cfg, {"type": "DiscriminatorN_IN", "args": dict(D_ARGS)},
+                               dict(train_cfg, cuda_graph=graphed, share_generator_pass=shared),
                                {"generator": dict(adam), "discriminator": dict(adam)}, {"additional_channels": {}})
         m.generator.load_state_dict(g_sd, strict=True)
         m.discriminator.load_state_dict(_group(gold, "d_init"), strict=True)
@@ -152,7 +154,7 @@ def test_gan_training_step_matches_oracle(gold):
             moved = max(moved, (now - g_sd[k].float()).abs().max().item())
             if not _feeds_instance_norm(k) and "running_" not in k:
                 cos_g[k] = float(torch.nn.functional.cosine_similarity((now - g_sd[k]).flatten(), (ref - g_sd[k]).flatten(), dim=0))
-        print(f"graphed={graphed} update cosines: critic {cos_d}  generator {cos_g}")
+        print(f"graphed={graphed} shared={shared} update cosines: critic {cos_d}  generator {cos_g}")
         assert min(cos_d.values()) > 0.99, cos_d
         assert min(cos_g.values()) > 0.95, cos_g
         for k in ("smoothers.2.running_mean", "smoothers.2.running_var"):
