@@ -141,7 +141,7 @@ class GeneratorJ(nn.Module):
         if self._engine is None:
             self._engine = _Engine(self)
         params = _param_list(self)
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
         if need_grad:
             y = _GeneratorFn.apply(x, self, *params)
         else:
@@ -157,7 +157,9 @@ class _GeneratorFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, gen, *params):
         ctx.gen = gen
-        ctx.x_needs_grad = x.requires_grad
+        ctx.x_needs_grad, ctx.x_dtype = x.requires_grad, x.dtype
+        if x.requires_grad:
+            gen._engine.input_grad = True      # also packs the two data-gradient kernels that reach the input
         y = gen._engine.forward(x, save=True)
         ctx.save_for_backward(y)
         return y
@@ -165,11 +167,8 @@ class _GeneratorFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         (y,) = ctx.saved_tensors
-        if ctx.x_needs_grad:
-            raise NotImplementedError("gradient w.r.t. the generator input is not computed by the native path "
-                                      "(the reference training never uses it)")
-        grads = ctx.gen._engine.backward(gy.contiguous().float(), y)
-        return (None, None, *grads)
+        grads, gx = ctx.gen._engine.backward(gy.contiguous().float(), y, want_input_grad=ctx.x_needs_grad)
+        return (None if gx is None else gx.to(ctx.x_dtype), None, *grads)
 
 
 class _Workspace:
@@ -229,6 +228,7 @@ class _Engine:
         self._ws: Dict[Any, _Workspace] = {}
         self._wslots: Dict[bool, Any] = {}
         self.grad_scale_target = 32.0 if self.dt == FP16 else 0.0  # dynamic power-of-two gradient scaling (fp16 only), see backward()
+        self.input_grad = False   # set once an input with requires_grad is seen: the backward sweep then also produces dL/dx
         self.grad_hook = None     # callable(name, grad) fired as each parameter gradient is produced (data parallel)
         self.kernel_timer = None  # bench.py: list collecting CUDA-event pairs around the dominant kernel (conv11)
 
@@ -274,6 +274,11 @@ class _Engine:
         f = self.gen.filters
         return _pad16(f[4] + f[0]) % 32 == 0 and self._blk(f[5]) == 32
 
+    def cat11x_channels(self) -> int:
+        """channel count of the conv11 data gradient when it also covers the x slot: [up1 | conv0 | x] padded to 32"""
+        f = self.gen.filters
+        return (f[4] + f[0] + self.cin_p + 31) // 32 * 32
+
     def _blk(self, cin: int) -> int:
         return 32 if cin % 32 == 0 or cin > 32 else 16
 
@@ -281,10 +286,11 @@ class _Engine:
         """packed 16-bit conv operands, rebuilt by ONE native launch whenever a parameter changed (version counters)"""
         g = self.gen
         key = tuple((p.data_ptr(), p._version) for p in g.parameters())
-        slot = self._wslots.get(with_dgrad)
+        slot_key = (with_dgrad, with_dgrad and self.input_grad)
+        slot = self._wslots.get(slot_key)
         if slot is None or slot["ptrs"] != tuple(p.data_ptr() for p in g.parameters()):
             slot = self._build_packer(with_dgrad)
-            self._wslots[with_dgrad] = slot
+            self._wslots[slot_key] = slot
         if slot["key"] != key:
             slot["packer"].run()
             slot["key"] = key
@@ -300,11 +306,11 @@ class _Engine:
             pk.add(name, conv.weight.detach(), s2d=s2d, k_pad=k_pad, n_out=co, n_keep=co, blk_c=blk or self._blk(k_pad), dt=dt,
                    pair=pair)
 
-        def dgr(name, conv, s2d=False, keep=None, pair=False):
+        def dgr(name, conv, s2d=False, keep=None, pair=False, n_out=None):
             co, ci = conv.weight.shape[0], conv.weight.shape[1]
             vi = 4 * ci if s2d else ci
             n_keep = vi if keep is None else keep
-            pk.add(name + ".d", conv.weight.detach(), s2d=s2d, dgrad=True, k_pad=co, n_out=_pad16(n_keep), n_keep=n_keep,
+            pk.add(name + ".d", conv.weight.detach(), s2d=s2d, dgrad=True, k_pad=co, n_out=n_out or _pad16(n_keep), n_keep=n_keep,
                    blk_c=self._blk(co), dt=dt, pair=pair)
 
         fwd("initial", g.initial_conv[0], cp)
@@ -330,6 +336,11 @@ class _Engine:
             dgr("conv11", g.conv11[0], keep=f[4] + f[0], pair=self.pair11_dgrad())
             dgr("smooth0", g.smoothers[0])
             dgr("smooth3", g.smoothers[3])
+            if self.input_grad:
+                # dL/dx has two sources: the x slot of conv11's input (all of cat11's channels, rows padded to a multiple
+                # of 32) and the initial conv
+                dgr("conv11x", g.conv11[0], n_out=self.cat11x_channels())
+                dgr("initial", g.initial_conv[0])
         W: Dict[str, Any] = dict(pk.out)
 
         def f32(t):
@@ -504,7 +515,7 @@ class _Engine:
         return wg + sums + 64 * 64   # slack for the 64-float alignment of each carve
 
     # -------------------------------------------------------------- backward
-    def backward(self, gy: Tensor, y: Tensor):
-        """returns gradients for `list(gen.parameters())` in order"""
+    def backward(self, gy: Tensor, y: Tensor, want_input_grad: bool = False):
+        """returns (gradients for `list(gen.parameters())` in order, dL/dx or None)"""
         from .generator_bwd import generator_backward
-        return generator_backward(self, gy, y)
+        return generator_backward(self, gy, y, want_input_grad)

@@ -31,7 +31,7 @@ def _wgrad_to_param(dw: torch.Tensor, cout: int, cin: int, kh: int, kw: int) -> 
     return dw[:, :cin].permute(2, 1, 0).reshape(cout, cin, kh, kw).contiguous()
 
 
-def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor) -> List[torch.Tensor]:
+def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor, want_input_grad: bool = False):
     g, dt, dev = eng.gen, eng.dt, eng.device
     ws, W = eng._saved
     f = g.filters
@@ -177,8 +177,13 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor) -> List[torch.Ten
     cin11 = f[4] + f[0] + g.input_channels
     wgrad_side("conv11.0.weight", ws.cat11, g_c11, 7, 3, lambda dw: _wgrad_to_param(dw, f[5], cin11, 7, 7))
     grads["conv11.0.bias"] = db_11
-    g_cat = E(f[4] + f[0], h, w)
-    dgrad("conv11", g_c11, f[4] + f[0], 7, 3, out=g_cat, T_pref=3, cta_pair=eng.pair11_dgrad())
+    if want_input_grad:
+        # the same data gradient over ALL of cat11's channels: [up1 | conv0 | x]; the x slot is one source of dL/dx
+        g_cat = E(eng.cat11x_channels(), h, w)
+        dgrad("conv11x", g_c11, g_cat.c, 7, 3, out=g_cat, T_pref=3)
+    else:
+        g_cat = E(f[4] + f[0], h, w)
+        dgrad("conv11", g_c11, f[4] + f[0], 7, 3, out=g_cat, T_pref=3, cta_pair=eng.pair11_dgrad())
     join()   # tail group complete (output head, smoothers, conv11)
     del g_c11, g_s0, g_s0n, g_s3
     # ---- upsample1 block
@@ -241,6 +246,16 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor) -> List[torch.Ten
     in_bwd(ws.raw0, ws.stats["initial"], ACT_LEAKY, g_raw0, h * w, ga=g_s2d0, ga_is_s2d=True, gb16=g_cat.view(f[4], f[0]))
     wgrad_side("initial_conv.0.weight", ws.cat11.view(f[4] + f[0], cp), g_raw0, 7, 3,
                lambda dw: _wgrad_to_param(dw, f[0], g.input_channels, 7, 7))
+    gx = None
+    if want_input_grad:
+        # dL/dx = (x slot of conv11's data gradient) + (data gradient of the initial conv); never used by the reference
+        # training, so it is assembled with tensor-library glue instead of a fused epilogue
+        g_x0 = E(cp, h, w)
+        dgrad("initial", g_raw0, cp, 7, 3, out=g_x0)
+        ci = g.input_channels
+        gx = g_cat.view(f[4] + f[0], cp).to_nchw()[:, :ci] + g_x0.to_nchw()[:, :ci]
+        if inv is not None:
+            gx = gx * inv
     join()   # trunk group complete
     if eng.grad_scale_target > 0:
         # an fp16 overflow anywhere in the sweep ends up as inf/nan in this most-downstream gradient: shrink the scale
@@ -254,4 +269,4 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor) -> List[torch.Ten
         if gr is None:
             raise RuntimeError(f"no gradient produced for {name}")
         out.append(gr.reshape(p.shape).to(p.dtype))
-    return out
+    return out, gx
