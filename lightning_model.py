@@ -279,7 +279,16 @@ class StyleTransferModel(_Base):
             _, target_features = self.perception_loss_model(batch["post"].detach())
             losses["g_perception_loss"] = ((fake_features - target_features) ** 2).mean() * self.perception_loss_weight
         if self.discriminator is not None:              # reference lightning_model.py:277-283
-            fake_labels, _ = self.discriminator(generated)
+            # only dL/d(generated) is needed from this pass: the critic's own gradients of the generator loss are
+            # discarded by the reference (opt_d.zero_grad() opens the next step), so they are not computed at all
+            frozen = [p for p in self.discriminator.parameters() if p.requires_grad]
+            for p in frozen:
+                p.requires_grad_(False)
+            try:
+                fake_labels, _ = self.discriminator(generated)
+            finally:
+                for p in frozen:
+                    p.requires_grad_(True)
             losses["g_adversarial_loss"] = self.adversarial_criterion(fake_labels, torch.ones_like(fake_labels)) * \
                 self.training_config["adversarial_weight"]
         total = sum(losses.values())
