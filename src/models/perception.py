@@ -6,6 +6,7 @@ VGG convolutions on patch-sized inputs, evaluated by torchvision / cuDNN.  The I
 an offline box, so ``path=None`` raises a clear error unless torchvision finds them in its local cache; ``path=<file>``
 loads a custom checkpoint exactly like the reference does (8x8 classifier head with ``num_classes`` outputs).
 """
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -20,11 +21,15 @@ class PerceptualVGG19(nn.Module):
         super().__init__()
         from torchvision import models
         if path is None:
-            try:
-                net = models.vgg19(weights=models.VGG19_Weights.IMAGENET1K_V1)
-            except Exception as e:  # noqa: BLE001 - no network / no cached weights
-                raise RuntimeError("PerceptualVGG19: the ImageNet VGG19 weights are not available offline; pass "
-                                   "perception_model.args.path=<state_dict file> or disable model.perception_loss") from e
+            # the reference downloads the ImageNet weights here (perception.py:50); never start a download from inside a
+            # training job on a box that may have no route out - use torchvision's local cache or fail at once
+            w = models.VGG19_Weights.IMAGENET1K_V1
+            cached = os.path.join(torch.hub.get_dir(), "checkpoints", os.path.basename(w.url))
+            if not os.path.exists(cached) and os.environ.get("PBT_ALLOW_DOWNLOAD", "0") != "1":
+                raise RuntimeError(f"PerceptualVGG19: the ImageNet VGG19 weights are not available offline ({cached} is "
+                                   "missing); pass perception_model.args.path=<state_dict file>, set PBT_ALLOW_DOWNLOAD=1, "
+                                   "or disable training.use_perception_loss")
+            net = models.vgg19(weights=w)
         else:
             net = models.vgg19(weights=None)
             head = [nn.Linear(512 * 8 * 8, 4096), nn.ReLU(True), nn.Dropout(), nn.Linear(4096, 4096), nn.ReLU(True),

@@ -99,6 +99,7 @@ def test_perception_module_offline_behaviour(tmp_path):
     path = os.path.join(tmp_path, "vgg.pth")
     torch.save(net.state_dict(), path)
     p = PerceptualVGG19(feature_layers=[5, 0, 3], use_normalization=True, path=path)
+    os.remove(path)        # 0.5 GB (the reference's custom head is 512*8*8 x 4096): do not leave it in pytest's tmp retention
     assert not any(q.requires_grad for q in p.parameters())
     x = torch.rand(2, 3, 16, 16) * 2 - 1
     none, feats = p(x)
