@@ -164,3 +164,62 @@ def test_gan_training_step_matches_oracle(gold):
         assert moved > 3e-4            # the generator did step
         assert int(m.generator.state_dict()["smoothers.2.num_batches_tracked"]) == \
             int(g_sd["smoothers.2.num_batches_tracked"]) + 4     # two train-mode passes per step (critic + generator)
+
+
+@pytest.mark.gpu
+def test_perceptual_term_flows_into_the_native_backward(gold):
+    """generator loss = reconstruction + perceptual (feature MSE * weight): the feature extractor here is a small frozen
+    conv stack with PerceptualVGG19's interface (the ImageNet weights do not ship), the generator is the native one;
+    loss terms and the one-step gradient are compared with fp32 autograd through the oracle"""
+    from lightning_model import StyleTransferModel
+
+    class Taps(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            torch.manual_seed(11)
+            self.features = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3, padding=1), torch.nn.ReLU(inplace=True),
+                                                torch.nn.Conv2d(8, 8, 3, padding=1))
+            for p in self.parameters():
+                p.requires_grad = False
+
+        def forward(self, x):
+            h, taps = x, []
+            for i, layer in enumerate(self.features):
+                h = layer(h)
+                if i in (0, 2):
+                    taps.append(h.view(h.size(0), -1))
+            return None, torch.cat(taps, dim=1)
+
+    g_sd, x, post = _inputs()
+    train_cfg = {"batch_size": 8, "reconstruction_weight": 4.0, "adversarial_weight": 0.5, "use_image_loss": True,
+                 "reconstruction_criterion": "L1Loss", "adversarial_criterion": "MSELoss", "use_gradient_clipping": True,
+                 "gradient_clip_val": 0.5, "cuda_graph": False}
+    adam = {"lr": 0.0004, "betas": [0.9, 0.999], "weight_decay": 0.00001}
+    m = StyleTransferModel({"args": {"input_channels": 3, "use_bias": True}}, None, train_cfg, {"generator": dict(adam)},
+                           {"additional_channels": {}})
+    m.generator.load_state_dict(g_sd, strict=True)
+    taps = Taps()
+    m.perception_loss_model, m.perception_loss_weight = taps, 6.0
+    m = m.cuda().train()
+    out = m._generator_step(x.cuda(), {"post": post.cuda()})
+    out["loss"].backward()
+    # oracle
+    names = [k for k, v in g_sd.items() if v.is_floating_point() and "running_" not in k]
+    leaves = {k: g_sd[k].clone().requires_grad_(True) for k in names}
+    y = go.generator_forward({**g_sd, **leaves}, x, training=True)
+    taps_cpu = Taps()
+    rec = (y - post).abs().mean() * 4.0
+    per = ((taps_cpu(y)[1] - taps_cpu(post)[1]) ** 2).mean() * 6.0
+    ref = dict(zip(names, torch.autograd.grad(rec + per, [leaves[k] for k in names], allow_unused=True)))
+    assert float(out["margin_loss"]) == pytest.approx(float(rec), rel=1e-2)
+    assert float(out["g_perception_loss"]) == pytest.approx(float(per), rel=2e-2)
+    assert float(out["g_total_loss"]) == pytest.approx(float(rec + per), rel=1e-2)
+    for k in ("output.0.weight", "smoothers.3.weight", "conv11.0.weight", "upsample1.1.weight", "resnet_blocks.3.block.1.weight",
+              "initial_conv.0.weight"):
+        got, want = dict(m.generator.named_parameters())[k].grad.cpu(), ref[k]
+        cos = float(torch.nn.functional.cosine_similarity(got.flatten(), want.flatten(), dim=0))
+        peak = float(want.abs().max())
+        mse = float(((got.double() - want.double()) ** 2).mean())
+        ps = 10 * np.log10(peak * peak / mse)
+        print(f"{k}: cosine {cos:.5f} psnr {ps:.1f} dB")
+        assert cos > 0.99 and ps >= 40.0, k
