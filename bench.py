@@ -344,6 +344,46 @@ def run_native(args):
         yn = sty.stylize_device(frames[:1, :sh, :sw].contiguous())
         diff = (yn.cpu().int() - yc.int()).abs().max().item()
         cpu["max_abs_u8_diff_vs_native"] = int(diff)
+        # SURVEY section 8(d) also asks for: (i) the reference training step on the host cores (config C1: batch 40 of 32x32
+        # patches), (ii) the same-box "library bar": the reference network through stock torch / cuDNN kernels on this GPU
+        # (the oracle's functional forward is plain torch ops, so it runs on CUDA tensors unchanged).  Reported, not targets.
+        try:
+            sd1 = {k: v.clone() for k, v in sd.items()}
+            opt1 = go.AdamState([k for k, v in sd1.items() if v.is_floating_point() and "running_" not in k])
+            gcpu = torch.Generator().manual_seed(5)
+            x1, t1 = torch.rand(40, 3, 32, 32, generator=gcpu) * 2 - 1, torch.rand(40, 3, 32, 32, generator=gcpu) * 2 - 1
+            go.g_only_train_step(sd1, opt1, x1, t1)
+            t0, n1 = time.perf_counter(), 0
+            while n1 < 2 or time.perf_counter() - t0 < 4.0:
+                go.g_only_train_step(sd1, opt1, x1, t1)
+                n1 += 1
+            cpu["train_c1"] = {"value": 40 * n1 / (time.perf_counter() - t0), "unit": "patches/s", "cores": cores,
+                               "sample": f"{n1} G-only steps, batch 40 x 32x32, oracle port (fp32)"}
+        except Exception as e:  # noqa: BLE001
+            cpu["train_c1"] = {"unavailable": f"{type(e).__name__}: {e}"[:160]}
+        try:
+            lib_bar = {}
+            xg = (frames[:1].permute(0, 3, 1, 2).float() / 255 - 0.5) / 0.5
+            for name, dt_ in (("fp32", torch.float32), ("fp16", torch.float16)):
+                sdg = {k: (v.to(dev, dt_) if v.is_floating_point() else v.to(dev)) for k, v in sd.items()}
+                xin = xg.to(dt_)
+                with torch.no_grad():
+                    for _ in range(2):
+                        go.generator_forward(sdg, xin)
+                    torch.cuda.synchronize(dev)
+                    e0.record()
+                    for _ in range(3):
+                        go.generator_forward(sdg, xin)
+                    e1.record()
+                    torch.cuda.synchronize(dev)
+                lib_bar[name] = 3 / (e0.elapsed_time(e1) / 1e3)
+                del sdg, xin
+                torch.cuda.empty_cache()
+            cpu["same_gpu_torch_cudnn_frames_per_s"] = dict(lib_bar, note="reference network as stock torch ops (cuDNN convs, "
+                                                            "unfused norms / cat / upsample) on this B200, 1 frame per pass, "
+                                                            "generator only (no uint8 conversion)")
+        except Exception as e:  # noqa: BLE001
+            cpu["same_gpu_torch_cudnn_frames_per_s"] = {"unavailable": f"{type(e).__name__}: {e}"[:160]}
 
     frames_per_launch = min(F, max(1, int(sty.frames_per_pass)))
     conv11_flops = 2.0 * H * W * (49 * (160 + CIN)) * 64 * frames_per_launch
