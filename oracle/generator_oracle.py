@@ -4,6 +4,7 @@ CPU fp32 restatement of the reference generator path, written functionally over 
 shares no code with either the reference module tree or the CUDA implementation:
 
   generator_forward    <- GeneratorJ.forward                      reference src/models/generator.py:210-239
+  generator_forward_bn <- the same with norm_layer='batch_norm'                                   :83-87
   conv blocks          <- _make_conv_block / ResNetBlock / _make_upconv_block        :18-58,156-208
   g_only_train_step    <- StyleTransferModel.training_step (generator half) + _generator_step with
                           discriminator/perception disabled        reference lightning_model.py:239-250,260-292
@@ -37,6 +38,47 @@ def _conv(x: Tensor, sd: Dict[str, Tensor], key: str, stride: int, pad: int) -> 
 
 def _up2(x: Tensor) -> Tensor:
     return F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)
+
+
+def _bnorm(x: Tensor, sd: Dict[str, Tensor], key: str, training: bool, running: Optional[Dict[str, Tensor]]) -> Tensor:
+    """nn.BatchNorm2d(affine=True, eps 1e-5, momentum 0.1) at module path `key`; `running` (optional, train mode) maps
+    '<key>.running_mean' / '.running_var' / '.num_batches_tracked' to tensors that are advanced in place"""
+    g, b = sd[key + ".weight"].view(1, -1, 1, 1), sd[key + ".bias"].view(1, -1, 1, 1)
+    if training:
+        mean, var = x.mean(dim=(0, 2, 3)), x.var(dim=(0, 2, 3), unbiased=False)
+        if running is not None:
+            cnt = x.numel() / x.shape[1]
+            with torch.no_grad():
+                running[key + ".running_mean"].mul_(0.9).add_(0.1 * mean.detach())
+                running[key + ".running_var"].mul_(0.9).add_(0.1 * var.detach() * cnt / max(cnt - 1, 1))
+                running[key + ".num_batches_tracked"] += 1
+    else:
+        mean, var = sd[key + ".running_mean"], sd[key + ".running_var"]
+    return (x - mean.view(1, -1, 1, 1)) / torch.sqrt(var.view(1, -1, 1, 1) + 1e-5) * g + b
+
+
+def generator_forward_bn(sd: Dict[str, Tensor], x: Tensor, *, training: bool = False,
+                         running: Optional[Dict[str, Tensor]] = None, tanh: bool = True) -> Tensor:
+    """GeneratorJ(norm_layer='batch_norm') (reference src/models/generator.py:83-87 selects nn.BatchNorm2d for every norm
+    slot): same graph as generator_forward with BatchNorm2d at `<block>.1` (conv blocks), `block.2` / `block.5` (residual
+    blocks) and `<up block>.2`"""
+    n_blocks = 1 + max((int(k.split(".")[1]) for k in sd if k.startswith("resnet_blocks.")), default=-1)
+    bn = lambda t, key: _bnorm(t, sd, key, training, running)  # noqa: E731
+    conv0 = F.leaky_relu(bn(_conv(x, sd, "initial_conv.0", 1, 3), "initial_conv.1"), 0.2)
+    conv1 = F.leaky_relu(bn(_conv(conv0, sd, "downsample1.0", 2, 1), "downsample1.1"), 0.2)
+    conv2 = F.leaky_relu(bn(_conv(conv1, sd, "downsample2.0", 2, 1), "downsample2.1"), 0.2)
+    out = conv2
+    for b in range(n_blocks):
+        t = bn(_conv(F.relu(out), sd, f"resnet_blocks.{b}.block.1", 1, 1), f"resnet_blocks.{b}.block.2")
+        t = bn(_conv(F.relu(t), sd, f"resnet_blocks.{b}.block.4", 1, 1), f"resnet_blocks.{b}.block.5")
+        out = out + t
+    out = F.relu(bn(_conv(_up2(torch.cat([out, conv2], 1)), sd, "upsample2.1", 1, 1), "upsample2.2"))
+    out = F.relu(bn(_conv(_up2(torch.cat([out, conv1], 1)), sd, "upsample1.1", 1, 1), "upsample1.2"))
+    out = F.relu(_conv(torch.cat([out, conv0, x], 1), sd, "conv11.0", 1, 3))
+    out = F.relu(_conv(out, sd, "smoothers.0", 1, 1))
+    out = F.relu(_conv(bn(out, "smoothers.2"), sd, "smoothers.3", 1, 1))
+    out = _conv(out, sd, "output.0", 1, 0)
+    return torch.tanh(out) if tanh else out
 
 
 def generator_forward(sd: Dict[str, Tensor], x: Tensor, *, training: bool = False, n_blocks: Optional[int] = None,

@@ -112,9 +112,11 @@ def test_generator_has_no_cpu_path_and_validates_input():
     g = GeneratorJ(input_channels=3)
     with pytest.raises(RuntimeError, match="no CPU path"):
         g(torch.zeros(1, 3, 32, 32))
+    gg = GeneratorJ(input_channels=3, norm_layer="batch_norm")
+    gg._check_supported()                            # both norm options of the reference constructor are built
+    assert "initial_conv.1.running_var" in gg.state_dict() and "resnet_blocks.0.block.5.weight" in gg.state_dict()
     with pytest.raises(NotImplementedError):
-        gg = GeneratorJ(input_channels=3, norm_layer="batch_norm")
-        gg._check_supported()
+        GeneratorJ(input_channels=3, norm_layer="none")._check_supported()
 
 
 def test_config_compose_and_overrides():

@@ -123,8 +123,9 @@ class GeneratorJ(nn.Module):
     # ------------------------------------------------------------------ forward
     def _check_supported(self):
         f = self.filters
-        if self.norm_layer != "instance_norm":
-            raise NotImplementedError("native GeneratorJ supports norm_layer='instance_norm' only (the reference default)")
+        if self.norm_layer not in ("instance_norm", "batch_norm"):
+            raise NotImplementedError("native GeneratorJ supports norm_layer='instance_norm' (the reference default) and "
+                                      "'batch_norm'; the norm-free variant is not built")
         if any(c % 16 for c in (f[0], f[1], f[2], f[4], f[5])) or max(f) > 256 or 2 * f[2] > 256:
             raise NotImplementedError(f"native GeneratorJ needs filter counts that are multiples of 16 and <= 256, got {f}")
         if not self.append_smoothers:
@@ -274,6 +275,27 @@ class _Engine:
         f = self.gen.filters
         return _pad16(f[4] + f[0]) % 32 == 0 and self._blk(f[5]) == 32
 
+    def norm_modules(self):
+        """engine layer name -> (conv module, norm module) for every conv that is followed by a norm layer"""
+        g = self.gen
+        m = {"initial": (g.initial_conv[0], g.initial_conv[1]), "down1": (g.downsample1[0], g.downsample1[1]),
+             "down2": (g.downsample2[0], g.downsample2[1]), "up2": (g.upsample2[1], g.upsample2[2]),
+             "up1": (g.upsample1[1], g.upsample1[2])}
+        for i, blk in enumerate(g.resnet_blocks):
+            m[f"res{i}.a"] = (blk.block[1], blk.block[2])
+            m[f"res{i}.b"] = (blk.block[4], blk.block[5])
+        return m
+
+    def norm_param_names(self):
+        """engine layer name -> state_dict prefix of its norm module ('initial_conv.1', 'resnet_blocks.3.block.5', ...)"""
+        g = self.gen
+        m = {"initial": "initial_conv.1", "down1": "downsample1.1", "down2": "downsample2.1", "up2": "upsample2.2",
+             "up1": "upsample1.2"}
+        for i in range(len(g.resnet_blocks)):
+            m[f"res{i}.a"] = f"resnet_blocks.{i}.block.2"
+            m[f"res{i}.b"] = f"resnet_blocks.{i}.block.5"
+        return m
+
     def cat11x_channels(self) -> int:
         """channel count of the conv11 data gradient when it also covers the x slot: [up1 | conv0 | x] padded to 32"""
         f = self.gen.filters
@@ -363,6 +385,7 @@ class _Engine:
             n, _, h, w = x.shape
         h2, w2, h4, w4 = h // 2, w // 2, h // 4, w // 4
         train_bn = g.training
+        bn_mode = g.norm_layer == "batch_norm"
         ws = self.workspace(n, h, w, save)
         W = self._weights(with_dgrad=save)
         cp = self.cin_p
@@ -379,11 +402,36 @@ class _Engine:
             T = self._T(T_pref, ow)
             st = ws.stat(name, cout, oh, ow, T, dev)
             cin = (xin.c if xin is not None else 0) + (pre.c if pre is not None else 0)
+            frozen = bn_mode and not train_bn      # eval-mode BatchNorm: running statistics, no reduction
             ops.conv_fwd(xin, W[name], cout, k, k, pad, pad, dt, blk_c=self._blk(cin), tiles_per_cta=T, out=raw,
-                         stats_partial=st["partial"], upsample2x=up, pre=pre,
+                         stats_partial=None if frozen else st["partial"], upsample2x=up, pre=pre,
                          pre_scale=None if pre is None else pre_st["scale"], pre_shift=None if pre is None else pre_st["shift"],
                          pre_act=pre_act, ctas_per_sm=cps)
-            ops.norm_finalize(st["partial"], n, st["tiles"], cout, oh * ow, st["scale"], st["shift"], eps=EPS)
+            if not bn_mode:
+                ops.norm_finalize(st["partial"], n, st["tiles"], cout, oh * ow, st["scale"], st["shift"], eps=EPS)
+                return st
+            # norm_layer='batch_norm' (reference :83-87): the same scale/shift tables, filled from batch statistics pooled
+            # over the images (train) or from the running statistics (eval).  The conv bias is still skipped by the kernel:
+            # batch statistics remove it; the running mean and the eval-mode shift account for it on the host.
+            conv, bn = self.norm_modules()[name]
+            gamma, beta = bn.weight.detach().float(), bn.bias.detach().float()
+            bias = None if conv.bias is None else conv.bias.detach().float()
+            if frozen:
+                sc = gamma * torch.rsqrt(bn.running_var.float() + bn.eps)
+                sh = beta - bn.running_mean.float() * sc + (0 if bias is None else bias * sc)
+                st["scale"].copy_(sc.expand(n, cout))
+                st["shift"].copy_(sh.expand(n, cout))
+                return st
+            if "mean" not in st:
+                st["mean"] = torch.empty((cout,), device=dev)
+                st["rstd"] = torch.empty((cout,), device=dev)
+            mom = bn.momentum if bn.momentum is not None else 0.1
+            ops.norm_finalize(st["partial"], n, st["tiles"], cout, oh * ow, st["scale"], st["shift"], eps=bn.eps,
+                              batch_mode=True, gamma=gamma, beta=beta, running_mean=bn.running_mean,
+                              running_var=bn.running_var, momentum=mom, mean_out=st["mean"], rstd_out=st["rstd"])
+            if bias is not None:
+                bn.running_mean.add_(bias, alpha=mom)      # the module's statistics are those of conv output + bias
+            bn.num_batches_tracked += 1
             return st
 
         # input -> tail channels of cat11 (pad channels zeroed every call)

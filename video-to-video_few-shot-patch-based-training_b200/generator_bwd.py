@@ -23,8 +23,6 @@ from . import ops
 from ._native import ACT_LEAKY, ACT_NONE, ACT_RELU, P8
 
 
-_BIAS_BEFORE_IN = ("initial_conv.", "downsample1.", "downsample2.", "resnet_blocks.", "upsample1.", "upsample2.")
-
 
 def _wgrad_to_param(dw: torch.Tensor, cout: int, cin: int, kh: int, kw: int) -> torch.Tensor:
     """[taps, cin_pad, cout] -> [cout, cin, kh, kw]"""
@@ -121,9 +119,37 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor, want_input_grad: 
         pending.clear()
         keep.clear()
 
-    def in_bwd(x: P8, st, act, dx: P8, count, **kw):
-        sums = Z(n, 2, x.c)
-        ops.norm_bwd(x, dt, scale=st["scale"], shift=st["shift"], act=act, sums=sums, kmul=st["scale"], count=count, dx=dx, **kw)
+    bn_mode = g.norm_layer == "batch_norm"
+    norm_mods, norm_names = (eng.norm_modules(), eng.norm_param_names()) if bn_mode else ({}, {})
+
+    def in_bwd(x: P8, st, act, dx: P8, count, name=None, **kw):
+        if not bn_mode:
+            sums = Z(n, 2, x.c)
+            ops.norm_bwd(x, dt, scale=st["scale"], shift=st["shift"], act=act, sums=sums, kmul=st["scale"], count=count, dx=dx,
+                         **kw)
+            return
+        # BatchNorm2d (batch statistics) + activation.  The kernels evaluate the activation derivative at x*scale+shift,
+        # so they get the post-affine value y = gamma*xhat+beta there; the reduce then returns S1 = sum(gact) and
+        # S2 = sum(gact*y), from which A = sum(gact*xhat) = (S2 - beta*S1)/gamma gives d(gamma) = A, d(beta) = S1, and the
+        # apply, which computes k*(gact - s1/cnt - y*s2/cnt), yields the BatchNorm input gradient
+        # gamma*rstd*(gact - S1/cnt - xhat*A/cnt) when it is handed s1 = S1 - beta*A/gamma, s2 = A/gamma, k = gamma*rstd.
+        bn = norm_mods[name][1]
+        gamma, beta = bn.weight.detach().float(), bn.bias.detach().float()
+        gsafe = torch.where(gamma.abs() < 1e-12, torch.full_like(gamma, 1e-12), gamma)
+        sc = (gamma * st["rstd"]).contiguous()
+        sh = (beta - st["mean"] * sc).contiguous()
+        sums = Z(2, x.c)
+
+        def fix(sums_):
+            s1, s2 = sums_[0].clone(), sums_[1].clone()
+            a = (s2 - beta * s1) / gsafe
+            grads[norm_names[name] + ".weight"] = a * inv if inv is not None else a
+            grads[norm_names[name] + ".bias"] = s1 * inv if inv is not None else s1
+            sums_[0].copy_(s1 - beta * a / gsafe)
+            sums_[1].copy_(a / gsafe)
+
+        ops.norm_bwd(x, dt, scale=sc, shift=sh, per_channel=True, act=act, sums=sums, kmul=sc, count=n * count,
+                     batch_mode=True, dx=dx, between=fix, **kw)
 
     hook = getattr(eng, "grad_hook", None)   # data-parallel training: parallel.GradAllReduce.grad_ready
 
@@ -135,8 +161,10 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor, want_input_grad: 
 
     grads = _Grads()
     # a bias in front of an affine-less InstanceNorm has exactly zero gradient: publish those first
+    # (the same holds in front of a train-mode BatchNorm; the norm's own beta is not one of these)
+    silent = {id(conv.bias) for conv, _ in eng.norm_modules().values() if conv.bias is not None}
     for name, p in g.named_parameters():
-        if name.endswith(".bias") and name.startswith(_BIAS_BEFORE_IN):
+        if id(p) in silent:
             grads[name] = torch.zeros_like(p, dtype=torch.float32)
 
     # ---- head (1x1 + tanh) and the ReLU of smoothers.3
@@ -188,7 +216,7 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor, want_input_grad: 
     del g_c11, g_s0, g_s0n, g_s3
     # ---- upsample1 block
     g_rawU1 = E(f[4], h, w)
-    in_bwd(ws.rawU1, ws.stats["up1"], ACT_RELU, g_rawU1, h * w, ga=g_cat.view(0, f[4]))
+    in_bwd(ws.rawU1, ws.stats["up1"], ACT_RELU, g_rawU1, h * w, name="up1", ga=g_cat.view(0, f[4]))
     wgrad_side("upsample1.1.weight", ws.u1in, g_rawU1, 3, 1, lambda dw: _wgrad_to_param(dw, f[4], f[4] + f[1], 3, 3))
     g_u1in = E(f[4] + f[1], h, w)
     dgrad("up1", g_rawU1, f[4] + f[1], 3, 1, out=g_u1in)
@@ -198,7 +226,7 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor, want_input_grad: 
     del g_u1in
     # ---- upsample2 block
     g_rawU2 = E(f[4], h2, w2)
-    in_bwd(ws.rawU2, ws.stats["up2"], ACT_RELU, g_rawU2, h2 * w2, ga=g_c1cat.view(0, f[4]))
+    in_bwd(ws.rawU2, ws.stats["up2"], ACT_RELU, g_rawU2, h2 * w2, name="up2", ga=g_c1cat.view(0, f[4]))
     wgrad_side("upsample2.1.weight", ws.u2in, g_rawU2, 3, 1, lambda dw: _wgrad_to_param(dw, f[4], 2 * f[2], 3, 3))
     g_u2in = E(2 * f[2], h2, w2)
     dgrad("up2", g_rawU2, 2 * f[2], 3, 1, out=g_u2in)
@@ -218,32 +246,32 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor, want_input_grad: 
     for b in range(nb - 1, -1, -1):
         if evB is not None:
             main.wait_event(evB)
-        in_bwd(ws.rawB[b], ws.stats[f"res{b}.b"], ACT_NONE, g_rawB, h4 * w4, gb32=g_r)
+        in_bwd(ws.rawB[b], ws.stats[f"res{b}.b"], ACT_NONE, g_rawB, h4 * w4, name=f"res{b}.b", gb32=g_r)
         evB = wgrad_side(f"resnet_blocks.{b}.block.4.weight", ws.hmid[b], g_rawB, 3, 1, res_cv)
         dgrad(f"res{b}.b", g_rawB, f[2], 3, 1, out=g_h)
         if evA is not None:
             main.wait_event(evA)
-        in_bwd(ws.rawA[b], ws.stats[f"res{b}.a"], ACT_RELU, g_rawA, h4 * w4, ga=g_h)
+        in_bwd(ws.rawA[b], ws.stats[f"res{b}.a"], ACT_RELU, g_rawA, h4 * w4, name=f"res{b}.a", ga=g_h)
         evA = wgrad_side(f"resnet_blocks.{b}.block.1.weight", ws.a[b], g_rawA, 3, 1, res_cv)
         # g_r <- g_r + relu'(r_b) * dgrad   (in place: every element is read then written by the same thread)
         dgrad(f"res{b}.a", g_rawA, f[2], 3, 1, out=None, mask=ws.a[b], addend32=g_r, out32=g_r)
     # ---- downsample2 (conv2 feeds the residual stream and the decoder skip)
     g_raw2 = E(f[2], h4, w4)
-    in_bwd(ws.raw2, ws.stats["down2"], ACT_LEAKY, g_raw2, h4 * w4, gb16=g_c2skip, gb32=g_r)
+    in_bwd(ws.raw2, ws.stats["down2"], ACT_LEAKY, g_raw2, h4 * w4, name="down2", gb16=g_c2skip, gb32=g_r)
     wgrad_side("downsample2.0.weight", ws.s2d1, g_raw2, 2, 1,                # dw: [4, 4*f1, f2]
                lambda dw: ops.s2d_weight_grad(dw.permute(2, 1, 0).reshape(f[2], 4 * f[1], 2, 2), f[1]))
     g_s2d1 = E(4 * f[1], h4, w4)
     dgrad("down2", g_raw2, 4 * f[1], 2, 1, out=g_s2d1)
     # ---- downsample1
     g_raw1 = E(f[1], h2, w2)
-    in_bwd(ws.raw1, ws.stats["down1"], ACT_LEAKY, g_raw1, h2 * w2, ga=g_s2d1, ga_is_s2d=True, gb16=g_c1cat.view(f[4], f[1]))
+    in_bwd(ws.raw1, ws.stats["down1"], ACT_LEAKY, g_raw1, h2 * w2, name="down1", ga=g_s2d1, ga_is_s2d=True, gb16=g_c1cat.view(f[4], f[1]))
     wgrad_side("downsample1.0.weight", ws.s2d0, g_raw1, 2, 1,
                lambda dw: ops.s2d_weight_grad(dw.permute(2, 1, 0).reshape(f[1], 4 * f[0], 2, 2), f[0]))
     g_s2d0 = E(4 * f[0], h2, w2)
     dgrad("down1", g_raw1, 4 * f[0], 2, 1, out=g_s2d0)
     # ---- initial conv
     g_raw0 = E(f[0], h, w)
-    in_bwd(ws.raw0, ws.stats["initial"], ACT_LEAKY, g_raw0, h * w, ga=g_s2d0, ga_is_s2d=True, gb16=g_cat.view(f[4], f[0]))
+    in_bwd(ws.raw0, ws.stats["initial"], ACT_LEAKY, g_raw0, h * w, name="initial", ga=g_s2d0, ga_is_s2d=True, gb16=g_cat.view(f[4], f[0]))
     wgrad_side("initial_conv.0.weight", ws.cat11.view(f[4] + f[0], cp), g_raw0, 7, 3,
                lambda dw: _wgrad_to_param(dw, f[0], g.input_channels, 7, 7))
     gx = None

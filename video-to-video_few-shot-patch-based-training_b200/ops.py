@@ -179,8 +179,9 @@ def upsample2x_bwd(gout: P8, dt: int, gin16: P8 | None = None, gin32=None) -> No
 
 def norm_bwd(x: P8, dt: int, *, scale, shift, per_channel=False, act=ACT_NONE, ga: P8 | None = None, ga_is_s2d=False,
              gb16: P8 | None = None, gb32=None, sums, kmul, count: int, batch_mode=False, dx: P8,
-             relu_mask_x=False) -> None:
-    """reduce + apply of the (norm -> act) backward; `sums` must be zeroed by the caller."""
+             relu_mask_x=False, between=None) -> None:
+    """reduce + apply of the (norm -> act) backward; `sums` must be zeroed by the caller.  `between(sums)` (two-launch
+    path only) runs after the reduce and may rewrite the sums the apply will read."""
     d = nv.NormBwdDesc()
     d.x = x.act()
     d.scale, d.shift, d.per_channel, d.act = ptr(scale), ptr(shift), int(per_channel), act
@@ -192,6 +193,8 @@ def norm_bwd(x: P8, dt: int, *, scale, shift, per_channel=False, act=ACT_NONE, g
         check(lib().pbt_norm_bwd_fused(C.byref(d), stream_ptr()), "pbt_norm_bwd_fused")
         return
     check(lib().pbt_norm_bwd_reduce(C.byref(d), stream_ptr()), "pbt_norm_bwd_reduce")
+    if between is not None:
+        between(sums)
     check(lib().pbt_norm_bwd_apply(C.byref(d), stream_ptr()), "pbt_norm_bwd_apply")
 
 
