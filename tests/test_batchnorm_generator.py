@@ -98,3 +98,37 @@ def test_native_bn_generator_matches_reference(gold):
     err_e = (ye.cpu() - torch.from_numpy(gold["y_eval"])).abs().max().item()
     print(f"bn eval forward: max_abs={err_e:.5f}")
     assert err_e <= 2e-2
+
+
+@pytest.mark.gpu
+def test_bn_generator_graph_replay_equals_eager_steps(gold):
+    """the G-only step of the BatchNorm variant as one CUDA graph follows the eager trajectory (running statistics and
+    Adam state included: the capture's warm-up passes are rolled back)"""
+    from pbt_b200.graphs import GraphedGeneratorStep
+    from pbt_b200.optim import FusedClipAdam
+    x, tgt = torch.from_numpy(gold["x"]).cuda(), torch.from_numpy(gold["target"]).cuda()
+    runs = []
+    for graphed in (False, True):
+        g = build().cuda().train()
+        opt = FusedClipAdam(g.parameters(), lr=4e-4, betas=(0.9, 0.999), weight_decay=1e-5, max_grad_norm=0.5)
+        losses = []
+        if graphed:
+            step = GraphedGeneratorStep(g, opt, tuple(x.shape), clip=0.5)
+            for _ in range(4):
+                losses.append(float(step(x, tgt)))
+        else:
+            for _ in range(4):
+                opt.zero_grad(set_to_none=True)
+                loss = torch.nn.functional.l1_loss(g(x), tgt) * 4.0
+                loss.backward()
+                opt.step(max_grad_norm=0.5)
+                losses.append(float(loss))
+        runs.append((losses, {k: v.detach().float().cpu().clone() for k, v in g.state_dict().items()}))
+    (le, se), (lg, sg) = runs
+    print("eager", le, "graph", lg)
+    assert le[0] == pytest.approx(float(gold["loss"]), abs=1e-2)
+    assert lg == pytest.approx(le, rel=2e-3)
+    assert le[-1] < le[0]
+    for k in ("initial_conv.1.running_mean", "resnet_blocks.3.block.5.running_var", "smoothers.2.running_mean"):
+        assert torch.allclose(se[k], sg[k], rtol=1e-2, atol=1e-3), k
+    assert int(se["initial_conv.1.num_batches_tracked"]) == int(sg["initial_conv.1.num_batches_tracked"]) == 4
