@@ -5,6 +5,7 @@ shares no code with either the reference module tree or the CUDA implementation:
 
   generator_forward    <- GeneratorJ.forward                      reference src/models/generator.py:210-239
   generator_forward_bn <- the same with norm_layer='batch_norm'                                   :83-87
+  generator_forward_plain <- the same with a norm_layer string that selects no norm layers        :83-87
   conv blocks          <- _make_conv_block / ResNetBlock / _make_upconv_block        :18-58,156-208
   g_only_train_step    <- StyleTransferModel.training_step (generator half) + _generator_step with
                           discriminator/perception disabled        reference lightning_model.py:239-250,260-292
@@ -77,6 +78,27 @@ def generator_forward_bn(sd: Dict[str, Tensor], x: Tensor, *, training: bool = F
     out = F.relu(_conv(torch.cat([out, conv0, x], 1), sd, "conv11.0", 1, 3))
     out = F.relu(_conv(out, sd, "smoothers.0", 1, 1))
     out = F.relu(_conv(bn(out, "smoothers.2"), sd, "smoothers.3", 1, 1))
+    out = _conv(out, sd, "output.0", 1, 0)
+    return torch.tanh(out) if tanh else out
+
+
+def generator_forward_plain(sd: Dict[str, Tensor], x: Tensor, *, training: bool = False,
+                            running: Optional[Dict[str, Tensor]] = None, tanh: bool = True) -> Tensor:
+    """GeneratorJ with a norm_layer string that selects no norm (reference src/models/generator.py:83-87 leaves norm = None):
+    conv -> activation everywhere, the residual convs sit at block.1 / block.3 (:38-52); only smoothers.2 normalises"""
+    n_blocks = 1 + max((int(k.split(".")[1]) for k in sd if k.startswith("resnet_blocks.")), default=-1)
+    conv0 = F.leaky_relu(_conv(x, sd, "initial_conv.0", 1, 3), 0.2)
+    conv1 = F.leaky_relu(_conv(conv0, sd, "downsample1.0", 2, 1), 0.2)
+    conv2 = F.leaky_relu(_conv(conv1, sd, "downsample2.0", 2, 1), 0.2)
+    out = conv2
+    for b in range(n_blocks):
+        t = _conv(F.relu(out), sd, f"resnet_blocks.{b}.block.1", 1, 1)
+        out = out + _conv(F.relu(t), sd, f"resnet_blocks.{b}.block.3", 1, 1)
+    out = F.relu(_conv(_up2(torch.cat([out, conv2], 1)), sd, "upsample2.1", 1, 1))
+    out = F.relu(_conv(_up2(torch.cat([out, conv1], 1)), sd, "upsample1.1", 1, 1))
+    out = F.relu(_conv(torch.cat([out, conv0, x], 1), sd, "conv11.0", 1, 3))
+    out = F.relu(_conv(out, sd, "smoothers.0", 1, 1))
+    out = F.relu(_conv(_bnorm(out, sd, "smoothers.2", training, running), sd, "smoothers.3", 1, 1))
     out = _conv(out, sd, "output.0", 1, 0)
     return torch.tanh(out) if tanh else out
 

@@ -132,3 +132,71 @@ def test_bn_generator_graph_replay_equals_eager_steps(gold):
     for k in ("initial_conv.1.running_mean", "resnet_blocks.3.block.5.running_var", "smoothers.2.running_mean"):
         assert torch.allclose(se[k], sg[k], rtol=1e-2, atol=1e-3), k
     assert int(se["initial_conv.1.num_batches_tracked"]) == int(sg["initial_conv.1.num_batches_tracked"]) == 4
+
+
+# ------------------------------------------------------------------ norm-free variant (any other norm_layer string)
+def build_plain(seed=32):
+    from pbt_b200.generator import GeneratorJ
+    torch.manual_seed(seed)
+    g = GeneratorJ(input_channels=3, use_bias=True, norm_layer="none")
+    with torch.no_grad():
+        for m in g.modules():
+            if isinstance(m, torch.nn.Conv2d):
+                m.weight.mul_(3.0)
+                m.bias.copy_(0.05 * torch.sin(torch.arange(m.bias.numel(), dtype=torch.float32)))
+    return g
+
+
+@pytest.fixture(scope="module")
+def gold_plain():
+    return np.load(os.path.join(GOLD, "gen_plain_vectors.npz"))
+
+
+def test_oracle_plain_variant_matches_reference_fixture(gold, gold_plain):
+    g = build_plain()
+    sd = {k: v.detach().clone() for k, v in g.state_dict().items()}
+    assert "resnet_blocks.0.block.3.weight" in sd and "initial_conv.1.weight" not in sd     # reference module indices
+    x, tgt = torch.from_numpy(gold["x"]), torch.from_numpy(gold["target"])
+    names = [k for k, v in sd.items() if v.is_floating_point() and "running_" not in k]
+    leaves = {k: sd[k].clone().requires_grad_(True) for k in names}
+    running = {k: v for k, v in sd.items() if "running_" in k or "num_batches" in k}
+    y = go.generator_forward_plain({**sd, **leaves}, x, training=True, running=running)
+    loss = (y - tgt).abs().mean() * 4.0
+    assert (y.detach() - torch.from_numpy(gold_plain["y_train"])).abs().max().item() < 5e-5
+    grads = dict(zip(names, torch.autograd.grad(loss, [leaves[k] for k in names])))
+    for k, ref in _group(gold_plain, "grad/full").items():
+        assert (grads[k] - ref).abs().max().item() <= 1e-3 * float(ref.abs().max()) + 2e-6, k
+    y_eval = go.generator_forward_plain({**sd, **running}, x, training=False)
+    assert (y_eval - torch.from_numpy(gold_plain["y_eval"])).abs().max().item() < 5e-5
+
+
+@pytest.mark.gpu
+def test_native_plain_generator_matches_reference(gold, gold_plain):
+    g = build_plain().cuda().train()
+    x, tgt = torch.from_numpy(gold["x"]).cuda(), torch.from_numpy(gold["target"]).cuda()
+    y = g(x)
+    loss = torch.nn.functional.l1_loss(y, tgt) * 4.0
+    loss.backward()
+    err = (y.detach().cpu() - torch.from_numpy(gold_plain["y_train"])).abs().max().item()
+    print(f"plain train forward: max_abs={err:.5f} loss={float(loss):.5f} ref={float(gold_plain['loss']):.5f}")
+    assert err <= 2e-2 and abs(float(loss) - float(gold_plain["loss"])) < 1e-2
+    worst_cos, worst_ps = 1.0, 1e9
+    for k, ref in _group(gold_plain, "grad/full").items():
+        got = dict(g.named_parameters())[k].grad.cpu()
+        peak = float(ref.abs().max())
+        cos = float(torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0))
+        mse = float(((got.double() - ref.double()) ** 2).mean())
+        ps = 200.0 if mse == 0 else 10 * math.log10(peak * peak / mse)
+        print(f"   {k:36s} cosine={cos:.4f} psnr={ps:5.1f}")
+        worst_cos, worst_ps = min(worst_cos, cos), min(worst_ps, ps)
+    assert worst_cos > 0.97 and worst_ps >= 28.0, (worst_cos, worst_ps)       # random-init weights, see the BatchNorm test
+    for k, ref in _group(gold_plain, "grad/moments").items():
+        got = dict(g.named_parameters())[k].grad.double()
+        if float(ref[1]) > 1e-12:
+            assert abs(float((got * got).sum()) / float(ref[1]) - 1.0) < 0.15, k
+    g.eval()
+    with torch.no_grad():
+        ye = g(x)
+    err_e = (ye.cpu() - torch.from_numpy(gold_plain["y_eval"])).abs().max().item()
+    print(f"plain eval forward: max_abs={err_e:.5f}")
+    assert err_e <= 2e-2

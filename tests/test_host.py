@@ -115,8 +115,11 @@ def test_generator_has_no_cpu_path_and_validates_input():
     gg = GeneratorJ(input_channels=3, norm_layer="batch_norm")
     gg._check_supported()                            # both norm options of the reference constructor are built
     assert "initial_conv.1.running_var" in gg.state_dict() and "resnet_blocks.0.block.5.weight" in gg.state_dict()
+    plain = GeneratorJ(input_channels=3, norm_layer="none")           # any other string: no norm layers (reference :83-87)
+    plain._check_supported()
+    assert "resnet_blocks.0.block.3.weight" in plain.state_dict() and "initial_conv.1.weight" not in plain.state_dict()
     with pytest.raises(NotImplementedError):
-        GeneratorJ(input_channels=3, norm_layer="none")._check_supported()
+        GeneratorJ(input_channels=3, filters=[24, 64, 128, 128, 128, 64])._check_supported()
 
 
 def test_config_compose_and_overrides():

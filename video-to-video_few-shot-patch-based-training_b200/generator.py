@@ -123,9 +123,6 @@ class GeneratorJ(nn.Module):
     # ------------------------------------------------------------------ forward
     def _check_supported(self):
         f = self.filters
-        if self.norm_layer not in ("instance_norm", "batch_norm"):
-            raise NotImplementedError("native GeneratorJ supports norm_layer='instance_norm' (the reference default) and "
-                                      "'batch_norm'; the norm-free variant is not built")
         if any(c % 16 for c in (f[0], f[1], f[2], f[4], f[5])) or max(f) > 256 or 2 * f[2] > 256:
             raise NotImplementedError(f"native GeneratorJ needs filter counts that are multiples of 16 and <= 256, got {f}")
         if not self.append_smoothers:
@@ -275,26 +272,41 @@ class _Engine:
         f = self.gen.filters
         return _pad16(f[4] + f[0]) % 32 == 0 and self._blk(f[5]) == 32
 
+    def norm_mode(self) -> str:
+        """'instance' | 'batch' | 'none' — reference src/models/generator.py:83-87 (any other string means no norm layers)"""
+        return {"instance_norm": "instance", "batch_norm": "batch"}.get(self.gen.norm_layer, "none")
+
+    def res_conv_index(self):
+        """positions of the two convs inside ResNetBlock.block: (1, 4) with norm layers, (1, 3) without (reference :31-56)"""
+        return (1, 4) if self.norm_mode() != "none" else (1, 3)
+
     def norm_modules(self):
-        """engine layer name -> (conv module, norm module) for every conv that is followed by a norm layer"""
+        """engine layer name -> (conv module, norm module or None) for every conv of a (conv -> norm -> act) block"""
         g = self.gen
-        m = {"initial": (g.initial_conv[0], g.initial_conv[1]), "down1": (g.downsample1[0], g.downsample1[1]),
-             "down2": (g.downsample2[0], g.downsample2[1]), "up2": (g.upsample2[1], g.upsample2[2]),
-             "up1": (g.upsample1[1], g.upsample1[2])}
+        has = self.norm_mode() != "none"
+        ia, ib = self.res_conv_index()
+        m = {"initial": (g.initial_conv[0], g.initial_conv[1] if has else None),
+             "down1": (g.downsample1[0], g.downsample1[1] if has else None),
+             "down2": (g.downsample2[0], g.downsample2[1] if has else None),
+             "up2": (g.upsample2[1], g.upsample2[2] if has else None), "up1": (g.upsample1[1], g.upsample1[2] if has else None)}
         for i, blk in enumerate(g.resnet_blocks):
-            m[f"res{i}.a"] = (blk.block[1], blk.block[2])
-            m[f"res{i}.b"] = (blk.block[4], blk.block[5])
+            m[f"res{i}.a"] = (blk.block[ia], blk.block[ia + 1] if has else None)
+            m[f"res{i}.b"] = (blk.block[ib], blk.block[ib + 1] if has else None)
+        return m
+
+    def conv_param_names(self):
+        """engine layer name -> state_dict prefix of its conv module ('initial_conv.0', 'resnet_blocks.3.block.4', ...)"""
+        ia, ib = self.res_conv_index()
+        m = {"initial": "initial_conv.0", "down1": "downsample1.0", "down2": "downsample2.0", "up2": "upsample2.1",
+             "up1": "upsample1.1"}
+        for i in range(len(self.gen.resnet_blocks)):
+            m[f"res{i}.a"] = f"resnet_blocks.{i}.block.{ia}"
+            m[f"res{i}.b"] = f"resnet_blocks.{i}.block.{ib}"
         return m
 
     def norm_param_names(self):
         """engine layer name -> state_dict prefix of its norm module ('initial_conv.1', 'resnet_blocks.3.block.5', ...)"""
-        g = self.gen
-        m = {"initial": "initial_conv.1", "down1": "downsample1.1", "down2": "downsample2.1", "up2": "upsample2.2",
-             "up1": "upsample1.2"}
-        for i in range(len(g.resnet_blocks)):
-            m[f"res{i}.a"] = f"resnet_blocks.{i}.block.2"
-            m[f"res{i}.b"] = f"resnet_blocks.{i}.block.5"
-        return m
+        return {k: v.rsplit(".", 1)[0] + "." + str(int(v.rsplit(".", 1)[1]) + 1) for k, v in self.conv_param_names().items()}
 
     def cat11x_channels(self) -> int:
         """channel count of the conv11 data gradient when it also covers the x slot: [up1 | conv0 | x] padded to 32"""
@@ -339,11 +351,12 @@ class _Engine:
         fwd("down1", g.downsample1[0], 4 * f[0], s2d=True)
         fwd("down2", g.downsample2[0], 4 * f[1], s2d=True)
         for i, blk in enumerate(g.resnet_blocks):
-            fwd(f"res{i}.a", blk.block[1], f[2])
-            fwd(f"res{i}.b", blk.block[4], f[2])
+            ia, ib = self.res_conv_index()
+            fwd(f"res{i}.a", blk.block[ia], f[2])
+            fwd(f"res{i}.b", blk.block[ib], f[2])
             if with_dgrad:
-                dgr(f"res{i}.a", blk.block[1])
-                dgr(f"res{i}.b", blk.block[4])
+                dgr(f"res{i}.a", blk.block[ia])
+                dgr(f"res{i}.b", blk.block[ib])
         fwd("up2", g.upsample2[1], 2 * f[2])
         fwd("up1", g.upsample1[1], f[4] + f[1])
         # conv11 input order = [out(f4), conv0(f0), x(cin)] — identical to the reference cat (:230), zero padded
@@ -385,7 +398,7 @@ class _Engine:
             n, _, h, w = x.shape
         h2, w2, h4, w4 = h // 2, w // 2, h // 4, w // 4
         train_bn = g.training
-        bn_mode = g.norm_layer == "batch_norm"
+        bn_mode, no_norm = self.norm_mode() == "batch", self.norm_mode() == "none"
         ws = self.workspace(n, h, w, save)
         W = self._weights(with_dgrad=save)
         cp = self.cin_p
@@ -403,10 +416,20 @@ class _Engine:
             st = ws.stat(name, cout, oh, ow, T, dev)
             cin = (xin.c if xin is not None else 0) + (pre.c if pre is not None else 0)
             frozen = bn_mode and not train_bn      # eval-mode BatchNorm: running statistics, no reduction
+            plain_bias = None
+            if no_norm:                            # conv -> activation: the bias counts, the "norm" is the identity table
+                cb = self.norm_modules()[name][0].bias
+                plain_bias = None if cb is None else cb.detach().float()
             ops.conv_fwd(xin, W[name], cout, k, k, pad, pad, dt, blk_c=self._blk(cin), tiles_per_cta=T, out=raw,
-                         stats_partial=None if frozen else st["partial"], upsample2x=up, pre=pre,
+                         stats_partial=None if (frozen or no_norm) else st["partial"], upsample2x=up, pre=pre,
                          pre_scale=None if pre is None else pre_st["scale"], pre_shift=None if pre is None else pre_st["shift"],
-                         pre_act=pre_act, ctas_per_sm=cps)
+                         pre_act=pre_act, ctas_per_sm=cps, bias=plain_bias)
+            if no_norm:
+                if not st.get("identity"):
+                    st["scale"].fill_(1.0)
+                    st["shift"].zero_()
+                    st["identity"] = True
+                return st
             if not bn_mode:
                 ops.norm_finalize(st["partial"], n, st["tiles"], cout, oh * ow, st["scale"], st["shift"], eps=EPS)
                 return st

@@ -119,10 +119,25 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor, want_input_grad: 
         pending.clear()
         keep.clear()
 
-    bn_mode = g.norm_layer == "batch_norm"
-    norm_mods, norm_names = (eng.norm_modules(), eng.norm_param_names()) if bn_mode else ({}, {})
+    bn_mode, no_norm = eng.norm_mode() == "batch", eng.norm_mode() == "none"
+    norm_mods, norm_names, conv_names = eng.norm_modules(), eng.norm_param_names(), eng.conv_param_names()
 
     def in_bwd(x: P8, st, act, dx: P8, count, name=None, **kw):
+        if no_norm:
+            # conv (+bias) -> activation: dx = g * act'(x).  The norm-backward kernels do exactly that with identity tables
+            # and zero sums in the apply; the pooled reduce returns S1 = sum(dx), the gradient of the conv bias.
+            one, zero = torch.ones(x.c, device=dev), torch.zeros(x.c, device=dev)
+            sums = Z(2, x.c)
+
+            def bias_grad(sums_):
+                if norm_mods[name][0].bias is not None:
+                    s1 = sums_[0].clone()
+                    grads[conv_names[name] + ".bias"] = s1 * inv if inv is not None else s1
+                sums_.zero_()
+
+            ops.norm_bwd(x, dt, scale=one, shift=zero, per_channel=True, act=act, sums=sums, kmul=one, count=n * count,
+                         batch_mode=True, dx=dx, between=bias_grad, **kw)
+            return
         if not bn_mode:
             sums = Z(n, 2, x.c)
             ops.norm_bwd(x, dt, scale=st["scale"], shift=st["shift"], act=act, sums=sums, kmul=st["scale"], count=count, dx=dx,
@@ -162,7 +177,7 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor, want_input_grad: 
     grads = _Grads()
     # a bias in front of an affine-less InstanceNorm has exactly zero gradient: publish those first
     # (the same holds in front of a train-mode BatchNorm; the norm's own beta is not one of these)
-    silent = {id(conv.bias) for conv, _ in eng.norm_modules().values() if conv.bias is not None}
+    silent = set() if no_norm else {id(conv.bias) for conv, _ in norm_mods.values() if conv.bias is not None}
     for name, p in g.named_parameters():
         if id(p) in silent:
             grads[name] = torch.zeros_like(p, dtype=torch.float32)
@@ -247,12 +262,12 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor, want_input_grad: 
         if evB is not None:
             main.wait_event(evB)
         in_bwd(ws.rawB[b], ws.stats[f"res{b}.b"], ACT_NONE, g_rawB, h4 * w4, name=f"res{b}.b", gb32=g_r)
-        evB = wgrad_side(f"resnet_blocks.{b}.block.4.weight", ws.hmid[b], g_rawB, 3, 1, res_cv)
+        evB = wgrad_side(conv_names[f"res{b}.b"] + ".weight", ws.hmid[b], g_rawB, 3, 1, res_cv)
         dgrad(f"res{b}.b", g_rawB, f[2], 3, 1, out=g_h)
         if evA is not None:
             main.wait_event(evA)
         in_bwd(ws.rawA[b], ws.stats[f"res{b}.a"], ACT_RELU, g_rawA, h4 * w4, name=f"res{b}.a", ga=g_h)
-        evA = wgrad_side(f"resnet_blocks.{b}.block.1.weight", ws.a[b], g_rawA, 3, 1, res_cv)
+        evA = wgrad_side(conv_names[f"res{b}.a"] + ".weight", ws.a[b], g_rawA, 3, 1, res_cv)
         # g_r <- g_r + relu'(r_b) * dgrad   (in place: every element is read then written by the same thread)
         dgrad(f"res{b}.a", g_rawA, f[2], 3, 1, out=None, mask=ws.a[b], addend32=g_r, out32=g_r)
     # ---- downsample2 (conv2 feeds the residual stream and the decoder skip)
