@@ -268,3 +268,38 @@ def test_sampler_cut_patch_edges_and_getitem():
     np.random.seed(1)
     item = ds[3]
     assert set(item) == {"pre", "post"} and item["pre"].shape == (3, 7, 7)
+
+
+@pytest.mark.parametrize("opts", [dict(use_bias=False), dict(use_bias=True, tanh=False), dict(use_bias=True, resnet_blocks=3),
+                                  dict(use_bias=False, resnet_blocks=1, tanh=False)],
+                         ids=lambda o: "-".join(f"{k}={v}" for k, v in o.items()))
+def test_constructor_options_forward_and_gradients(opts):
+    """the other GeneratorJ constructor arguments of the reference (use_bias default False, tanh, resnet_blocks) against
+    fp32 autograd through the oracle; the module is seeded (its init equals the reference's bit for bit, test_host.py)"""
+    from oracle import generator_oracle as go
+    from pbt_b200.generator import GeneratorJ
+    torch.manual_seed(17)
+    g = GeneratorJ(input_channels=6, **opts).cuda().train()
+    sd = {k: v.detach().cpu().clone() for k, v in g.state_dict().items()}
+    assert ("conv11.0.bias" in sd) == opts.get("use_bias", False)
+    x, tgt = torch.rand(6, 6, 48, 32) * 2 - 1, torch.rand(6, 3, 48, 32) * 2 - 1
+    y = g(x.cuda())
+    (torch.nn.functional.l1_loss(y, tgt.cuda()) * 4.0).backward()
+    names = [k for k, v in sd.items() if v.is_floating_point() and "running_" not in k]
+    leaves = {k: sd[k].clone().requires_grad_(True) for k in names}
+    yr = go.generator_forward({**sd, **leaves}, x, training=True, tanh=opts.get("tanh", True))
+    ref = dict(zip(names, torch.autograd.grad((yr - tgt).abs().mean() * 4.0, [leaves[k] for k in names], allow_unused=True)))
+    err = (y.detach().cpu() - yr.detach()).abs().max().item()
+    worst = 1.0
+    for k, p in g.named_parameters():
+        r = ref[k]
+        if r is None or float(r.abs().max()) < 1e-9 or float(p.grad.abs().max()) == 0.0:
+            continue            # biases in front of an InstanceNorm
+        worst = min(worst, float(torch.nn.functional.cosine_similarity(p.grad.cpu().flatten(), r.flatten(), dim=0)))
+    print(f"{opts}: forward max_abs={err:.5f}, worst gradient cosine={worst:.4f}")
+    assert err <= MAX_ABS and worst > 0.97        # random-init weights: direction check (see test_gradient_wrt_input)
+    g.eval()
+    with torch.no_grad():
+        ye = g(x.cuda()).cpu()
+    assert (ye - go.generator_forward(sd | {k: v.cpu() for k, v in g.state_dict().items()}, x, training=False,
+                                      tanh=opts.get("tanh", True))).abs().max().item() <= MAX_ABS

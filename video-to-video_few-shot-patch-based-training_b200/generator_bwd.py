@@ -168,10 +168,12 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor, want_input_grad: 
 
     hook = getattr(eng, "grad_hook", None)   # data-parallel training: parallel.GradAllReduce.grad_ready
 
+    known = {k for k, _ in g.named_parameters()}      # use_bias=False: the bias sums below have no parameter to go to
+
     class _Grads(dict):
         def __setitem__(self, k, v):
             super().__setitem__(k, v)
-            if hook is not None:
+            if hook is not None and k in known:
                 hook(k, v)
 
     grads = _Grads()
