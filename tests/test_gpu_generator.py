@@ -271,7 +271,8 @@ def test_sampler_cut_patch_edges_and_getitem():
 
 
 @pytest.mark.parametrize("opts", [dict(use_bias=False), dict(use_bias=True, tanh=False), dict(use_bias=True, resnet_blocks=3),
-                                  dict(use_bias=False, resnet_blocks=1, tanh=False)],
+                                  dict(use_bias=False, resnet_blocks=1, tanh=False), dict(use_bias=True, append_smoothers=False),
+                                  dict(use_bias=False, append_smoothers=False, tanh=False)],
                          ids=lambda o: "-".join(f"{k}={v}" for k, v in o.items()))
 def test_constructor_options_forward_and_gradients(opts):
     """the other GeneratorJ constructor arguments of the reference (use_bias default False, tanh, resnet_blocks) against

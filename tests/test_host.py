@@ -118,6 +118,9 @@ def test_generator_has_no_cpu_path_and_validates_input():
     plain = GeneratorJ(input_channels=3, norm_layer="none")           # any other string: no norm layers (reference :83-87)
     plain._check_supported()
     assert "resnet_blocks.0.block.3.weight" in plain.state_dict() and "initial_conv.1.weight" not in plain.state_dict()
+    bare = GeneratorJ(input_channels=3, append_smoothers=False)
+    bare._check_supported()
+    assert not any(k.startswith("smoothers.") for k in bare.state_dict())
     with pytest.raises(NotImplementedError):
         GeneratorJ(input_channels=3, filters=[24, 64, 128, 128, 128, 64])._check_supported()
 

@@ -125,8 +125,6 @@ class GeneratorJ(nn.Module):
         f = self.filters
         if any(c % 16 for c in (f[0], f[1], f[2], f[4], f[5])) or max(f) > 256 or 2 * f[2] > 256:
             raise NotImplementedError(f"native GeneratorJ needs filter counts that are multiples of 16 and <= 256, got {f}")
-        if not self.append_smoothers:
-            raise NotImplementedError("native GeneratorJ is built for append_smoothers=True (the reference default)")
 
     def forward(self, x: Tensor) -> Tensor:
         if not x.is_cuda:
@@ -361,16 +359,18 @@ class _Engine:
         fwd("up1", g.upsample1[1], f[4] + f[1])
         # conv11 input order = [out(f4), conv0(f0), x(cin)] — identical to the reference cat (:230), zero padded
         fwd("conv11", g.conv11[0], f[4] + f[0] + cp, pair=self.pair11())
-        fwd("smooth0", g.smoothers[0], f[5], blk=self.SMOOTH_BLK)
-        fwd("smooth3", g.smoothers[3], f[5], blk=self.SMOOTH_BLK)
+        if g.append_smoothers:
+            fwd("smooth0", g.smoothers[0], f[5], blk=self.SMOOTH_BLK)
+            fwd("smooth3", g.smoothers[3], f[5], blk=self.SMOOTH_BLK)
         if with_dgrad:
             dgr("down1", g.downsample1[0], s2d=True)
             dgr("down2", g.downsample2[0], s2d=True)
             dgr("up2", g.upsample2[1])
             dgr("up1", g.upsample1[1])
             dgr("conv11", g.conv11[0], keep=f[4] + f[0], pair=self.pair11_dgrad())
-            dgr("smooth0", g.smoothers[0])
-            dgr("smooth3", g.smoothers[3])
+            if g.append_smoothers:
+                dgr("smooth0", g.smoothers[0])
+                dgr("smooth3", g.smoothers[3])
             if self.input_grad:
                 # dL/dx has two sources: the x slot of conv11's input (all of cat11's channels, rows padded to a multiple
                 # of 32) and the initial conv
@@ -384,7 +384,8 @@ class _Engine:
         # fp32 parameters are used in place (views); a .half()-ed module gets fp32 copies refreshed with the packer key
         W["head_w"] = f32(g.output[0].weight).reshape(3, f[5])
         W["head_b"] = f32(g.output[0].bias)
-        W["b11"], W["bs0"], W["bs3"] = f32(g.conv11[0].bias), f32(g.smoothers[0].bias), f32(g.smoothers[3].bias)
+        W["b11"] = f32(g.conv11[0].bias)
+        W["bs0"], W["bs3"] = (f32(g.smoothers[0].bias), f32(g.smoothers[3].bias)) if g.append_smoothers else (None, None)
         return {"packer": pk, "W": W, "key": None, "ptrs": tuple(p.data_ptr() for p in g.parameters())}
 
     # -------------------------------------------------------------- forward
@@ -485,7 +486,7 @@ class _Engine:
         # inference: IN + ReLU of a conv's raw output are applied inside the NEXT conv's shared-memory tile
         # (normalise-on-load), so hmid and the up1 half of cat11 are never written; training keeps them for wgrad
         nol_res = not save and f[2] % self._blk(f[2]) == 0 and f[2] <= 256
-        nol_11 = not save and f[4] % 32 == 0 and f[4] <= 256
+        nol_11 = not save and f[4] % 32 == 0 and f[4] <= 256 and g.append_smoothers
         for b in range(nb):
             k = b if save else 0
             st = conv_in(f"res{b}.a", a_of(b), f[2], 3, 1, ws.rawA[k], 2, cps=4)
@@ -519,16 +520,25 @@ class _Engine:
         if ev is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
+        y = torch.empty((n, 3, h, w), device=dev)  # fresh result tensor: callers may keep it across calls
+        # append_smoothers=False (reference :233-237): the 1x1 head + tanh sits directly on conv11's ReLU output
+        head = {} if g.append_smoothers else dict(head_w=W["head_w"], head_b=W["head_b"], head_out=y, head_tanh=g.use_tanh)
         if nol_11:
             ops.conv_fwd(ws.cat11.view(f[4], f[0] + cp), W["conv11"], f[5], 7, 7, 3, 3, dt, blk_c=32,
                          tiles_per_cta=self._T11(w), bias=W["b11"], act=ACT_RELU, out=ws.c11, pre=ws.rawU1,
                          pre_scale=st["scale"], pre_shift=st["shift"], pre_act=ACT_RELU, cta_pair=self.pair11())
         else:
             ops.conv_fwd(ws.cat11, W["conv11"], f[5], 7, 7, 3, 3, dt, blk_c=32, tiles_per_cta=self._T11(w), bias=W["b11"],
-                         act=ACT_RELU, out=ws.c11, cta_pair=self.pair11())
+                         act=ACT_RELU, out=ws.c11, cta_pair=self.pair11(), **head)
         if ev is not None:
             e1.record()
             ev.append((e0, e1))
+        if not g.append_smoothers:
+            if save:
+                if not train_bn:
+                    raise RuntimeError("autograd through GeneratorJ in eval() mode is not supported by the native path")
+                self._saved = (ws, W)
+            return y
         bn = g.smoothers[2]
         T3, sblk = self._T(self.SMOOTH_T, w), self.SMOOTH_BLK
         if train_bn:
@@ -554,7 +564,6 @@ class _Engine:
                          post_scale=sc, post_shift=sh, out=ws.s0n, ctas_per_sm=4)
             if save:
                 raise RuntimeError("autograd through GeneratorJ in eval() mode is not supported by the native path")
-        y = torch.empty((n, 3, h, w), device=dev)  # fresh result tensor: callers may keep it across calls
         ops.conv_fwd(ws.s0n, W["smooth3"], f[5], 3, 3, 1, 1, dt, blk_c=sblk, tiles_per_cta=T3, bias=W["bs3"], act=ACT_RELU,
                      out=ws.s3 if save else None, head_w=W["head_w"], head_b=W["head_b"], head_out=y, head_tanh=g.use_tanh,
                      ctas_per_sm=4)

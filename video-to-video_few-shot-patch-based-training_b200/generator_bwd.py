@@ -184,40 +184,51 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor, want_input_grad: 
         if id(p) in silent:
             grads[name] = torch.zeros_like(p, dtype=torch.float32)
 
-    # ---- head (1x1 + tanh) and the ReLU of smoothers.3
-    dw_out, db_out, db_s3 = Z(3, f[5]), Z(3), Z(f[5])
-    g_s3 = E(f[5], h, w)
-    ops.head_bwd(gy, y, ws.s3, W["head_w"], dt, gscale=gscale, head_tanh=g.use_tanh, dw=dw_out, db=db_out, gs=g_s3,
-                 dbias_prev=db_s3)
-    if inv is not None:
-        dw_out, db_out, db_s3 = dw_out * inv, db_out * inv, db_s3 * inv
-    grads["output.0.weight"] = dw_out.reshape(3, f[5], 1, 1)
-    grads["output.0.bias"] = db_out
-    # ---- smoothers.3
-    wgrad_side("smoothers.3.weight", ws.s0n, g_s3, 3, 1, lambda dw: _wgrad_to_param(dw, f[5], f[5], 3, 3))
-    grads["smoothers.3.bias"] = db_s3
-    g_s0n = E(f[5], h, w)
-    dgrad("smooth3", g_s3, f[5], 3, 1, out=g_s0n, T_pref=3)
-    # ---- BatchNorm (batch statistics) + the ReLU in front of it
-    st = ws.stats["bn"]
-    bn = g.smoothers[2]
-    bn_rstd, bn_mean = st["rstd"], st["mean"]
-    bn_sums = Z(2, f[5])
-    g_s0 = E(f[5], h, w)
-    ops.norm_bwd(ws.s0, dt, scale=bn_rstd, shift=(-bn_mean * bn_rstd).contiguous(), per_channel=True, act=ACT_NONE, ga=g_s0n,
-                 sums=bn_sums, kmul=(bn.weight.detach().float() * bn_rstd).contiguous(), count=n * h * w, batch_mode=True,
-                 dx=g_s0, relu_mask_x=True)
-    grads["smoothers.2.weight"] = bn_sums[1] * inv if inv is not None else bn_sums[1].clone()
-    grads["smoothers.2.bias"] = bn_sums[0] * inv if inv is not None else bn_sums[0].clone()
-    db_s0 = Z(f[5])
-    ops.channel_sum(g_s0, db_s0, dt, inv_scale=inv)
-    # ---- smoothers.0
-    wgrad_side("smoothers.0.weight", ws.c11, g_s0, 3, 1, lambda dw: _wgrad_to_param(dw, f[5], f[5], 3, 3))
-    grads["smoothers.0.bias"] = db_s0
-    g_c11 = E(f[5], h, w)
-    dgrad("smooth0", g_s0, f[5], 3, 1, out=g_c11, T_pref=3, mask=ws.c11)
-    db_11 = Z(f[5])
-    ops.channel_sum(g_c11, db_11, dt, inv_scale=inv)
+    if g.append_smoothers:
+        # ---- head (1x1 + tanh) and the ReLU of smoothers.3
+        dw_out, db_out, db_s3 = Z(3, f[5]), Z(3), Z(f[5])
+        g_s3 = E(f[5], h, w)
+        ops.head_bwd(gy, y, ws.s3, W["head_w"], dt, gscale=gscale, head_tanh=g.use_tanh, dw=dw_out, db=db_out, gs=g_s3,
+                     dbias_prev=db_s3)
+        if inv is not None:
+            dw_out, db_out, db_s3 = dw_out * inv, db_out * inv, db_s3 * inv
+        grads["output.0.weight"] = dw_out.reshape(3, f[5], 1, 1)
+        grads["output.0.bias"] = db_out
+        # ---- smoothers.3
+        wgrad_side("smoothers.3.weight", ws.s0n, g_s3, 3, 1, lambda dw: _wgrad_to_param(dw, f[5], f[5], 3, 3))
+        grads["smoothers.3.bias"] = db_s3
+        g_s0n = E(f[5], h, w)
+        dgrad("smooth3", g_s3, f[5], 3, 1, out=g_s0n, T_pref=3)
+        # ---- BatchNorm (batch statistics) + the ReLU in front of it
+        st = ws.stats["bn"]
+        bn = g.smoothers[2]
+        bn_rstd, bn_mean = st["rstd"], st["mean"]
+        bn_sums = Z(2, f[5])
+        g_s0 = E(f[5], h, w)
+        ops.norm_bwd(ws.s0, dt, scale=bn_rstd, shift=(-bn_mean * bn_rstd).contiguous(), per_channel=True, act=ACT_NONE, ga=g_s0n,
+                     sums=bn_sums, kmul=(bn.weight.detach().float() * bn_rstd).contiguous(), count=n * h * w, batch_mode=True,
+                     dx=g_s0, relu_mask_x=True)
+        grads["smoothers.2.weight"] = bn_sums[1] * inv if inv is not None else bn_sums[1].clone()
+        grads["smoothers.2.bias"] = bn_sums[0] * inv if inv is not None else bn_sums[0].clone()
+        db_s0 = Z(f[5])
+        ops.channel_sum(g_s0, db_s0, dt, inv_scale=inv)
+        # ---- smoothers.0
+        wgrad_side("smoothers.0.weight", ws.c11, g_s0, 3, 1, lambda dw: _wgrad_to_param(dw, f[5], f[5], 3, 3))
+        grads["smoothers.0.bias"] = db_s0
+        g_c11 = E(f[5], h, w)
+        dgrad("smooth0", g_s0, f[5], 3, 1, out=g_c11, T_pref=3, mask=ws.c11)
+        db_11 = Z(f[5])
+        ops.channel_sum(g_c11, db_11, dt, inv_scale=inv)
+    else:
+        # ---- head (1x1 + tanh) directly on conv11's ReLU output (append_smoothers=False)
+        dw_out, db_out, db_11 = Z(3, f[5]), Z(3), Z(f[5])
+        g_c11 = E(f[5], h, w)
+        ops.head_bwd(gy, y, ws.c11, W["head_w"], dt, gscale=gscale, head_tanh=g.use_tanh, dw=dw_out, db=db_out, gs=g_c11,
+                     dbias_prev=db_11)
+        if inv is not None:
+            dw_out, db_out, db_11 = dw_out * inv, db_out * inv, db_11 * inv
+        grads["output.0.weight"] = dw_out.reshape(3, f[5], 1, 1)
+        grads["output.0.bias"] = db_out
     # ---- conv11 (input = cat11 = [up1 | conv0 | x])
     cin11 = f[4] + f[0] + g.input_channels
     wgrad_side("conv11.0.weight", ws.cat11, g_c11, 7, 3, lambda dw: _wgrad_to_param(dw, f[5], cin11, 7, 7))
@@ -230,7 +241,9 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor, want_input_grad: 
         g_cat = E(f[4] + f[0], h, w)
         dgrad("conv11", g_c11, f[4] + f[0], 7, 3, out=g_cat, T_pref=3, cta_pair=eng.pair11_dgrad())
     join()   # tail group complete (output head, smoothers, conv11)
-    del g_c11, g_s0, g_s0n, g_s3
+    del g_c11
+    if g.append_smoothers:
+        del g_s0, g_s0n, g_s3
     # ---- upsample1 block
     g_rawU1 = E(f[4], h, w)
     in_bwd(ws.rawU1, ws.stats["up1"], ACT_RELU, g_rawU1, h * w, name="up1", ga=g_cat.view(0, f[4]))
