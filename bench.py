@@ -5,7 +5,7 @@
   python bench.py --impl reference ...                     (the reference's CPU path = oracle port, rank 0 only)
 
 Workload (BASELINE.json configs[3], "C4"): synthetic 1920x1080 RGB video, full-frame GeneratorJ inference,
-frames sharded across ranks (no collective).  One step = FRAMES_PER_STEP frames per rank; the timed region
+frames sharded across ranks (no collective).  One step = FRAMES_PER_STEP frames per rank (one generator pass of four frames); the timed region
 holds exactly K steps between barrier+synchronize pairs and the slowest rank's device time counts.
   value      frames/s with the uint8 frames already resident in HBM (u8 -> generator -> u8 on device)
   e2e        the same through the public API with PINNED HOST buffers: H2D of each frame and D2H of each
@@ -385,7 +385,7 @@ def run_native(args):
         except Exception as e:  # noqa: BLE001
             cpu["same_gpu_torch_cudnn_frames_per_s"] = {"unavailable": f"{type(e).__name__}: {e}"[:160]}
 
-    frames_per_launch = min(F, max(1, int(sty.frames_per_pass)))
+    frames_per_launch = min(F, sty.pass_size(H, W))
     conv11_flops = 2.0 * H * W * (49 * (160 + CIN)) * 64 * frames_per_launch
     peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
     achieved = conv11_flops / (k_ms / 1e3) / 1e12 if k_ms > 0 else 0.0

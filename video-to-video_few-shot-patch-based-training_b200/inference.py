@@ -18,9 +18,18 @@ from .generator import GeneratorJ, _Engine
 
 
 class FrameStylizer:
-    #: frames per generator pass.  Two frames per pass fill the GPU better on the 1/16-resolution layers (their
-    #: grids are ~1.7 waves at 1080p) and amortise the ~70 launches of a pass; InstanceNorm stays per frame.
-    frames_per_pass = 2
+    #: frames per generator pass; None = chosen from the frame size (`pass_size`).  Several frames per pass fill the GPU
+    #: better on the 1/16-resolution layers (their grids are ~1.7 waves per 1080p frame), shorten the last-wave tail of
+    #: the persistent conv CTAs and amortise the ~70 launches of a pass; InstanceNorm stays per frame.  Measured
+    #: (tools/frames_per_pass_sweep.py): 1080p 190 / 197 / 202 / 202 frames/s at 1 / 2 / 4 / 8 frames per pass,
+    #: 960x540 (6 channels) 598 / 698 / 737 / 754.
+    frames_per_pass = None
+
+    def pass_size(self, h: int, w: int) -> int:
+        """about 8 Mpixel of frames per pass: 8 at 960x540, 4 at 1080p, 2 at 4K (14 GB of activations per 4K frame)"""
+        if self.frames_per_pass is not None:
+            return max(1, int(self.frames_per_pass))
+        return int(min(8, max(2, round(8.3e6 / float(h * w)))))
 
     def __init__(self, gen: GeneratorJ):
         if not next(gen.parameters()).is_cuda:
@@ -41,7 +50,7 @@ class FrameStylizer:
             raise ValueError(f"expected {self.gen.input_channels} channels, got {c}")
         if out_u8 is None:
             out_u8 = torch.empty((n, h, w, 3), dtype=torch.uint8, device=self.device)
-        step = max(1, int(self.frames_per_pass))
+        step = self.pass_size(h, w)
         for i in range(0, n, step):
             y = self.eng.forward(frames_u8[i:i + step], save=False, u8_hwc=True)
             ops.nchw_to_u8hwc(y, out_u8[i:i + step])
@@ -57,7 +66,7 @@ class FrameStylizer:
             self._streams = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
         copy_in, copy_out = self._streams
         main = torch.cuda.current_stream(self.device)
-        step = max(1, int(self.frames_per_pass))
+        step = self.pass_size(h, w)
         dev_in = [torch.empty((step, h, w, c), dtype=torch.uint8, device=self.device) for _ in range(2)]
         dev_out = [torch.empty((step, h, w, 3), dtype=torch.uint8, device=self.device) for _ in range(2)]
         in_ready = [torch.cuda.Event() for _ in range(2)]
