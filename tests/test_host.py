@@ -164,6 +164,6 @@ def test_frames_per_pass_follows_the_frame_size():
     from pbt_b200.inference import FrameStylizer
     sty = FrameStylizer.__new__(FrameStylizer)           # host logic only: no engine, no device
     assert sty.pass_size(540, 960) == 8 and sty.pass_size(1080, 1920) == 4 and sty.pass_size(2160, 3840) == 2
-    assert sty.pass_size(64, 96) == 8 and sty.pass_size(4320, 7680) == 2
+    assert sty.pass_size(64, 96) == 8 and sty.pass_size(4320, 7680) == 1
     sty.frames_per_pass = 3                              # explicit setting wins
     assert sty.pass_size(1080, 1920) == 3

@@ -29,7 +29,8 @@ class FrameStylizer:
         """about 8 Mpixel of frames per pass: 8 at 960x540, 4 at 1080p, 2 at 4K (14 GB of activations per 4K frame)"""
         if self.frames_per_pass is not None:
             return max(1, int(self.frames_per_pass))
-        return int(min(8, max(2, round(8.3e6 / float(h * w)))))
+        floor = 2 if h * w <= 12e6 else 1        # beyond ~4K a single frame holds > 20 GB of activations
+        return int(min(8, max(floor, round(8.3e6 / float(h * w)))))
 
     def __init__(self, gen: GeneratorJ):
         if not next(gen.parameters()).is_cuda:
