@@ -167,3 +167,18 @@ def test_frames_per_pass_follows_the_frame_size():
     assert sty.pass_size(64, 96) == 8 and sty.pass_size(4320, 7680) == 1
     sty.frames_per_pass = 3                              # explicit setting wins
     assert sty.pass_size(1080, 1920) == 3
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    # the driver runs `bench.py --impl reference` beside the native arm and computes the ratio itself
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["n_gpus"] == 1 and line["higher_is_better"] is True
+    assert line["metric"] == "1080p stylized frames/s" and line["unit"] == "frames/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
