@@ -1,23 +1,33 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the B200-native hot path.
 
-  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
-  python bench.py --impl reference ...                     (the reference's CPU path = oracle port, rank 0 only)
+  python bench.py --gpus N --steps K --warmup W [--config C4|C5|C2]   (N>1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference ...        (the reference's own CPU implementation of the path, rank 0 only)
 
-Workload (BASELINE.json configs[3], "C4"): synthetic 1920x1080 RGB video, full-frame GeneratorJ inference,
-frames sharded across ranks (no collective).  One step = FRAMES_PER_STEP frames per rank (one generator pass of four frames); the timed region
-holds exactly K steps between barrier+synchronize pairs and the slowest rank's device time counts.
-  value      frames/s with the uint8 frames already resident in HBM (u8 -> generator -> u8 on device)
-  e2e        the same through the public API with PINNED HOST buffers: H2D of each frame and D2H of each
-             stylised frame inside the timed region (FrameStylizer.stylize_host)
-  roofline   the dominant kernel (conv11 7x7 implicit GEMM, 50 % of all FLOPs): algorithmic FLOPs per launch /
-             mean CUDA-event duration of its launches inside the timed region, against the measured bf16 peak
-  cpu_baseline  the oracle port of the reference generator on the host cores, bounded sample (rank 0, N=1)
-  train      secondary metric: G-only patch-training step (config C3: batch 80 x 80x80 patches, Cin 9) per rank
+Workload (default C4 = BASELINE.json configs[3]): a synthetic 1920x1080 RGB video of 2000 frames, full-frame GeneratorJ
+inference, frames sharded across the ranks by the product API (`FrameStylizer.stylize_video` -> `parallel.shard_range`: one
+contiguous frame range per GPU, no collective).  STRONG scaling: the video is the same for every N.
+One step = one 200-frame segment of the video (a tenth of it; the video is walked cyclically, so --steps 20 = two passes);
+every rank stylises its contiguous share of the segment.  The timed region holds exactly K steps between barrier +
+synchronize pairs and the slowest rank's device time counts.
+  value      frames/s with the uint8 video already resident in HBM (u8 -> generator -> u8 on device)
+  e2e        the same through the same call with PINNED HOST segments: H2D of every frame and D2H of every stylised frame
+             inside the timed region (copies double-buffered against compute)
+  roofline   the dominant kernel (conv11 7x7 implicit GEMM, 50 % of all FLOPs): algorithmic FLOPs per launch / mean
+             CUDA-event duration of its launches inside the timed region, against the measured bf16 peak
+  cpu_baseline  the reference generator (baseline/_ref copy of the unmodified module; oracle port if absent) on the host
+             cores, whole frames, bounded sample (rank 0, N=1)
+  cudnn_bar  same-GPU library bar: the reference network as stock torch ops on cuDNN, channels_last, fp16 and bf16,
+             cudnn.benchmark, the native arm's frames per pass
+  train      config C3: patch training step INCLUDING the sampler (host draws + order tree + gather kernel) on synthetic
+             keyframes with two guide directories (Cin 9), batch 80 x 80x80 per GPU, NCCL gradient all-reduce when N>1
+--config C5 (3840x2160, 5 channels, 500 frames) and C2 (960x540, 6 channels, 7 frames looped x100) run the same legs on the
+other BASELINE.json inference configurations.
 """
 from __future__ import annotations
 
 import argparse
+import importlib.util
 import json
 import os
 import subprocess
@@ -27,10 +37,18 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+GOLD = os.path.join(ROOT, "tests", "golden")
 
-H, W, CIN = 1080, 1920, 3
-FRAMES_PER_STEP = 4
-METRIC = "1080p stylized frames/s"
+CONFIGS = {
+    # name: frame H, W, input channels, frames of the video, frames per step, fixture weights, description
+    "C4": dict(h=1080, w=1920, cin=3, video=2000, seg=200, weights="gen_c3_trained.npz", metric="1080p stylized frames/s",
+               what="C4: synthetic 1920x1080 RGB video, 2000 frames, full-frame GeneratorJ inference"),
+    "C5": dict(h=2160, w=3840, cin=5, video=500, seg=50, weights="gen_cin5_trained.npz", metric="2160p stylized frames/s",
+               what="C5: synthetic 3840x2160 video with 5 input channels (RGB + mask + flow guide), 500 frames, full-frame inference"),
+    "C2": dict(h=960, w=540, cin=6, video=700, seg=70, weights="gen_cin6_trained.npz", metric="960x540 stylized frames/s",
+               what="C2: 960x540 frames with the tracking guide (6 channels): one real PlatinumChan_x0.5_train frame (fixture) + 6 "
+                    "synthetic ones, looped x100 = 700 frames, full-frame inference"),
+}
 UNIT = "frames/s"
 
 
@@ -42,8 +60,7 @@ def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         with open(p) as f:
-            d = json.load(f)
-        return d, "measured"
+            return json.load(f), "measured"
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
@@ -72,7 +89,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
         self.proc.terminate()
-        sm, mx, reasons = [], None, set()
+        sm, mx, pw, reasons = [], None, [], set()
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
@@ -80,73 +97,118 @@ class ClockSampler:
             try:
                 sm.append(float(f[1]))
                 mx = float(f[2])
+                pw.append(float(f[3]))
             except ValueError:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(pw) if pw else None}
 
 
-def synthetic_frames(n, h, w, c, seed, device):
-    """low-frequency noise + detail so that InstanceNorm statistics are non-degenerate"""
+def synthetic_frames(idx, h, w, c, device, base_seed=1234):
+    """frames `idx` (iterable of frame numbers) of the synthetic video: low-frequency noise + fine detail so that
+    InstanceNorm statistics are non-degenerate; seeded per frame, so the video does not depend on
+    how it is sharded.  Channels beyond RGB: a binary blob mask (channel 3) and smooth guide fields."""
     import torch
-    g = torch.Generator(device=device).manual_seed(seed)
-    low = torch.rand((n, c, h // 16 + 1, w // 16 + 1), generator=g, device=device) * 255
-    img = torch.nn.functional.interpolate(low, size=(h, w), mode="bilinear", align_corners=False)
-    img = img + (torch.rand((n, c, h, w), generator=g, device=device) * 16 - 8)
-    return img.clamp(0, 255).round().to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+    out = []
+    for i in idx:
+        g = torch.Generator(device=device).manual_seed(base_seed + int(i))
+        low = torch.rand((1, c, h // 16 + 1, w // 16 + 1), generator=g, device=device) * 255
+        img = torch.nn.functional.interpolate(low, size=(h, w), mode="bilinear", align_corners=False)
+        img = img + (torch.rand((1, c, h, w), generator=g, device=device) * 16 - 8)
+        if c in (4, 5):
+            img[:, 3] = (img[:, 3] > 128).float() * 255
+        out.append(img.clamp(0, 255).round().to(torch.uint8).permute(0, 2, 3, 1)[0])
+    return torch.stack(out).contiguous()
 
 
-def trained_like_generator(cin, device):
-    """GeneratorJ with the reference-trained fixture weights when cin == 3 (tests/golden), else reference init"""
+def fixture_state_dict(name):
     import numpy as np
     import torch
+    z = np.load(os.path.join(GOLD, name))
+    return {k: torch.from_numpy(z[k]) for k in z.files}
+
+
+def native_generator(cfg, device, operand):
+    """GeneratorJ with the reference-trained fixture weights of this channel count (tests/golden, oracle/make_golden*.py)"""
     from pbt_b200.generator import GeneratorJ
-    torch.manual_seed(0)
-    g = GeneratorJ(input_channels=cin, use_bias=True)
-    fix = os.path.join(ROOT, "tests", "golden", "gen_c3_trained.npz")
-    weights = "reference init (seed 0)"
-    if cin == 3 and os.path.exists(fix):
-        z = np.load(fix)
-        g.load_state_dict({k: torch.from_numpy(z[k]) for k in z.files}, strict=True)
-        weights = "tests/golden/gen_c3_trained.npz (100 reference training steps)"
-    return g.to(device), weights
+    g = GeneratorJ(input_channels=cfg["cin"], use_bias=True)
+    g.load_state_dict(fixture_state_dict(cfg["weights"]), strict=True)
+    g.operand_dtype = operand
+    return g.to(device)
+
+
+def reference_generator_module():
+    """the UNMODIFIED reference module from baseline/_ref (copied there by __graft_entry__.build(); git-ignored, travels to
+    the GPU box), or None"""
+    p = os.path.join(ROOT, "baseline", "_ref", "src", "models", "generator.py")
+    if not os.path.exists(p):
+        return None
+    spec = importlib.util.spec_from_file_location("_ref_generator", p)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def cpu_forward_fn(cfg):
+    """(callable x[N,C,H,W] fp32 -> y, kind): the reference's CPU implementation of the generator"""
+    import torch
+    sd = fixture_state_dict(cfg["weights"])
+    ref = reference_generator_module()
+    if ref is not None:
+        g = ref.GeneratorJ(input_channels=cfg["cin"], use_bias=True)
+        g.load_state_dict(sd, strict=True)
+        g.eval()
+        return (lambda x: g(x)), "reference"
+    from oracle import generator_oracle as go
+    return (lambda x: go.generator_forward(sd, x)), "port"
+
+
+def to_u8(y):
+    """reference generator.py:643-647"""
+    import torch
+    return ((y.float().clamp(-1, 1) + 1) * 127.5).clamp(0, 255).permute(0, 2, 3, 1).round().to(torch.uint8)
+
+
+def normalise(u8):
+    return ((u8.permute(0, 3, 1, 2).float() / 255.0) - 0.5) / 0.5
 
 
 # ------------------------------------------------------------------------------------------ reference arm
 def run_reference(args):
-    """the reference's own CPU implementation of the path (oracle port: the reference is Python and cannot be
-    vendored; the port is pinned to reference outputs in tests/test_oracle.py), all host threads."""
+    """the reference's own CPU implementation of the path on the host cores, all threads: WHOLE frames of the configured
+    size through the unmodified reference GeneratorJ (baseline/_ref) - the oracle port only if that copy is absent.
+    One step = one frame (a bounded sample of the 200-frame step of the native arm)."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    import numpy as np
     import torch
-    from oracle import generator_oracle as go
+    cfg = CONFIGS[args.config]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    z = np.load(os.path.join(ROOT, "tests", "golden", "gen_c3_trained.npz"))
-    sd = {k: torch.from_numpy(z[k]) for k in z.files}
-    sh, sw = H // 2, W // 4          # bounded sample: 1/8 of a 1080p frame per step (the net is fully convolutional)
-    frac = (sh * sw) / (H * W)
-    x = (synthetic_frames(1, sh, sw, CIN, 1234, "cpu").permute(0, 3, 1, 2).float() / 255 - 0.5) / 0.5
+    fwd, kind = cpu_forward_fn(cfg)
+    h, w, c = cfg["h"], cfg["w"], cfg["cin"]
+    frames = synthetic_frames(range(2), h, w, c, "cpu")
+    warm = max(1, min(args.warmup, 2))
     with torch.no_grad():
-        for _ in range(max(1, min(args.warmup, 1))):
-            go.frame_to_uint8(go.generator_forward(sd, x))
+        for i in range(warm):
+            to_u8(fwd(normalise(frames[i % 2:i % 2 + 1])))
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            go.frame_to_uint8(go.generator_forward(sd, x))
+        for i in range(args.steps):
+            to_u8(fwd(normalise(frames[i % 2:i % 2 + 1])))
         dt = time.perf_counter() - t0
-    fps = args.steps * frac / dt
-    sample = f"{args.steps} x one {sh}x{sw} crop ({frac:.3f} of a 1080p frame) through the oracle port, scaled by pixel count"
+    fps = args.steps / dt
+    sample = (f"{args.steps} whole {w}x{h}x{c} frames, one per step (+{warm} warm-up), through "
+              + ("the unmodified reference GeneratorJ (baseline/_ref)" if kind == "reference" else "the oracle port") + ", fp32, eval")
     emit({
-        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": cfg["metric"], "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C4: 1920x1080 RGB full-frame GeneratorJ inference", "frame": [H, W, CIN]},
-        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": cfg["what"], "frame": [h, w, c], "frames_per_step": 1},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
 
@@ -157,8 +219,10 @@ def run_native(args):
     import torch.distributed as dist
     from pbt_b200 import _native
     from pbt_b200.inference import FrameStylizer
-    from pbt_b200.parallel import GradAllReduce, init_distributed
+    from pbt_b200.parallel import init_distributed, shard_range
 
+    cfg = CONFIGS[args.config]
+    H, W, CIN, VIDEO, SEG = cfg["h"], cfg["w"], cfg["cin"], cfg["video"], cfg["seg"]
     rank, world, local = init_distributed("nccl")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -177,19 +241,34 @@ def run_native(args):
             return float(t.item())
         return ms
 
-    gen, weights = trained_like_generator(CIN, dev)
-    gen.operand_dtype = operand
+    gen = native_generator(cfg, dev, operand)
     sty = FrameStylizer(gen)
     if os.environ.get("PBT_FRAMES_PER_PASS"):   # experiment knob; the default is the library's
         sty.frames_per_pass = int(os.environ["PBT_FRAMES_PER_PASS"])
-    F = FRAMES_PER_STEP
-    n_frames = F * (args.steps + args.warmup)
-    frames = synthetic_frames(min(n_frames, 16), H, W, CIN, 1234 + rank, dev)   # cycled; >> L2 per frame anyway
-    out = torch.empty((F, H, W, 3), dtype=torch.uint8, device=dev)
+    n_seg = VIDEO // SEG
+    # the whole video is indexable on every rank; a rank only materialises the frames of its shares of the segments
+    video = torch.empty((VIDEO, H, W, CIN), dtype=torch.uint8, device=dev)
+    out = torch.empty((VIDEO, H, W, 3), dtype=torch.uint8, device=dev)
+    segs_used = min(n_seg, args.steps + args.warmup)
+    real = None
+    if args.config == "C2":
+        import numpy as np
+        real = torch.from_numpy(np.load(os.path.join(GOLD, "gen_cin6_vectors.npz"))["frame_u8"]).to(dev)
+    clip = None
+    if real is not None:    # the 7-frame clip, looped
+        clip = synthetic_frames(range(7), H, W, CIN, dev)
+        clip[0] = real
+    for s in range(segs_used):
+        lo, hi = shard_range(SEG, rank, world)
+        a = s * SEG
+        for i in range(a + lo, a + hi, 8):
+            j = min(i + 8, a + hi)
+            video[i:j] = synthetic_frames(range(i, j), H, W, CIN, dev) if clip is None else clip[[k % 7 for k in range(i, j)]]
+    torch.cuda.synchronize()
 
     def step(i):
-        lo = (i * F) % frames.shape[0]
-        sty.stylize_device(frames[lo:lo + F], out)
+        a = (i % n_seg) * SEG
+        sty.stylize_video(video[a:a + SEG], out[a:a + SEG], rank, world)
 
     for i in range(args.warmup):
         step(i)
@@ -210,215 +289,333 @@ def run_native(args):
     clk = clocks.stop() if rank == 0 else None
     kt = sty.eng.kernel_timer
     sty.eng.kernel_timer = None
-    k_ms = sum(a.elapsed_time(b) for a, b in kt) / max(1, len(kt))
-    value = world * F * args.steps / (ms_total / 1e3)
+    per_pass = sty.pass_size(H, W)
+    full = [(a, b) for a, b, nf in kt if nf == per_pass]      # launches carrying a full pass (the ragged last pass of a share is left out)
+    k_ms = sum(a.elapsed_time(b) for a, b in full) / max(1, len(full))
+    value = SEG * args.steps / (ms_total / 1e3)
+    out_checksum = int(out[(args.warmup % n_seg) * SEG + shard_range(SEG, rank, world)[0]].sum())
 
-    # ---- e2e: pinned host frames in, pinned host frames out, copies inside the timed region
-    host_in = torch.empty((F, H, W, CIN), dtype=torch.uint8).pin_memory()
-    host_in.copy_(frames[:F].cpu())
-    host_out = torch.empty((F, H, W, 3), dtype=torch.uint8).pin_memory()
-    for _ in range(max(1, args.warmup // 2)):
-        sty.stylize_host(host_in, host_out)
+    # ---- e2e: the same call on PINNED HOST segments: copies of every frame in and out inside the timed region
+    host_in = torch.empty((SEG, H, W, CIN), dtype=torch.uint8).pin_memory()
+    host_out = torch.empty((SEG, H, W, 3), dtype=torch.uint8).pin_memory()
+    lo, hi = shard_range(SEG, rank, world)
+    host_in[lo:hi].copy_(video[lo:hi].cpu())
+    for _ in range(max(1, min(2, args.warmup))):
+        sty.stylize_video(host_in, host_out, rank, world)
     barrier()
     e0.record()
     for _ in range(args.steps):
-        sty.stylize_host(host_in, host_out)
+        sty.stylize_video(host_in, host_out, rank, world)
     e1.record()
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
-    e2e_value = world * F * args.steps / (ms_e2e / 1e3)
-    checksum = int(host_out.sum())   # the result is really read on the host
+    e2e_value = SEG * args.steps / (ms_e2e / 1e3)
+    checksum = int(host_out[lo:hi].sum()) if hi > lo else 0   # the result is really read on the host
+    same = bool(torch.equal(host_out[lo:lo + 1].to(dev), out[lo:lo + 1])) if hi > lo else True
+    del video, out
+    torch.cuda.empty_cache()
 
-    # ---- secondary metric: patch training step (C3 shape), data-parallel gradient all-reduce when world > 1
     train = None
     if not args.no_train:
-        from pbt_b200.generator import GeneratorJ
-        torch.manual_seed(0)
-        tg = GeneratorJ(input_channels=9, use_bias=True).to(dev).train()
-        tg.operand_dtype = operand
-        from pbt_b200.optim import FusedClipAdam
-        opt = FusedClipAdam(tg.parameters(), lr=4e-4, betas=(0.9, 0.999), weight_decay=1e-5, max_grad_norm=0.5)
-        B, P = 80, 80
-        g = torch.Generator(device=dev).manual_seed(99 + rank)
-        xs = torch.rand((B, 9, P, P), generator=g, device=dev) * 2 - 1
-        ts = torch.rand((B, 3, P, P), generator=g, device=dev) * 2 - 1
-        ar = GradAllReduce(list(tg.named_parameters()), world=world) if world > 1 else None
-        tg(xs[:1])  # builds the engine
-        if ar is not None:
-            tg._engine.grad_hook = ar.grad_ready
-
-        def eager_step():
-            opt.zero_grad(set_to_none=True)
-            loss = torch.nn.functional.l1_loss(tg(xs), ts) * 4.0
-            loss.backward()
-            if ar is not None:
-                ar.finish()
-            opt.step()          # clip_grad_norm_(0.5) + Adam, fused (pbt_clip_adam_step)
-            return loss.detach()
-
-        mode = "cuda-graph replay of the whole step"
         try:
-            from pbt_b200.graphs import GraphedGeneratorStep
-            gstep = GraphedGeneratorStep(tg, opt, (B, 9, P, P), clip=0.5, grad_sync=ar)
-
-            def train_step():
-                return gstep(xs, ts)
-        except Exception as e:  # noqa: BLE001 - e.g. a collective that cannot be captured on this stack
-            mode = f"eager launches (graph capture failed: {type(e).__name__})"
-            train_step = eager_step
-
-        tsteps = max(3, args.steps)
-        for _ in range(3):
-            train_step()
-        barrier()
-        e0.record()
-        for _ in range(tsteps):
-            loss = train_step()
-        e1.record()
-        barrier()
-        ms_t = max_over_ranks(e0.elapsed_time(e1))
-        pps = world * B * tsteps / (ms_t / 1e3)
-        train = {"metric": "train patches/s", "value": pps, "unit": "patches/s", "ms_per_step": ms_t / tsteps,
-                 "config": {"workload": "C3: G-only step (L1*4, clip 0.5, Adam lr 4e-4 wd 1e-5; clip+Adam fused) batch 80 x 80x80 patches, Cin 9 per GPU",
-                            "allreduce_bytes_per_step": (ar.nbytes if ar else 0), "launch_mode": mode},
-                 "tflops_algorithmic": 3 * flops_per_pixel(9) * P * P * B * world / (ms_t / tsteps) / 1e9,
-                 "final_loss": float(loss)}
-        if world == 1:
-            # the reference's full step with the adversarial branch on (critic + generator, lightning_model.py:224-250),
-            # same shape, replayed as one CUDA graph; reported next to the G-only step, never as the headline
-            try:
-                from lightning_model import StyleTransferModel
-                tcfg = {"batch_size": B, "reconstruction_weight": 4.0, "adversarial_weight": 0.5, "use_image_loss": True,
-                        "reconstruction_criterion": "L1Loss", "adversarial_criterion": "MSELoss",
-                        "use_gradient_clipping": True, "gradient_clip_val": 0.5, "cuda_graph": True}
-                adam = {"lr": 4e-4, "betas": [0.9, 0.999], "weight_decay": 1e-5}
-                torch.manual_seed(0)
-                gm = StyleTransferModel({"args": {"input_channels": 9, "use_bias": True}},
-                                        {"args": {"input_channels": 3, "num_filters": 12, "n_layers": 2, "use_bias": True}},
-                                        tcfg, {"generator": dict(adam), "discriminator": dict(adam)},
-                                        {"additional_channels": {}}).to(dev).train()
-                gm.generator.operand_dtype = operand
-                gm._optimizers = gm.configure_optimizers()
-                gbatch = {"combined_input": xs, "post": ts}
-                for i in range(4):
-                    gm.graphed_training_step(gbatch, i)
-                barrier()
-                e0.record()
-                for i in range(tsteps):
-                    gout = gm.graphed_training_step(gbatch, i)
-                e1.record()
-                barrier()
-                ms_g = e0.elapsed_time(e1) / tsteps
-                train["gan_step"] = {"value": B / (ms_g / 1e3), "unit": "patches/s", "ms_per_step": ms_g,
-                                     "workload": "C3 shape, critic (DiscriminatorN_IN 12 filters, 2 layers) + generator update, "
-                                                 "one generator forward shared by both halves, one CUDA-graph replay",
-                                     "g_total_loss": float(gout["g_total_loss"]), "d_total_loss": float(gout["d_total_loss"])}
-            except Exception as e:  # noqa: BLE001 - secondary figure: never fail the bench line over it
-                train["gan_step"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+            train = train_leg(args, rank, world, dev, operand, barrier, max_over_ranks)
+        except Exception as e:  # noqa: BLE001 - secondary metric: never lose the headline line over it
+            train = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
 
     if rank != 0:
         return
-    # ---- CPU baseline (oracle port), bounded sample, N=1 only
-    cpu = None
+    cpu = bar = None
     if world == 1 and not args.no_cpu:
-        import numpy as np
-        from oracle import generator_oracle as go
-        cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
-        z = np.load(os.path.join(ROOT, "tests", "golden", "gen_c3_trained.npz"))
-        sd = {k: torch.from_numpy(z[k]) for k in z.files}
-        sh, sw = H // 2, W // 4
-        xc = (frames[:1, :sh, :sw].cpu().permute(0, 3, 1, 2).float() / 255 - 0.5) / 0.5
-        with torch.no_grad():
-            go.generator_forward(sd, xc)
-            t0 = time.perf_counter()
-            reps = 0
-            while reps < 2 or time.perf_counter() - t0 < 10.0:
-                yc = go.frame_to_uint8(go.generator_forward(sd, xc))
-                reps += 1
-            dtc = time.perf_counter() - t0
-        frac = sh * sw / (H * W)
-        cpu = {"value": reps * frac / dtc, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{reps} x one {sh}x{sw} crop ({frac:.3f} of a frame) through oracle/generator_oracle.py, scaled by pixel count"}
-        # the same crop through the native path must agree with the oracle (parity guard on the benchmark itself)
-        yn = sty.stylize_device(frames[:1, :sh, :sw].contiguous())
-        diff = (yn.cpu().int() - yc.int()).abs().max().item()
-        cpu["max_abs_u8_diff_vs_native"] = int(diff)
-        # SURVEY section 8(d) also asks for: (i) the reference training step on the host cores (config C1: batch 40 of 32x32
-        # patches), (ii) the same-box "library bar": the reference network through stock torch / cuDNN kernels on this GPU
-        # (the oracle's functional forward is plain torch ops, so it runs on CUDA tensors unchanged).  Reported, not targets.
-        try:
-            sd1 = {k: v.clone() for k, v in sd.items()}
-            opt1 = go.AdamState([k for k, v in sd1.items() if v.is_floating_point() and "running_" not in k])
-            gcpu = torch.Generator().manual_seed(5)
-            x1, t1 = torch.rand(40, 3, 32, 32, generator=gcpu) * 2 - 1, torch.rand(40, 3, 32, 32, generator=gcpu) * 2 - 1
-            go.g_only_train_step(sd1, opt1, x1, t1)
-            t0, n1 = time.perf_counter(), 0
-            while n1 < 2 or time.perf_counter() - t0 < 4.0:
-                go.g_only_train_step(sd1, opt1, x1, t1)
-                n1 += 1
-            cpu["train_c1"] = {"value": 40 * n1 / (time.perf_counter() - t0), "unit": "patches/s", "cores": cores,
-                               "sample": f"{n1} G-only steps, batch 40 x 32x32, oracle port (fp32)"}
-        except Exception as e:  # noqa: BLE001
-            cpu["train_c1"] = {"unavailable": f"{type(e).__name__}: {e}"[:160]}
-        try:
-            lib_bar = {}
-            xg = (frames[:1].permute(0, 3, 1, 2).float() / 255 - 0.5) / 0.5
-            for name, dt_ in (("fp32", torch.float32), ("fp16", torch.float16)):
-                sdg = {k: (v.to(dev, dt_) if v.is_floating_point() else v.to(dev)) for k, v in sd.items()}
-                xin = xg.to(dt_)
-                with torch.no_grad():
-                    for _ in range(2):
-                        go.generator_forward(sdg, xin)
-                    torch.cuda.synchronize(dev)
-                    e0.record()
-                    for _ in range(3):
-                        go.generator_forward(sdg, xin)
-                    e1.record()
-                    torch.cuda.synchronize(dev)
-                lib_bar[name] = 3 / (e0.elapsed_time(e1) / 1e3)
-                del sdg, xin
-                torch.cuda.empty_cache()
-            cpu["same_gpu_torch_cudnn_frames_per_s"] = dict(lib_bar, note="reference network as stock torch ops (cuDNN convs, "
-                                                            "unfused norms / cat / upsample) on this B200, 1 frame per pass, "
-                                                            "generator only (no uint8 conversion)")
-        except Exception as e:  # noqa: BLE001
-            cpu["same_gpu_torch_cudnn_frames_per_s"] = {"unavailable": f"{type(e).__name__}: {e}"[:160]}
+        cpu = cpu_leg(cfg, sty, dev)
+        bar = cudnn_bar(cfg, per_pass, dev)
 
-    frames_per_launch = min(F, sty.pass_size(H, W))
-    conv11_flops = 2.0 * H * W * (49 * (160 + CIN)) * 64 * frames_per_launch
+    conv11_flops = 2.0 * H * W * (49 * (160 + CIN)) * 64 * per_pass
     peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
     achieved = conv11_flops / (k_ms / 1e3) / 1e12 if k_ms > 0 else 0.0
     traffic = None
     tp = os.path.join(ROOT, "profiles", "conv11_traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and args.config == "C4":
         with open(tp) as f:
             tj = json.load(f)
-        traffic = tj.get("dram_bytes_per_launch")   # ncu capture of one conv11 launch (tj["frames_per_launch"] frames)
+        traffic = tj.get("dram_bytes_per_launch")   # one ncu --set full capture of a conv11 launch (profiles/)
         if traffic is not None:
-            traffic = int(traffic * frames_per_launch / max(1, int(tj.get("frames_per_launch", 1))))
+            traffic = int(traffic * per_pass / max(1, int(tj.get("frames_per_launch", 1))))
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": cfg["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": operand + " operands, f32 accumulate", "data": "synthetic",
-        "config": {"workload": "C4: synthetic 1920x1080 RGB video, full-frame GeneratorJ inference, frames sharded per GPU",
-                   "frames_per_step_per_gpu": F, "frame": [H, W, CIN], "weights": weights,
-                   "l2": "per-frame working set ~3.5 GB of activations >> 126 MB L2; 16 distinct input frames cycled"},
+        "config": {"workload": cfg["what"] + "; frames sharded by FrameStylizer.stylize_video (one contiguous range per GPU, no collective)",
+                   "frames_per_step": SEG, "video_frames": VIDEO, "frames_per_generator_pass": per_pass, "frame": [H, W, CIN],
+                   "weights": f"tests/golden/{cfg['weights']} (100 reference training steps)",
+                   "l2": f"the {min(segs_used * SEG, VIDEO)} resident frames are distinct and each pass streams ~{3.5 * per_pass * H * W / (1080 * 1920):.0f} GB of activations >> 126 MB L2"},
+        "timed_region_s": ms_total / 1e3,
         "tflops_algorithmic": flops_per_pixel(CIN) * H * W * value / 1e12,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": F * H * W * CIN, "d2h_bytes_per_step": F * H * W * 3,
-                "ms_per_step": ms_e2e / args.steps, "host_checksum": checksum},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": SEG * H * W * CIN, "d2h_bytes_per_step": SEG * H * W * 3,
+                "ms_per_step": ms_e2e / args.steps, "timed_region_s": ms_e2e / 1e3, "host_checksum": checksum,
+                "host_result_equals_device_result": same},
         "gpu_launches": launches,
-        "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (conv11 7x7, 163->64, CTA-pair configuration, norm+ReLU of up1 on load)", "achieved": achieved, "peak": peak_tf,
-                     "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None, "traffic": traffic,
-                     "peak_source": f"{peak_src} bf16_tflops_sustained", "launch_ms": k_ms, "launches_timed": len(kt),
-                     "frames_per_launch": frames_per_launch},
-        "clocks": clk,
+        "roofline": {"bound": "tensor", "kernel": f"conv_igemm_kernel (conv11 7x7, {160 + CIN}->64, CTA-pair configuration, norm+ReLU of up1 on load)",
+                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
+                     "frac_of_burst_peak": achieved / peaks["bf16_tflops"] if peaks.get("bf16_tflops") else None,
+                     "traffic": traffic, "traffic_algorithmic": int(per_pass * H * W * 2 * (128 + 32 + 16 + 64)),
+                     "traffic_source": "profiles/conv11_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one launch)" if traffic else None,
+                     "peak_source": f"{peak_src} bf16_tflops_sustained (the kernel is timed inside a {ms_total / 1e3:.1f}-s step loop)",
+                     "launch_ms": k_ms, "launches_timed": len(full), "frames_per_launch": per_pass},
+        "clocks": clk, "device_checksum": out_checksum,
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if bar is not None:
+        line["cudnn_bar"] = bar
     if train is not None:
         line["train"] = train
     emit(line)
+
+
+def cpu_leg(cfg, sty, dev):
+    """the reference generator on the host cores: WHOLE frames of this configuration, about 10-20 s of CPU work; the same
+    frame through the native path must agree (parity guard on the benchmark itself)"""
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    H, W, CIN = cfg["h"], cfg["w"], cfg["cin"]
+    fwd, kind = cpu_forward_fn(cfg)
+    u8 = synthetic_frames(range(1), H, W, CIN, "cpu")
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        reps = 0
+        while reps < 2 or (time.perf_counter() - t0 < 10.0 and reps < 8):
+            yc = to_u8(fwd(normalise(u8)))
+            reps += 1
+        dtc = time.perf_counter() - t0
+    cpu = {"value": reps / dtc, "unit": UNIT, "cores": cores, "kind": kind,
+           "sample": f"{reps} whole {W}x{H}x{CIN} frames through " +
+                     ("the unmodified reference GeneratorJ (baseline/_ref)" if kind == "reference" else "oracle/generator_oracle.py") +
+                     ", fp32, all host threads (no warm-up pass excluded)"}
+    yn = sty.stylize_device(u8.to(dev))
+    diff = (yn.cpu().int() - yc.int()).abs()
+    cpu["max_abs_u8_diff_vs_native"] = int(diff.max())
+    cpu["frac_u8_pixels_differing"] = float((diff > 0).float().mean())
+    try:
+        # SURVEY section 8(d): the reference training step on the host cores (config C1: batch 40 of 32x32 patches)
+        from oracle import generator_oracle as go
+        sd1 = fixture_state_dict("gen_c3_trained.npz")
+        opt1 = go.AdamState([k for k, v in sd1.items() if v.is_floating_point() and "running_" not in k])
+        gcpu = torch.Generator().manual_seed(5)
+        x1, t1 = torch.rand(40, 3, 32, 32, generator=gcpu) * 2 - 1, torch.rand(40, 3, 32, 32, generator=gcpu) * 2 - 1
+        go.g_only_train_step(sd1, opt1, x1, t1)
+        t0, n1 = time.perf_counter(), 0
+        while n1 < 2 or time.perf_counter() - t0 < 4.0:
+            go.g_only_train_step(sd1, opt1, x1, t1)
+            n1 += 1
+        cpu["train_c1"] = {"value": 40 * n1 / (time.perf_counter() - t0), "unit": "patches/s", "cores": cores,
+                           "sample": f"{n1} G-only steps, batch 40 x 32x32, oracle port (fp32)"}
+    except Exception as e:  # noqa: BLE001
+        cpu["train_c1"] = {"unavailable": f"{type(e).__name__}: {e}"[:160]}
+    return cpu
+
+
+def cudnn_bar(cfg, per_pass, dev):
+    """same-GPU library bar: the reference network as stock torch ops - cuDNN convolutions, unfused norms,
+    cat and Upsample - in channels_last, fp16 and bf16 (+ fp32 as trained), cudnn.benchmark on, the native arm's frames
+    per pass, >= 20 timed passes"""
+    import torch
+    from oracle import generator_oracle as go
+    H, W, CIN = cfg["h"], cfg["w"], cfg["cin"]
+    res = {"frames_per_pass": per_pass, "memory_format": "channels_last", "cudnn_benchmark": True,
+           "note": "generator only (no uint8 conversion); functional torch graph of the reference network on this B200"}
+    sd = fixture_state_dict(cfg["weights"])
+    xg = normalise(synthetic_frames(range(per_pass), H, W, CIN, dev))
+    old = torch.backends.cudnn.benchmark
+    torch.backends.cudnn.benchmark = True
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    try:
+        for name, dt_, reps in (("fp16", torch.float16, 20), ("bf16", torch.bfloat16, 20), ("fp32", torch.float32, 5)):
+            try:
+                sdg = {k: (v.to(dev, dt_) if v.is_floating_point() else v.to(dev)) for k, v in sd.items()}
+                sdg = {k: (v.contiguous(memory_format=torch.channels_last) if v.dim() == 4 else v) for k, v in sdg.items()}
+                xin = xg.to(dt_).contiguous(memory_format=torch.channels_last)
+                with torch.no_grad():
+                    for _ in range(3):
+                        go.generator_forward(sdg, xin)
+                    torch.cuda.synchronize(dev)
+                    e0.record()
+                    for _ in range(reps):
+                        go.generator_forward(sdg, xin)
+                    e1.record()
+                    torch.cuda.synchronize(dev)
+                res[name] = per_pass * reps / (e0.elapsed_time(e1) / 1e3)
+                del sdg, xin
+            except Exception as e:  # noqa: BLE001 - e.g. out of memory at 4K fp32
+                res[name] = f"unavailable: {type(e).__name__}"
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.benchmark = old
+    res["unit"] = UNIT
+    return res
+
+
+def synthetic_keyframes(n, h, w, seed):
+    """n keyframes for the C3 training leg: (pre, post, gauss guide, flow guide) uint8 [h,w,3] and ellipse masks covering
+    ~12 % of the frame"""
+    import numpy as np
+    from PIL import Image
+    rng = np.random.RandomState(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+
+    def smooth():
+        base = rng.randint(0, 256, (h // 24, w // 24, 3)).astype(np.uint8)
+        img = np.asarray(Image.fromarray(base).resize((w, h), Image.BILINEAR)).astype(np.int16)
+        return np.clip(img + rng.randint(-6, 7, (h, w, 1)), 0, 255).astype(np.uint8)
+
+    pre, post, ga, fl, mask = [], [], [], [], []
+    for _ in range(n):
+        pre.append(smooth()); post.append(smooth()); ga.append(smooth()); fl.append(smooth())  # noqa: E702
+        cy, cx = rng.randint(h // 3, 2 * h // 3), rng.randint(w // 3, 2 * w // 3)
+        mask.append(((((yy - cy) / (0.24 * h)) ** 2 + ((xx - cx) / (0.16 * w)) ** 2) <= 1).astype(np.uint8) * 255)
+    return pre, post, ga, fl, mask
+
+
+def train_leg(args, rank, world, dev, operand, barrier, max_over_ranks):
+    """config C3: the generator half of the reference training_step (lightning_model.py:211-250,260-292) per rank: sampler
+    draw + gather -> forward -> L1*4 -> backward -> (NCCL mean all-reduce) -> clip 0.5 -> Adam, batch 80 x 80x80, Cin 9"""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from lightning_model import _IndexLoader
+    from pbt_b200.generator import GeneratorJ
+    from pbt_b200.graphs import GraphedGeneratorStep
+    from pbt_b200.optim import FusedClipAdam
+    from pbt_b200.parallel import GradAllReduce, broadcast_module_state, replicas_identical
+    from pbt_b200.sampler import StyleTransferDataset
+
+    B, P = 80, 80
+    pre, post, ga, fl, mask = synthetic_keyframes(6, 1080, 1920, seed=7)     # same keyframes on every rank
+    ds = StyleTransferDataset.from_arrays(pre, post, mask, P, additional={"gauss": ga, "flow": fl}, device=str(dev))
+    del pre, post, ga, fl, mask
+    np.random.seed(1000 + rank)            # per-rank draw stream (the reference: per-worker numpy seeds)
+    torch.manual_seed(0)
+    tg = GeneratorJ(input_channels=9, use_bias=True)
+    tg.load_state_dict(fixture_state_dict("gen_cin9_trained.npz"), strict=True)
+    tg = tg.to(dev).train()
+    tg.operand_dtype = operand
+    broadcast_module_state(tg)
+    opt = FusedClipAdam(tg.parameters(), lr=4e-4, betas=(0.9, 0.999), weight_decay=1e-5, max_grad_norm=0.5)
+    loader = iter(_IndexLoader(ds, B, rank, world))
+    checks = {}
+    ar = None
+    if world > 1:
+        # (1) the NCCL-reduced gradient equals the mean of the per-rank gradients: one sweep without the exchange,
+        # all-gathered and averaged with tensor-library ops, against one sweep through GradAllReduce on the same batch
+        b0 = next(loader)
+        x0, t0_ = b0["combined_input"], b0["post"]
+        bn = tg.smoothers[2]
+        keep = (bn.running_mean.clone(), bn.running_var.clone(), bn.num_batches_tracked.clone())
+        (torch.nn.functional.l1_loss(tg(x0), t0_) * 4.0).backward()
+        mine = tg._engine.grad_bucket().flat.clone()
+        every = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        expect = torch.stack(every).mean(0)
+        tg.zero_grad(set_to_none=True)
+        ar = GradAllReduce(list(tg.named_parameters()), world=world).attach(tg)
+        (torch.nn.functional.l1_loss(tg(x0), t0_) * 4.0).backward()
+        ar.finish()
+        torch.cuda.synchronize()
+        err = float((ar.flat - expect).abs().max() / expect.abs().max().clamp_min(1e-30))
+        checks["allreduce_max_err_rel_to_peak"] = err       # wgrad accumulates with fp32 atomics: two sweeps differ in the last bits
+        checks["allreduce_matches_mean_of_rank_gradients"] = bool(err < 1e-3)
+        tg.zero_grad(set_to_none=True)
+        with torch.no_grad():
+            bn.running_mean.copy_(keep[0]); bn.running_var.copy_(keep[1]); bn.num_batches_tracked.copy_(keep[2])  # noqa: E702
+
+    gstep = GraphedGeneratorStep(tg, opt, (B, 9, P, P), clip=0.5, grad_sync=ar)
+    mode = "cuda-graph replay of the whole step (forward, loss, backward, all-reduce, clip, Adam)"
+
+    def pipeline_step():
+        b = next(loader)                    # host draws + order-statistic tree + H2D of the positions + gather kernel
+        return gstep(b["combined_input"], b["post"])
+
+    tsteps = max(20, args.steps)
+    for _ in range(5):
+        pipeline_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(tsteps):
+        loss = pipeline_step()
+    e1.record()
+    barrier()
+    ms_p = max_over_ranks(e0.elapsed_time(e1))
+    # the step alone on a resident batch (comparable with round 1's figure)
+    fixed = next(loader)
+    xs, ts = fixed["combined_input"].clone(), fixed["post"].clone()
+    barrier()
+    e0.record()
+    for _ in range(tsteps):
+        loss = gstep(xs, ts)
+    e1.record()
+    barrier()
+    ms_s = max_over_ranks(e0.elapsed_time(e1))
+    lt = loss.detach().clone().reshape(1)
+    if world > 1:
+        dist.all_reduce(lt)
+        lt /= world
+        # (2) after all those graph-replayed steps every rank must hold bit-identical weights (BatchNorm running statistics
+        # are per-rank by design: DDP would overwrite them with rank 0's before each forward, and rank 0 writes the checkpoint)
+        checks["replicas_identical"] = bool(replicas_identical(tg, buffers=False))
+    flops = 3 * flops_per_pixel(9) * P * P * B * world
+    res = {"metric": "train patches/s", "value": world * B * tsteps / (ms_p / 1e3), "unit": "patches/s",
+           "ms_per_step": ms_p / tsteps, "steps": tsteps,
+           "config": {"workload": "C3: sampler (numpy draws, order-statistic tree, patch gather kernel) + G-only step (L1*4, clip 0.5, Adam "
+                                  "lr 4e-4 wd 1e-5; clip+Adam fused), batch 80 x 80x80 patches per GPU, Cin 9 (RGB + 2 guide dirs), "
+                                  "6 synthetic 1080p keyframes resident per GPU, weights tests/golden/gen_cin9_trained.npz",
+                      "allreduce_bytes_per_step": (ar.nbytes if ar else 0), "allreduce_groups": (len(ar.group_bounds) if ar else 0),
+                      "launch_mode": mode},
+           "tflops_algorithmic": flops / (ms_p / tsteps) / 1e9,
+           "step_only": {"value": world * B * tsteps / (ms_s / 1e3), "ms_per_step": ms_s / tsteps,
+                         "tflops_algorithmic": flops / (ms_s / tsteps) / 1e9, "note": "graph replay on a resident batch, sampler excluded"},
+           "final_loss_mean_over_ranks": float(lt), "skipped_steps": opt.skipped_steps, **checks}
+    if world == 1:
+        res["gan_step"] = gan_leg(xs, ts, dev, operand, tsteps, barrier)
+    return res
+
+
+def gan_leg(xs, ts, dev, operand, tsteps, barrier):
+    """the reference's full step with the adversarial branch on (critic + generator, lightning_model.py:224-250), same
+    shape, replayed as one CUDA graph; reported next to the G-only step, never as the headline"""
+    import torch
+    try:
+        from lightning_model import StyleTransferModel
+        B = xs.shape[0]
+        tcfg = {"batch_size": B, "reconstruction_weight": 4.0, "adversarial_weight": 0.5, "use_image_loss": True,
+                "reconstruction_criterion": "L1Loss", "adversarial_criterion": "MSELoss",
+                "use_gradient_clipping": True, "gradient_clip_val": 0.5, "cuda_graph": True}
+        adam = {"lr": 4e-4, "betas": [0.9, 0.999], "weight_decay": 1e-5}
+        torch.manual_seed(0)
+        gm = StyleTransferModel({"args": {"input_channels": 9, "use_bias": True}},
+                                {"args": {"input_channels": 3, "num_filters": 12, "n_layers": 2, "use_bias": True}},
+                                tcfg, {"generator": dict(adam), "discriminator": dict(adam)},
+                                {"additional_channels": {}}).to(dev).train()
+        gm.generator.load_state_dict(fixture_state_dict("gen_cin9_trained.npz"), strict=True)
+        gm.generator.operand_dtype = operand
+        gm._optimizers = gm.configure_optimizers()
+        gbatch = {"combined_input": xs, "post": ts}
+        for i in range(4):
+            gm.graphed_training_step(gbatch, i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(tsteps):
+            gout = gm.graphed_training_step(gbatch, i)
+        e1.record()
+        barrier()
+        ms_g = e0.elapsed_time(e1) / tsteps
+        return {"value": B / (ms_g / 1e3), "unit": "patches/s", "ms_per_step": ms_g,
+                "workload": "C3 shape, critic (DiscriminatorN_IN 12 filters, 2 layers) + generator update, one generator forward "
+                            "shared by both halves, one CUDA-graph replay",
+                "g_total_loss": float(gout["g_total_loss"]), "d_total_loss": float(gout["d_total_loss"])}
+    except Exception as e:  # noqa: BLE001 - secondary figure: never fail the bench line over it
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
 
 
 def emit(line: dict) -> None:
@@ -437,9 +634,10 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--config", default="C4", choices=sorted(CONFIGS))
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

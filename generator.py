@@ -21,6 +21,7 @@ from PIL import Image
 from pbt_b200 import ops, tiled
 from pbt_b200.config import compose, to_container
 from pbt_b200.inference import FrameStylizer
+from pbt_b200.parallel import dist_env, shard_range
 from src.models.generator import GeneratorJ
 
 
@@ -33,7 +34,8 @@ class StyleTransferInference:
         self.logger = logging.getLogger(__name__)
         if not (torch.cuda.is_available() and cfg.inference.get("use_gpu", True)):
             raise RuntimeError("the B200-native inference path needs a CUDA device (inference.use_gpu=true); no CPU path")
-        self.device = torch.device("cuda")
+        self.device = torch.device("cuda", dist_env()[2] % max(1, torch.cuda.device_count()))   # torchrun: LOCAL_RANK
+        torch.cuda.set_device(self.device)
         self.additional_channels = to_container(dict(cfg.paths.get("additional_channels", {}) or {}))
         self.patch_size = cfg.data.patch_size
         self.tiled = bool(cfg.inference.get("tiled", False))
@@ -83,10 +85,12 @@ class StyleTransferInference:
         m = Image.open(mask_file).point(lambda p: p > 128 and 255).convert("L")
         return u8, np.asarray(m, dtype=np.uint8).copy()
 
-    def _erode(self, mask_u8, h, w):
-        t = torch.from_numpy(mask_u8).to(self.device, non_blocking=True).float().div_(255.0)[None, None]
-        box = F.conv2d(t, torch.ones((1, 1, 7, 7), device=self.device), padding=3)
-        return torch.where(box < 49, torch.zeros_like(t), t)[:, :, :h, :w]   # true erosion: all 49 pixels set
+    def _erode(self, mask_u8):
+        """thresholded uint8 mask [H,W] -> device fp32 [1,H,W]: 1 where all 49 pixels of the 7x7 window are set (:327-351)"""
+        m = torch.from_numpy(mask_u8).to(self.device, non_blocking=True)[None].contiguous()
+        out = torch.empty(m.shape, dtype=torch.float32, device=self.device)
+        ops.mask_erode7(m, out)
+        return out
 
     @torch.no_grad()
     def _stylize(self, u8_np, mask_np):
@@ -96,20 +100,19 @@ class StyleTransferInference:
         if self.tiled:
             # reference behaviour (generator.py:567-652): windows -> generator -> Gaussian blend -> mask composite
             x = ((u8.permute(2, 0, 1)[None].float() / 255.0) - 0.5) / 0.5      # ToTensor + Normalize(0.5, 0.5) (:91-95)
-            mt = torch.from_numpy(mask_np).to(self.device).float().div_(255.0)[None]
-            mt = tiled.process_mask(mt)[:, :h, :w].unsqueeze(0)
+            mt = self._erode(mask_np)[:, :h, :w].unsqueeze(0)      # the thresholded mask is binary: process_mask == erosion
             out = tiled.process_large_image(self.generator, x, mt, int(self.patch_size), self.overlap_percent)
-        else:
-            ph, pw = (-h) % 4, (-w) % 4
-            if ph or pw:  # GeneratorJ needs multiples of 4: replicate the border, crop afterwards
-                u8 = F.pad(u8.permute(2, 0, 1)[None].float(), (0, pw, 0, ph), mode="replicate")[0].permute(1, 2, 0).to(torch.uint8)
-            y = self.stylizer.eng.forward(u8[None].contiguous(), save=False, u8_hwc=True)[:, :, :h, :w]
-            m = self._erode(mask_np, h, w)
-            rgb = ((u8[:h, :w, :3].permute(2, 0, 1)[None].float() / 255.0) - 0.5) / 0.5
-            out = rgb * (1 - m) + y * m
-        res = torch.empty((1, h, w, 3), dtype=torch.uint8, device=self.device)
-        ops.nchw_to_u8hwc(out.contiguous(), res)                               # clamp, (x+1)*127.5, round (:643-647)
-        return res[0].cpu().numpy()
+            res = torch.empty((1, h, w, 3), dtype=torch.uint8, device=self.device)
+            ops.composite_to_u8(out.contiguous(), res)                         # clamp, (x+1)*127.5, round (:643-647)
+            return res[0].cpu().numpy()
+        ph, pw = (-h) % 4, (-w) % 4
+        m = self._erode(mask_np)
+        if ph or pw:  # GeneratorJ needs multiples of 4: replicate the border, crop afterwards
+            u8 = F.pad(u8.permute(2, 0, 1)[None].float(), (0, pw, 0, ph), mode="replicate")[0].permute(1, 2, 0).to(torch.uint8)
+            m = F.pad(m, (0, pw, 0, ph))
+        # generator pass, mask composite rgb*(1-m) + y*m (:562-563) and uint8 conversion (:643-647), all native
+        res = self.stylizer.stylize_device(u8[None].contiguous(), masks=m.contiguous())
+        return res[0, :h, :w].cpu().numpy()
 
     @staticmethod
     def _save(arr, save_path):
@@ -132,6 +135,13 @@ class StyleTransferInference:
         self.logger.info(f"Found {len(files)} images to process")
         jobs = [(f, os.path.join(paths.mask_dir, os.path.basename(f)), os.path.join(paths.output_dir, os.path.basename(f)))
                 for f in files]
+        # one process per GPU under torchrun: this rank takes its contiguous range of the frame list (no collective;
+        # the reference's loop :674-705 is the world-size-1 case)
+        rank, world, local = dist_env()
+        if world > 1:
+            lo, hi = shard_range(len(jobs), rank, world)
+            self.logger.info(f"rank {rank}/{world}: frames [{lo}, {hi})")
+            jobs = jobs[lo:hi]
         workers = int(self.cfg.inference.get("io_workers", min(16, os.cpu_count() or 1)))
         if workers <= 0:
             for f, mp, sp in jobs:

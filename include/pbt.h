@@ -333,6 +333,16 @@ int pbt_patch_gather(const float* const* src_ptrs, int32_t n_src, int32_t n_imag
  * mask pixel > 0 in the 7x7 window. mask: uint8 [h][w] (already thresholded 0/255). */
 int pbt_mask_dilate7(const uint8_t* mask, int32_t h, int32_t w, uint8_t* out, void* stream);
 
+/* 7x7 erosion of thresholded masks (generator.py:327-351 `_process_mask`, :627-631): out[i][y][x] = 1.0f where all 49
+ * pixels of the zero-padded 7x7 window are set, else 0.0f.  mask: uint8 [n][h][w] (0 / non-zero), out: float [n][h][w]. */
+int pbt_mask_erode7(const uint8_t* mask, int32_t n, int32_t h, int32_t w, float* out, void* stream);
+/* mask composite + uint8 conversion of the frame loop (generator.py:562-563,643-647):
+ * out[n][h][w][3] = round(clamp((clamp(rgb*(1-m) + y*m, -1, 1) + 1)*127.5, 0, 255)) with rgb = ToTensor+Normalize of the
+ * first three channels of frame uint8 [n][h][w][c]; y: float NCHW [n][3][h][w]; mask: float [n][h][w] or NULL (then
+ * out is the plain conversion of y and `frame` is not read). */
+int pbt_composite_to_u8(const float* y, const uint8_t* frame, int32_t c, const float* mask, int32_t n, int32_t h, int32_t w,
+                        uint8_t* out, void* stream);
+
 /* ------------------------------------------------------------------------
  * Loss / optimiser tail helpers.
  * ---------------------------------------------------------------------- */

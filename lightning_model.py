@@ -5,7 +5,8 @@ Scope: the generator half of ``training_step`` is the acce
 sampler -> native GeneratorJ forward/backward -> L1*reconstruction_weight -> (data-parallel mean all-reduce)
 -> clip_grad_norm_ -> Adam; the G-only step is what BASELINE.md times.
 The adversarial and perceptual branches (section 8f rank 4; reference lightning_model.py:224-236,270-283,294-319) are
-available behind ``training.use_adversarial_loss`` / ``training.use_perception_loss`` (default off = the G-only step):
+available behind ``training.use_adversarial_loss`` (default on, as the reference trains) / ``training.use_perception_loss``
+(default off: the ImageNet VGG19 weights cannot be downloaded here):
 the PatchGAN critic (3->12->24->48->1 channels in the shipped config, 0.2 % of the generator's FLOPs) and the VGG taps
 run on the tensor library, the generator passes inside them — the no-grad pass of the critic step, the forward and the
 backward that receives dL/dy from both loss terms — run on the native kernels, and both Adam steps use the fused
@@ -38,16 +39,30 @@ class _IndexLoader:
         self.ds, self.bs, self.rank, self.world = dataset, batch_size, rank, world
 
     def __len__(self):
-        return (len(self.ds) // self.world + self.bs - 1) // self.bs
+        return (self._per_rank() + self.bs - 1) // self.bs
+
+    def _per_rank(self) -> int:
+        return (len(self.ds) + self.world - 1) // self.world
 
     def __iter__(self):
         n = len(self.ds)
-        seed = int(torch.empty((), dtype=torch.int64).random_().item())
+        seed = torch.empty((), dtype=torch.int64).random_()
+        if self.world > 1:                      # one permutation for all ranks (DistributedSampler: shared seed + epoch)
+            import torch.distributed as dist
+            if dist.is_initialized():
+                dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+                seed = seed.to(dev)
+                dist.broadcast(seed, src=0)
         gen = torch.Generator()
-        gen.manual_seed(seed)
+        gen.manual_seed(int(seed.item()))
         perm = torch.randperm(n, generator=gen)
-        if self.world > 1:                      # DistributedSampler-style strided shard of the permutation
-            perm = perm[self.rank::self.world]
+        if self.world > 1:
+            # DistributedSampler semantics: pad the permutation by wrapping around so that it divides evenly, then take
+            # the strided shard - every rank runs the same number of steps (unequal counts would leave a collective unmatched)
+            total = self._per_rank() * self.world
+            if total > n:
+                perm = torch.cat([perm, perm[:total - n]])
+            perm = perm[self.rank:total:self.world]
         for i in range(0, len(perm), self.bs):
             yield self.ds.sample_batch(perm[i:i + self.bs].tolist())
 

@@ -20,11 +20,15 @@ def _worker(rank, world, port, q):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, root)
     from pbt_b200.generator import GeneratorJ
-    from pbt_b200.parallel import GradAllReduce, init_distributed, shard_range
+    from pbt_b200.parallel import GradAllReduce, broadcast_module_state, init_distributed, replicas_identical, shard_range
     r, w, _ = init_distributed("gloo")
     assert (r, w) == (rank, world)
-    torch.manual_seed(0)
+    # NO common seed: every process initialises its own weights; the trainer's broadcast (DDP's initial broadcast in the
+    # reference, train.py:93-94) is what makes the replicas identical
     g = GeneratorJ(input_channels=3, use_bias=True)        # parameters only; no forward on the CPU
+    differs = not replicas_identical(g)
+    broadcast_module_state(g)
+    same = replicas_identical(g)
     named = list(g.named_parameters())
     ar = GradAllReduce(named, world=world)
     # emulate the order in which the backward sweep publishes gradients: tail, decoder, trunk
@@ -38,7 +42,7 @@ def _worker(rank, world, port, q):
         ar.grad_ready(name, local[name])
     ar.finish()
     # expected mean over ranks, recomputed locally from both ranks' generators
-    ok = True
+    ok = differs and same
     gens = [torch.Generator().manual_seed(100 + k) for k in range(world)]
     for i in order:
         name, p = named[i]

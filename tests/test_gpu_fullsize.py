@@ -162,9 +162,11 @@ def test_4k_frame_matches_oracle_and_is_batch_invariant():
     determinism / batch invariance - 4x the units of full HD, every conv layer runs persistent CTAs here."""
     from oracle import generator_oracle as go
     from pbt_b200.generator import GeneratorJ
-    torch.manual_seed(21)
-    g = GeneratorJ(input_channels=5, use_bias=True).cuda().eval()
-    sd = {k: v.detach().cpu().clone() for k, v in g.state_dict().items()}
+    z = np.load(os.path.join(GOLD, "gen_cin5_trained.npz"))      # reference-trained Cin-5 weights (oracle/make_golden_guides.py)
+    sd = {k: torch.from_numpy(z[k]) for k in z.files}
+    g = GeneratorJ(input_channels=5, use_bias=True)
+    g.load_state_dict(sd, strict=True)
+    g = g.cuda().eval()
     gen = torch.Generator(device="cuda").manual_seed(3)
     low = torch.rand((2, 5, 135, 240), generator=gen, device="cuda") * 2 - 1
     x = torch.nn.functional.interpolate(low, size=(2160, 3840), mode="bilinear", align_corners=False)

@@ -141,10 +141,9 @@ def test_gradient_wrt_input(trained_sd, vec, cin):
         g, sd = load_gen("fp16", trained_sd).train(), trained_sd
         x0, tgt = torch.from_numpy(vec["x"][:16]).contiguous(), torch.from_numpy(vec["target"][:16]).contiguous()
     else:
-        torch.manual_seed(5)
-        g = load_gen("fp16", None, cin=cin).train()
-        sd = {k: v.detach().cpu() for k, v in g.state_dict().items()}
-        x0, tgt = torch.rand(4, cin, 32, 48) * 2 - 1, torch.rand(4, 3, 32, 48) * 2 - 1
+        sd, v9 = _fixture(cin)
+        g = load_gen("fp16", sd, cin=cin).train()
+        x0, tgt = torch.from_numpy(v9["x"][:16]).contiguous(), torch.from_numpy(v9["target"][:16]).contiguous()
     # oracle: autograd through the functional fp32 restatement
     xr = x0.clone().requires_grad_(True)
     yr = go.generator_forward(sd, xr, training=True)
@@ -162,10 +161,7 @@ def test_gradient_wrt_input(trained_sd, vec, cin):
     absd, ps = float((got - ref).abs().max()), psnr(got, ref, peak)
     cos = float(torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0))
     print(f"cin={cin} dL/dx: peak={peak:.3e} max_abs={absd:.3e} rel={absd / peak:.4f} psnr={ps:.1f} dB cosine={cos:.5f}")
-    # the north-star tolerance is stated for trained weights; with random-init weights ANY 16-bit forward pass flips
-    # enough ReLU masks to sit near 30-35 dB (tests/emulation.py, __graft_entry__.smoke), so that case checks the
-    # channel mapping of the nine-channel input through the direction of the gradient
-    assert absd <= MAX_ABS and ps >= (PSNR_MIN if cin == 3 else 30.0) and cos >= (0.999 if cin == 3 else 0.98)
+    assert absd <= MAX_ABS and ps >= PSNR_MIN and cos >= 0.999      # reference-trained weights for both channel counts
     for k, p in g.named_parameters():
         a, b = with_x[k], p.grad
         tol = 2e-3 * float(b.abs().max()) + 1e-9     # wgrad accumulates with atomics: not bit-reproducible
@@ -194,18 +190,67 @@ def test_training_reduces_loss_like_the_reference(trained_sd, vec):
     assert all(abs(a - b) < 2e-2 for a, b in zip(losses, ref_losses))
 
 
-def test_guide_channels_forward_matches_oracle():
-    """Cin = 9 (RGB + two RGB-converted guide dirs, config C3): random reference init, oracle on the host"""
+def _fixture(cin):
+    z = np.load(os.path.join(GOLD, f"gen_cin{cin}_trained.npz"))
+    return {k: torch.from_numpy(z[k]) for k in z.files}, np.load(os.path.join(GOLD, f"gen_cin{cin}_vectors.npz"))
+
+
+@pytest.mark.parametrize("cin,prefix", [(9, ""), (9, "p80_"), (6, ""), (5, "")], ids=["cin9-C1batch", "cin9-C3patch80", "cin6", "cin5"])
+def test_guide_channel_models_match_reference(cin, prefix):
+    """reference-TRAINED generators with guide channels (oracle/make_golden_guides.py; config C3: RGB + two guide dirs =
+    9 channels, at the C1 batch and at the C3 patch size; C2's 6; C5's 5): eval / train forward against the reference
+    outputs and one-step gradients against the oracle, at the north-star bounds"""
     from oracle import generator_oracle as go
-    torch.manual_seed(5)
-    g = load_gen("fp16", cin=9)
-    sd = {k: v.detach().cpu().clone() for k, v in g.state_dict().items()}
-    x = torch.randn(2, 9, 80, 80).clamp(-1, 1)
-    g.eval()
+    sd, vec = _fixture(cin)
+    x, tgt = torch.from_numpy(vec[prefix + "x"]), torch.from_numpy(vec[prefix + "target"])
+    g = load_gen("fp16", sd, cin=cin).eval()
     with torch.no_grad():
-        y = g(x.cuda()).cpu()
-    ref = go.generator_forward(sd, x, training=False)
-    assert (y - ref).abs().max().item() <= MAX_ABS and psnr(y, ref, 2.0) >= PSNR_MIN
+        ye = g(x.cuda()).cpu()
+    ref = torch.from_numpy(vec[prefix + "y_eval"])
+    err, p = (ye - ref).abs().max().item(), psnr(ye, ref, 2.0)
+    assert err <= MAX_ABS and p >= PSNR_MIN, ("eval", err, p)
+    g.train()
+    y = g(x.cuda())
+    loss = torch.nn.functional.l1_loss(y, tgt.cuda()) * 4.0
+    loss.backward()
+    ref = torch.from_numpy(vec[prefix + "y_train"])
+    err_t = (y.detach().cpu() - ref).abs().max().item()
+    assert err_t <= MAX_ABS and abs(loss.item() - float(vec[prefix + "loss"])) < 5e-3, ("train", err_t, loss.item())
+    assert torch.allclose(g.smoothers[2].running_mean.cpu(), torch.from_numpy(vec[prefix + "bn_rm_after"]), atol=2e-3)
+    _, _, ref_grads = go.loss_and_grads(sd, x, tgt)
+    worst, worst_abs = 200.0, 0.0
+    for k, prm in g.named_parameters():
+        r = ref_grads[k]
+        peak = float(r.abs().max())
+        got = prm.grad.detach().cpu()
+        if float(got.abs().max()) == 0.0 and k.endswith(".bias"):
+            continue                                  # biases in front of an InstanceNorm: exact zeros here
+        worst = min(worst, psnr(got, r, peak))
+        worst_abs = max(worst_abs, float((got - r).abs().max()))
+    print(f"cin={cin} {prefix or 'C1 batch'}: eval max_abs={err:.5f} psnr={p:.1f} dB; train max_abs={err_t:.5f}; "
+          f"worst gradient PSNR {worst:.1f} dB, max_abs {worst_abs:.2e}")
+    assert worst >= PSNR_MIN and worst_abs <= MAX_ABS, (worst, worst_abs)
+
+
+def test_c2_full_frame_matches_reference_output():
+    """config C2 of BASELINE.json: one whole 960x540 frame of PlatinumChan_x0.5_train (RGB + tracking guide, 6 channels)
+    through the reference-trained Cin-6 model; expected output = the unmodified reference module's (fixture)"""
+    from pbt_b200.inference import FrameStylizer
+    sd, vec = _fixture(6)
+    u8 = torch.from_numpy(vec["frame_u8"]).cuda()
+    x = ((u8.permute(2, 0, 1)[None].float() / 255.0) - 0.5) / 0.5
+    g = load_gen("fp16", sd, cin=6).eval()
+    with torch.no_grad():
+        y = g(x).cpu()
+    ref = torch.from_numpy(vec["y_frame_f16"]).float()[None]
+    err, p = (y - ref).abs().max().item(), psnr(y, ref, 2.0)
+    print(f"C2 frame 960x540x6: max_abs={err:.5f} psnr={p:.1f} dB")
+    assert err <= MAX_ABS and p >= PSNR_MIN, (err, p)
+    # the uint8 product path on the same frame: at most one code value from the reference output's conversion
+    out = FrameStylizer(g).stylize_device(u8[None].contiguous())[0].cpu()
+    q = ((ref.clamp(-1, 1) + 1) * 127.5).clamp(0, 255).round().to(torch.uint8)[0].permute(1, 2, 0)
+    d = (out.int() - q.int()).abs()
+    assert int(d.max()) <= 2 and float((d > 1).float().mean()) < 1e-4, (int(d.max()), float((d > 1).float().mean()))
 
 
 @pytest.mark.parametrize("cin,h,w,n", [(3, 100, 140, 2), (6, 960, 540, 1), (5, 68, 52, 3)],

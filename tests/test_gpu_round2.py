@@ -1,0 +1,168 @@
+"""GPU tests of the round-2 additions: sampler augmentation branch and in-memory constructor, native mask erosion and
+composite, the sharded frame loop (`FrameStylizer.stylize_video`), flat gradient bucket semantics, and - on a box with two
+or more GPUs - NCCL data-parallel parity under torchrun (tests/dist_gpu_check.py)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _mini(s):
+    return os.path.join(GOLD, "mini_dataset", s)
+
+
+def test_sampler_augmentation_branch_bit_exact_vs_reference_golden():
+    """augmentation_factor=2 (reference src/data/dataset.py:276-292): both draws of every item and the extra patches"""
+    from pbt_b200.sampler import StyleTransferDataset
+    z = np.load(os.path.join(GOLD, "sampler_aug_golden.npz"))
+    ds = StyleTransferDataset(_mini("input"), _mini("output"), _mini("mask"), 32, augmentation_factor=2,
+                              additional_channels={"guide": {"path": _mini("guide"), "depth": 3}})
+    assert len(ds) == int(z["length"])
+    log = z["log"]
+    np.random.seed(321)
+    for bi in range(len(log) // 8):
+        rows = log[bi * 8:(bi + 1) * 8]
+        batch = ds.sample_batch(rows[:, 0].tolist())
+        assert torch.equal(batch["positions"], torch.from_numpy(rows[:, 1:4])), bi
+        assert ds.last_patch_positions == [rows[-1, 2:4].tolist(), rows[-1, 4:6].tolist()], bi
+        if bi < 2:
+            for key in ("pre", "post", "channel_guide", "already", "channel_guide_aug"):
+                assert np.array_equal(batch[key].cpu().numpy(), z[f"b{bi}_{key}"]), (bi, key)
+
+
+def test_dataset_from_arrays_equals_directory_dataset():
+    from PIL import Image
+    from pbt_b200.sampler import StyleTransferDataset
+    names = sorted(os.listdir(_mini("input")))
+    rgb = lambda d: [np.asarray(Image.open(os.path.join(_mini(d), n)).convert("RGB")) for n in names]  # noqa: E731
+    masks = [np.asarray(Image.open(os.path.join(_mini("mask"), n)).convert("L")) for n in names]
+    a = StyleTransferDataset(_mini("input"), _mini("output"), _mini("mask"), 32,
+                             additional_channels={"guide": {"path": _mini("guide"), "depth": 3}})
+    b = StyleTransferDataset.from_arrays(rgb("input"), rgb("output"), masks, 32, additional={"guide": rgb("guide")})
+    assert len(a) == len(b) and all(torch.equal(x, y) for x, y in zip(a.valid_indices, b.valid_indices))
+    idx = list(range(0, 40, 3))
+    np.random.seed(5)
+    ba = a.sample_batch(idx)
+    np.random.seed(5)
+    bb = b.sample_batch(idx)
+    for k in ("combined_input", "post", "positions"):
+        assert torch.equal(ba[k], bb[k]), k
+
+
+def test_mask_erode_and_composite_kernels_match_the_reference_expressions():
+    from pbt_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(0)
+    n, h, w = 2, 61, 83
+    m = (torch.rand((n, h, w), generator=g, device="cuda") > 0.03).to(torch.uint8) * 255
+    m[:, 20:45, 30:70] = 255
+    out = torch.empty((n, h, w), device="cuda")
+    ops.mask_erode7(m.contiguous(), out)
+    # reference generator.py:327-351 on the 0/1 mask
+    t = (m.float() / 255.0)[:, None]
+    conv = torch.nn.functional.conv2d(t, torch.ones((1, 1, 7, 7), device="cuda"), padding=3)
+    ref = torch.where(conv < 49, torch.zeros_like(conv), conv) / 49
+    assert torch.equal(out, ref[:, 0]) and 0 < float(out.mean()) < 1
+    # composite rgb*(1-m) + y*m (:562-563) then clamp / (x+1)*127.5 / round (:643-647)
+    frame = torch.randint(0, 256, (n, h, w, 5), generator=g, device="cuda", dtype=torch.uint8)
+    y = torch.rand((n, 3, h, w), generator=g, device="cuda") * 2.4 - 1.2
+    mask = torch.rand((n, h, w), generator=g, device="cuda").round()
+    mask[0, :10] = 0.5
+    res = torch.empty((n, h, w, 3), dtype=torch.uint8, device="cuda")
+    ops.composite_to_u8(y, res, frame, mask)
+    rgb = ((frame[..., :3].permute(0, 3, 1, 2).float() / 255.0) - 0.5) / 0.5
+    comp = rgb * (1 - mask[:, None]) + y * mask[:, None]
+    q = ((comp.clamp(-1, 1) + 1) * 127.5).clamp(0, 255).permute(0, 2, 3, 1).round().to(torch.uint8)
+    assert torch.equal(res, q)
+    ops.composite_to_u8(y, res)
+    q = ((y.clamp(-1, 1) + 1) * 127.5).clamp(0, 255).permute(0, 2, 3, 1).round().to(torch.uint8)
+    assert torch.equal(res, q)
+
+
+def _small_gen(cin=3):
+    from pbt_b200.generator import GeneratorJ
+    z = np.load(os.path.join(GOLD, "gen_c3_trained.npz" if cin == 3 else f"gen_cin{cin}_trained.npz"))
+    g = GeneratorJ(input_channels=cin, use_bias=True)
+    g.load_state_dict({k: torch.from_numpy(z[k]) for k in z.files}, strict=True)
+    return g.cuda()
+
+
+def test_stylize_video_shards_cover_the_video_exactly_once():
+    """every (rank, world) share written by stylize_video is the single-process result of those frames, the shares tile
+    the video, device- and host-resident videos agree (reference frame loop generator.py:674-705, sharded)"""
+    from pbt_b200.inference import FrameStylizer
+    g = torch.Generator(device="cuda").manual_seed(3)
+    video = torch.randint(0, 256, (11, 64, 96, 3), generator=g, device="cuda", dtype=torch.uint8)
+    sty = FrameStylizer(_small_gen())
+    sty.frames_per_pass = 2
+    whole = sty.stylize_device(video).clone()
+    for world in (1, 2, 3, 4):
+        out = torch.zeros_like(whole)
+        covered = torch.zeros(11, dtype=torch.int32)
+        for rank in range(world):
+            lo, hi = sty.stylize_video(video, out, rank, world)
+            covered[lo:hi] += 1
+        assert covered.eq(1).all() and torch.equal(out, whole), world
+    hin = video.cpu().pin_memory()
+    hout = torch.zeros((11, 64, 96, 3), dtype=torch.uint8).pin_memory()
+    for rank in range(3):
+        sty.stylize_video(hin, hout, rank, 3)
+    torch.cuda.synchronize()
+    assert torch.equal(hout, whole.cpu())
+    mask = (torch.rand((11, 64, 96), generator=g, device="cuda") > 0.5).float()
+    comp = sty.stylize_device(video, masks=mask)
+    assert torch.equal(comp[mask.bool()], whole[mask.bool()]) and torch.equal(comp[~mask.bool()], video[~mask.bool()])
+
+
+def test_gradient_bucket_aliases_param_grads_and_survives_accumulation():
+    """p.grad are views of one flat fp32 bucket (no per-tensor copies; stable addresses for the fused optimiser and the
+    all-reduce); a second backward without zero_grad must ACCUMULATE like autograd does for the reference module"""
+    vec = np.load(os.path.join(GOLD, "gen_c3_vectors.npz"))
+    x, t = torch.from_numpy(vec["x"][:8]).cuda(), torch.from_numpy(vec["target"][:8]).cuda()
+    g = _small_gen().train()
+
+    def sweep():
+        (torch.nn.functional.l1_loss(g(x), t) * 4.0).backward()
+
+    sweep()
+    flat = g._engine.grad_bucket().flat
+    lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * 4
+    assert all(lo <= p.grad.data_ptr() < hi for p in g.parameters())
+    ptrs = [p.grad.data_ptr() for p in g.parameters()]
+    first = [p.grad.clone() for p in g.parameters()]
+    g.zero_grad(set_to_none=True)
+    sweep()
+    assert ptrs == [p.grad.data_ptr() for p in g.parameters()]
+    sweep()                                            # no zero_grad: gradients add up
+    for p, f in zip(g.parameters(), first):
+        peak = float(f.abs().max())
+        assert float((p.grad - 2 * f).abs().max()) <= 4e-3 * peak + 1e-12     # wgrad atomics reorder fp32 sums run to run
+
+
+def test_backward_of_a_stale_forward_raises():
+    vec = np.load(os.path.join(GOLD, "gen_c3_vectors.npz"))
+    x = torch.from_numpy(vec["x"][:4]).cuda()
+    g = _small_gen().train()
+    y1 = g(x)
+    y2 = g(x * 0.5)
+    with pytest.raises(RuntimeError, match="overwritten"):
+        y1.sum().backward()
+    y2.sum().backward()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (run with gpurun --gpus 2)")
+def test_nccl_data_parallel_parity_under_torchrun():
+    """two ranks: broadcast of the initial weights, NCCL-reduced gradient == mean of rank gradients, graph-replayed steps
+    keep the replicas bit-identical, the sharded inference covers a video exactly (tests/dist_gpu_check.py)"""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29631", os.path.join(ROOT, "tests", "dist_gpu_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    print(r.stdout[-3000:], r.stderr[-3000:])
+    assert r.returncode == 0 and "DIST_GPU_CHECK_OK" in r.stdout

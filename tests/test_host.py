@@ -174,11 +174,58 @@ def test_bench_reference_arm_prints_the_contract_line():
     import json
     import subprocess
     import sys
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "C2", "--steps", "1", "--warmup", "0"],
                          capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["n_gpus"] == 1 and line["higher_is_better"] is True
-    assert line["metric"] == "1080p stylized frames/s" and line["unit"] == "frames/s" and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
+    assert line["metric"] == "960x540 stylized frames/s" and line["unit"] == "frames/s" and line["value"] > 0
+    # whole frames through the unmodified reference module when baseline/_ref exists (build() copies it), else the port
+    ref_copy = os.path.exists(os.path.join(ROOT, "baseline", "_ref", "src", "models", "generator.py"))
+    assert line["cpu_baseline"]["kind"] == ("reference" if ref_copy else "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["config"]["frame"] == [960, 540, 6] and line["config"]["frames_per_step"] == 1
     assert line["e2e"] == {"value": line["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_grad_bucket_groups_follow_the_backward_sweep():
+    """flat gradient bucket: tail | decoder | one group per residual block (last first) | encoder; 16-byte aligned slices"""
+    import torch
+    from pbt_b200.generator import GeneratorJ
+    from pbt_b200.parallel import GradBucket
+    g = GeneratorJ(input_channels=9, use_bias=True)
+    named = list(g.named_parameters())
+    b = GradBucket(named)
+    assert len(b.group_bounds) == 2 + 7 + 1
+    assert b.group_index("output.0.weight") == 0 and b.group_index("conv11.0.bias") == 0
+    assert b.group_index("upsample2.1.weight") == 1
+    assert b.group_index("resnet_blocks.6.block.1.weight") == 2 and b.group_index("resnet_blocks.0.block.4.bias") == 8
+    assert b.group_index("initial_conv.0.weight") == 9 and b.group_index("downsample2.0.weight") == 9
+    assert all(lo % 4 == 0 for lo, _ in b.slices.values())
+    spans = sorted(b.slices.values())
+    assert all(a[1] <= c[0] for a, c in zip(spans, spans[1:]))                   # no overlap
+    assert all(b.views[n].shape == p.shape and b.views[n].data_ptr() == b.flat[b.slices[n][0]:].data_ptr() for n, p in named)
+    assert not b.aliased_by_param_grads()
+    named[3][1].grad = b.views[named[3][0]]
+    assert b.aliased_by_param_grads()
+
+
+def test_index_loader_gives_every_rank_the_same_number_of_steps():
+    """DistributedSampler semantics (pad by wrapping, strided shard): unequal step counts would deadlock the all-reduce"""
+    from lightning_model import _IndexLoader
+
+    class _DS:
+        def __len__(self):
+            return 161
+
+        def sample_batch(self, idx):
+            return list(idx)
+
+    seen = []
+    for rank in range(2):
+        import torch
+        torch.manual_seed(4)                      # stands in for the seed broadcast (no process group in this test)
+        ld = _IndexLoader(_DS(), 80, rank, 2)
+        batches = list(ld)
+        assert len(batches) == len(ld) == 2 and sum(len(b) for b in batches) == 81
+        seen += [i for b in batches for i in b]
+    assert set(seen) == set(range(161)) and len(seen) == 162       # one wrapped-around index, as DistributedSampler pads

@@ -1,5 +1,5 @@
 import os, sys, time, torch
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pbt_b200.generator import GeneratorJ
 def timeit(fn, warm=3, reps=6):
     for _ in range(warm): fn()

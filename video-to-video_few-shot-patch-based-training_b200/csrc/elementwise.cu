@@ -187,6 +187,43 @@ __global__ void mask_dilate7_kernel(const uint8_t* __restrict__ m, int h, int w,
   }
 }
 
+// 7x7 erosion of a thresholded mask (reference generator.py:327-351 `_process_mask`: box sum of the 0/1 mask, zero padded,
+// kept only where all 49 pixels are set): out = 1.0 where the whole window is inside the mask, else 0.0
+__global__ void mask_erode7_kernel(const uint8_t* __restrict__ m, int n, int h, int w, float* __restrict__ out) {
+  const long long hw = (long long)h * w, total = (long long)n * hw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i % hw;
+    const uint8_t* mi = m + (i - pix);
+    const int y = (int)(pix / w), x = (int)(pix % w);
+    int all = (y >= 3 && y < h - 3 && x >= 3 && x < w - 3) ? 1 : 0;   // zero padding: border windows are never full
+    for (int dy = -3; dy <= 3 && all; ++dy)
+      for (int dx = -3; dx <= 3; ++dx) all &= (mi[(long long)(y + dy) * w + x + dx] != 0);
+    out[i] = all ? 1.f : 0.f;
+  }
+}
+
+// mask composite + uint8 conversion of the frame loop (reference generator.py:562-563,643-647):
+//   out = round(clamp((clamp(rgb*(1-m) + y*m, -1, 1) + 1) * 127.5, 0, 255)),  rgb = the frame's first three channels
+// normalised like the generator input; every step rounded to fp32 like the tensor-library expression (no FMA contraction)
+__global__ void composite_to_u8_kernel(const float* __restrict__ y, const uint8_t* __restrict__ frame, int c,
+                                       const float* __restrict__ mask, int n, int h, int w, uint8_t* __restrict__ out) {
+  const long long hw = (long long)h * w, total = (long long)n * hw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i % hw;
+    const int ni = (int)(i / hw);
+    const float mk = mask ? mask[i] : 1.f;
+    const float one_m = __fsub_rn(1.f, mk);
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      float v = y[((long long)ni * 3 + ch) * hw + pix];
+      if (mask) v = __fadd_rn(__fmul_rn(u8_to_norm(frame[i * c + ch]), one_m), __fmul_rn(v, mk));
+      v = fminf(fmaxf(v, -1.f), 1.f);
+      v = fminf(fmaxf(__fmul_rn(__fadd_rn(v, 1.f), 127.5f), 0.f), 255.f);
+      out[i * 3 + ch] = (uint8_t)rintf(v);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ norm finalize
 // Stage 1 of the deterministic statistics reduction (large images have thousands of tiles): block
 // (32-channel group, chunk, image) sums the tiles of its chunk in a fixed order (double accumulation) and
@@ -1132,6 +1169,24 @@ extern "C" int pbt_mask_dilate7(const uint8_t* mask, int32_t h, int32_t w, uint8
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   PBT_REQUIRE(mask && out && h > 0 && w > 0, "mask_dilate7: bad tensors");
   mask_dilate7_kernel<<<ew_grid((long long)h * w), kEwThreads, 0, st>>>(mask, h, w, out);
+  PBT_CUDA_CHECK(cudaGetLastError());
+  return PBT_OK;
+}
+
+extern "C" int pbt_mask_erode7(const uint8_t* mask, int32_t n, int32_t h, int32_t w, float* out, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  PBT_REQUIRE(mask && out && n > 0 && h > 0 && w > 0, "mask_erode7: bad tensors");
+  mask_erode7_kernel<<<ew_grid((long long)n * h * w), kEwThreads, 0, st>>>(mask, n, h, w, out);
+  PBT_CUDA_CHECK(cudaGetLastError());
+  return PBT_OK;
+}
+
+extern "C" int pbt_composite_to_u8(const float* y, const uint8_t* frame, int32_t c, const float* mask, int32_t n, int32_t h,
+                                   int32_t w, uint8_t* out, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  PBT_REQUIRE(y && out && n > 0 && h > 0 && w > 0, "composite_to_u8: bad tensors");
+  PBT_REQUIRE(!mask || (frame && c >= 3), "composite_to_u8: a mask needs the uint8 frame with >= 3 channels");
+  composite_to_u8_kernel<<<ew_grid((long long)n * h * w), kEwThreads, 0, st>>>(y, frame, c, mask, n, h, w, out);
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
 }

@@ -157,12 +157,18 @@ class _GeneratorFn(torch.autograd.Function):
         if x.requires_grad:
             gen._engine.input_grad = True      # also packs the two data-gradient kernels that reach the input
         y = gen._engine.forward(x, save=True)
+        ctx.stamp = gen._engine._saved_stamp
         ctx.save_for_backward(y)
         return y
 
     @staticmethod
     def backward(ctx, gy):
         (y,) = ctx.saved_tensors
+        if ctx.stamp != ctx.gen._engine._saved_stamp:
+            # the activations of a forward pass live in ONE workspace per engine: a second grad-enabled forward has
+            # overwritten them (gradient accumulation over several forwards, G(x1) and G(x2) in one loss)
+            raise RuntimeError("native GeneratorJ: backward of a forward pass whose saved activations were overwritten by a "
+                               "later grad-enabled forward; call backward() before the next forward (one outstanding pass per module)")
         grads, gx = ctx.gen._engine.backward(gy.contiguous().float(), y, want_input_grad=ctx.x_needs_grad)
         return (None if gx is None else gx.to(ctx.x_dtype), None, *grads)
 
@@ -226,7 +232,9 @@ class _Engine:
         self.grad_scale_target = 32.0 if self.dt == FP16 else 0.0  # dynamic power-of-two gradient scaling (fp16 only), see backward()
         self.input_grad = False   # set once an input with requires_grad is seen: the backward sweep then also produces dL/dx
         self.grad_hook = None     # callable(name, grad) fired as each parameter gradient is produced (data parallel)
-        self.kernel_timer = None  # bench.py: list collecting CUDA-event pairs around the dominant kernel (conv11)
+        self._saved_stamp = 0     # counts grad-enabled forward passes: a backward must match the pass that saved its activations
+        self.bucket = None        # parallel.GradBucket: flat fp32 storage the backward sweep writes the parameter gradients into
+        self.kernel_timer = None  # bench.py: list collecting (start event, end event, frames) around the dominant kernel (conv11)
 
     # -------------------------------------------------------------- helpers
     def workspace(self, n, h, w, train) -> _Workspace:
@@ -532,12 +540,13 @@ class _Engine:
                          act=ACT_RELU, out=ws.c11, cta_pair=self.pair11(), **head)
         if ev is not None:
             e1.record()
-            ev.append((e0, e1))
+            ev.append((e0, e1, n))
         if not g.append_smoothers:
             if save:
                 if not train_bn:
                     raise RuntimeError("autograd through GeneratorJ in eval() mode is not supported by the native path")
                 self._saved = (ws, W)
+                self._saved_stamp += 1
             return y
         bn = g.smoothers[2]
         T3, sblk = self._T(self.SMOOTH_T, w), self.SMOOTH_BLK
@@ -569,6 +578,7 @@ class _Engine:
                      ctas_per_sm=4)
         if save:
             self._saved = (ws, W)
+            self._saved_stamp += 1
         return y
 
     def grad_scale_adjust(self) -> Tensor:
@@ -577,6 +587,15 @@ class _Engine:
         if getattr(self, "_gs_adjust", None) is None:
             self._gs_adjust = torch.tensor([1.0, 0.0, 0.0], device=self.device)
         return self._gs_adjust
+
+    def grad_bucket(self):
+        """flat gradient storage of this generator's parameters (shared with parallel.GradAllReduce when data parallel)"""
+        params = list(self.gen.named_parameters())
+        if self.bucket is None or len(self.bucket.params) != len(params) or \
+                any(a is not b for a, (_, b) in zip(self.bucket.params, params)) or self.bucket.flat.device != params[0][1].device:
+            from .parallel import GradBucket
+            self.bucket = GradBucket(params)
+        return self.bucket
 
     def side_stream(self) -> "torch.cuda.Stream":
         """second stream of the backward sweep (weight gradients overlap the data-gradient chain)"""

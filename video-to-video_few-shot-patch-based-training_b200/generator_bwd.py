@@ -24,9 +24,21 @@ from ._native import ACT_LEAKY, ACT_NONE, ACT_RELU, P8
 
 
 
-def _wgrad_to_param(dw: torch.Tensor, cout: int, cin: int, kh: int, kw: int) -> torch.Tensor:
-    """[taps, cin_pad, cout] -> [cout, cin, kh, kw]"""
-    return dw[:, :cin].permute(2, 1, 0).reshape(cout, cin, kh, kw).contiguous()
+def _wgrad_to_param(dw: torch.Tensor, dst: torch.Tensor) -> None:
+    """wgrad layout [taps, cin_pad, cout] -> parameter layout [cout, cin, kh, kw], written into `dst` (a bucket view)"""
+    cout, cin = dst.shape[0], dst.shape[1]
+    dst.view(cout, cin, -1).copy_(dw[:, :cin].permute(2, 1, 0))
+
+
+def _s2d_wgrad_to_param(dw: torch.Tensor, dst: torch.Tensor) -> None:
+    """wgrad of a stride-2 conv run as 2x2 conv over the space-to-depth input: [4, 4*cin, cout] -> [cout, cin, 3, 3]
+    (inverse of ops.s2d_weight; the nine (tap, phase) pairs cover the nine 3x3 taps exactly once)"""
+    cout, cin = dst.shape[0], dst.shape[1]
+    dw2 = dw.permute(2, 1, 0).reshape(cout, 4 * cin, 2, 2)
+    for ty, py, dy in ops._S2D_TAPS:
+        for tx, px, dx in ops._S2D_TAPS:
+            ph = py * 2 + px
+            dst[:, :, dy, dx].copy_(dw2[:, ph * cin:(ph + 1) * cin, ty, tx])
 
 
 def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor, want_input_grad: bool = False):
@@ -88,35 +100,31 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor, want_input_grad: 
     # published (grad hook -> all-reduce bucket) at the join points, on the main stream.
     main = torch.cuda.current_stream(dev)
     side = eng.side_stream()
-    capturing = torch.cuda.is_current_stream_capturing()
-    pending, keep = [], []
+    keep = []
 
-    def wgrad_side(name, x: P8, dy: P8, k, pad, convert):
-        """enqueue wgrad(x, dy) + `convert(dw)` on the side stream after everything enqueued so far on the main stream;
-        returns the event that marks the side job's completion (wait for it before overwriting x or dy)"""
+    def wgrad_side(name, x: P8, dy: P8, k, pad, convert=_wgrad_to_param):
+        """enqueue wgrad(x, dy) + `convert(dw, bucket view)` on the side stream after everything enqueued so far on the
+        main stream and publish the gradient from there (a data-parallel exchange that this gradient completes is then
+        ordered behind the side stream without holding up the data-gradient chain); returns the event that marks the side
+        job's completion (wait for it before overwriting x or dy)"""
         dw = Z(k * k, x.c, dy.c)
         fork = torch.cuda.Event()
         fork.record(main)
         side.wait_event(fork)
         with torch.cuda.stream(side):
             ops.conv_wgrad(x, dy, k, k, pad, pad, dt, dw, inv_scale=inv)
-            gr = convert(dw)
-            if not capturing:
-                gr.record_stream(main)
-            pending.append((name, gr))
+            convert(dw, bucket.views[name])
+            grads[name] = bucket.views[name]
             done = torch.cuda.Event()
             done.record(side)
         keep.append((x, dy))
         return done
 
     def join():
-        """main stream waits for the side stream; publish the finished parameter gradients"""
+        """main stream waits for the side stream"""
         ev = torch.cuda.Event()
         ev.record(side)
         main.wait_event(ev)
-        for name, gr in pending:
-            grads[name] = gr
-        pending.clear()
         keep.clear()
 
     bn_mode, no_norm = eng.norm_mode() == "batch", eng.norm_mode() == "none"
@@ -132,7 +140,7 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor, want_input_grad: 
             def bias_grad(sums_):
                 if norm_mods[name][0].bias is not None:
                     s1 = sums_[0].clone()
-                    grads[conv_names[name] + ".bias"] = s1 * inv if inv is not None else s1
+                    put(conv_names[name] + ".bias", s1, inv)
                 sums_.zero_()
 
             ops.norm_bwd(x, dt, scale=one, shift=zero, per_channel=True, act=act, sums=sums, kmul=one, count=n * count,
@@ -158,8 +166,8 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor, want_input_grad: 
         def fix(sums_):
             s1, s2 = sums_[0].clone(), sums_[1].clone()
             a = (s2 - beta * s1) / gsafe
-            grads[norm_names[name] + ".weight"] = a * inv if inv is not None else a
-            grads[norm_names[name] + ".bias"] = s1 * inv if inv is not None else s1
+            put(norm_names[name] + ".weight", a, inv)
+            put(norm_names[name] + ".bias", s1, inv)
             sums_[0].copy_(s1 - beta * a / gsafe)
             sums_[1].copy_(a / gsafe)
 
@@ -170,19 +178,46 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor, want_input_grad: 
 
     known = {k for k, _ in g.named_parameters()}      # use_bias=False: the bias sums below have no parameter to go to
 
+    # Every parameter gradient is written straight into its slice of the engine's flat fp32 bucket (parallel.GradBucket):
+    # autograd adopts the views as p.grad (no copy), the data-parallel all-reduce and the fused optimiser read them in
+    # place, and their addresses never change.  If p.grad still aliases the bucket (gradient accumulation: no zero_grad
+    # since the last sweep) this sweep goes to a fresh one, which autograd then adds to p.grad.
+    bucket = eng.grad_bucket()
+    if bucket.aliased_by_param_grads():
+        from .parallel import GradBucket
+        bucket = GradBucket(list(g.named_parameters()))
+
     class _Grads(dict):
         def __setitem__(self, k, v):
-            super().__setitem__(k, v)
-            if hook is not None and k in known:
-                hook(k, v)
+            if k not in known:
+                return
+            dst = bucket.views[k]
+            if v is not dst:
+                dst.copy_(v.reshape(dst.shape))
+            super().__setitem__(k, dst)
+            if hook is not None:
+                hook(k, dst)
 
     grads = _Grads()
+
+    def put(name, src, scale=None):
+        """publish `src` (optionally times the device scalar `scale`) as the gradient of parameter `name`"""
+        if name not in known:
+            return
+        dst = bucket.views[name]
+        if scale is not None:
+            torch.mul(src.reshape(dst.shape), scale, out=dst)
+            grads[name] = dst
+        else:
+            grads[name] = src
+
     # a bias in front of an affine-less InstanceNorm has exactly zero gradient: publish those first
-    # (the same holds in front of a train-mode BatchNorm; the norm's own beta is not one of these)
+    # (the same holds in front of a train-mode BatchNorm; the norm's own beta is not one of these).  Their bucket slices
+    # are zero from the allocation on and never written.
     silent = set() if no_norm else {id(conv.bias) for conv, _ in norm_mods.values() if conv.bias is not None}
     for name, p in g.named_parameters():
         if id(p) in silent:
-            grads[name] = torch.zeros_like(p, dtype=torch.float32)
+            grads[name] = bucket.views[name]
 
     if g.append_smoothers:
         # ---- head (1x1 + tanh) and the ReLU of smoothers.3
@@ -190,13 +225,11 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor, want_input_grad: 
         g_s3 = E(f[5], h, w)
         ops.head_bwd(gy, y, ws.s3, W["head_w"], dt, gscale=gscale, head_tanh=g.use_tanh, dw=dw_out, db=db_out, gs=g_s3,
                      dbias_prev=db_s3)
-        if inv is not None:
-            dw_out, db_out, db_s3 = dw_out * inv, db_out * inv, db_s3 * inv
-        grads["output.0.weight"] = dw_out.reshape(3, f[5], 1, 1)
-        grads["output.0.bias"] = db_out
+        put("output.0.weight", dw_out, inv)
+        put("output.0.bias", db_out, inv)
         # ---- smoothers.3
-        wgrad_side("smoothers.3.weight", ws.s0n, g_s3, 3, 1, lambda dw: _wgrad_to_param(dw, f[5], f[5], 3, 3))
-        grads["smoothers.3.bias"] = db_s3
+        wgrad_side("smoothers.3.weight", ws.s0n, g_s3, 3, 1)
+        put("smoothers.3.bias", db_s3, inv)
         g_s0n = E(f[5], h, w)
         dgrad("smooth3", g_s3, f[5], 3, 1, out=g_s0n, T_pref=3)
         # ---- BatchNorm (batch statistics) + the ReLU in front of it
@@ -208,13 +241,13 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor, want_input_grad: 
         ops.norm_bwd(ws.s0, dt, scale=bn_rstd, shift=(-bn_mean * bn_rstd).contiguous(), per_channel=True, act=ACT_NONE, ga=g_s0n,
                      sums=bn_sums, kmul=(bn.weight.detach().float() * bn_rstd).contiguous(), count=n * h * w, batch_mode=True,
                      dx=g_s0, relu_mask_x=True)
-        grads["smoothers.2.weight"] = bn_sums[1] * inv if inv is not None else bn_sums[1].clone()
-        grads["smoothers.2.bias"] = bn_sums[0] * inv if inv is not None else bn_sums[0].clone()
+        put("smoothers.2.weight", bn_sums[1], inv)
+        put("smoothers.2.bias", bn_sums[0], inv)
         db_s0 = Z(f[5])
         ops.channel_sum(g_s0, db_s0, dt, inv_scale=inv)
         # ---- smoothers.0
-        wgrad_side("smoothers.0.weight", ws.c11, g_s0, 3, 1, lambda dw: _wgrad_to_param(dw, f[5], f[5], 3, 3))
-        grads["smoothers.0.bias"] = db_s0
+        wgrad_side("smoothers.0.weight", ws.c11, g_s0, 3, 1)
+        put("smoothers.0.bias", db_s0)
         g_c11 = E(f[5], h, w)
         dgrad("smooth0", g_s0, f[5], 3, 1, out=g_c11, T_pref=3, mask=ws.c11)
         db_11 = Z(f[5])
@@ -225,14 +258,13 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor, want_input_grad: 
         g_c11 = E(f[5], h, w)
         ops.head_bwd(gy, y, ws.c11, W["head_w"], dt, gscale=gscale, head_tanh=g.use_tanh, dw=dw_out, db=db_out, gs=g_c11,
                      dbias_prev=db_11)
+        put("output.0.weight", dw_out, inv)
+        put("output.0.bias", db_out, inv)
         if inv is not None:
-            dw_out, db_out, db_11 = dw_out * inv, db_out * inv, db_11 * inv
-        grads["output.0.weight"] = dw_out.reshape(3, f[5], 1, 1)
-        grads["output.0.bias"] = db_out
+            db_11 = db_11 * inv
     # ---- conv11 (input = cat11 = [up1 | conv0 | x])
-    cin11 = f[4] + f[0] + g.input_channels
-    wgrad_side("conv11.0.weight", ws.cat11, g_c11, 7, 3, lambda dw: _wgrad_to_param(dw, f[5], cin11, 7, 7))
-    grads["conv11.0.bias"] = db_11
+    wgrad_side("conv11.0.weight", ws.cat11, g_c11, 7, 3)
+    put("conv11.0.bias", db_11)
     if want_input_grad:
         # the same data gradient over ALL of cat11's channels: [up1 | conv0 | x]; the x slot is one source of dL/dx
         g_cat = E(eng.cat11x_channels(), h, w)
@@ -247,7 +279,7 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor, want_input_grad: 
     # ---- upsample1 block
     g_rawU1 = E(f[4], h, w)
     in_bwd(ws.rawU1, ws.stats["up1"], ACT_RELU, g_rawU1, h * w, name="up1", ga=g_cat.view(0, f[4]))
-    wgrad_side("upsample1.1.weight", ws.u1in, g_rawU1, 3, 1, lambda dw: _wgrad_to_param(dw, f[4], f[4] + f[1], 3, 3))
+    wgrad_side("upsample1.1.weight", ws.u1in, g_rawU1, 3, 1)
     g_u1in = E(f[4] + f[1], h, w)
     dgrad("up1", g_rawU1, f[4] + f[1], 3, 1, out=g_u1in)
     del g_rawU1
@@ -257,7 +289,7 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor, want_input_grad: 
     # ---- upsample2 block
     g_rawU2 = E(f[4], h2, w2)
     in_bwd(ws.rawU2, ws.stats["up2"], ACT_RELU, g_rawU2, h2 * w2, name="up2", ga=g_c1cat.view(0, f[4]))
-    wgrad_side("upsample2.1.weight", ws.u2in, g_rawU2, 3, 1, lambda dw: _wgrad_to_param(dw, f[4], 2 * f[2], 3, 3))
+    wgrad_side("upsample2.1.weight", ws.u2in, g_rawU2, 3, 1)
     g_u2in = E(2 * f[2], h2, w2)
     dgrad("up2", g_rawU2, 2 * f[2], 3, 1, out=g_u2in)
     g_r = torch.empty((n, f[2] // 8, h4, w4, 8), device=dev)          # fp32 gradient of the residual stream
@@ -272,38 +304,34 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor, want_input_grad: 
     g_rawB, g_rawA = E(f[2], h4, w4), E(f[2], h4, w4)
     g_h = E(f[2], h4, w4)
     evB = evA = None
-    res_cv = lambda dw: _wgrad_to_param(dw, f[2], f[2], 3, 3)  # noqa: E731
     for b in range(nb - 1, -1, -1):
         if evB is not None:
             main.wait_event(evB)
         in_bwd(ws.rawB[b], ws.stats[f"res{b}.b"], ACT_NONE, g_rawB, h4 * w4, name=f"res{b}.b", gb32=g_r)
-        evB = wgrad_side(conv_names[f"res{b}.b"] + ".weight", ws.hmid[b], g_rawB, 3, 1, res_cv)
+        evB = wgrad_side(conv_names[f"res{b}.b"] + ".weight", ws.hmid[b], g_rawB, 3, 1)
         dgrad(f"res{b}.b", g_rawB, f[2], 3, 1, out=g_h)
         if evA is not None:
             main.wait_event(evA)
         in_bwd(ws.rawA[b], ws.stats[f"res{b}.a"], ACT_RELU, g_rawA, h4 * w4, name=f"res{b}.a", ga=g_h)
-        evA = wgrad_side(conv_names[f"res{b}.a"] + ".weight", ws.a[b], g_rawA, 3, 1, res_cv)
+        evA = wgrad_side(conv_names[f"res{b}.a"] + ".weight", ws.a[b], g_rawA, 3, 1)
         # g_r <- g_r + relu'(r_b) * dgrad   (in place: every element is read then written by the same thread)
         dgrad(f"res{b}.a", g_rawA, f[2], 3, 1, out=None, mask=ws.a[b], addend32=g_r, out32=g_r)
     # ---- downsample2 (conv2 feeds the residual stream and the decoder skip)
     g_raw2 = E(f[2], h4, w4)
     in_bwd(ws.raw2, ws.stats["down2"], ACT_LEAKY, g_raw2, h4 * w4, name="down2", gb16=g_c2skip, gb32=g_r)
-    wgrad_side("downsample2.0.weight", ws.s2d1, g_raw2, 2, 1,                # dw: [4, 4*f1, f2]
-               lambda dw: ops.s2d_weight_grad(dw.permute(2, 1, 0).reshape(f[2], 4 * f[1], 2, 2), f[1]))
+    wgrad_side("downsample2.0.weight", ws.s2d1, g_raw2, 2, 1, _s2d_wgrad_to_param)               # dw: [4, 4*f1, f2]
     g_s2d1 = E(4 * f[1], h4, w4)
     dgrad("down2", g_raw2, 4 * f[1], 2, 1, out=g_s2d1)
     # ---- downsample1
     g_raw1 = E(f[1], h2, w2)
     in_bwd(ws.raw1, ws.stats["down1"], ACT_LEAKY, g_raw1, h2 * w2, name="down1", ga=g_s2d1, ga_is_s2d=True, gb16=g_c1cat.view(f[4], f[1]))
-    wgrad_side("downsample1.0.weight", ws.s2d0, g_raw1, 2, 1,
-               lambda dw: ops.s2d_weight_grad(dw.permute(2, 1, 0).reshape(f[1], 4 * f[0], 2, 2), f[0]))
+    wgrad_side("downsample1.0.weight", ws.s2d0, g_raw1, 2, 1, _s2d_wgrad_to_param)
     g_s2d0 = E(4 * f[0], h2, w2)
     dgrad("down1", g_raw1, 4 * f[0], 2, 1, out=g_s2d0)
     # ---- initial conv
     g_raw0 = E(f[0], h, w)
     in_bwd(ws.raw0, ws.stats["initial"], ACT_LEAKY, g_raw0, h * w, name="initial", ga=g_s2d0, ga_is_s2d=True, gb16=g_cat.view(f[4], f[0]))
-    wgrad_side("initial_conv.0.weight", ws.cat11.view(f[4] + f[0], cp), g_raw0, 7, 3,
-               lambda dw: _wgrad_to_param(dw, f[0], g.input_channels, 7, 7))
+    wgrad_side("initial_conv.0.weight", ws.cat11.view(f[4] + f[0], cp), g_raw0, 7, 3)
     gx = None
     if want_input_grad:
         # dL/dx = (x slot of conv11's data gradient) + (data gradient of the initial conv); never used by the reference
@@ -326,5 +354,5 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor, want_input_grad: 
         gr = grads.get(name)
         if gr is None:
             raise RuntimeError(f"no gradient produced for {name}")
-        out.append(gr.reshape(p.shape).to(p.dtype))
+        out.append(gr if gr.dtype == p.dtype else gr.to(p.dtype))
     return out, gx

@@ -15,6 +15,7 @@ import torch
 
 from . import ops
 from .generator import GeneratorJ, _Engine
+from .parallel import dist_env, shard_range
 
 
 class FrameStylizer:
@@ -44,8 +45,11 @@ class FrameStylizer:
         self._streams = None
 
     @torch.no_grad()
-    def stylize_device(self, frames_u8: torch.Tensor, out_u8: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """frames_u8: device uint8 [N,H,W,Cin] -> device uint8 [N,H,W,3]; one generator pass per frame"""
+    def stylize_device(self, frames_u8: torch.Tensor, out_u8: Optional[torch.Tensor] = None,
+                       masks: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """frames_u8: device uint8 [N,H,W,Cin] -> device uint8 [N,H,W,3]; `pass_size` frames per generator pass.
+        masks (optional, device fp32 [N,H,W] in [0,1], e.g. from ops.mask_erode7): the frame's own RGB shows through
+        where the mask is 0 (reference generator.py:562-563), fused into the uint8 conversion."""
         n, h, w, c = frames_u8.shape
         if c != self.gen.input_channels:
             raise ValueError(f"expected {self.gen.input_channels} channels, got {c}")
@@ -54,8 +58,30 @@ class FrameStylizer:
         step = self.pass_size(h, w)
         for i in range(0, n, step):
             y = self.eng.forward(frames_u8[i:i + step], save=False, u8_hwc=True)
-            ops.nchw_to_u8hwc(y, out_u8[i:i + step])
+            ops.composite_to_u8(y, out_u8[i:i + step], frames_u8[i:i + step], None if masks is None else masks[i:i + step])
         return out_u8
+
+    def stylize_video(self, frames_u8: torch.Tensor, out_u8: Optional[torch.Tensor] = None, rank: Optional[int] = None,
+                      world: Optional[int] = None, masks: Optional[torch.Tensor] = None):
+        """The frame loop of the reference driver (generator.py:674-705) over a whole video, sharded: rank r of R stylises
+        the contiguous frame range `shard_range(N, r, R)` and leaves the rest to the other ranks - frames are independent,
+        so there is no collective.  rank / world default to the torchrun environment (one process per GPU).
+        frames_u8 / out_u8 index the WHOLE video; they may live on this rank's device or in pinned host memory (then the
+        copies are overlapped with compute, see stylize_host).  Returns (lo, hi), the range this rank wrote."""
+        env_rank, env_world, _ = dist_env()
+        rank = env_rank if rank is None else rank
+        world = env_world if world is None else world
+        lo, hi = shard_range(frames_u8.shape[0], rank, world)
+        if hi > lo:
+            if frames_u8.is_cuda:
+                if out_u8 is None:
+                    raise ValueError("stylize_video writes into a caller-owned output video: pass out_u8")
+                self.stylize_device(frames_u8[lo:hi], out_u8[lo:hi], None if masks is None else masks[lo:hi])
+            else:
+                if masks is not None:
+                    raise NotImplementedError("host-resident videos: composite on the device path")
+                self.stylize_host(frames_u8[lo:hi], out_u8[lo:hi])
+        return lo, hi
 
     @torch.no_grad()
     def stylize_host(self, frames_pinned: torch.Tensor, out_pinned: torch.Tensor) -> None:
@@ -86,7 +112,7 @@ class FrameStylizer:
             main.wait_event(in_ready[b])
             main.wait_event(out_free[b])
             y = self.eng.forward(dev_in[b][:m], save=False, u8_hwc=True)
-            ops.nchw_to_u8hwc(y, dev_out[b][:m])
+            ops.composite_to_u8(y, dev_out[b][:m])
             in_free[b].record(main)
             out_ready[b].record(main)
             with torch.cuda.stream(copy_out):

@@ -16,6 +16,7 @@ __all__ = [
     "pack_conv_weight", "s2d_weight", "s2d_weight_grad", "dgrad_weight", "conv_fwd", "conv_wgrad", "conv_num_tiles",
     "norm_finalize", "norm_apply", "upsample2x", "upsample2x_bwd", "norm_bwd", "head_bwd", "channel_sum", "nchw_to_p8",
     "p8_to_nchw", "p8f_to_nchw", "u8hwc_to_p8", "nchw_to_u8hwc", "u8hwc_to_norm_chw", "patch_gather", "mask_dilate7",
+    "mask_erode7", "composite_to_u8",
     "absmax", "make_grad_scale", "grad_scale_feedback",
 ]
 
@@ -248,6 +249,27 @@ def u8hwc_to_norm_chw(img: torch.Tensor, out: torch.Tensor) -> None:
 def mask_dilate7(mask: torch.Tensor, out: torch.Tensor) -> None:
     h, w = mask.shape
     check(lib().pbt_mask_dilate7(mask.data_ptr(), h, w, out.data_ptr(), stream_ptr()), "pbt_mask_dilate7")
+
+
+def mask_erode7(mask_u8: torch.Tensor, out: torch.Tensor) -> None:
+    """mask_u8 uint8 [n,h,w] (thresholded) -> out fp32 [n,h,w]: 1 where the whole 7x7 window is set (reference generator.py:327-351)"""
+    n, h, w = mask_u8.shape
+    assert mask_u8.is_contiguous() and out.is_contiguous() and out.dtype == torch.float32 and out.numel() == mask_u8.numel()
+    check(lib().pbt_mask_erode7(mask_u8.data_ptr(), n, h, w, out.data_ptr(), stream_ptr()), "pbt_mask_erode7")
+
+
+def composite_to_u8(y: torch.Tensor, out: torch.Tensor, frame_u8: torch.Tensor | None = None, mask: torch.Tensor | None = None) -> None:
+    """y fp32 [n,3,h,w] -> out uint8 [n,h,w,3]; with `mask` (fp32 [n,h,w]) the frame's RGB shows through where the mask
+    is 0: rgb*(1-m) + y*m (reference generator.py:562-563), then clamp / (x+1)*127.5 / round (:643-647)"""
+    n, c3, h, w = y.shape
+    assert c3 == 3 and y.is_contiguous() and y.dtype == torch.float32 and out.is_contiguous() and out.dtype == torch.uint8
+    fc = 0
+    if mask is not None:
+        assert frame_u8 is not None and frame_u8.is_contiguous() and frame_u8.shape[:3] == (n, h, w)
+        assert mask.is_contiguous() and mask.dtype == torch.float32 and mask.numel() == n * h * w
+        fc = frame_u8.shape[3]
+    check(lib().pbt_composite_to_u8(y.data_ptr(), ptr(frame_u8) if mask is not None else None, fc, ptr(mask), n, h, w,
+                                    out.data_ptr(), stream_ptr()), "pbt_composite_to_u8")
 
 
 def patch_gather(src_table: torch.Tensor, n_src: int, n_images: int, ch: int, img_hw: torch.Tensor, pos: torch.Tensor,

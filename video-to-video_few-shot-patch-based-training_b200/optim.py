@@ -49,9 +49,7 @@ class FusedClipAdam(torch.optim.Optimizer):
                              "exp_avg_sq": self._v[off:off + n].view_as(p)}
             off += n
         self._max = max(p.numel() for p in ps)
-        self._table = None
-        self._table_key = None
-        self._pinned = []   # host tables referenced by captured graphs must stay alive
+        self._tables = {}   # pointer set -> (pinned host table, device table, built during graph capture)
 
     @property
     def skipped_steps(self) -> int:
@@ -75,10 +73,15 @@ class FusedClipAdam(torch.optim.Optimizer):
             self._state[1] = step
 
     def _job_table(self) -> torch.Tensor:
+        """device table of (param, grad, m, v, n) per tensor for the current pointer set.  Tables are cached per pointer
+        set together with the pinned host copy they were uploaded from: a table built while a CUDA graph is being
+        captured is re-uploaded from that host buffer by EVERY replay, so captured entries are never evicted (an evicted
+        pinned block would be recycled by the caching host allocator and later replays would upload garbage pointers)."""
         ps = self.param_groups[0]["params"]
         key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in ps)
-        if key == self._table_key:
-            return self._table
+        hit = self._tables.get(key)
+        if hit is not None:
+            return hit[1]
         jobs = (nv.OptimJob * len(ps))()
         for i, p in enumerate(ps):
             g = p.grad
@@ -87,13 +90,17 @@ class FusedClipAdam(torch.optim.Optimizer):
             st = self.state[p]
             jobs[i] = nv.OptimJob(p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel())
         host = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8).pin_memory()
-        self._pinned.append(host)
-        if len(self._pinned) > 8 and not torch.cuda.is_current_stream_capturing():
-            del self._pinned[:-8]
-        # a fresh device table per pointer set: a captured graph keeps replaying with the table it was captured with
-        self._table = host.to(self._dev, non_blocking=True)
-        self._table_key = key
-        return self._table
+        capturing = torch.cuda.is_current_stream_capturing()
+        table = host.to(self._dev, non_blocking=True)
+        if not capturing:
+            # eager pointer sets come and go (e.g. the ragged last batch of an epoch): keep the newest few; the upload
+            # above is ordered before any later reuse of the pinned block only once it has completed
+            torch.cuda.current_stream(self._dev).synchronize()
+            stale = [k for k, v in self._tables.items() if not v[2]]
+            for k in stale[:-7]:
+                del self._tables[k]
+        self._tables[key] = (host, table, capturing)
+        return table
 
     @torch.no_grad()
     def step(self, closure=None, max_grad_norm: Optional[float] = "default"):

@@ -86,24 +86,65 @@ class StyleTransferDataset(Dataset):
                 return p
         return os.path.join(base_dir, image_name)
 
+    def _norm_u8(self, arr: np.ndarray) -> torch.Tensor:
+        """uint8 HWC RGB -> resident fp32 CHW in [-1,1]: ToTensor + Normalize(0.5, 0.5) (reference dataset.py:34-38)"""
+        u8 = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.uint8)).to(self.device)
+        out = torch.empty((3, u8.shape[0], u8.shape[1]), device=self.device)
+        ops.u8hwc_to_norm_chw(u8, out)
+        return out
+
     def _to_device_norm(self, path: str) -> torch.Tensor:
         img = Image.open(path)
         if img.mode != "RGB":
             img = img.convert("RGB")
-        u8 = torch.from_numpy(np.asarray(img, dtype=np.uint8).copy()).to(self.device)
-        out = torch.empty((3, u8.shape[0], u8.shape[1]), device=self.device)
-        ops.u8hwc_to_norm_chw(u8, out)
-        return out
+        return self._norm_u8(np.asarray(img, dtype=np.uint8).copy())
+
+    def _valid_from_mask_u8(self, m: np.ndarray) -> torch.Tensor:
+        """thresholded 'L' mask (0 / 255) -> int64 [K,2] (y,x) centres whose 7x7 window touches the mask (dataset.py:150-174)"""
+        u8 = torch.from_numpy(np.ascontiguousarray(m, dtype=np.uint8)).to(self.device)
+        dil = torch.empty_like(u8)
+        ops.mask_dilate7(u8, dil)
+        return dil.nonzero(as_tuple=False).cpu()
 
     def _valid_from_mask(self, path: str) -> torch.Tensor:
         m = Image.open(path)
         m = m.point(lambda p: p > 128 and 255)
         if m.mode != "L":
             m = m.convert("L")
-        u8 = torch.from_numpy(np.asarray(m, dtype=np.uint8).copy()).to(self.device)
-        dil = torch.empty_like(u8)
-        ops.mask_dilate7(u8, dil)
-        return dil.nonzero(as_tuple=False).cpu()
+        return self._valid_from_mask_u8(np.asarray(m, dtype=np.uint8).copy())
+
+    @classmethod
+    def from_arrays(cls, pre: Sequence[np.ndarray], post: Sequence[np.ndarray], mask: Sequence[np.ndarray], patch_size: int,
+                    augmentation_factor: int = 1, additional: Optional[Dict[str, Sequence[np.ndarray]]] = None,
+                    device: Optional[str] = None) -> "StyleTransferDataset":
+        """the same dataset from decoded keyframes already in memory: uint8 [H,W,3] RGB arrays for pre / post / every
+        guide and uint8 [H,W] single-band masks (thresholded at 128 like the file path).  Used where the frames come from
+        a video decoder or a generator instead of image directories."""
+        if not torch.cuda.is_available():
+            raise RuntimeError("StyleTransferDataset (B200-native) keeps its keyframes on a CUDA device; none is available")
+        self = cls.__new__(cls)
+        Dataset.__init__(self)
+        self.dir_pre = self.dir_post = self.dir_mask = None
+        self.patch_size = int(patch_size)
+        self.additional_channels = {k: {"depth": 3} for k in (additional or {})}
+        self.augmentation_factor = max(1, int(augmentation_factor))
+        self.device = torch.device(device or f"cuda:{torch.cuda.current_device()}")
+        self.verbose = False
+        self.image_paths = [f"{i:03d}" for i in range(len(pre))]
+        self.images_pre, self.images_post, self.valid_indices, self._valid_np, self._left = [], [], [], [], []
+        self.additional_channel_data = {k: [] for k in self.additional_channels}
+        self.last_patch_positions = []
+        for i in range(len(pre)):
+            self.images_pre.append(self._norm_u8(pre[i]))
+            self.images_post.append(self._norm_u8(post[i]))
+            valid = self._valid_from_mask_u8(np.where(np.asarray(mask[i]) > 128, 255, 0).astype(np.uint8))
+            self.valid_indices.append(valid)
+            self._valid_np.append(valid.numpy())
+            self._left.append(_OsTree(len(valid)))
+            for k in self.additional_channels:
+                self.additional_channel_data[k].append(self._norm_u8(additional[k][i]))
+        self._build_tables()
+        return self
 
     def _load_images(self):
         for name in self.image_paths:

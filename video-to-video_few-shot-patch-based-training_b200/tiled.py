@@ -22,15 +22,15 @@ Box = Tuple[int, int, int, int]
 
 
 def process_mask(mask_tensor: torch.Tensor) -> torch.Tensor:
-    """reference generator.py:327-351: threshold 0.4, 7x7 erosion (value = box sum / 49 where all 49 pixels are set).
+    """reference generator.py:327-351: threshold 0.4, 7x7 box sum (zero padded), zero where the sum is below 49, divide by
+    49.  For mask values in [0, 1] (ToTensor output) the sum reaches 49 only where all 49 pixels equal 1.0, so the result
+    is the binary erosion of (mask == 1) - computed by the native `pbt_mask_erode7`.
     mask_tensor [1, H, W] on the GPU, values in [0, 1]."""
-    m = mask_tensor.clone()
-    m[m < 0.4] = 0
-    w = torch.ones((1, 1, 7, 7), device=m.device, dtype=m.dtype)
-    conv = F.conv2d(m.unsqueeze(0), w, stride=1, padding=3)
-    conv[conv < w.numel()] = 0
-    conv /= w.numel()
-    return conv.squeeze(0)
+    from . import ops
+    full = (mask_tensor >= 1.0).to(torch.uint8).contiguous()
+    out = torch.empty(full.shape, dtype=torch.float32, device=full.device)
+    ops.mask_erode7(full, out)
+    return out.to(mask_tensor.dtype)
 
 
 def valid_patch_positions(mask_tensor: torch.Tensor, patch_size: int, overlap_percent: float = 50.0) -> List[Box]:

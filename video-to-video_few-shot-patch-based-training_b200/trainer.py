@@ -2,8 +2,12 @@
 reference-shaped ``StyleTransferModel``: setup -> train_dataloader -> training_step, manual optimisation,
 `{'state_dict': ...}` checkpoints with the `generator.` key prefix the inference driver expects
 (reference generator.py:115-118,180), top-k on g_total_loss + last.ckpt (reference train.py:22-31), early
-stopping on the epoch mean (train.py:39-46).  With WORLD_SIZE > 1 (torchrun, one process per GPU) the
-generator gradients are mean all-reduced over NCCL before clipping (parallel.GradAllReduce)."""
+stopping on the epoch mean (train.py:39-46).  With WORLD_SIZE > 1 (torchrun, one process per GPU) rank 0's initial
+weights are broadcast to every rank (what DDP does when Lightning wraps the reference model, train.py:93-94), the
+generator gradients are mean all-reduced over NCCL before clipping (parallel.GradAllReduce), and every decision that
+changes control flow (epoch loss -> top-k / early stop) is taken on a value averaged over the ranks, so that no rank
+can leave the loop while another waits in a collective.  Checkpoints carry the optimiser states (`optimizer_states`,
+Lightning's key) and `fit(ckpt_path=...)` resumes from one."""
 from __future__ import annotations
 
 import os
@@ -12,7 +16,7 @@ from typing import Any, Dict, List, Optional
 
 import torch
 
-from .parallel import GradAllReduce, init_distributed
+from .parallel import GradAllReduce, broadcast_module_state, init_distributed
 
 
 class Trainer:
@@ -40,25 +44,49 @@ class Trainer:
     def save_checkpoint(self, model, path: str) -> None:
         if self.rank == 0:
             os.makedirs(os.path.dirname(path), exist_ok=True)
-            torch.save({"state_dict": model.state_dict(), "global_step": self.global_step}, path)
+            torch.save({"state_dict": model.state_dict(), "global_step": self.global_step, "epoch": self.epoch,
+                        "optimizer_states": [o.state_dict() for o in (model.optimizers() or [])]}, path)
 
-    def fit(self, model) -> None:
+    def _resume(self, model, ckpt_path: str) -> None:
+        ckpt = torch.load(ckpt_path, map_location=torch.device("cuda", self.local))
+        model.load_state_dict(ckpt["state_dict"], strict=True)
+        for opt, st in zip(model.optimizers(), ckpt.get("optimizer_states", [])):
+            opt.load_state_dict(st)
+        self.global_step = int(ckpt.get("global_step", 0))
+        self.epoch = int(ckpt.get("epoch", -1)) + 1
+
+    def _mean_over_ranks(self, value: float) -> float:
+        if self.world == 1:
+            return value
+        import torch.distributed as dist
+        t = torch.tensor([value], dtype=torch.float64, device=torch.device("cuda", self.local) if dist.get_backend() == "nccl" else "cpu")
+        dist.all_reduce(t)
+        return float(t.item()) / self.world
+
+    def fit(self, model, ckpt_path: Optional[str] = None) -> None:
         model.trainer = self
         model.to(torch.device("cuda", self.local))
+        gen = model.generator
+        if self.world > 1:
+            # identical replicas from the first step on: rank 0's parameters and buffers (reference: DDP's initial broadcast)
+            broadcast_module_state(gen)
+            if getattr(model, "discriminator", None) is not None:
+                broadcast_module_state(model.discriminator)
         model.setup("fit")
         opts = model.configure_optimizers()
         model._optimizers = opts
-        gen = model.generator
+        self.epoch = 0
+        if ckpt_path:
+            self._resume(model, ckpt_path)
         if self.world > 1:
-            gen(torch.zeros(1, gen.input_channels, 16, 16, device=torch.device("cuda", self.local)))  # builds the engine
-            model.grad_sync = GradAllReduce(list(gen.named_parameters()), world=self.world)
-            gen._engine.grad_hook = model.grad_sync.grad_ready
+            model.grad_sync = GradAllReduce(list(gen.named_parameters()), world=self.world).attach(gen)
             if getattr(model, "discriminator", None) is not None:     # the critic's 98 kB of gradients: one exchange per step
                 model.d_grad_sync = GradAllReduce(list(model.discriminator.named_parameters()), world=self.world)
         loader = model.train_dataloader()
         bad_epochs, best_epoch_loss = 0, float("inf")
         model.train()
-        for epoch in range(self.max_epochs):
+        for epoch in range(self.epoch, self.max_epochs):
+            self.epoch = epoch
             t0, losses = time.time(), []
             for batch_idx, batch in enumerate(loader):
                 graphed = getattr(model, "use_cuda_graph", False) and hasattr(model, "graphed_training_step")
@@ -72,7 +100,8 @@ class Trainer:
                         (self.steps_per_epoch and batch_idx + 1 >= self.steps_per_epoch):
                     break
             vals = [v for v in losses if v is not None]
-            epoch_loss = sum(vals) / max(1, len(vals))
+            # one value for every rank: top-k, early stopping and the loop exit must not diverge between ranks
+            epoch_loss = self._mean_over_ranks(sum(vals) / max(1, len(vals)))
             if self.rank == 0:
                 print(f"[epoch {epoch}] g_total_loss={epoch_loss:.4f} ({time.time() - t0:.1f}s)", flush=True)
                 name = os.path.join(self.ckpt_dir, f"style_transfer-epoch={epoch:02d}-g_total_loss={epoch_loss:.4f}.ckpt")
@@ -87,7 +116,7 @@ class Trainer:
                 best_epoch_loss, bad_epochs = epoch_loss, 0
             else:
                 bad_epochs += 1
-            if self.patience is not None and bad_epochs > self.patience:
+            if self.patience is not None and bad_epochs >= self.patience:   # Lightning: wait_count >= patience
                 if self.rank == 0:
                     print(f"[trainer] early stop: g_total_loss did not improve for {bad_epochs} epochs")
                 break
