@@ -485,7 +485,7 @@ def check_conv_norm_on_load(n=2, cpre=64, cin=32, cout=32, h=37, w=45, T=2, blk_
     return ok, err, f"err={err:.4g}"
 
 
-def check_conv_upsample(n=2, cin=64, cout=32, h=20, w=28, T=2, blk_c=32, dt=FP16, seed=11, stats=True):
+def check_conv_upsample(n=2, cin=64, cout=32, h=20, w=28, T=2, blk_c=32, dt=FP16, seed=11, stats=True, pair=False):
     """conv3x3(pad 1) over the bilinear x2 (align_corners=True) upsample of a low-res input, interpolated in-kernel"""
     g = torch.Generator(device="cuda").manual_seed(seed)
     tdt = torch_dtype(dt)
@@ -496,8 +496,8 @@ def check_conv_upsample(n=2, cin=64, cout=32, h=20, w=28, T=2, blk_c=32, dt=FP16
     out = P8.empty(n, cout, 2 * h, 2 * w, dt)
     tiles = ops.conv_num_tiles(2 * h, 2 * w, T)
     part = torch.full((n, tiles, 2, cout), float("nan"), device="cuda") if stats else None
-    ops.conv_fwd(P8.from_nchw(x, dt), ops.pack_conv_weight(wt, cin, blk_c, dt), cout, 3, 3, 1, 1, dt, blk_c=blk_c,
-                 tiles_per_cta=T, out=out, stats_partial=part, upsample2x=True)
+    ops.conv_fwd(P8.from_nchw(x, dt), ops.pack_conv_weight(wt, cin, blk_c, dt, pair=pair), cout, 3, 3, 1, 1, dt, blk_c=blk_c,
+                 tiles_per_cta=T, out=out, stats_partial=part, upsample2x=True, cta_pair=pair)
     torch.cuda.synchronize()
     got = out.to_nchw().double()
     err = (got - exp).abs().max().item()

@@ -932,7 +932,7 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
   const int pair = d->cta_pair ? 1 : 0;
   if (pair) {
     // instantiated pair configurations: default footprint (blk_c 32, T 1|2|3) and small footprint (blk_c 16, T 2)
-    PBT_REQUIRE(!up && p.NC % 32 == 0, "conv: cta_pair needs cout % 32 == 0 and no upsample-on-load");
+    PBT_REQUIRE(p.NC % 32 == 0, "conv: cta_pair needs cout % 32 == 0");
     if (d->ctas_per_sm == 4)
       PBT_REQUIRE(d->blk_c == 16 && T == 2 && p.NC <= 64, "conv: cta_pair + ctas_per_sm=4 needs blk_c 16, tiles_per_cta 2, cout <= 64");
     else

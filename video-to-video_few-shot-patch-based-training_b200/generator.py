@@ -18,6 +18,7 @@ Data flow of one forward (reference :210-239; fused differently):
 """
 from __future__ import annotations
 
+import os
 from typing import Any, Dict, List, Optional
 
 import torch
@@ -232,6 +233,10 @@ class _Engine:
         self.grad_scale_target = 32.0 if self.dt == FP16 else 0.0  # dynamic power-of-two gradient scaling (fp16 only), see backward()
         self.input_grad = False   # set once an input with requires_grad is seen: the backward sweep then also produces dL/dx
         self.grad_hook = None     # callable(name, grad) fired as each parameter gradient is produced (data parallel)
+        # inference-time kernel configuration switches (tools/infer_knobs.py measures them): CTA-pair configuration for the
+        # 128-channel layers and the smoothers
+        env = lambda k, d: os.environ.get(k, d) == "1"  # noqa: E731
+        self.pair_res, self.pair_up, self.pair_smooth = env("PBT_PAIR_RES", "0"), env("PBT_PAIR_UP", "0"), env("PBT_PAIR_SMOOTH", "0")
         self._saved_stamp = 0     # counts grad-enabled forward passes: a backward must match the pass that saved its activations
         self.bucket = None        # parallel.GradBucket: flat fp32 storage the backward sweep writes the parameter gradients into
         self.kernel_timer = None  # bench.py: list collecting (start event, end event, frames) around the dominant kernel (conv11)
@@ -322,11 +327,18 @@ class _Engine:
     def _blk(self, cin: int) -> int:
         return 32 if cin % 32 == 0 or cin > 32 else 16
 
+    def _pairs(self, train: bool):
+        """(residual convs, decoder convs, smoothers) run in the CTA-pair configuration - inference passes only"""
+        f = self.gen.filters
+        ok128 = f[2] % 32 == 0 and f[4] % 32 == 0
+        return (self.pair_res and ok128 and not train, self.pair_up and ok128 and not train,
+                self.pair_smooth and f[5] % 32 == 0 and f[5] <= 64 and not train)
+
     def _weights(self, with_dgrad: bool):
         """packed 16-bit conv operands, rebuilt by ONE native launch whenever a parameter changed (version counters)"""
         g = self.gen
         key = tuple((p.data_ptr(), p._version) for p in g.parameters())
-        slot_key = (with_dgrad, with_dgrad and self.input_grad)
+        slot_key = (with_dgrad, with_dgrad and self.input_grad, self._pairs(with_dgrad))
         slot = self._wslots.get(slot_key)
         if slot is None or slot["ptrs"] != tuple(p.data_ptr() for p in g.parameters()):
             slot = self._build_packer(with_dgrad)
@@ -353,23 +365,24 @@ class _Engine:
             pk.add(name + ".d", conv.weight.detach(), s2d=s2d, dgrad=True, k_pad=co, n_out=n_out or _pad16(n_keep), n_keep=n_keep,
                    blk_c=self._blk(co), dt=dt, pair=pair)
 
+        pr, pu, ps = self._pairs(with_dgrad)
         fwd("initial", g.initial_conv[0], cp)
         fwd("down1", g.downsample1[0], 4 * f[0], s2d=True)
         fwd("down2", g.downsample2[0], 4 * f[1], s2d=True)
         for i, blk in enumerate(g.resnet_blocks):
             ia, ib = self.res_conv_index()
-            fwd(f"res{i}.a", blk.block[ia], f[2])
-            fwd(f"res{i}.b", blk.block[ib], f[2])
+            fwd(f"res{i}.a", blk.block[ia], f[2], pair=pr)
+            fwd(f"res{i}.b", blk.block[ib], f[2], pair=pr)
             if with_dgrad:
                 dgr(f"res{i}.a", blk.block[ia])
                 dgr(f"res{i}.b", blk.block[ib])
-        fwd("up2", g.upsample2[1], 2 * f[2])
-        fwd("up1", g.upsample1[1], f[4] + f[1])
+        fwd("up2", g.upsample2[1], 2 * f[2], pair=pu)
+        fwd("up1", g.upsample1[1], f[4] + f[1], pair=pu)
         # conv11 input order = [out(f4), conv0(f0), x(cin)] — identical to the reference cat (:230), zero padded
         fwd("conv11", g.conv11[0], f[4] + f[0] + cp, pair=self.pair11())
         if g.append_smoothers:
-            fwd("smooth0", g.smoothers[0], f[5], blk=self.SMOOTH_BLK)
-            fwd("smooth3", g.smoothers[3], f[5], blk=self.SMOOTH_BLK)
+            fwd("smooth0", g.smoothers[0], f[5], blk=self.SMOOTH_BLK, pair=ps)
+            fwd("smooth3", g.smoothers[3], f[5], blk=self.SMOOTH_BLK, pair=ps)
         if with_dgrad:
             dgr("down1", g.downsample1[0], s2d=True)
             dgr("down2", g.downsample2[0], s2d=True)
@@ -411,11 +424,12 @@ class _Engine:
         ws = self.workspace(n, h, w, save)
         W = self._weights(with_dgrad=save)
         cp = self.cin_p
+        pr, pu, ps = self._pairs(save)
         x = x.contiguous()
         if not u8_hwc and x.dtype not in (torch.float32, torch.float16):
             x = x.float()
 
-        def conv_in(name, xin, cout, k, pad, raw, T_pref, up=False, pre=None, pre_st=None, pre_act=ACT_NONE, cps=0):
+        def conv_in(name, xin, cout, k, pad, raw, T_pref, up=False, pre=None, pre_st=None, pre_act=ACT_NONE, cps=0, pair=False):
             """conv (bias skipped: a constant per channel is removed by the following InstanceNorm) + IN statistics;
             up=True: xin is the low-res tensor, the conv consumes its bilinear x2 upsample (interpolated in-kernel);
             pre: raw output of the previous conv, its InstanceNorm (pre_st) + activation applied on load"""
@@ -432,7 +446,7 @@ class _Engine:
             ops.conv_fwd(xin, W[name], cout, k, k, pad, pad, dt, blk_c=self._blk(cin), tiles_per_cta=T, out=raw,
                          stats_partial=None if (frozen or no_norm) else st["partial"], upsample2x=up, pre=pre,
                          pre_scale=None if pre is None else pre_st["scale"], pre_shift=None if pre is None else pre_st["shift"],
-                         pre_act=pre_act, ctas_per_sm=cps, bias=plain_bias)
+                         pre_act=pre_act, ctas_per_sm=0 if pair else cps, bias=plain_bias, cta_pair=pair)
             if no_norm:
                 if not st.get("identity"):
                     st["scale"].fill_(1.0)
@@ -497,12 +511,12 @@ class _Engine:
         nol_11 = not save and f[4] % 32 == 0 and f[4] <= 256 and g.append_smoothers
         for b in range(nb):
             k = b if save else 0
-            st = conv_in(f"res{b}.a", a_of(b), f[2], 3, 1, ws.rawA[k], 2, cps=4)
+            st = conv_in(f"res{b}.a", a_of(b), f[2], 3, 1, ws.rawA[k], 2, cps=4, pair=pr)
             if nol_res:
-                st = conv_in(f"res{b}.b", None, f[2], 3, 1, ws.rawB[k], 2, pre=ws.rawA[k], pre_st=st, pre_act=ACT_RELU)
+                st = conv_in(f"res{b}.b", None, f[2], 3, 1, ws.rawB[k], 2, pre=ws.rawA[k], pre_st=st, pre_act=ACT_RELU, pair=pr)
             else:
                 ops.norm_apply(ws.rawA[k], dt, scale=st["scale"], shift=st["shift"], act=ACT_RELU, out=ws.hmid[k])
-                st = conv_in(f"res{b}.b", ws.hmid[k], f[2], 3, 1, ws.rawB[k], 2, cps=4)
+                st = conv_in(f"res{b}.b", ws.hmid[k], f[2], 3, 1, ws.rawB[k], 2, cps=4, pair=pr)
             lastb = b == nb - 1
             ops.norm_apply(ws.rawB[k], dt, scale=st["scale"], shift=st["shift"], act=ACT_NONE, residual32=r_cur,
                            out32=None if lastb else r_nxt, out=last16 if lastb else None,
@@ -518,9 +532,9 @@ class _Engine:
             ops.upsample2x(ws.c1cat.view(f[4], f[1]), ws.u1in.view(f[4], f[1]), dt)
             st = conv_in("up1", ws.u1in, f[4], 3, 1, ws.rawU1, 2)
         else:
-            st = conv_in("up2", ws.c2cat, f[4], 3, 1, ws.rawU2, 2, up=True)
+            st = conv_in("up2", ws.c2cat, f[4], 3, 1, ws.rawU2, 2, up=True, pair=pu)
             ops.norm_apply(ws.rawU2, dt, scale=st["scale"], shift=st["shift"], act=ACT_RELU, out=ws.c1cat.view(0, f[4]))
-            st = conv_in("up1", ws.c1cat, f[4], 3, 1, ws.rawU1, 2, up=True)
+            st = conv_in("up1", ws.c1cat, f[4], 3, 1, ws.rawU1, 2, up=True, pair=pu)
         if not nol_11:
             ops.norm_apply(ws.rawU1, dt, scale=st["scale"], shift=st["shift"], act=ACT_RELU, out=ws.cat11.view(0, f[4]))
         # conv11 + smoothers + fused head
@@ -550,6 +564,8 @@ class _Engine:
             return y
         bn = g.smoothers[2]
         T3, sblk = self._T(self.SMOOTH_T, w), self.SMOOTH_BLK
+        if ps:
+            T3 = 2       # the small-footprint CTA-pair configuration is built for two tiles per CTA
         if train_bn:
             st = ws.stat("bn", f[5], h, w, T3, dev)
             ops.conv_fwd(ws.c11, W["smooth0"], f[5], 3, 3, 1, 1, dt, blk_c=sblk, tiles_per_cta=T3, bias=W["bs0"], act=ACT_RELU,
@@ -570,12 +586,12 @@ class _Engine:
             sc = (bn.weight.detach().float() * rstd).contiguous()
             sh = (bn.bias.detach().float() - bn.running_mean.float() * sc).contiguous()
             ops.conv_fwd(ws.c11, W["smooth0"], f[5], 3, 3, 1, 1, dt, blk_c=sblk, tiles_per_cta=T3, bias=W["bs0"], act=ACT_RELU,
-                         post_scale=sc, post_shift=sh, out=ws.s0n, ctas_per_sm=4)
+                         post_scale=sc, post_shift=sh, out=ws.s0n, ctas_per_sm=4, cta_pair=ps)
             if save:
                 raise RuntimeError("autograd through GeneratorJ in eval() mode is not supported by the native path")
         ops.conv_fwd(ws.s0n, W["smooth3"], f[5], 3, 3, 1, 1, dt, blk_c=sblk, tiles_per_cta=T3, bias=W["bs3"], act=ACT_RELU,
                      out=ws.s3 if save else None, head_w=W["head_w"], head_b=W["head_b"], head_out=y, head_tanh=g.use_tanh,
-                     ctas_per_sm=4)
+                     ctas_per_sm=4, cta_pair=ps)
         if save:
             self._saved = (ws, W)
             self._saved_stamp += 1

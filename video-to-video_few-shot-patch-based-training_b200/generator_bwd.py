@@ -354,5 +354,7 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor, want_input_grad: 
         gr = grads.get(name)
         if gr is None:
             raise RuntimeError(f"no gradient produced for {name}")
-        out.append(gr if gr.dtype == p.dtype else gr.to(p.dtype))
+        # a fresh alias per call: autograd adopts a returned gradient as p.grad without a copy only when nothing else
+        # references that tensor object (the bucket keeps its own views)
+        out.append(gr.detach() if gr.dtype == p.dtype else gr.to(p.dtype))
     return out, gx
