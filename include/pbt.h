@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define PBT_ABI_VERSION 1
+#define PBT_ABI_VERSION 2
 
 typedef enum {
   PBT_OK = 0,
@@ -145,10 +145,12 @@ int pbt_pack_weights(const pbt_pack_job_t* jobs_dev, int32_t n_jobs, int64_t max
 /* ------------------------------------------------------------------------
  * Fused optimiser tail of the G-only step: clip_grad_norm_ (lightning_model.py:245-248) + Adam with L2 weight decay
  * (torch.optim.Adam semantics; lightning_model.py:326-329, config/optimizer/default.yaml:2-10) over a DEVICE table
- * of fp32 tensors in two launches.  state = device float[3]: [0] scratch (sum of squares), [1] step count (advanced
- * by one per call, so the call is CUDA-graph capturable), [2] skipped steps: when the gradient norm is inf/nan (fp16
- * overflow in the backward sweep) nothing is updated and the step does not count (AMP semantics).  max_norm <= 0
- * disables clipping.  norm_out (optional) receives the un-clipped total gradient norm.
+ * of fp32 tensors in two launches.  state = device float[3 + 32*n_jobs]: [0] squared gradient norm of the last call,
+ * [1] step count (advanced by one per call, so the call is CUDA-graph capturable), [2] skipped steps: when the gradient
+ * norm is inf/nan (fp16 overflow in the backward sweep) nothing is updated and the step does not count (AMP semantics),
+ * [3..] scratch: per-block partial sums of the norm, added up in a fixed order (no atomics), so that identical
+ * gradients give bit-identical updates - data-parallel replicas stay bit-identical.  max_norm <= 0 disables clipping.
+ * norm_out (optional) receives the un-clipped total gradient norm.
  * ---------------------------------------------------------------------- */
 typedef struct {
   void*       param;       /* fp32 [count], updated in place */

@@ -23,7 +23,7 @@ def test_library_loads_and_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/pbt.h but not exported"
     assert sorted(_native.EXPORTED_SYMBOLS) == declared
     L = _native.lib()
-    assert L.pbt_abi_version() == 1
+    assert L.pbt_abi_version() == 2
     assert L.pbt_error_string(0) == b"ok" and b"argument" in L.pbt_error_string(-1)
     assert L.pbt_conv_num_tiles(1080, 1920, 3) == 68 * 80
     # no GPU here: a compute call must fail loudly, never fall back

@@ -9,6 +9,7 @@ from pbt_b200 import ops  # noqa: E402
 from pbt_b200._native import ACT_RELU, FP16, P8  # noqa: E402
 
 dt = FP16
+DBG = int(os.environ.get("PBT_DEBUG_FLAGS", "0"))
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 cases = [("smooth 64->64 3x3 @1080p", 64, 64, 3, 1080, 1920, 32, [(3, 0), (2, 4.16), (2, "pair4")]),
          ("initial 16->32 7x7 @1080p", 16, 32, 7, 1080, 1920, 16, [(3, 0), (3, 4), (2, 4)]),
@@ -50,7 +51,7 @@ for name, cin, cout, k, h, w, blk, cfgs in cases:
             wp = ops.pack_conv_weight(wt, cin, b, dt, pair=pair)
             out = P8.empty(N, cout, h, w, dt)
             run = lambda: ops.conv_fwd(x, wp, cout, k, k, k // 2, k // 2, dt, blk_c=b, tiles_per_cta=T, out=out, bias=bias,
-                                       act=ACT_RELU, ctas_per_sm=cps, cta_pair=pair)
+                                       act=ACT_RELU, ctas_per_sm=cps, cta_pair=pair, debug_flags=DBG)
             for _ in range(3):
                 run()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -140,7 +140,7 @@ def lib() -> C.CDLL:
         fn = getattr(L, name)  # AttributeError here = header/library mismatch
         fn.restype = res
         fn.argtypes = args
-    if L.pbt_abi_version() != 1:
+    if L.pbt_abi_version() != 2:
         raise RuntimeError("libpbt.so ABI version mismatch")
     _lib = L
     return L

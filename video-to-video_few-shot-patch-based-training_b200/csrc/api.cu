@@ -1,5 +1,7 @@
 // api.cu — C-ABI plumbing of libpbt: status strings, error capture, TMA tensor-map construction,
 // and the host-only order-statistics tree used by the patch sampler.
+#include <stdlib.h>
+
 #include "internal.h"
 
 namespace pbt {
@@ -63,6 +65,15 @@ int num_sms() {
   if (cudaGetDevice(&dev) != cudaSuccess) return 148;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   return sms;
+}
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("PBT_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
 }
 
 }  // namespace pbt

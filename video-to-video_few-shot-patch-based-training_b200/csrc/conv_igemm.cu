@@ -67,6 +67,7 @@ struct ConvKParams {
   const float* pre_scale;
   const float* pre_shift;
   uint32_t l_stage_bytes;
+  int rot;               // channel blocks are walked starting at (unit % n_blk): co-resident CTAs stream different weights
   int debug_flags;
   long long* debug_buf;  // bring-up: per-CTA phase timestamps (clock64), 8 slots per CTA
 };
@@ -229,6 +230,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   __syncthreads();
   if (PAIR) cluster_sync_all();  // the peer's barriers are initialised before any remote arrive / multicast commit
   tc_fence_after();
+  // programmatic dependent launch: barriers, tensor memory and descriptors were set up while the previous launch of the
+  // stream was still draining; from here on global memory written by earlier launches is read
+  pdl_sync();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) {
     PBT_STAMP(1);
@@ -248,8 +252,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       PBT_UNIT_GEOM(unit)
       (void)rem;
       // activation tile (or, with upsample-on-load, its low-res footprint) of channel block `cb`
-      auto issue_act = [&](int cb) {
-        const int c = cbt + cb;
+      const int rot = p.rot ? unit % p.n_blk : 0;
+      auto issue_act = [&](int cb_seq) {
+        const int c = cbt + cb_seq;
+        const int cb = cb_seq + rot < p.n_blk ? cb_seq + rot : cb_seq + rot - p.n_blk;
         if (p.up) {
           const int sl = c & 1;
           mbar_wait(&l_empty[sl], ((uint32_t)(c >> 1) & 1u) ^ 1u);
@@ -269,7 +275,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         }
       };
       issue_act(0);
-      for (int cb = 0; cb < p.n_blk; ++cb) {
+      for (int cb_seq = 0; cb_seq < p.n_blk; ++cb_seq) {
+        const int cb = cb_seq + rot < p.n_blk ? cb_seq + rot : cb_seq + rot - p.n_blk;
         // Block cb+1 is requested once the weight ring of block cb is primed (b_stages groups in flight): by then
         // the MMAs of block cb-1 have retired (its stage is free, no blocking wait here), and the load — plus the
         // upsample transform — overlaps almost a whole block of MMAs instead of starting when the ring drains.
@@ -286,7 +293,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
           mbar_arrive_expect_tx(&b_full[sb], chunk * (uint32_t)nt);
           // the taps of a group are contiguous in the packed weights: one bulk copy per group
           bulk_load_1d(sB + (size_t)sb * p.b_stage_bytes, wsrc + (size_t)tap0 * chunk, chunk * (uint32_t)nt, &b_full[sb]);
-          if (g == gpre && cb + 1 < p.n_blk && p.a_stages > 1) issue_act(cb + 1);
+          if (g == gpre && cb_seq + 1 < p.n_blk && p.a_stages > 1) issue_act(cb_seq + 1);
         }
       }
      }
@@ -829,7 +836,7 @@ template <int T, int KB, int EW>
 static int launch_conv(const CUtensorMap& tmap, const CUtensorMap& tmapP, const ConvKParams& p, int grid, uint32_t smem_bytes,
                        cudaStream_t stream) {
   PBT_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<T, KB, EW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-  conv_igemm_kernel<T, KB, EW, false><<<grid, conv_threads(T, EW), smem_bytes, stream>>>(tmap, tmapP, p);
+  pbt::launch(conv_igemm_kernel<T, KB, EW, false>, grid, conv_threads(T, EW), smem_bytes, stream, tmap, tmapP, p);
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
 }
@@ -846,13 +853,15 @@ static int launch_conv_pair(const CUtensorMap& tmap, const CUtensorMap& tmapP, c
   cfg.blockDim = dim3((unsigned)conv_threads(T, EW), 1, 1);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   PBT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kfn, tmap, tmapP, p));
   return PBT_OK;
 }
@@ -966,6 +975,8 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
   PBT_REQUIRE(!d->head_w || (d->head_b && d->head_out), "conv: head needs head_b and head_out");
   p.debug_flags = d->debug_flags;
   p.debug_buf = static_cast<long long*>(d->debug_buf);
+  // (experiment, bit 4) rotate the channel-block order per unit; needs equal-sized blocks and no on-load `pre` split
+  p.rot = ((d->debug_flags & 16) && !has_pre && p.Cp % p.blk_p == 0 && p.n_blk > 1) ? 1 : 0;
 
   // shared memory budget: A ring + B ring (groups of taps) + barriers + tmem slot + stats scratch.
   // Aim at two co-resident CTAs per SM (one CTA's epilogue/prologue overlaps the other's main loop).

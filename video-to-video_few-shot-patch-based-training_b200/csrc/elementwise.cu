@@ -60,6 +60,7 @@ __device__ __forceinline__ float act_grad(float xhat, int act) {
 // ------------------------------------------------------------------ NCHW -> P8
 template <int DT, bool SRC_HALF>
 __global__ void nchw_to_p8_kernel(const void* __restrict__ x, int n, int c, int h, int w, ActView out) {
+  pdl_sync();
   const long long hw = (long long)h * w;
   const int planes = out.c / 8;
   const long long total = (long long)n * planes * hw;
@@ -84,6 +85,7 @@ __global__ void nchw_to_p8_kernel(const void* __restrict__ x, int n, int c, int 
 
 template <int DT>
 __global__ void p8_to_nchw_kernel(ActView in, int c, float* __restrict__ out, float mul) {
+  pdl_sync();
   const long long hw = (long long)in.h * in.w;
   const int planes = (c + 7) / 8;
   const long long total = (long long)in.n * planes * hw;
@@ -103,6 +105,7 @@ __global__ void p8_to_nchw_kernel(ActView in, int c, float* __restrict__ out, fl
 
 __global__ void p8f_to_nchw_kernel(const float* __restrict__ in, int n, int c_total, int c, int h, int w,
                                    float* __restrict__ out) {
+  pdl_sync();
   const long long hw = (long long)h * w;
   const int planes = (c + 7) / 8;
   const long long total = (long long)n * planes * hw;
@@ -127,6 +130,7 @@ __device__ __forceinline__ float u8_to_norm(uint8_t u) {
 
 template <int DT>
 __global__ void u8hwc_to_p8_kernel(const uint8_t* __restrict__ img, int n, int h, int w, int c, ActView out) {
+  pdl_sync();
   const long long hw = (long long)h * w;
   const int planes = out.c / 8;
   const long long total = (long long)n * planes * hw;
@@ -145,6 +149,7 @@ __global__ void u8hwc_to_p8_kernel(const uint8_t* __restrict__ img, int n, int h
 }
 
 __global__ void nchw_to_u8hwc_kernel(const float* __restrict__ y, int n, int c, int h, int w, uint8_t* __restrict__ out) {
+  pdl_sync();
   const long long hw = (long long)h * w;
   const long long total = (long long)n * hw;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -160,6 +165,7 @@ __global__ void nchw_to_u8hwc_kernel(const float* __restrict__ y, int n, int c, 
 }
 
 __global__ void u8hwc_to_norm_chw_kernel(const uint8_t* __restrict__ img, int h, int w, int c, float* __restrict__ out) {
+  pdl_sync();
   const long long hw = (long long)h * w;
   const long long total = hw * c;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -170,6 +176,7 @@ __global__ void u8hwc_to_norm_chw_kernel(const uint8_t* __restrict__ img, int h,
 }
 
 __global__ void mask_dilate7_kernel(const uint8_t* __restrict__ m, int h, int w, uint8_t* __restrict__ out) {
+  pdl_sync();
   const long long total = (long long)h * w;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int y = (int)(i / w), x = (int)(i % w);
@@ -190,6 +197,7 @@ __global__ void mask_dilate7_kernel(const uint8_t* __restrict__ m, int h, int w,
 // 7x7 erosion of a thresholded mask (reference generator.py:327-351 `_process_mask`: box sum of the 0/1 mask, zero padded,
 // kept only where all 49 pixels are set): out = 1.0 where the whole window is inside the mask, else 0.0
 __global__ void mask_erode7_kernel(const uint8_t* __restrict__ m, int n, int h, int w, float* __restrict__ out) {
+  pdl_sync();
   const long long hw = (long long)h * w, total = (long long)n * hw;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long pix = i % hw;
@@ -207,6 +215,7 @@ __global__ void mask_erode7_kernel(const uint8_t* __restrict__ m, int n, int h, 
 // normalised like the generator input; every step rounded to fp32 like the tensor-library expression (no FMA contraction)
 __global__ void composite_to_u8_kernel(const float* __restrict__ y, const uint8_t* __restrict__ frame, int c,
                                        const float* __restrict__ mask, int n, int h, int w, uint8_t* __restrict__ out) {
+  pdl_sync();
   const long long hw = (long long)h * w, total = (long long)n * hw;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long pix = i % hw;
@@ -229,6 +238,7 @@ __global__ void composite_to_u8_kernel(const float* __restrict__ y, const uint8_
 // (32-channel group, chunk, image) sums the tiles of its chunk in a fixed order (double accumulation) and
 // overwrites the FIRST tile slot of its own chunk with the result, so stage 2 only visits tiles/chunk slots.
 __global__ void norm_reduce_partials_kernel(float* __restrict__ partial, int tiles, int c, int chunk) {
+  pdl_sync();
   __shared__ double s_sum[8][32], s_sq[8][32];
   const int cg = blockIdx.x * 32 + (threadIdx.x & 31);
   const int row = threadIdx.x >> 5;
@@ -264,6 +274,7 @@ __global__ void norm_finalize_kernel(const float* __restrict__ partial, int n, i
                                      float eps, int batch_mode, const float* __restrict__ gamma,
                                      const float* __restrict__ beta, float* running_mean, float* running_var, float momentum,
                                      float* __restrict__ scale, float* __restrict__ shift, float* mean_out, float* rstd_out) {
+  pdl_sync();
   __shared__ double s_sum[8][32], s_sq[8][32];
   const int cg = blockIdx.x * 32 + (threadIdx.x & 31);
   const int row = threadIdx.x >> 5;  // 0..7
@@ -329,6 +340,7 @@ struct NormApplyK {
 
 template <int DT>
 __global__ void norm_apply_kernel(NormApplyK p) {
+  pdl_sync();
   const int hw = p.x.h * p.x.w;
   const int planes = p.x.c / 8;
   const int pl = blockIdx.y, ni = blockIdx.z;  // grid = (pixel chunks, planes, images): no 64-bit div/mod per element
@@ -400,6 +412,7 @@ __device__ __forceinline__ void src_index(int dst, float scale, int in_size, int
 template <int DT>
 __global__ void upsample2x_kernel(ActView in, ActView out, const float* __restrict__ scale, const float* __restrict__ shift,
                                   int act) {
+  pdl_sync();
   const int oh = out.h, ow = out.w;
   // flat index over the 2x2 output blocks of one (image, plane): no idle threads on patch-sized maps (a 64x16-pixel
   // thread block covered an 80-pixel-wide map at 62 %)
@@ -544,6 +557,7 @@ __global__ void upsample2x_kernel(ActView in, ActView out, const float* __restri
 // transpose of the above: each low-res pixel gathers the high-res gradients that read it
 template <int DT>
 __global__ void upsample2x_bwd_kernel(ActView gout, ActView gin16, float* gin32, int ih, int iw) {
+  pdl_sync();
   const int oh = gout.h, ow = gout.w;
   const long long ihw = (long long)ih * iw;
   const int planes = gout.c / 8;
@@ -704,6 +718,7 @@ __device__ __forceinline__ void load_gact(const NormBwdK& p, int ni, int pl, lon
 // grid: (chunks, planes, n); each block reduces a pixel range of one (image, plane)
 template <int DT>
 __global__ void norm_bwd_reduce_kernel(NormBwdK p) {
+  pdl_sync();
   const long long hw = (long long)p.x.h * p.x.w;
   const int planes = p.x.c / 8;
   const int pl = blockIdx.y, ni = blockIdx.z;
@@ -748,6 +763,7 @@ __global__ void norm_bwd_reduce_kernel(NormBwdK p) {
 
 template <int DT>
 __global__ void norm_bwd_apply_kernel(NormBwdK p) {
+  pdl_sync();
   const long long hw = (long long)p.x.h * p.x.w;
   const int planes = p.x.c / 8;
   const int pl = blockIdx.y, ni = blockIdx.z;
@@ -772,6 +788,7 @@ __global__ void norm_bwd_apply_kernel(NormBwdK p) {
 // (L2 hits only while the resident CTAs' slices fit L2 - at 80 x 128 x 80x80 they do not).  grid: (planes, n).
 template <int DT, bool STAGE>
 __global__ void __launch_bounds__(512) norm_bwd_fused_kernel(NormBwdK p) {
+  pdl_sync();
   extern __shared__ __align__(16) uint4 s_slice[];  // STAGE: [hw][2] = (x chunk, gact chunk)
   const int hw = p.x.h * p.x.w;
   const int planes = p.x.c / 8;
@@ -857,6 +874,7 @@ __global__ void __launch_bounds__(512) norm_bwd_fused_kernel(NormBwdK p) {
 constexpr int kNbCluster = 4;
 template <int DT>
 __global__ void __launch_bounds__(kEwThreads) norm_bwd_fused_cluster_kernel(NormBwdK p) {
+  pdl_sync();
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(16) uint4 s_slice[];  // [pixels of this CTA][2] = (x chunk, gact chunk)
@@ -948,6 +966,7 @@ template <int DT>
 __global__ void head_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ y, ActView s,
                                 const float* __restrict__ head_w, const float* __restrict__ gscale, int head_tanh,
                                 float* dw, float* db, ActView gs, float* dbias_prev) {
+  pdl_sync();
   const long long hw = (long long)s.h * s.w;
   const long long total = (long long)s.n * hw;
   const int pl = blockIdx.y;
@@ -1015,6 +1034,7 @@ __global__ void head_bwd_kernel(const float* __restrict__ gy, const float* __res
 // grid: (chunks, planes)
 template <int DT>
 __global__ void channel_sum_kernel(ActView g, float* out, const float* __restrict__ inv_scale) {
+  pdl_sync();
   const long long hw = (long long)g.h * g.w;
   const long long total = (long long)g.n * hw;
   const int pl = blockIdx.y;
@@ -1044,6 +1064,7 @@ __global__ void channel_sum_kernel(ActView g, float* out, const float* __restric
 }
 
 __global__ void absmax_kernel(const float* __restrict__ g, long long count, float* out) {
+  pdl_sync();
   float m = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
     m = fmaxf(m, fabsf(g[i]));
@@ -1053,6 +1074,7 @@ __global__ void absmax_kernel(const float* __restrict__ g, long long count, floa
 }
 
 __global__ void make_grad_scale_kernel(const float* amax, float target, float* scale2, const float* adjust) {
+  pdl_sync();
   const float a = *amax;
   if (adjust) target *= *adjust;
   float s = 1.f;
@@ -1070,6 +1092,7 @@ __global__ void make_grad_scale_kernel(const float* amax, float target, float* s
 // upstream reaches it as inf/nan.  adjust[0] is the multiplier applied to the scale target of the NEXT sweep:
 // /16 on overflow (floor 2^-20), x2 after 256 clean sweeps (cap 1).  adjust[1] counts clean sweeps, adjust[2] overflows.
 __global__ void grad_scale_feedback_kernel(const float* __restrict__ probe, long long count, float* adjust) {
+  pdl_sync();
   __shared__ int bad;
   if (threadIdx.x == 0) bad = 0;
   __syncthreads();
@@ -1112,8 +1135,8 @@ extern "C" int pbt_nchw_to_p8(const void* x, int32_t src_is_half, int32_t n, int
   PBT_REQUIRE(out->n == n && out->h == h && out->w == w && out->c >= c, "nchw_to_p8: shape mismatch");
   const long long items = (long long)n * (out->c / 8) * h * w;
   DISPATCH_DT(dtype, {
-    if (src_is_half) nchw_to_p8_kernel<DT, true><<<ew_grid(items), kEwThreads, 0, st>>>(x, n, c, h, w, view(*out));
-    else nchw_to_p8_kernel<DT, false><<<ew_grid(items), kEwThreads, 0, st>>>(x, n, c, h, w, view(*out));
+    if (src_is_half) pbt::launch(nchw_to_p8_kernel<DT, true>, ew_grid(items), kEwThreads, 0, st, x, n, c, h, w, view(*out));
+    else pbt::launch(nchw_to_p8_kernel<DT, false>, ew_grid(items), kEwThreads, 0, st, x, n, c, h, w, view(*out));
   });
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
@@ -1123,7 +1146,7 @@ extern "C" int pbt_p8_to_nchw_f32(const pbt_act_t* in, int32_t c, float* out, fl
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   PBT_REQUIRE(in && out && act_ok(*in) && c > 0 && c <= in->c, "p8_to_nchw: bad tensors");
   const long long items = (long long)in->n * ((c + 7) / 8) * in->h * in->w;
-  DISPATCH_DT(dtype, p8_to_nchw_kernel<DT><<<ew_grid(items), kEwThreads, 0, st>>>(view(*in), c, out, mul));
+  DISPATCH_DT(dtype, pbt::launch(p8_to_nchw_kernel<DT>, ew_grid(items), kEwThreads, 0, st, view(*in), c, out, mul));
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
 }
@@ -1133,7 +1156,7 @@ extern "C" int pbt_p8f_to_nchw_f32(const float* in, int32_t n, int32_t c_total, 
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   PBT_REQUIRE(in && out && c_total % 8 == 0 && c <= c_total && n > 0, "p8f_to_nchw: bad tensors");
   const long long items = (long long)n * ((c + 7) / 8) * h * w;
-  p8f_to_nchw_kernel<<<ew_grid(items), kEwThreads, 0, st>>>(in, n, c_total, c, h, w, out);
+  pbt::launch(p8f_to_nchw_kernel, ew_grid(items), kEwThreads, 0, st, in, n, c_total, c, h, w, out);
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
 }
@@ -1144,7 +1167,7 @@ extern "C" int pbt_u8hwc_to_p8(const uint8_t* img, int32_t n, int32_t h, int32_t
   PBT_REQUIRE(img && out && act_ok(*out), "u8hwc_to_p8: bad tensors");
   PBT_REQUIRE(out->n == n && out->h == h && out->w == w && out->c >= c, "u8hwc_to_p8: shape mismatch");
   const long long items = (long long)n * (out->c / 8) * h * w;
-  DISPATCH_DT(dtype, u8hwc_to_p8_kernel<DT><<<ew_grid(items), kEwThreads, 0, st>>>(img, n, h, w, c, view(*out)));
+  DISPATCH_DT(dtype, pbt::launch(u8hwc_to_p8_kernel<DT>, ew_grid(items), kEwThreads, 0, st, img, n, h, w, c, view(*out)));
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
 }
@@ -1152,7 +1175,7 @@ extern "C" int pbt_u8hwc_to_p8(const uint8_t* img, int32_t n, int32_t h, int32_t
 extern "C" int pbt_nchw_to_u8hwc(const float* y, int32_t n, int32_t c, int32_t h, int32_t w, uint8_t* out, void* stream_) {
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   PBT_REQUIRE(y && out && n > 0 && c > 0, "nchw_to_u8hwc: bad tensors");
-  nchw_to_u8hwc_kernel<<<ew_grid((long long)n * h * w), kEwThreads, 0, st>>>(y, n, c, h, w, out);
+  pbt::launch(nchw_to_u8hwc_kernel, ew_grid((long long)n * h * w), kEwThreads, 0, st, y, n, c, h, w, out);
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
 }
@@ -1160,7 +1183,7 @@ extern "C" int pbt_nchw_to_u8hwc(const float* y, int32_t n, int32_t c, int32_t h
 extern "C" int pbt_u8hwc_to_norm_chw(const uint8_t* img, int32_t h, int32_t w, int32_t c, float* out, void* stream_) {
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   PBT_REQUIRE(img && out && h > 0 && w > 0 && c > 0, "u8hwc_to_norm_chw: bad tensors");
-  u8hwc_to_norm_chw_kernel<<<ew_grid((long long)h * w * c), kEwThreads, 0, st>>>(img, h, w, c, out);
+  pbt::launch(u8hwc_to_norm_chw_kernel, ew_grid((long long)h * w * c), kEwThreads, 0, st, img, h, w, c, out);
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
 }
@@ -1168,7 +1191,7 @@ extern "C" int pbt_u8hwc_to_norm_chw(const uint8_t* img, int32_t h, int32_t w, i
 extern "C" int pbt_mask_dilate7(const uint8_t* mask, int32_t h, int32_t w, uint8_t* out, void* stream_) {
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   PBT_REQUIRE(mask && out && h > 0 && w > 0, "mask_dilate7: bad tensors");
-  mask_dilate7_kernel<<<ew_grid((long long)h * w), kEwThreads, 0, st>>>(mask, h, w, out);
+  pbt::launch(mask_dilate7_kernel, ew_grid((long long)h * w), kEwThreads, 0, st, mask, h, w, out);
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
 }
@@ -1176,7 +1199,7 @@ extern "C" int pbt_mask_dilate7(const uint8_t* mask, int32_t h, int32_t w, uint8
 extern "C" int pbt_mask_erode7(const uint8_t* mask, int32_t n, int32_t h, int32_t w, float* out, void* stream_) {
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   PBT_REQUIRE(mask && out && n > 0 && h > 0 && w > 0, "mask_erode7: bad tensors");
-  mask_erode7_kernel<<<ew_grid((long long)n * h * w), kEwThreads, 0, st>>>(mask, n, h, w, out);
+  pbt::launch(mask_erode7_kernel, ew_grid((long long)n * h * w), kEwThreads, 0, st, mask, n, h, w, out);
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
 }
@@ -1186,7 +1209,7 @@ extern "C" int pbt_composite_to_u8(const float* y, const uint8_t* frame, int32_t
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   PBT_REQUIRE(y && out && n > 0 && h > 0 && w > 0, "composite_to_u8: bad tensors");
   PBT_REQUIRE(!mask || (frame && c >= 3), "composite_to_u8: a mask needs the uint8 frame with >= 3 channels");
-  composite_to_u8_kernel<<<ew_grid((long long)n * h * w), kEwThreads, 0, st>>>(y, frame, c, mask, n, h, w, out);
+  pbt::launch(composite_to_u8_kernel, ew_grid((long long)n * h * w), kEwThreads, 0, st, y, frame, c, mask, n, h, w, out);
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
 }
@@ -1209,11 +1232,11 @@ extern "C" int pbt_norm_finalize(const float* partial, int32_t n, int32_t tiles,
     slots = ceil_div(tiles, chunk);
     stride = chunk;
     dim3 g1(ceil_div(c, 32), slots, n);
-    norm_reduce_partials_kernel<<<g1, 256, 0, st>>>(const_cast<float*>(partial), tiles, c, chunk);
+    pbt::launch(norm_reduce_partials_kernel, g1, 256, 0, st, const_cast<float*>(partial), tiles, c, chunk);
     PBT_CUDA_CHECK(cudaGetLastError());
   }
   dim3 grid(ceil_div(c, 32), batch_mode ? 1 : n);
-  norm_finalize_kernel<<<grid, 256, 0, st>>>(partial, n, slots, stride, tiles, c, count_per_image, eps, batch_mode, gamma, beta,
+  pbt::launch(norm_finalize_kernel, grid, 256, 0, st, partial, n, slots, stride, tiles, c, count_per_image, eps, batch_mode, gamma, beta,
                                             running_mean, running_var, momentum, scale, shift, mean_out, rstd_out);
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
@@ -1238,7 +1261,7 @@ extern "C" int pbt_norm_apply(const pbt_norm_apply_desc_t* d, void* stream_) {
   p.scale = d->scale; p.shift = d->shift; p.per_channel = d->per_channel; p.act = d->act;
   p.residual32 = d->residual32; p.out32 = d->out32;
   PBT_REQUIRE(d->x.n <= 65535 && (long long)d->x.h * d->x.w < (1ll << 31), "norm_apply: tensor too large for one launch");
-  DISPATCH_DT(d->dtype, norm_apply_kernel<DT><<<ew_grid3(d->x.h * d->x.w, d->x.c / 8, d->x.n), kEwThreads, 0, st>>>(p));
+  DISPATCH_DT(d->dtype, pbt::launch(norm_apply_kernel<DT>, ew_grid3(d->x.h * d->x.w, d->x.c / 8, d->x.n), kEwThreads, 0, st, p));
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
 }
@@ -1251,7 +1274,7 @@ extern "C" int pbt_upsample2x(const pbt_act_t* in, const pbt_act_t* out, const f
   PBT_REQUIRE((scale == nullptr) == (shift == nullptr), "upsample2x: scale/shift must come together");
   PBT_REQUIRE(in->n <= 65535 && in->c / 8 <= 65535, "upsample2x: too many images / planes for one launch");
   dim3 grid(ceil_div(((out->w + 1) / 2) * ((out->h + 1) / 2), kEwThreads), in->c / 8, in->n);
-  DISPATCH_DT(dtype, upsample2x_kernel<DT><<<grid, kEwThreads, 0, st>>>(view(*in), view(*out), scale, shift, act));
+  DISPATCH_DT(dtype, pbt::launch(upsample2x_kernel<DT>, grid, kEwThreads, 0, st, view(*in), view(*out), scale, shift, act));
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
 }
@@ -1268,7 +1291,7 @@ extern "C" int pbt_upsample2x_bwd(const pbt_act_t* gout, const pbt_act_t* gin16,
     g16 = view(*gin16);
   }
   PBT_REQUIRE(g16.ptr || gin32, "upsample2x_bwd: no output");
-  DISPATCH_DT(dtype, upsample2x_bwd_kernel<DT><<<ew_grid3(ih * iw, gout->c / 8, gout->n), kEwThreads, 0, st>>>(view(*gout), g16, gin32, ih, iw));
+  DISPATCH_DT(dtype, pbt::launch(upsample2x_bwd_kernel<DT>, ew_grid3(ih * iw, gout->c / 8, gout->n), kEwThreads, 0, st, view(*gout), g16, gin32, ih, iw));
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
 }
@@ -1308,7 +1331,7 @@ extern "C" int pbt_norm_bwd_reduce(const pbt_norm_bwd_desc_t* d, void* stream_) 
   if (chunks < 1) chunks = 1;
   if (chunks > 64) chunks = 64;
   dim3 grid(chunks, d->x.c / 8, d->x.n);
-  DISPATCH_DT(d->dtype, norm_bwd_reduce_kernel<DT><<<grid, kEwThreads, 0, st>>>(p));
+  DISPATCH_DT(d->dtype, pbt::launch(norm_bwd_reduce_kernel<DT>, grid, kEwThreads, 0, st, p));
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
 }
@@ -1321,7 +1344,7 @@ extern "C" int pbt_norm_bwd_apply(const pbt_norm_bwd_desc_t* d, void* stream_) {
   PBT_REQUIRE(d->kmul && act_ok(d->dx) && d->dx.h == d->x.h && d->dx.w == d->x.w && d->dx.c >= d->x.c && d->dx.n == d->x.n,
               "norm_bwd_apply: dx shape mismatch");
   p.dx = view(d->dx);
-  DISPATCH_DT(d->dtype, norm_bwd_apply_kernel<DT><<<ew_grid3(d->x.h * d->x.w, d->x.c / 8, d->x.n), kEwThreads, 0, st>>>(p));
+  DISPATCH_DT(d->dtype, pbt::launch(norm_bwd_apply_kernel<DT>, ew_grid3(d->x.h * d->x.w, d->x.c / 8, d->x.n), kEwThreads, 0, st, p));
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
 }
@@ -1349,13 +1372,15 @@ extern "C" int pbt_norm_bwd_fused(const pbt_norm_bwd_desc_t* d, void* stream_) {
     cfg.blockDim = dim3(kEwThreads, 1, 1);
     cfg.dynamicSmemBytes = part_bytes;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = kNbCluster;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     if (d->dtype == PBT_BF16) {
       PBT_CUDA_CHECK(cudaFuncSetAttribute(norm_bwd_fused_cluster_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_bytes));
       PBT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, norm_bwd_fused_cluster_kernel<0>, p));
@@ -1369,16 +1394,16 @@ extern "C" int pbt_norm_bwd_fused(const pbt_norm_bwd_desc_t* d, void* stream_) {
   } else if (slice <= 200 * 1024) {
     if (d->dtype == PBT_BF16) {
       PBT_CUDA_CHECK(cudaFuncSetAttribute(norm_bwd_fused_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slice));
-      norm_bwd_fused_kernel<0, true><<<grid, threads, slice, st>>>(p);
+      pbt::launch(norm_bwd_fused_kernel<0, true>, grid, threads, slice, st, p);
     } else if (d->dtype == PBT_FP16) {
       PBT_CUDA_CHECK(cudaFuncSetAttribute(norm_bwd_fused_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slice));
-      norm_bwd_fused_kernel<1, true><<<grid, threads, slice, st>>>(p);
+      pbt::launch(norm_bwd_fused_kernel<1, true>, grid, threads, slice, st, p);
     } else {
       pbt::set_last_error("bad dtype");
       return PBT_ERR_ARG;
     }
   } else {
-    DISPATCH_DT(d->dtype, norm_bwd_fused_kernel<DT, false><<<grid, kEwThreads, 0, st>>>(p));
+    DISPATCH_DT(d->dtype, pbt::launch(norm_bwd_fused_kernel<DT, false>, grid, kEwThreads, 0, st, p));
   }
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
@@ -1395,7 +1420,7 @@ extern "C" int pbt_head_bwd(const float* gy, const float* y, const pbt_act_t* s,
   if (chunks < 1) chunks = 1;
   if (chunks > 2 * num_sms()) chunks = 2 * num_sms();
   dim3 grid(chunks, s->c / 8);
-  DISPATCH_DT(dtype, head_bwd_kernel<DT><<<grid, kEwThreads, 0, st>>>(gy, y, view(*s), head_w, gscale, head_tanh, dw, db,
+  DISPATCH_DT(dtype, pbt::launch(head_bwd_kernel<DT>, grid, kEwThreads, 0, st, gy, y, view(*s), head_w, gscale, head_tanh, dw, db,
                                                                       view(*gs), dbias_prev));
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
@@ -1409,7 +1434,7 @@ extern "C" int pbt_channel_sum(const pbt_act_t* g, float* out, const float* inv_
   if (chunks < 1) chunks = 1;
   if (chunks > 2 * num_sms()) chunks = 2 * num_sms();
   dim3 grid(chunks, g->c / 8);
-  DISPATCH_DT(dtype, channel_sum_kernel<DT><<<grid, kEwThreads, 0, st>>>(view(*g), out, inv_scale));
+  DISPATCH_DT(dtype, pbt::launch(channel_sum_kernel<DT>, grid, kEwThreads, 0, st, view(*g), out, inv_scale));
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
 }
@@ -1418,7 +1443,7 @@ extern "C" int pbt_absmax_f32(const float* g, int64_t count, float* out, void* s
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   PBT_REQUIRE(g && out && count > 0, "absmax: bad arguments");
   PBT_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(float), st));
-  absmax_kernel<<<ew_grid(count), kEwThreads, 0, st>>>(g, count, out);
+  pbt::launch(absmax_kernel, ew_grid(count), kEwThreads, 0, st, g, count, out);
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
 }
@@ -1426,7 +1451,7 @@ extern "C" int pbt_absmax_f32(const float* g, int64_t count, float* out, void* s
 extern "C" int pbt_grad_scale_feedback(const float* probe, int64_t count, float* adjust, void* stream_) {
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   PBT_REQUIRE(probe && adjust && count > 0, "grad_scale_feedback: bad arguments");
-  grad_scale_feedback_kernel<<<1, 1024, 0, st>>>(probe, count, adjust);
+  pbt::launch(grad_scale_feedback_kernel, 1, 1024, 0, st, probe, count, adjust);
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
 }
@@ -1434,7 +1459,7 @@ extern "C" int pbt_grad_scale_feedback(const float* probe, int64_t count, float*
 extern "C" int pbt_make_grad_scale(const float* amax, float target, float* scale2, const float* adjust, void* stream_) {
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   PBT_REQUIRE(amax && scale2 && target > 0.f, "make_grad_scale: bad arguments");
-  make_grad_scale_kernel<<<1, 1, 0, st>>>(amax, target, scale2, adjust);
+  pbt::launch(make_grad_scale_kernel, 1, 1, 0, st, amax, target, scale2, adjust);
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
 }

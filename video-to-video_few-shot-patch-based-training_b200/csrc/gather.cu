@@ -20,6 +20,7 @@ struct GatherOut {
 __global__ void patch_gather_kernel(const float* const* __restrict__ src_ptrs, int n_src, int n_images, int ch,
                                     const int* __restrict__ img_hw, const int* __restrict__ pos, int n_patches, int P,
                                     GatherOut o) {
+  pdl_sync();
   const int gx = threadIdx.x;
   const int b = blockIdx.z;
   const int half = P / 2;
@@ -84,7 +85,7 @@ extern "C" int pbt_patch_gather(const float* const* src_ptrs, int32_t n_src, int
   if (ygroups > n_src * ch) ygroups = n_src * ch;
   if (ygroups < 1) ygroups = 1;
   dim3 block((unsigned)qx, (unsigned)rpb), grid(1u, (unsigned)ygroups, (unsigned)n_patches);
-  patch_gather_kernel<<<grid, block, 0, st>>>(src_ptrs, n_src, n_images, ch, img_hw, pos, n_patches, patch, o);
+  pbt::launch(patch_gather_kernel, grid, block, 0, st, src_ptrs, n_src, n_images, ch, img_hw, pos, n_patches, patch, o);
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
 }

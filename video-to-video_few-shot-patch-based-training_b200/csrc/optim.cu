@@ -25,8 +25,11 @@ __device__ __forceinline__ float block_sum(float v) {
   return v;  // valid in thread 0
 }
 
-// grid: (chunks, jobs).  state[0] += sum g^2 ; state[1] (step count) += 1 once per launch.  state = float[3].
+// grid: (chunks, jobs).  state[3 + job * chunks + chunk] = this block's sum g^2 ; state[1] (step count) += 1 once per
+// launch.  No atomics: the total is later summed in a fixed order, so identical gradients give a bit-identical norm -
+// data-parallel replicas, which all hold the same all-reduced gradients, therefore apply bit-identical updates.
 __global__ void grad_sqnorm_kernel(const pbt_optim_job_t* __restrict__ jobs, float* __restrict__ state) {
+  pdl_sync();
   const pbt_optim_job_t j = jobs[blockIdx.y];
   const float* g = static_cast<const float*>(j.grad);
   float acc = 0.f;
@@ -46,7 +49,7 @@ __global__ void grad_sqnorm_kernel(const pbt_optim_job_t* __restrict__ jobs, flo
   }
   acc = block_sum(acc);
   if (threadIdx.x == 0) {
-    if (acc != 0.f) atomicAdd(&state[0], acc);
+    state[3 + blockIdx.y * gridDim.x + blockIdx.x] = acc;
     if (blockIdx.x == 0 && blockIdx.y == 0) state[1] += 1.f;
   }
 }
@@ -55,11 +58,26 @@ struct AdamK {
   float max_norm, lr, b1, b2, omb1, omb2, eps, wd;  // omb = 1 - beta rounded from double, as torch passes it
 };
 
-__global__ void clip_adam_kernel(const pbt_optim_job_t* __restrict__ jobs, const float* __restrict__ state, AdamK k,
+__global__ void clip_adam_kernel(const pbt_optim_job_t* __restrict__ jobs, float* state, AdamK k,
                                  float* __restrict__ norm_out) {
+  pdl_sync();
   const pbt_optim_job_t j = jobs[blockIdx.y];
-  const float total = sqrtf(state[0]);
-  if (norm_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *norm_out = total;
+  // every block sums the per-block partials in the same fixed order (strided per thread, then a fixed tree)
+  __shared__ float s_total;
+  {
+    float acc = 0.f;
+    const int n_part = (int)(gridDim.x * gridDim.y);
+    for (int i = threadIdx.x; i < n_part; i += blockDim.x) acc += state[3 + i];
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) s_total = acc;
+    __syncthreads();
+  }
+  const float total_sq = s_total;
+  const float total = sqrtf(total_sq);
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    if (norm_out) *norm_out = total;
+    state[0] = total_sq;   // read by clip_adam_skip_kernel
+  }
   if (!isfinite(total)) return;  // inf/nan gradients (fp16 overflow): the step is skipped, AMP-style (see clip_adam_skip_kernel)
   const float t = state[1];
   float coef = 1.f;
@@ -88,6 +106,7 @@ __global__ void clip_adam_kernel(const pbt_optim_job_t* __restrict__ jobs, const
 // L1Loss(G(x), post) * reconstruction_weight):  loss += weight/count * sum|y - t| ;  gy = weight/count * sign(y - t).
 __global__ void l1_loss_kernel(const float* __restrict__ y, const float* __restrict__ t, long long count, float scale,
                                float* __restrict__ loss, float* __restrict__ gy) {
+  pdl_sync();
   float acc = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
     const float d = y[i] - t[i];
@@ -100,6 +119,7 @@ __global__ void l1_loss_kernel(const float* __restrict__ y, const float* __restr
 
 // a skipped step does not count: take back the increment of grad_sqnorm_kernel, count the skip in state[2]
 __global__ void clip_adam_skip_kernel(float* state) {
+  pdl_sync();
   if (!isfinite(state[0])) {
     state[1] -= 1.f;
     state[2] += 1.f;
@@ -116,19 +136,18 @@ extern "C" int pbt_clip_adam_step(const pbt_optim_job_t* jobs_dev, int32_t n_job
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   PBT_REQUIRE(jobs_dev && state && n_jobs > 0 && n_jobs <= 65535 && max_elems > 0, "clip_adam: bad arguments");
   PBT_REQUIRE(lr >= 0.0 && beta1 >= 0.0 && beta1 < 1.0 && beta2 >= 0.0 && beta2 < 1.0 && eps >= 0.0, "clip_adam: bad hyper-parameters");
-  PBT_CUDA_CHECK(cudaMemsetAsync(state, 0, sizeof(float), st));  // squared norm; state[1] (the step count) persists
   long long bx = (max_elems + 256 * 8 - 1) / (256 * 8);
   if (bx > 32) bx = 32;
   if (bx < 1) bx = 1;
   dim3 grid((unsigned)bx, (unsigned)n_jobs);
-  grad_sqnorm_kernel<<<grid, 256, 0, st>>>(jobs_dev, state);
+  pbt::launch(grad_sqnorm_kernel, grid, 256, 0, st, jobs_dev, state);
   PBT_CUDA_CHECK(cudaGetLastError());
   // hyper-parameters arrive as doubles (Python floats) and are rounded once, the way torch's kernels receive them
   AdamK k{(float)max_norm, (float)lr, (float)beta1, (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps,
           (float)weight_decay};
-  clip_adam_kernel<<<grid, 256, 0, st>>>(jobs_dev, state, k, norm_out);
+  pbt::launch(clip_adam_kernel, grid, 256, 0, st, jobs_dev, state, k, norm_out);
   PBT_CUDA_CHECK(cudaGetLastError());
-  clip_adam_skip_kernel<<<1, 1, 0, st>>>(state);
+  pbt::launch(clip_adam_skip_kernel, 1, 1, 0, st, state);
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
 }
@@ -140,7 +159,7 @@ extern "C" int pbt_l1_loss_fwd_bwd(const float* y, const float* target, int64_t 
   PBT_CUDA_CHECK(cudaMemsetAsync(loss, 0, sizeof(float), st));
   long long blocks = (count + 256 * 8 - 1) / (256 * 8);
   if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
-  l1_loss_kernel<<<(unsigned)blocks, 256, 0, st>>>(y, target, count, (float)((double)weight / (double)count), loss, gy);
+  pbt::launch(l1_loss_kernel, (unsigned)blocks, 256, 0, st, y, target, count, (float)((double)weight / (double)count), loss, gy);
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
 }

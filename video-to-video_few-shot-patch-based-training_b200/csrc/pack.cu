@@ -29,6 +29,7 @@ __device__ __forceinline__ float virt(const pbt_pack_job_t& j, int o, int i, int
 }
 
 __global__ void pack_weights_kernel(const pbt_pack_job_t* __restrict__ jobs) {
+  pdl_sync();
   const pbt_pack_job_t j = jobs[blockIdx.y];
   const bool s2d = j.mode & 1, dgrad = j.mode & 2;
   const int vkh = s2d ? 2 : j.kh, vkw = s2d ? 2 : j.kw;
@@ -77,7 +78,7 @@ extern "C" int pbt_pack_weights(const pbt_pack_job_t* jobs_dev, int32_t n_jobs, 
   long long bx = (max_elems + 255) / 256;
   if (bx > 64) bx = 64;
   dim3 grid((unsigned)bx, (unsigned)n_jobs);
-  pack_weights_kernel<<<grid, 256, 0, st>>>(jobs_dev);
+  pbt::launch(pack_weights_kernel, grid, 256, 0, st, jobs_dev);
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
 }

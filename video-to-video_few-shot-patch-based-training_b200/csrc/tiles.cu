@@ -13,6 +13,7 @@ namespace pbt {
 // grid: (pixel chunks of P*P, channels, tiles)
 __global__ void tile_gather_kernel(const float* __restrict__ src, int h, int w, const int* __restrict__ boxes, int patch,
                                    float* __restrict__ out, int channels) {
+  pdl_sync();
   const int b = blockIdx.z, ch = blockIdx.y;
   const int y0 = boxes[4 * b + 0], y1 = boxes[4 * b + 1], x0 = boxes[4 * b + 2], x1 = boxes[4 * b + 3];
   const int hc = min(y1 - y0, patch), wc = min(x1 - x0, patch);
@@ -32,6 +33,7 @@ __global__ void tile_gather_kernel(const float* __restrict__ src, int h, int w, 
 __global__ void tile_blend_kernel(const float* __restrict__ proc, const int* __restrict__ boxes, const int* __restrict__ widx,
                                   const float* __restrict__ wtab, int patch, int h, int w, float* __restrict__ acc,
                                   float* __restrict__ wsum) {
+  pdl_sync();
   const int b = blockIdx.y;
   const int y0 = boxes[4 * b + 0], x0 = boxes[4 * b + 2];
   const float* wt = wtab + (long long)widx[b] * patch * patch;
@@ -52,6 +54,7 @@ __global__ void tile_blend_kernel(const float* __restrict__ proc, const int* __r
 
 __global__ void tile_finish_kernel(const float* __restrict__ acc, const float* __restrict__ wsum, const float* __restrict__ rgb,
                                    const float* __restrict__ mask, long long hw, float* __restrict__ out) {
+  pdl_sync();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < hw; i += (long long)gridDim.x * blockDim.x) {
     const float ws = wsum[i];
     const float d = ws > 1e-8f ? ws : 1.f;
@@ -75,7 +78,7 @@ extern "C" int pbt_tile_gather(const float* src, int32_t channels, int32_t h, in
   PBT_REQUIRE(src && boxes_dev && out && channels > 0 && channels <= 65535 && h > 0 && w > 0 && patch > 0 && n_tiles > 0 &&
                   n_tiles <= 65535, "tile_gather: bad arguments");
   dim3 grid(ceil_div(patch * patch, 256), channels, n_tiles);
-  tile_gather_kernel<<<grid, 256, 0, st>>>(src, h, w, boxes_dev, patch, out, channels);
+  pbt::launch(tile_gather_kernel, grid, 256, 0, st, src, h, w, boxes_dev, patch, out, channels);
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
 }
@@ -88,7 +91,7 @@ extern "C" int pbt_tile_blend(const float* proc, const int32_t* boxes_dev, const
   PBT_REQUIRE(proc && boxes_dev && weight_index_dev && weight_table && acc && wsum && patch > 0 && h > 0 && w > 0 &&
                   n_tiles > 0 && n_tiles <= 65535, "tile_blend: bad arguments");
   dim3 grid(ceil_div(patch * patch, 256), n_tiles);
-  tile_blend_kernel<<<grid, 256, 0, st>>>(proc, boxes_dev, weight_index_dev, weight_table, patch, h, w, acc, wsum);
+  pbt::launch(tile_blend_kernel, grid, 256, 0, st, proc, boxes_dev, weight_index_dev, weight_table, patch, h, w, acc, wsum);
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
 }
@@ -100,7 +103,7 @@ extern "C" int pbt_tile_finish(const float* acc, const float* wsum, const float*
   const long long hw = (long long)h * w;
   long long blocks = (hw + 255) / 256;
   if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
-  tile_finish_kernel<<<(unsigned)blocks, 256, 0, st>>>(acc, wsum, rgb, mask, hw, out);
+  pbt::launch(tile_finish_kernel, (unsigned)blocks, 256, 0, st, acc, wsum, rgb, mask, hw, out);
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
 }

@@ -74,6 +74,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_sync();   // programmatic dependent launch: set-up above overlapped the previous launch's drain
   const uint32_t tmem_base = *tmem_slot;
 
   if (my_tiles > 0) {
@@ -201,6 +202,7 @@ wgrad_taps_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_sync();   // programmatic dependent launch: set-up above overlapped the previous launch's drain
   const uint32_t tmem_base = *tmem_slot;
 
   if (my_tiles > 0) {
@@ -352,7 +354,7 @@ extern "C" int pbt_conv_wgrad(const pbt_wgrad_desc_t* d, void* stream_) {
     if (rc != PBT_OK) return rc;
     PBT_CUDA_CHECK(cudaFuncSetAttribute(wgrad_taps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     dim3 grid(p.splits, p.n_units, 1);
-    wgrad_taps_kernel<<<grid, kWgThreads, smem_bytes, stream>>>(tx, tg, p);
+    pbt::launch(wgrad_taps_kernel, grid, kWgThreads, smem_bytes, stream, tx, tg, p);
     PBT_CUDA_CHECK(cudaGetLastError());
     return PBT_OK;
   }
@@ -415,7 +417,7 @@ extern "C" int pbt_conv_wgrad(const pbt_wgrad_desc_t* d, void* stream_) {
 
   PBT_CUDA_CHECK(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   dim3 grid(p.splits, p.n_units, m_blocks);
-  wgrad_kernel<<<grid, kWgThreads, smem_bytes, stream>>>(tx, tg, p);
+  pbt::launch(wgrad_kernel, grid, kWgThreads, smem_bytes, stream, tx, tg, p);
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
 }

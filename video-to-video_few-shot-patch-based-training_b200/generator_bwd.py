@@ -101,6 +101,7 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor, want_input_grad: 
     main = torch.cuda.current_stream(dev)
     side = eng.side_stream()
     keep = []
+    last_dw = [None]
 
     def wgrad_side(name, x: P8, dy: P8, k, pad, convert=_wgrad_to_param):
         """enqueue wgrad(x, dy) + `convert(dw, bucket view)` on the side stream after everything enqueued so far on the
@@ -114,6 +115,7 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor, want_input_grad: 
         with torch.cuda.stream(side):
             ops.conv_wgrad(x, dy, k, k, pad, pad, dt, dw, inv_scale=inv)
             convert(dw, bucket.views[name])
+            last_dw[0] = dw
             grads[name] = bucket.views[name]
             done = torch.cuda.Event()
             done.record(side)
@@ -346,7 +348,8 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor, want_input_grad: 
     if eng.grad_scale_target > 0:
         # an fp16 overflow anywhere in the sweep ends up as inf/nan in this most-downstream gradient: shrink the scale
         # of the next sweep (the optimiser skips a non-finite step - FusedClipAdam does; AMP semantics)
-        ops.grad_scale_feedback(grads["initial_conv.0.weight"], eng.grad_scale_adjust())
+        # (probed in its wgrad accumulator: the bucket slice may already be under the data-parallel all-reduce)
+        ops.grad_scale_feedback(last_dw[0], eng.grad_scale_adjust())
 
     # ---- assemble in parameter order
     out: List[torch.Tensor] = []

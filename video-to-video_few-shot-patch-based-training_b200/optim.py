@@ -37,7 +37,8 @@ class FusedClipAdam(torch.optim.Optimizer):
         dev = ps[0].device
         self._dev = dev
         # device state: [0] sum of squares scratch, [1] step count; total norm of the last step
-        self._state = torch.zeros(3, device=dev)      # [sum of squares, step count, skipped (non-finite) steps]
+        # [squared norm, step count, skipped (non-finite) steps, per-block partial sums of the norm (32 per tensor)]
+        self._state = torch.zeros(3 + 32 * len(ps), device=dev)
         self.last_grad_norm = torch.zeros((), device=dev)
         total = sum(p.numel() for p in ps)
         self._m = torch.zeros(total, device=dev)
