@@ -120,6 +120,10 @@ typedef struct {
                               * Needs blk_c 32 and cout % 32 == 0 (or blk_c 16, tiles_per_cta 2 with ctas_per_sm = 4); no upsample2x */
   int32_t      concurrent;   /* 1: kernels of other streams are expected to run next to this launch: never use persistent CTAs
                               * (they would hold every SM slot / tensor-memory column until the launch ends) */
+  int32_t      batch_tiles;  /* 1: the tiles_per_cta (>= 2) tiles of a CTA are the SAME 8x16 tile of consecutive IMAGES instead of
+                              * x-adjacent tiles of one image: on patch-sized maps (20x20 ... 40x40) the packed weights are then
+                              * streamed from L2 once per T images and no tile columns are wasted.  `stats_partial` is indexed
+                              * with pbt_conv_num_tiles(h, w, 1) tiles per image.  Excludes upsample2x / pre / cta_pair */
   int32_t      debug_flags;  /* bring-up only; 0 in production */
   void*        debug_buf;    /* bring-up only: int64[grid][8] per-CTA phase timestamps, NULL in production */
 } pbt_conv_desc_t;

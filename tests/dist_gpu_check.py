@@ -65,10 +65,13 @@ def main():
     cnt = torch.tensor([hi - lo], device=dev)
     dist.all_reduce(cnt)
     assert int(cnt) == 9
+    del step                      # a live CUDA graph that captured NCCL work keeps the communicator busy at shutdown
+    torch.cuda.synchronize()
     dist.barrier()
     if rank == 0:
         print(f"DIST_GPU_CHECK_OK world={world} allreduce_err={err:.2e} losses {losses[0]:.4f}->{losses[-1]:.4f}")
-    dist.destroy_process_group()
+    sys.stdout.flush()
+    os._exit(0)                   # skip the process-group teardown: it can block behind graph-captured collectives
 
 
 if __name__ == "__main__":

@@ -32,7 +32,7 @@ def act_ref(v, act):
 
 def check_conv(n=1, cin=16, cout=16, h=16, w=8, kh=1, kw=1, pad_t=0, pad_l=0, T=1, blk_c=16, dt=BF16, seed=0,
                debug_flags=0, in_off=0, in_extra=0, out_off=0, out_extra=0, bias=False, act=ACT_NONE, affine=False,
-               mask=False, addend=False, out32=False, stats=False, head=False, integer=True, store16=True, cps=0, pair=False):
+               mask=False, addend=False, out32=False, stats=False, head=False, integer=True, store16=True, cps=0, pair=False, bt=False):
     """returns (ok, max_abs_err, message); cps = ctas_per_sm configuration of the kernel"""
     g = torch.Generator(device="cuda").manual_seed(seed)
     if integer:
@@ -50,7 +50,7 @@ def check_conv(n=1, cin=16, cout=16, h=16, w=8, kh=1, kw=1, pad_t=0, pad_l=0, T=
                                           torch.full((n, in_extra, h, w), -5.0, device="cuda")], 1), dt).t)
     xin = xfull.view(in_off, cin)
     wp = ops.pack_conv_weight(wt, cin, blk_c, dt, pair=pair)   # pair: CTA-pair (cta_group::2) configuration
-    kwargs = {"cta_pair": pair}
+    kwargs = {"cta_pair": pair, "batch_tiles": bt}
     exp = ref_conv(x, wt, pad_t, pad_l)
     if bias:
         b = _ints((cout,), -4, 4, g)
@@ -79,7 +79,7 @@ def check_conv(n=1, cin=16, cout=16, h=16, w=8, kh=1, kw=1, pad_t=0, pad_l=0, T=
         ofull = P8.empty(n, out_off + cout + out_extra, h, w, dt, zero=True)
         ofull.t.fill_(9.0)
         kwargs["out"] = ofull.view(out_off, cout)
-    tiles = ops.conv_num_tiles(h, w, T)
+    tiles = ops.conv_num_tiles(h, w, 1 if bt else T)
     part = None
     if stats:
         part = torch.full((n, tiles, 2, cout), float("nan"), device="cuda")

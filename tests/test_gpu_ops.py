@@ -51,6 +51,16 @@ CONV_CASES = [
     dict(n=2, cin=64, cout=64, h=40, w=56, kh=3, kw=3, pad_t=1, pad_l=1, T=2, blk_c=16, bias=True, act=1, pair=True, cps=4),
     dict(n=1, cin=48, cout=64, h=33, w=40, kh=7, kw=7, pad_t=3, pad_l=3, T=2, blk_c=16, stats=True, integer=False, pair=True,
          cps=4),
+    # batch tiles: the T tiles of a CTA are the same spatial tile of T consecutive images (patch-sized maps)
+    dict(n=5, cin=128, cout=128, h=20, w=20, kh=3, kw=3, pad_t=1, pad_l=1, T=2, blk_c=32, stats=True, integer=False, bt=True),
+    dict(n=4, cin=64, cout=32, h=20, w=20, kh=3, kw=3, pad_t=1, pad_l=1, T=2, blk_c=32, stats=True, bt=True),
+    dict(n=7, cin=32, cout=64, h=40, w=40, kh=3, kw=3, pad_t=1, pad_l=1, T=3, blk_c=32, bias=True, act=1, bt=True),
+    dict(n=3, cin=128, cout=128, h=20, w=20, kh=3, kw=3, pad_t=1, pad_l=1, T=2, blk_c=32, mask=True, addend=True, out32=True,
+         store16=False, bt=True),
+    dict(n=6, cin=128, cout=256, h=20, w=20, kh=2, kw=2, pad_t=0, pad_l=0, T=2, blk_c=32, bt=True),
+    dict(n=2, cin=64, cout=64, h=24, w=40, kh=3, kw=3, pad_t=1, pad_l=1, T=2, blk_c=32, bias=True, act=1, head=True, integer=False,
+         bt=True),
+    dict(n=170, cin=64, cout=128, h=20, w=20, kh=3, kw=3, pad_t=1, pad_l=1, T=2, blk_c=32, stats=True, integer=False, bt=True),
     # more units than one wave of CTAs: every CTA walks several units (persistent loop, barrier phases carried over)
     dict(n=2, cin=64, cout=128, h=272, w=480, kh=3, kw=3, pad_t=1, pad_l=1, T=2, blk_c=32, stats=True, integer=False),
     dict(n=3, cin=32, cout=64, h=200, w=330, kh=3, kw=3, pad_t=1, pad_l=1, T=2, blk_c=16, bias=True, act=1, head=True,

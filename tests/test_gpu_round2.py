@@ -163,6 +163,6 @@ def test_nccl_data_parallel_parity_under_torchrun():
     keep the replicas bit-identical, the sharded inference covers a video exactly (tests/dist_gpu_check.py)"""
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29631", os.path.join(ROOT, "tests", "dist_gpu_check.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, cwd=ROOT)
     print(r.stdout[-3000:], r.stderr[-3000:])
     assert r.returncode == 0 and "DIST_GPU_CHECK_OK" in r.stdout

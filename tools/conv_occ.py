@@ -19,9 +19,11 @@ cases = [("smooth 64->64 3x3 @1080p", 64, 64, 3, 1080, 1920, 32, [(3, 0), (2, 4.
          ("conv11 176->64 7x7 @1080p", 176, 64, 7, 1080, 1920, 32, [(3, 0), (3, "pair"), (2, "pair4")])]
 if len(sys.argv) > 2 and sys.argv[2] == "train":   # C3 training shapes: 80 patches of 80x80 (N = batch)
     N = 80
-    cases = [("res 128->128 3x3 @20x20", 128, 128, 3, 20, 20, 32, [(1, 0), (1, 4), (1, "pair"), (2, "pair")]),
-             ("down2 s2d 256->128 2x2 @20x20", 256, 128, 2, 20, 20, 32, [(1, 0), (1, 4), (1, "pair")]),
-             ("up2 256->128 3x3 @40x40", 256, 128, 3, 40, 40, 32, [(2, 0), (1, 4), (1, "pair"), (2, "pair")]),
+    cases = [("res 128->128 3x3 @20x20", 128, 128, 3, 20, 20, 32, [(1, 0), (1, 4), (2, "bt"), (3, "bt")]),
+             ("down2 s2d 256->128 2x2 @20x20", 256, 128, 2, 20, 20, 32, [(1, 0), (1, 4), (2, "bt")]),
+             ("up2 256->128 3x3 @40x40", 256, 128, 3, 40, 40, 32, [(2, 0), (1, 4), (2, "bt")]),
+             ("down1 s2d 128->64 2x2 @40x40 ", 128, 64, 2, 40, 40, 32, [(2, 4), (2, "bt"), (3, "bt")]),
+             ("up2 dgrad-like 128->128 3x3 @40x40", 128, 128, 3, 40, 40, 32, [(2, 0), (2, "bt")]),
              ("up1 192->128 3x3 @80x80", 192, 128, 3, 80, 80, 32, [(2, 0), (2, "pair"), (1, "pair")]),
              ("conv11 176->64 7x7 @80x80", 176, 64, 7, 80, 80, 32, [(2, 0), (2, "pair"), (1, "pair"), (2, "pair4")]),
              ("conv11 dgrad 64->160 7x7 @80x80", 64, 160, 7, 80, 80, 32, [(2, 0), (1, 0), (1, "pair")]),
@@ -41,6 +43,9 @@ for name, cin, cout, k, h, w, blk, cfgs in cases:
     for T, cps in cfgs:
         try:
             b = blk
+            bt = cps == "bt"
+            if bt:
+                cps = 0
             pair = cps in ("pair", "pair4")
             if pair:
                 cps = 4.16 if cps == "pair4" else 0
@@ -51,7 +56,7 @@ for name, cin, cout, k, h, w, blk, cfgs in cases:
             wp = ops.pack_conv_weight(wt, cin, b, dt, pair=pair)
             out = P8.empty(N, cout, h, w, dt)
             run = lambda: ops.conv_fwd(x, wp, cout, k, k, k // 2, k // 2, dt, blk_c=b, tiles_per_cta=T, out=out, bias=bias,
-                                       act=ACT_RELU, ctas_per_sm=cps, cta_pair=pair, debug_flags=DBG)
+                                       act=ACT_RELU, ctas_per_sm=cps, cta_pair=pair, debug_flags=DBG, batch_tiles=bt)
             for _ in range(3):
                 run()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -65,6 +70,6 @@ for name, cin, cout, k, h, w, blk, cfgs in cases:
             if ref is None:
                 ref = out.t.float().clone()
             tf = 2.0 * N * h * w * k * k * cin * cout / ms / 1e9
-            print(f"{name}: T={T} cps={'pair' if pair else (cps or 2)} blk={b}: {ms * 1e3:8.1f} us ({ms * 1e3 / N:8.1f} us/frame)  {tf:7.1f} TFLOP/s  maxdiff vs first {diff:.3g}", flush=True)
+            print(f"{name}: T={T} cps={'pair' if pair else ('bt' if bt else (cps or 2))} blk={b}: {ms * 1e3:8.1f} us ({ms * 1e3 / N:8.1f} us/frame)  {tf:7.1f} TFLOP/s  maxdiff vs first {diff:.3g}", flush=True)
         except Exception as e:  # noqa: BLE001
             print(f"{name}: T={T} cps={cps}: EXC {e}", flush=True)

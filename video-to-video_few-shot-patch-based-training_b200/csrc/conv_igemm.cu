@@ -67,7 +67,9 @@ struct ConvKParams {
   const float* pre_scale;
   const float* pre_shift;
   uint32_t l_stage_bytes;
-  int rot;               // channel blocks are walked starting at (unit % n_blk): co-resident CTAs stream different weights
+  int bt;                // batch tiles: the T tiles of a CTA are the SAME spatial tile of T consecutive images (small maps)
+  uint32_t a_tile16;     // A-descriptor step from tile t to t+1 in 16-byte units: 8 pixels (x-adjacent) or one staged tile (bt)
+  uint32_t a_tile_bytes; // bt: shared-memory pitch of the T per-image tiles inside an A stage
   int debug_flags;
   long long* debug_buf;  // bring-up: per-CTA phase timestamps (clock64), 8 slots per CTA
 };
@@ -167,7 +169,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   uint64_t* acc_peer = acc_empty + 1;  // CTA-pair mode, leader only: the peer's accumulators are drained too
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_peer + 1);
   float* s_stats = reinterpret_cast<float*>(tmem_slot + 2);  // [8 warps][2][NC]
-  float* s_head = s_stats + EW * 2 * p.NC;             // [T][4 quadrants][32 lanes][3]
+  const int TS = p.bt ? T : 1;                         // statistics slots per CTA: one per image in batch-tile mode
+  float* s_head = s_stats + EW * 2 * p.NC * TS;        // [T][4 quadrants][32 lanes][3]
   float* s_norm = s_head + (EW == 8 ? 3 * 4 * 32 * 3 : 0);                    // [2][pre_c] scale / shift of this image
 
   const int warp = threadIdx.x >> 5;
@@ -185,12 +188,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   // blockIdx.x, blockIdx.x + gridDim.x, ...  Barrier stages / parities run on counters that continue across units, so the
   // producer prefetches the next unit's first tiles while the current unit's last MMAs and epilogue run, and the
   // per-CTA launch gap + setup (~10-25 % of a short CTA's life, tools/conv_timeline.py) is paid once.
-#define PBT_UNIT_GEOM(unit)                      \
-  const int n = (unit) / tiles_per_img;          \
-  const int rem = (unit) - n * tiles_per_img;    \
-  const int tyi = rem / p.tiles_x;               \
-  const int txi = rem - tyi * p.tiles_x;         \
-  const int x0 = txi * 8 * T;                    \
+#define PBT_UNIT_GEOM(unit)                                  \
+  const int ngrp = (unit) / tiles_per_img;                   \
+  const int n = p.bt ? ngrp * T : ngrp;                      \
+  const int rem = (unit) - ngrp * tiles_per_img;             \
+  const int tyi = rem / p.tiles_x;                           \
+  const int txi = rem - tyi * p.tiles_x;                     \
+  const int x0 = txi * (p.bt ? 8 : 8 * T);                   \
   const int y0 = tyi * 16;
   const int ntaps = p.KH * p.KW;
   const int ngroups = (ntaps + p.b_group - 1) / p.b_group;
@@ -252,10 +256,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       PBT_UNIT_GEOM(unit)
       (void)rem;
       // activation tile (or, with upsample-on-load, its low-res footprint) of channel block `cb`
-      const int rot = p.rot ? unit % p.n_blk : 0;
-      auto issue_act = [&](int cb_seq) {
-        const int c = cbt + cb_seq;
-        const int cb = cb_seq + rot < p.n_blk ? cb_seq + rot : cb_seq + rot - p.n_blk;
+      auto issue_act = [&](int cb) {
+        const int c = cbt + cb;
         if (p.up) {
           const int sl = c & 1;
           mbar_wait(&l_empty[sl], ((uint32_t)(c >> 1) & 1u) ^ 1u);
@@ -266,6 +268,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
           const int sa = c % p.a_stages;
           mbar_wait(&a_empty[sa], ((uint32_t)(c / p.a_stages) & 1u) ^ 1u);
           uint64_t* bar = p.nrm ? &a_land[sa] : &a_full[sa];
+          if (p.bt) {   // the same haloed tile of T consecutive images (images past the batch are zero-filled by TMA)
+            mbar_arrive_expect_tx(bar, (uint32_t)(p.blk_p * p.BH * p.BW * 16 * T));
+            for (int tt = 0; tt < T; ++tt)
+              tma_load_4d(sA + (size_t)sa * p.a_stage_bytes + (size_t)tt * p.a_tile_bytes, &tmapA, bar, (x0 - p.pad_l) * 8,
+                          y0 - p.pad_t, cb * p.blk_p, n + tt);
+            return;
+          }
           mbar_arrive_expect_tx(bar, (uint32_t)(p.blk_p * p.BH * p.BW * 16));
           if (cb < p.nblk0)
             tma_load_4d(sA + (size_t)sa * p.a_stage_bytes, &tmapP, bar, (x0 - p.pad_l) * 8, y0 - p.pad_t, cb * p.blk_p, n);
@@ -275,8 +284,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         }
       };
       issue_act(0);
-      for (int cb_seq = 0; cb_seq < p.n_blk; ++cb_seq) {
-        const int cb = cb_seq + rot < p.n_blk ? cb_seq + rot : cb_seq + rot - p.n_blk;
+      for (int cb = 0; cb < p.n_blk; ++cb) {
         // Block cb+1 is requested once the weight ring of block cb is primed (b_stages groups in flight): by then
         // the MMAs of block cb-1 have retired (its stage is free, no blocking wait here), and the load — plus the
         // upsample transform — overlaps almost a whole block of MMAs instead of starting when the ring drains.
@@ -293,7 +301,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
           mbar_arrive_expect_tx(&b_full[sb], chunk * (uint32_t)nt);
           // the taps of a group are contiguous in the packed weights: one bulk copy per group
           bulk_load_1d(sB + (size_t)sb * p.b_stage_bytes, wsrc + (size_t)tap0 * chunk, chunk * (uint32_t)nt, &b_full[sb]);
-          if (g == gpre && cb_seq + 1 < p.n_blk && p.a_stages > 1) issue_act(cb_seq + 1);
+          if (g == gpre && cb + 1 < p.n_blk && p.a_stages > 1) issue_act(cb + 1);
         }
       }
      }
@@ -342,6 +350,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       const uint32_t a_kstep = (2u * plane_bytes) >> 4;  // two channel planes per K=16
       const uint32_t b_kstep = (2u * b_kstride) >> 4;
       const uint32_t acc_stride = (uint32_t)p.acc_stride;
+      const uint32_t a_tstep = p.a_tile16;
       const uint32_t idesc = p.idesc;
       int bi = 0, cbt = 0, it = 0;
       for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x, cbt += p.n_blk, ++it) {
@@ -384,11 +393,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
                     if (NI == 1 || t == ti) {
                       if (PAIR)
                         umma_f16_pair(tmem_base + (uint32_t)t * acc_stride,
-                                      desc64(a_tap + (uint32_t)(t * 8) + (uint32_t)k * a_kstep, a_hi),
+                                      desc64(a_tap + (uint32_t)t * a_tstep + (uint32_t)k * a_kstep, a_hi),
                                       desc64(b_lo + (uint32_t)k * b_kstep, b_hi), idesc, (k == 0) ? first : 1u);
                       else
                         umma_f16(tmem_base + (uint32_t)t * acc_stride,
-                                 desc64(a_tap + (uint32_t)(t * 8) + (uint32_t)k * a_kstep, a_hi),
+                                 desc64(a_tap + (uint32_t)t * a_tstep + (uint32_t)k * a_kstep, a_hi),
                                  desc64(b_lo + (uint32_t)k * b_kstep, b_hi), idesc, (k == 0) ? first : 1u);
                     }
                 }
@@ -427,12 +436,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     const int NC = p.NC;
     const int dt = p.dt;
     const bool do_stats = p.stats_partial != nullptr;
-    float* my_stats = s_stats + (size_t)ew * 2 * NC;
+    float* my_stats = s_stats + (size_t)ew * 2 * NC * TS;   // [TS][2][NC]
     int cbt = 0, it = 0;
     for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x, cbt += p.n_blk, ++it) {
     PBT_UNIT_GEOM(unit)
     if (do_stats) {
-      for (int i = lane; i < 2 * NC; i += 32) my_stats[i] = 0.f;
+      for (int i = lane; i < 2 * NC * TS; i += 32) my_stats[i] = 0.f;
       __syncwarp();
     }
     const int r = q * 32 + lane;
@@ -636,8 +645,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       constexpr bool kColOuter = CF != kFGeneric && (CF & kFStats) != 0 && (CF & kFHead) == 0;
       // one 16-column chunk of tile t: accumulator -> registers -> fused pointwise work -> stores
       auto chunk = [&](int t, int c0, float (&hd)[3], float* sacc) {
-        const int x = x0 + 8 * t + tx;
-        const bool valid = (y < p.H) && (x < p.W) && (n < p.n_img);
+        const int x = p.bt ? x0 + tx : x0 + 8 * t + tx;
+        const int nt = p.bt ? n + t : n;                      // image of tile t
+        float* st_t = my_stats + (p.bt ? t * 2 * NC : 0);
+        const bool valid = (y < p.H) && (x < p.W) && (nt < p.n_img);
         const long long pix = (long long)y * p.W + x;
         uint32_t raw[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * p.acc_stride + c0), raw);
@@ -665,7 +676,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
               const uint4 m = *reinterpret_cast<const uint4*>(
-                  p.mask + 2 * ((long long)n * p.mask_img_stride + ((long long)(c0 / 8 + hh) * plane_px + pix) * 8));
+                  p.mask + 2 * ((long long)nt * p.mask_img_stride + ((long long)(c0 / 8 + hh) * plane_px + pix) * 8));
               float mf[8];
               unpack8_rt(dt, m, mf);
 #pragma unroll
@@ -676,7 +687,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
               const float4* ap = reinterpret_cast<const float4*>(
-                  p.addend32 + (((long long)n * (NC / 8) + (c0 / 8 + hh)) * plane_px + pix) * 8);
+                  p.addend32 + (((long long)nt * (NC / 8) + (c0 / 8 + hh)) * plane_px + pix) * 8);
               const float4 a0 = ap[0], a1 = ap[1];
               v[hh * 8 + 0] += a0.x; v[hh * 8 + 1] += a0.y; v[hh * 8 + 2] += a0.z; v[hh * 8 + 3] += a0.w;
               v[hh * 8 + 4] += a1.x; v[hh * 8 + 5] += a1.y; v[hh * 8 + 6] += a1.z; v[hh * 8 + 7] += a1.w;
@@ -685,7 +696,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
           if (fm & kFOut32) {
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
-              float4* op = reinterpret_cast<float4*>(p.out32 + (((long long)n * (NC / 8) + (c0 / 8 + hh)) * plane_px + pix) * 8);
+              float4* op = reinterpret_cast<float4*>(p.out32 + (((long long)nt * (NC / 8) + (c0 / 8 + hh)) * plane_px + pix) * 8);
               op[0] = make_float4(v[hh * 8 + 0], v[hh * 8 + 1], v[hh * 8 + 2], v[hh * 8 + 3]);
               op[1] = make_float4(v[hh * 8 + 4], v[hh * 8 + 5], v[hh * 8 + 6], v[hh * 8 + 7]);
             }
@@ -695,7 +706,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
           // round to the storage type; statistics and the head see the rounded values
           const uint4 u0 = pack8_rt(dt, v), u1 = pack8_rt(dt, v + 8);
           if (valid) {
-            uint8_t* ob = p.out + 2 * ((long long)n * p.out_img_stride + ((long long)(c0 / 8) * plane_px + pix) * 8);
+            uint8_t* ob = p.out + 2 * ((long long)nt * p.out_img_stride + ((long long)(c0 / 8) * plane_px + pix) * 8);
             *reinterpret_cast<uint4*>(ob) = u0;
             *reinterpret_cast<uint4*>(ob + 2 * plane_px * 8) = u1;
           }
@@ -728,8 +739,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
             const float cs = warp_colsum16(s, lane);
             const float cs2 = warp_colsum16(s2, lane);
             if ((lane & 1) == 0) {
-              my_stats[c0 + col_of_lane] += cs;
-              my_stats[NC + c0 + col_of_lane] += cs2;
+              st_t[c0 + col_of_lane] += cs;
+              st_t[NC + c0 + col_of_lane] += cs2;
             }
           }
         }
@@ -741,12 +752,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
           for (int i = 0; i < 32; ++i) sacc[i] = 0.f;
           float hd[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-          for (int t = 0; t < T; ++t) chunk(t, c0, hd, sacc);
-          const float cs = warp_colsum16(sacc, lane);
-          const float cs2 = warp_colsum16(sacc + 16, lane);
-          if ((lane & 1) == 0) {
-            my_stats[c0 + col_of_lane] += cs;
-            my_stats[NC + c0 + col_of_lane] += cs2;
+          for (int t = 0; t < T; ++t) {
+            chunk(t, c0, hd, sacc);
+            if (p.bt || t == T - 1) {   // batch tiles: every tile is another image -> its own statistics slot
+              const float cs = warp_colsum16(sacc, lane);
+              const float cs2 = warp_colsum16(sacc + 16, lane);
+              float* st_t = my_stats + (p.bt ? t * 2 * NC : 0);
+              if ((lane & 1) == 0) {
+                st_t[c0 + col_of_lane] += cs;
+                st_t[NC + c0 + col_of_lane] += cs2;
+              }
+#pragma unroll
+              for (int i = 0; i < 32; ++i) sacc[i] = 0.f;
+            }
           }
         }
       } else {
@@ -768,15 +786,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
               hd[2] += hs[2];
             }
           }
-          const int x = x0 + 8 * t + tx;
-          if (y < p.H && x < p.W && half == 0 && n < p.n_img) {
+          const int x = p.bt ? x0 + tx : x0 + 8 * t + tx;
+          const int nt = p.bt ? n + t : n;
+          if (y < p.H && x < p.W && half == 0 && nt < p.n_img) {
             float h0 = hd[0] + __ldg(&p.head_b[0]), h1 = hd[1] + __ldg(&p.head_b[1]), h2 = hd[2] + __ldg(&p.head_b[2]);
             if (p.head_tanh) {
               h0 = tanhf(h0);
               h1 = tanhf(h1);
               h2 = tanhf(h2);
             }
-            float* ho = p.head_out + (long long)n * 3 * plane_px + (long long)y * p.W + x;
+            float* ho = p.head_out + (long long)nt * 3 * plane_px + (long long)y * p.W + x;
             ho[0] = h0;
             ho[plane_px] = h1;
             ho[2 * plane_px] = h2;
@@ -802,12 +821,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     if (do_stats) {
       asm volatile("bar.sync 1, %0;" ::"r"(32 * EW) : "memory");
       const int e = threadIdx.x - kEpi0;  // 0..255
-      float* dst = p.stats_partial + ((long long)n * tiles_per_img + rem) * 2 * NC;
-      for (int i = e; i < 2 * NC && n < p.n_img; i += 32 * EW) {
-        float acc = 0.f;
+      for (int ts = 0; ts < TS; ++ts) {
+        float* dst = p.stats_partial + ((long long)(n + ts) * tiles_per_img + rem) * 2 * NC;
+        for (int i = e; i < 2 * NC && n + ts < p.n_img; i += 32 * EW) {
+          float acc = 0.f;
 #pragma unroll
-        for (int w8 = 0; w8 < EW; ++w8) acc += s_stats[w8 * 2 * NC + i];
-        dst[i] = acc;
+          for (int w8 = 0; w8 < EW; ++w8) acc += s_stats[(w8 * TS + ts) * 2 * NC + i];
+          dst[i] = acc;
+        }
       }
       if (unit + (int)gridDim.x < p.n_units)  // the scratch is zeroed again for the next unit: everyone has read it
         asm volatile("bar.sync 1, %0;" ::"r"(32 * EW) : "memory");
@@ -928,15 +949,18 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
   p.n_blk = ceil_div(p.Cp, p.blk_p);
   p.KH = d->kh; p.KW = d->kw; p.pad_t = d->pad_t; p.pad_l = d->pad_l;
   const int T = d->tiles_per_cta;
+  const int bt = d->batch_tiles ? 1 : 0;
+  PBT_REQUIRE(!bt || (!up && !has_pre && !d->cta_pair && T >= 2), "conv: batch_tiles needs tiles_per_cta >= 2 and excludes upsample2x / pre / cta_pair");
+  p.bt = bt;
   p.NC = d->cout;
   p.dt = d->dtype;
   p.acc_stride = (int)round_up((uint32_t)p.NC, 32);
   p.tmem_cols = pow2_cols(T * p.acc_stride);
   PBT_REQUIRE(p.tmem_cols <= 512, "conv: tiles_per_cta*cout exceeds tensor memory (512 columns)");
-  p.BW = 8 * T + p.KW - 1;
+  p.BW = (bt ? 8 : 8 * T) + p.KW - 1;
   p.BH = 16 + p.KH - 1;
   PBT_REQUIRE(p.BW <= 32, "conv: haloed tile wider than 32 pixels (reduce tiles_per_cta)");
-  p.tiles_x = ceil_div(p.W, 8 * T);
+  p.tiles_x = ceil_div(p.W, bt ? 8 : 8 * T);
   p.tiles_y = ceil_div(p.H, 16);
   const int pair = d->cta_pair ? 1 : 0;
   if (pair) {
@@ -948,7 +972,9 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
       PBT_REQUIRE(d->blk_c == 32 && T >= 1 && T <= 3, "conv: cta_pair needs blk_c 32");
   }
   p.idesc = make_idesc_f16(pair ? 256 : 128, p.NC, d->dtype == PBT_BF16 ? 1 : 0, 0, 0);
-  p.a_stage_bytes = round_up((uint32_t)(p.blk_p * p.BH * p.BW * 16), 128);
+  p.a_tile_bytes = round_up((uint32_t)(p.blk_p * p.BH * p.BW * 16), 128);
+  p.a_stage_bytes = bt ? (uint32_t)T * p.a_tile_bytes : p.a_tile_bytes;
+  p.a_tile16 = bt ? p.a_tile_bytes / 16 : 8;
   p.LBH = (p.BH + 1) / 2 + 2;
   p.LBW = (p.BW + 1) / 2 + 2;
   p.l_stage_bytes = up ? round_up((uint32_t)(p.blk_p * p.LBH * p.LBW * 16), 128) : 0;
@@ -975,8 +1001,6 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
   PBT_REQUIRE(!d->head_w || (d->head_b && d->head_out), "conv: head needs head_b and head_out");
   p.debug_flags = d->debug_flags;
   p.debug_buf = static_cast<long long*>(d->debug_buf);
-  // (experiment, bit 4) rotate the channel-block order per unit; needs equal-sized blocks and no on-load `pre` split
-  p.rot = ((d->debug_flags & 16) && !has_pre && p.Cp % p.blk_p == 0 && p.n_blk > 1) ? 1 : 0;
 
   // shared memory budget: A ring + B ring (groups of taps) + barriers + tmem slot + stats scratch.
   // Aim at two co-resident CTAs per SM (one CTA's epilogue/prologue overlaps the other's main loop).
@@ -989,7 +1013,7 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
   int ew = (d->ctas_per_sm == 4 && !up && (!has_pre || p.BH * p.BW <= 4 * 128) && p.tmem_cols <= 128) ? 4 : 8;  // epilogue warps
   uint32_t smem_bytes = 0;
   for (;;) {
-    const uint32_t tail = 8u * (2 * 2 + 2 * 8 + 1) + 16 + (uint32_t)(ew * 2 * p.NC * 4) + (ew == 8 ? 3 * 4 * 32 * 3 * 4 : 0) +
+    const uint32_t tail = 8u * (2 * 2 + 2 * 8 + 1) + 16 + (uint32_t)(ew * 2 * p.NC * 4 * (bt ? T : 1)) + (ew == 8 ? 3 * 4 * 32 * 3 * 4 : 0) +
                           8 * 14 + (uint32_t)(2 * p.pre_c * 4) + 128;
     const uint32_t budget = ew == 4 ? 55 * 1024 : 112 * 1024;
     int group = (int)((ew == 4 ? 8192u : 16384u) / chunk);
@@ -1029,7 +1053,7 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
   }
 
   // one wave of persistent CTAs: SMs x co-resident CTAs (registers: 2 or 4; tensor memory; shared memory)
-  int grid = p.n_img * p.tiles_x * p.tiles_y;
+  int grid = (bt ? ceil_div(p.n_img, T) : p.n_img) * p.tiles_x * p.tiles_y;
   if (pair) grid = (grid + 1) & ~1;   // a pair's padding unit loads zeros and stores nothing
   p.n_units = grid;
   int occ = ew == 4 ? 4 : 2;

@@ -237,6 +237,7 @@ class _Engine:
         # 128-channel layers and the smoothers
         env = lambda k, d: os.environ.get(k, d) == "1"  # noqa: E731
         self.pair_res, self.pair_up, self.pair_smooth = env("PBT_PAIR_RES", "0"), env("PBT_PAIR_UP", "0"), env("PBT_PAIR_SMOOTH", "0")
+        self.batch_tiles = env("PBT_BATCH_TILES", "1")   # small maps: one CTA = the same tile of two images (see _bt)
         self._saved_stamp = 0     # counts grad-enabled forward passes: a backward must match the pass that saved its activations
         self.bucket = None        # parallel.GradBucket: flat fp32 storage the backward sweep writes the parameter gradients into
         self.kernel_timer = None  # bench.py: list collecting (start event, end event, frames) around the dominant kernel (conv11)
@@ -266,6 +267,14 @@ class _Engine:
     # configuration: four co-resident CTAs per SM hide the per-CTA load / epilogue phases (tools/conv_occ.py: 10-25 %).
     SMOOTH_BLK = 16
     SMOOTH_T = 2
+
+    def _bt(self, n: int, oh: int, ow: int, cout: int) -> int:
+        """batch-tile factor for a conv on [n, *, oh, ow] maps: on patch-sized maps (<= 40x40) two images share one CTA, so
+        the packed weights are streamed from L2 once per two tiles (the 128->128 3x3 convs on 80 x 20x20 maps are bound by
+        that stream: 141 MB per launch, tools/conv_timeline.py) and no 8-pixel tile columns are wasted.  0 = off."""
+        if not self.batch_tiles or n < 2 or oh * ow > 40 * 40 or (cout + 31) // 32 * 32 * 2 > 256:
+            return 0
+        return 2
 
     def _T11(self, w: int) -> int:
         t = self._T(3, w)
@@ -436,7 +445,10 @@ class _Engine:
             src = xin if xin is not None else pre
             oh, ow = (2 * src.h, 2 * src.w) if up else (src.h, src.w)
             T = self._T(T_pref, ow)
-            st = ws.stat(name, cout, oh, ow, T, dev)
+            bt = 0 if (up or pre is not None or pair) else self._bt(n, oh, ow, cout)
+            if bt:
+                T, cps = bt, 0
+            st = ws.stat(name, cout, oh, ow, 1 if bt else T, dev)
             cin = (xin.c if xin is not None else 0) + (pre.c if pre is not None else 0)
             frozen = bn_mode and not train_bn      # eval-mode BatchNorm: running statistics, no reduction
             plain_bias = None
@@ -446,7 +458,7 @@ class _Engine:
             ops.conv_fwd(xin, W[name], cout, k, k, pad, pad, dt, blk_c=self._blk(cin), tiles_per_cta=T, out=raw,
                          stats_partial=None if (frozen or no_norm) else st["partial"], upsample2x=up, pre=pre,
                          pre_scale=None if pre is None else pre_st["scale"], pre_shift=None if pre is None else pre_st["shift"],
-                         pre_act=pre_act, ctas_per_sm=0 if pair else cps, bias=plain_bias, cta_pair=pair)
+                         pre_act=pre_act, ctas_per_sm=0 if pair else cps, bias=plain_bias, cta_pair=pair, batch_tiles=bool(bt))
             if no_norm:
                 if not st.get("identity"):
                     st["scale"].fill_(1.0)

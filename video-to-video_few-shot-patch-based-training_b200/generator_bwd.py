@@ -91,9 +91,12 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor, want_input_grad: 
             T -= 1
         if kw.get("cta_pair"):
             T = 1
+        bt = 0 if kw.get("cta_pair") else eng._bt(gin.n, gin.h, gin.w, cout)
+        if bt:
+            T = bt
         # small maps / narrow outputs get the small-footprint configuration (the kernel falls back when it does not fit)
         ops.conv_fwd(gin, W[name + ".d"], cout, k, k, k - 1 - pad, k - 1 - pad, dt, blk_c=eng._blk(gin.c), tiles_per_cta=T,
-                     out=out, ctas_per_sm=0 if kw.get("cta_pair") else 4, concurrent=True, **kw)
+                     out=out, ctas_per_sm=0 if (kw.get("cta_pair") or bt) else 4, concurrent=True, batch_tiles=bool(bt), **kw)
 
     # Weight gradients run on a side stream: a conv's wgrad and dgrad are independent, and on patch-sized maps neither
     # fills the GPU (a 128->128 3x3 wgrad is ~180 CTAs, its dgrad ~480 of 592 slots).  Their parameter gradients are

@@ -112,7 +112,7 @@ def conv_fwd(x: P8, wpack: torch.Tensor, cout: int, kh: int, kw: int, pad_t: int
              blk_c: int = 32, tiles_per_cta: int = 2, bias=None, act: int = ACT_NONE, post_scale=None, post_shift=None,
              mask: P8 | None = None, addend32=None, out32=None, out: P8 | None = None, stats_partial=None,
              head_w=None, head_b=None, head_out=None, head_tanh: bool = True, upsample2x: bool = False, debug_flags: int = 0,
-             debug_buf=None, pre: P8 | None = None, pre_scale=None, pre_shift=None, pre_act: int = ACT_NONE, ctas_per_sm: int = 0, cta_pair: bool = False, concurrent: bool = False) -> None:
+             debug_buf=None, pre: P8 | None = None, pre_scale=None, pre_shift=None, pre_act: int = ACT_NONE, ctas_per_sm: int = 0, cta_pair: bool = False, concurrent: bool = False, batch_tiles: bool = False) -> None:
     """`pre` (raw output of the previous conv) supplies the first channels, normalised + activated on load; `x` (may be
     None then) the remaining ones."""
     d = nv.ConvDesc()
@@ -122,6 +122,7 @@ def conv_fwd(x: P8, wpack: torch.Tensor, cout: int, kh: int, kw: int, pad_t: int
     d.ctas_per_sm = ctas_per_sm
     d.cta_pair = int(cta_pair)
     d.concurrent = int(concurrent)
+    d.batch_tiles = int(batch_tiles)
     d.wpack = wpack.data_ptr()
     d.cout, d.kh, d.kw, d.pad_t, d.pad_l = cout, kh, kw, pad_t, pad_l
     d.blk_c, d.tiles_per_cta, d.dtype = blk_c, tiles_per_cta, dt
