@@ -124,6 +124,10 @@ typedef struct {
                               * x-adjacent tiles of one image: on patch-sized maps (20x20 ... 40x40) the packed weights are then
                               * streamed from L2 once per T images and no tile columns are wasted.  `stats_partial` is indexed
                               * with pbt_conv_num_tiles(h, w, 1) tiles per image.  Excludes upsample2x / pre / cta_pair */
+  int32_t      valid_h, valid_w; /* 0 = whole map; else outputs with y >= valid_h or x >= valid_w are stored as ZERO and left out of
+                              * `stats_partial`: a 4x4 / pad 1 / stride 1 conv of the PatchGAN critic (src/models/discriminator.py:105-133)
+                              * shrinks the map by one pixel; it runs on the fixed grid with (pad_t, pad_l) = (1, 1) and the zero
+                              * border doubles as the next layer's padding */
   int32_t      debug_flags;  /* bring-up only; 0 in production */
   void*        debug_buf;    /* bring-up only: int64[grid][8] per-CTA phase timestamps, NULL in production */
 } pbt_conv_desc_t;
@@ -135,7 +139,9 @@ typedef struct {
   const void* w;        /* source parameter */
   void*       dst;      /* packed 16-bit destination: taps * k_pad * n_out elements */
   int32_t     co, ci, kh, kw;   /* source dims */
-  int32_t     mode;     /* bit 0: space-to-depth, bit 1: dgrad, bit 2: CTA-pair layout [cb][half][tap][k/8][n/2][8] */
+  int32_t     mode;     /* bit 0: space-to-depth, bit 1: dgrad, bit 2: CTA-pair layout [cb][half][tap][k/8][n/2][8],
+                         * bit 3: with bit 0, the source is a 4x4 stride-2 pad-1 kernel (critic): 3x3 stride-1 pad-1 kernel
+                         * over the space-to-depth input, `reserved` = channels per phase of that input (>= ci, 0 = ci) */
   int32_t     k_pad;    /* destination K channels (multiple of 16) */
   int32_t     n_out;    /* destination N rows (multiple of 16) */
   int32_t     n_keep;   /* rows taken from the source, remaining rows are zero */
@@ -338,6 +344,13 @@ int pbt_patch_gather(const float* const* src_ptrs, int32_t n_src, int32_t n_imag
 /* 7x7 box-sum != 0 of a binary mask (dilation), src/data/dataset.py:157-170: out[y][x] = 1 if any
  * mask pixel > 0 in the 7x7 window. mask: uint8 [h][w] (already thresholded 0/255). */
 int pbt_mask_dilate7(const uint8_t* mask, int32_t h, int32_t w, uint8_t* out, void* stream);
+
+/* zero everything outside the valid window [0,valid_h) x [0,valid_w) of a 16-bit P8 tensor (critic maps that shrink by one
+ * pixel per 4x4 stride-1 layer live on a fixed grid; the zero border is the next layer's padding) */
+int pbt_zero_border(const pbt_act_t* t, int32_t valid_h, int32_t valid_w, void* stream);
+/* space-to-depth P8 [n, 4*cpp, h, w] (channel = phase*cpp + c, phase = (y&1)*2 + (x&1)) -> NCHW fp32 [n, c, 2h, 2w], values
+ * multiplied by *mul_dev (device scalar, NULL = 1): the critic's gradient w.r.t. its input patches */
+int pbt_p8s2d_to_nchw_f32(const pbt_act_t* in, int32_t cpp, int32_t c, float* out, const float* mul_dev, int32_t dtype, void* stream);
 
 /* 7x7 erosion of thresholded masks (generator.py:327-351 `_process_mask`, :627-631): out[i][y][x] = 1.0f where all 49
  * pixels of the zero-padded 7x7 window are set, else 0.0f.  mask: uint8 [n][h][w] (0 / non-zero), out: float [n][h][w]. */

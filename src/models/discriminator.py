@@ -5,10 +5,11 @@ Same constructor, same ``state_dict`` keys and shapes (``initial.0.*``, ``interm
 ``output.0.*``), same ``forward(x) -> (logits, None)``, same N(0, 0.02) / zero-bias initialisation in the same module
 registration order, so a torch seed reproduces the reference init and reference checkpoints load with strict=True.
 
-Why this module stays on the tensor library instead of the tcgen05 implicit-GEMM kernels:
-with the shipped configuration (num_filters 12, n_layers 2) the critic has 3->12->24->48->1 channels, i.e. 31 MFLOP per
-80x80 patch against 13.5 GFLOP for the generator (0.2 %), and no layer reaches the 16-channel granularity of a UMMA
-tile.  Its two Adam steps do run on the native fused optimiser (pbt_b200.optim.FusedClipAdam).
+On a CUDA device the arithmetic runs on the library's own kernels (pbt_b200/critic.py: the generator's tcgen05 implicit-GEMM
+conv, wgrad and norm kernels over zero-padded channels; 4x4 stride-2 stages as 3x3 convs over a space-to-depth copy) - the
+nn.Conv2d / norm sub-modules are parameter containers there.  The tensor-library expression below is what runs for CPU
+tensors (host-side tests, the gloo data-parallel tests) and for configurations the native path does not cover
+(`norm_layer` other than instance_norm, layers wider than 256 channels); `native = False` forces it.
 """
 from typing import Any, Dict, Optional, Tuple
 
@@ -30,6 +31,9 @@ def _stage(cin: int, cout: int, stride: int, bias: bool, norm, leaky: bool) -> n
 
 
 class DiscriminatorN_IN(nn.Module):
+    #: run CUDA inputs through the native engine (pbt_b200/critic.py) when the configuration is supported
+    native = True
+
     def __init__(self, input_channels: int = 3, additional_channels: Optional[Dict[str, Any]] = None, num_filters: int = 64,
                  n_layers: int = 3, use_noise: bool = False, noise_sigma: float = 0.2, norm_layer: str = "instance_norm",
                  use_bias: bool = True):
@@ -49,6 +53,8 @@ class DiscriminatorN_IN(nn.Module):
         nxt = min(2 * width, cap)
         self.pre_output = _stage(width, nxt, 1, use_bias, norm, True)
         self.output = _stage(nxt, 1, 1, use_bias, None, False)
+        self._engine = None
+        self._native_reason = None
         for m in self.modules():
             if isinstance(m, nn.Conv2d):
                 nn.init.normal_(m.weight.data, 0.0, 0.02)
@@ -58,6 +64,14 @@ class DiscriminatorN_IN(nn.Module):
     def forward(self, x: Tensor) -> Tuple[Tensor, None]:
         if self.use_noise and self.training:
             x = x + torch.randn_like(x) * self.noise_sigma
+        if x.is_cuda and self.native and self._native_reason is None:
+            from pbt_b200 import critic
+            if self._engine is None:
+                self._native_reason = critic.supported(self)
+                if self._native_reason is None:
+                    self._engine = critic.CriticEngine(self)
+            if self._engine is not None:
+                return critic.critic_forward(self, self._engine, x), None
         h = self.initial(x)
         for stage in self.intermediate:
             h = stage(h)

@@ -166,3 +166,65 @@ def test_nccl_data_parallel_parity_under_torchrun():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, cwd=ROOT)
     print(r.stdout[-3000:], r.stderr[-3000:])
     assert r.returncode == 0 and "DIST_GPU_CHECK_OK" in r.stdout
+
+
+@pytest.mark.parametrize("cfg", [dict(num_filters=12, n_layers=2, n=6, hw=80), dict(num_filters=12, n_layers=2, n=160, hw=80),
+                                 dict(num_filters=8, n_layers=3, n=5, hw=64, use_bias=False), dict(num_filters=16, n_layers=1, n=3, hw=40)],
+                         ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
+def test_native_critic_matches_the_tensor_library_expression(cfg):
+    """DiscriminatorN_IN on the native kernels (pbt_b200/critic.py) against the same module through torch fp32 ops (the
+    reference's expression, src/models/discriminator.py:105-149): logits, parameter gradients of the critic loss, and the
+    gradient w.r.t. the input patches of the generator's adversarial loss (lightning_model.py:277-283,294-319)"""
+    from src.models.discriminator import DiscriminatorN_IN
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = dict(cfg)
+    n, hw = cfg.pop("n"), cfg.pop("hw")
+    torch.manual_seed(3)
+    d = DiscriminatorN_IN(input_channels=3, **cfg).cuda().train()
+    with torch.no_grad():                       # away from the N(0, 0.02) init: trained-like magnitudes
+        for p in d.parameters():
+            p.mul_(3.0).add_(torch.randn_like(p) * 0.01)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.rand((n, 3, hw, hw), generator=g, device="cuda") * 2 - 1
+    x[: n // 2] = torch.nn.functional.avg_pool2d(x[: n // 2], 5, 1, 2)         # smooth "real" half, noisy "fake" half
+    lab = torch.cat([torch.ones(n // 2), torch.zeros(n - n // 2)]).cuda().view(n, 1, 1, 1)
+
+    def run(native, with_input):
+        d.native = native
+        d.zero_grad(set_to_none=True)
+        xi = x.clone().requires_grad_(with_input)
+        if with_input:
+            for p in d.parameters():
+                p.requires_grad_(False)
+        try:
+            logits, _ = d(xi)
+            loss = torch.nn.functional.mse_loss(logits, lab.expand_as(logits))
+            loss.backward()
+        finally:
+            for p in d.parameters():
+                p.requires_grad_(True)
+        return logits.detach(), float(loss), [None if p.grad is None else p.grad.detach().clone() for p in d.parameters()], xi.grad
+
+    ref_l, ref_loss, ref_g, _ = run(False, False)
+    nat_l, nat_loss, nat_g, _ = run(True, False)
+    assert d._engine is not None, d._native_reason
+    assert nat_l.shape == ref_l.shape
+    err = float((nat_l - ref_l).abs().max())
+    assert err <= 2e-2 * max(1.0, float(ref_l.abs().max())) and abs(nat_loss - ref_loss) <= 1e-2 * abs(ref_loss), (err, nat_loss, ref_loss)
+    for (name, _), a, b in zip(d.named_parameters(), nat_g, ref_g):
+        peak = float(b.abs().max())
+        if peak < 1e-10:                                   # biases in front of an InstanceNorm
+            assert float(a.abs().max()) <= 1e-6, name
+            continue
+        cos = float(torch.nn.functional.cosine_similarity(a.flatten(), b.flatten(), dim=0))
+        rel = float((a - b).norm() / b.norm())
+        assert cos > 0.999 and rel < 3e-2, (name, cos, rel)
+    _, _, _, gx_ref = run(False, True)
+    _, _, pg, gx_nat = run(True, True)
+    assert all(v is None for v in pg)                      # frozen critic: no parameter gradients are produced
+    cos = float(torch.nn.functional.cosine_similarity(gx_nat.flatten(), gx_ref.flatten(), dim=0))
+    rel = float((gx_nat - gx_ref).norm() / gx_ref.norm())
+    print(f"{cfg} n={n}: logits err {err:.2e}, loss {nat_loss:.6f}/{ref_loss:.6f}, dL/dx cosine {cos:.5f} rel {rel:.4f}")
+    assert cos > 0.999 and rel < 3e-2, (cos, rel)
+    d.native = True

@@ -40,7 +40,7 @@ class ConvDesc(C.Structure):
         ("mask", Act), ("addend32", C.c_void_p), ("out32", C.c_void_p), ("out", Act),
         ("stats_partial", C.c_void_p), ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("head_out", C.c_void_p),
         ("head_tanh", C.c_int32), ("upsample2x", C.c_int32), ("pre", Act), ("pre_scale", C.c_void_p), ("pre_shift", C.c_void_p),
-        ("pre_act", C.c_int32), ("ctas_per_sm", C.c_int32), ("cta_pair", C.c_int32), ("concurrent", C.c_int32), ("batch_tiles", C.c_int32), ("debug_flags", C.c_int32), ("debug_buf", C.c_void_p),
+        ("pre_act", C.c_int32), ("ctas_per_sm", C.c_int32), ("cta_pair", C.c_int32), ("concurrent", C.c_int32), ("batch_tiles", C.c_int32), ("valid_h", C.c_int32), ("valid_w", C.c_int32), ("debug_flags", C.c_int32), ("debug_buf", C.c_void_p),
     ]
 
 
@@ -128,6 +128,8 @@ def lib() -> C.CDLL:
         "pbt_patch_gather": (C.c_int, [vp, i32, i32, i32, vp, vp, i32, i32, vp, vp, vp, vp]),
         "pbt_mask_dilate7": (C.c_int, [vp, i32, i32, vp, vp]),
         "pbt_mask_erode7": (C.c_int, [vp, i32, i32, i32, vp, vp]),
+        "pbt_zero_border": (C.c_int, [C.POINTER(Act), i32, i32, vp]),
+        "pbt_p8s2d_to_nchw_f32": (C.c_int, [C.POINTER(Act), i32, i32, vp, vp, i32, vp]),
         "pbt_composite_to_u8": (C.c_int, [vp, vp, i32, vp, i32, i32, i32, vp, vp]),
         "pbt_absmax_f32": (C.c_int, [vp, i64, vp, vp]),
         "pbt_make_grad_scale": (C.c_int, [vp, f32, vp, vp, vp]),
@@ -151,7 +153,7 @@ EXPORTED_SYMBOLS = [
     "pbt_conv_wgrad", "pbt_norm_finalize", "pbt_norm_apply", "pbt_upsample2x", "pbt_upsample2x_bwd",
     "pbt_norm_bwd_reduce", "pbt_norm_bwd_apply", "pbt_norm_bwd_fused", "pbt_clip_adam_step", "pbt_l1_loss_fwd_bwd", "pbt_tile_gather", "pbt_tile_blend", "pbt_tile_finish", "pbt_head_bwd", "pbt_channel_sum", "pbt_nchw_to_p8",
     "pbt_p8_to_nchw_f32", "pbt_p8f_to_nchw_f32", "pbt_u8hwc_to_p8", "pbt_nchw_to_u8hwc", "pbt_u8hwc_to_norm_chw",
-    "pbt_patch_gather", "pbt_mask_dilate7", "pbt_mask_erode7", "pbt_composite_to_u8", "pbt_absmax_f32", "pbt_make_grad_scale", "pbt_grad_scale_feedback", "pbt_ostree_reset",
+    "pbt_patch_gather", "pbt_mask_dilate7", "pbt_mask_erode7", "pbt_composite_to_u8", "pbt_zero_border", "pbt_p8s2d_to_nchw_f32", "pbt_absmax_f32", "pbt_make_grad_scale", "pbt_grad_scale_feedback", "pbt_ostree_reset",
     "pbt_ostree_take", "pbt_pack_weights",
 ]
 

@@ -67,6 +67,7 @@ struct ConvKParams {
   const float* pre_scale;
   const float* pre_shift;
   uint32_t l_stage_bytes;
+  int VH, VW;            // valid output window (<= H, W): outputs outside it are stored as zero and left out of the statistics
   int bt;                // batch tiles: the T tiles of a CTA are the SAME spatial tile of T consecutive images (small maps)
   uint32_t a_tile16;     // A-descriptor step from tile t to t+1 in 16-byte units: 8 pixels (x-adjacent) or one staged tile (bt)
   uint32_t a_tile_bytes; // bt: shared-memory pitch of the T per-image tiles inside an A stage
@@ -630,10 +631,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     // Feature bits live in a register: testing `p.<field>` inside the column loop costs one dependent constant-bank load
     // + uniform branch per feature per iteration (measured ~1000 cycles per 16-column chunk, 360 without them).
     enum : uint32_t { kFBias = 1, kFRelu = 2, kFLeaky = 4, kFAffine = 8, kFMask = 16, kFAddend = 32, kFOut32 = 64,
-                      kFOut16 = 128, kFHead = 256, kFStats = 512, kFGeneric = 0x80000000u };
+                      kFOut16 = 128, kFHead = 256, kFStats = 512, kFWindow = 1024, kFGeneric = 0x80000000u };
     uint32_t feat = (p.bias ? kFBias : 0u) | (p.act == PBT_ACT_RELU ? kFRelu : 0u) | (p.act == PBT_ACT_LEAKY02 ? kFLeaky : 0u) |
                     (p.post_scale ? kFAffine : 0u) | (p.mask ? kFMask : 0u) | (p.addend32 ? kFAddend : 0u) |
-                    (p.out32 ? kFOut32 : 0u) | (p.out ? kFOut16 : 0u) | (p.head_w ? kFHead : 0u) | (do_stats ? kFStats : 0u);
+                    (p.out32 ? kFOut32 : 0u) | (p.out ? kFOut16 : 0u) | (p.head_w ? kFHead : 0u) | (do_stats ? kFStats : 0u) |
+                    ((p.VH < p.H || p.VW < p.W) ? kFWindow : 0u);
     asm volatile("" : "+r"(feat));  // keep it a register value, not re-derived constant loads
     // The column loop is instantiated once per common feature set (compile-time mask) plus a generic copy (run-time
     // mask): the fully generic body is ~13 KB of mostly skipped code and ran at ~1000 cycles per 16-column chunk
@@ -670,6 +672,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         if (fm & kFAffine) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], __ldg(&p.post_scale[c0 + i]), __ldg(&p.post_shift[c0 + i]));
+        }
+        if (fm & kFWindow) {   // (generic variant only) outputs outside the valid window are zero for every consumer
+          if (!(y < p.VH && x < p.VW)) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = 0.f;
+          }
         }
         if (valid) {
           if (fm & kFMask) {
@@ -996,6 +1004,9 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
     p.out = static_cast<uint8_t*>(d->out.ptr);
     p.out_img_stride = d->out.img_stride;
   }
+  PBT_REQUIRE(d->valid_h >= 0 && d->valid_h <= p.H && d->valid_w >= 0 && d->valid_w <= p.W, "conv: valid window exceeds the map");
+  p.VH = d->valid_h ? d->valid_h : p.H;
+  p.VW = d->valid_w ? d->valid_w : p.W;
   p.stats_partial = d->stats_partial;
   p.head_w = d->head_w; p.head_b = d->head_b; p.head_out = d->head_out; p.head_tanh = d->head_tanh;
   PBT_REQUIRE(!d->head_w || (d->head_b && d->head_out), "conv: head needs head_b and head_out");

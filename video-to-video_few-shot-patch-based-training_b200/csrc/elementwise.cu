@@ -233,6 +233,36 @@ __global__ void composite_to_u8_kernel(const float* __restrict__ y, const uint8_
   }
 }
 
+// zero the 16-byte pixel chunks outside [0,vh) x [0,vw) of every (image, plane)
+__global__ void zero_border_kernel(ActView t, int vh, int vw) {
+  pdl_sync();
+  const int hw = t.h * t.w;
+  const int pl = blockIdx.y, ni = blockIdx.z;
+  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < hw; pix += gridDim.x * blockDim.x) {
+    const int y = pix / t.w, x = pix - y * t.w;
+    if (y >= vh || x >= vw) *chunk_ptr(t, ni, pl, pix) = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+// space-to-depth P8 -> NCHW fp32: out[n][ch][2y+py][2x+px] = in[n][(py*2+px)*cpp + ch][y][x] * mul
+template <int DT>
+__global__ void p8s2d_to_nchw_kernel(ActView in, int cpp, int c, float* __restrict__ out, const float* __restrict__ mul_dev) {
+  pdl_sync();
+  const float mul = mul_dev ? __ldg(mul_dev) : 1.f;
+  const int oh = 2 * in.h, ow = 2 * in.w;
+  const long long total = (long long)in.n * c * oh * ow;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int X = (int)(i % ow);
+    const int Y = (int)((i / ow) % oh);
+    const int ch = (int)((i / ((long long)ow * oh)) % c);
+    const int ni = (int)(i / ((long long)ow * oh * c));
+    const int sc = ((Y & 1) * 2 + (X & 1)) * cpp + ch;
+    float f[8];
+    unpack8<DT>(*chunk_ptr(in, ni, sc >> 3, (long long)(Y >> 1) * in.w + (X >> 1)), f);
+    out[i] = f[sc & 7] * mul;
+  }
+}
+
 // ------------------------------------------------------------------ norm finalize
 // Stage 1 of the deterministic statistics reduction (large images have thousands of tiles): block
 // (32-channel group, chunk, image) sums the tiles of its chunk in a fixed order (double accumulation) and
@@ -1192,6 +1222,25 @@ extern "C" int pbt_mask_dilate7(const uint8_t* mask, int32_t h, int32_t w, uint8
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   PBT_REQUIRE(mask && out && h > 0 && w > 0, "mask_dilate7: bad tensors");
   pbt::launch(mask_dilate7_kernel, ew_grid((long long)h * w), kEwThreads, 0, st, mask, h, w, out);
+  PBT_CUDA_CHECK(cudaGetLastError());
+  return PBT_OK;
+}
+
+extern "C" int pbt_zero_border(const pbt_act_t* t, int32_t valid_h, int32_t valid_w, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  PBT_REQUIRE(t && act_ok(*t) && valid_h >= 0 && valid_h <= t->h && valid_w >= 0 && valid_w <= t->w, "zero_border: bad arguments");
+  if (valid_h == t->h && valid_w == t->w) return PBT_OK;
+  pbt::launch(zero_border_kernel, ew_grid3(t->h * t->w, t->c / 8, t->n), kEwThreads, 0, st, view(*t), valid_h, valid_w);
+  PBT_CUDA_CHECK(cudaGetLastError());
+  return PBT_OK;
+}
+
+extern "C" int pbt_p8s2d_to_nchw_f32(const pbt_act_t* in, int32_t cpp, int32_t c, float* out, const float* mul_dev, int32_t dtype,
+                                     void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  PBT_REQUIRE(in && act_ok(*in) && out && cpp > 0 && c > 0 && c <= cpp && 4 * cpp <= in->c, "p8s2d_to_nchw: bad arguments");
+  const long long items = (long long)in->n * c * 4 * in->h * in->w;
+  DISPATCH_DT(dtype, pbt::launch(p8s2d_to_nchw_kernel<DT>, ew_grid(items), kEwThreads, 0, st, view(*in), cpp, c, out, mul_dev));
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
 }

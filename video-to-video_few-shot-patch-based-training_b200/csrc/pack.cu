@@ -19,6 +19,19 @@ __device__ __forceinline__ float load_src(const pbt_pack_job_t& j, int o, int i,
 // forward kernel V[o][i][ty][tx] (plain or space-to-depth view of the source)
 __device__ __forceinline__ float virt(const pbt_pack_job_t& j, int o, int i, int ty, int tx) {
   if (!(j.mode & 1)) return load_src(j, o, i, ty, tx);
+  if (j.mode & 8) {
+    // 4x4 stride-2 pad-1 kernel (critic, reference src/models/discriminator.py:44-76) as a 3x3 stride-1 pad-1 kernel over
+    // the space-to-depth input with `cpp` channels per phase: output row r reads input rows 2r-1..2r+2 = block r-1 phase 1
+    // (ky 0), block r phases 0/1 (ky 1/2), block r+1 phase 0 (ky 3)
+    const int cpp = j.reserved ? j.reserved : j.ci;
+    const int ph = i / cpp, c = i - ph * cpp;
+    if (ph >= 4 || c >= j.ci) return 0.f;
+    const int py = ph >> 1, px = ph & 1;
+    const int ky = ty == 0 ? (py == 1 ? 0 : -1) : (ty == 1 ? 1 + py : (py == 0 ? 3 : -1));
+    const int kx = tx == 0 ? (px == 1 ? 0 : -1) : (tx == 1 ? 1 + px : (px == 0 ? 3 : -1));
+    if (ky < 0 || kx < 0) return 0.f;
+    return load_src(j, o, c, ky, kx);
+  }
   const int ph = i / j.ci, c = i - ph * j.ci;
   const int py = ph >> 1, px = ph & 1;
   // (s2d tap, phase) -> original 3x3 tap: (0,1)->0, (1,0)->1, (1,1)->2, (0,0)-> no contribution
@@ -32,8 +45,9 @@ __global__ void pack_weights_kernel(const pbt_pack_job_t* __restrict__ jobs) {
   pdl_sync();
   const pbt_pack_job_t j = jobs[blockIdx.y];
   const bool s2d = j.mode & 1, dgrad = j.mode & 2;
-  const int vkh = s2d ? 2 : j.kh, vkw = s2d ? 2 : j.kw;
-  const int vo = j.co, vi = s2d ? 4 * j.ci : j.ci;
+  const bool s2d4 = s2d && (j.mode & 8);
+  const int vkh = s2d ? (s2d4 ? 3 : 2) : j.kh, vkw = s2d ? (s2d4 ? 3 : 2) : j.kw;
+  const int vo = j.co, vi = s2d ? 4 * (s2d4 && j.reserved ? j.reserved : j.ci) : j.ci;
   const int po = dgrad ? vi : vo, pi = dgrad ? vo : vi;  // packed conv: N = po rows, K = pi channels
   const int taps = vkh * vkw;
   const int n_lim = min(j.n_keep, po);

@@ -16,7 +16,7 @@ __all__ = [
     "pack_conv_weight", "s2d_weight", "s2d_weight_grad", "dgrad_weight", "conv_fwd", "conv_wgrad", "conv_num_tiles",
     "norm_finalize", "norm_apply", "upsample2x", "upsample2x_bwd", "norm_bwd", "head_bwd", "channel_sum", "nchw_to_p8",
     "p8_to_nchw", "p8f_to_nchw", "u8hwc_to_p8", "nchw_to_u8hwc", "u8hwc_to_norm_chw", "patch_gather", "mask_dilate7",
-    "mask_erode7", "composite_to_u8",
+    "mask_erode7", "composite_to_u8", "zero_border", "p8s2d_to_nchw",
     "absmax", "make_grad_scale", "grad_scale_feedback",
 ]
 
@@ -82,13 +82,15 @@ class WeightPacker:
         self._max = 0
 
     def add(self, name: str, param: torch.Tensor, *, s2d=False, dgrad=False, k_pad: int, n_out: int, n_keep: int, blk_c: int,
-            dt: int, pair: bool = False) -> torch.Tensor:
+            dt: int, pair: bool = False, s2d4_cpp: int = 0) -> torch.Tensor:
+        """s2d4_cpp > 0 (with s2d): the source is a 4x4 stride-2 pad-1 kernel, packed as the 3x3 stride-1 kernel over the
+        space-to-depth input that has s2d4_cpp channels per phase"""
         co, ci, kh, kw = param.shape
-        taps = 4 if s2d else kh * kw
+        taps = (9 if s2d4_cpp else 4) if s2d else kh * kw
         dst = torch.empty(taps * k_pad * n_out, dtype=nv.torch_dtype(dt), device=self.device)
         assert param.is_contiguous() and param.dtype in (torch.float32, torch.float16)
-        self.jobs.append(nv.PackJob(param.data_ptr(), dst.data_ptr(), co, ci, kh, kw, int(s2d) | (int(dgrad) << 1) | (int(pair) << 2), k_pad, n_out,
-                                    n_keep, blk_c, dt, int(param.dtype == torch.float16), 0))
+        self.jobs.append(nv.PackJob(param.data_ptr(), dst.data_ptr(), co, ci, kh, kw, int(s2d) | (int(dgrad) << 1) | (int(pair) << 2) | (8 if s2d4_cpp else 0),
+                                    k_pad, n_out, n_keep, blk_c, dt, int(param.dtype == torch.float16), int(s2d4_cpp)))
         self._src = getattr(self, "_src", []) + [param]   # keep the parameters alive / pointers stable
         self.out[name] = dst
         self._max = max(self._max, dst.numel())
@@ -112,7 +114,8 @@ def conv_fwd(x: P8, wpack: torch.Tensor, cout: int, kh: int, kw: int, pad_t: int
              blk_c: int = 32, tiles_per_cta: int = 2, bias=None, act: int = ACT_NONE, post_scale=None, post_shift=None,
              mask: P8 | None = None, addend32=None, out32=None, out: P8 | None = None, stats_partial=None,
              head_w=None, head_b=None, head_out=None, head_tanh: bool = True, upsample2x: bool = False, debug_flags: int = 0,
-             debug_buf=None, pre: P8 | None = None, pre_scale=None, pre_shift=None, pre_act: int = ACT_NONE, ctas_per_sm: int = 0, cta_pair: bool = False, concurrent: bool = False, batch_tiles: bool = False) -> None:
+             debug_buf=None, pre: P8 | None = None, pre_scale=None, pre_shift=None, pre_act: int = ACT_NONE, ctas_per_sm: int = 0, cta_pair: bool = False, concurrent: bool = False, batch_tiles: bool = False,
+             valid_hw=None) -> None:
     """`pre` (raw output of the previous conv) supplies the first channels, normalised + activated on load; `x` (may be
     None then) the remaining ones."""
     d = nv.ConvDesc()
@@ -123,6 +126,7 @@ def conv_fwd(x: P8, wpack: torch.Tensor, cout: int, kh: int, kw: int, pad_t: int
     d.cta_pair = int(cta_pair)
     d.concurrent = int(concurrent)
     d.batch_tiles = int(batch_tiles)
+    d.valid_h, d.valid_w = (0, 0) if valid_hw is None else (int(valid_hw[0]), int(valid_hw[1]))
     d.wpack = wpack.data_ptr()
     d.cout, d.kh, d.kw, d.pad_t, d.pad_l = cout, kh, kw, pad_t, pad_l
     d.blk_c, d.tiles_per_cta, d.dtype = blk_c, tiles_per_cta, dt
@@ -250,6 +254,18 @@ def u8hwc_to_norm_chw(img: torch.Tensor, out: torch.Tensor) -> None:
 def mask_dilate7(mask: torch.Tensor, out: torch.Tensor) -> None:
     h, w = mask.shape
     check(lib().pbt_mask_dilate7(mask.data_ptr(), h, w, out.data_ptr(), stream_ptr()), "pbt_mask_dilate7")
+
+
+def zero_border(t: P8, valid_h: int, valid_w: int) -> None:
+    """zero the pixels outside [0,valid_h) x [0,valid_w) of every plane (critic maps on a fixed grid)"""
+    a = t.act()
+    check(lib().pbt_zero_border(C.byref(a), valid_h, valid_w, stream_ptr()), "pbt_zero_border")
+
+
+def p8s2d_to_nchw(x: P8, cpp: int, c: int, out: torch.Tensor, dt: int, mul=None) -> None:
+    """space-to-depth P8 [n,4*cpp,h,w] -> NCHW fp32 [n,c,2h,2w] (times the device scalar `mul`)"""
+    a = x.act()
+    check(lib().pbt_p8s2d_to_nchw_f32(C.byref(a), cpp, c, out.data_ptr(), ptr(mul), dt, stream_ptr()), "pbt_p8s2d_to_nchw_f32")
 
 
 def mask_erode7(mask_u8: torch.Tensor, out: torch.Tensor) -> None:
