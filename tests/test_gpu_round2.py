@@ -213,9 +213,10 @@ def test_native_critic_matches_the_tensor_library_expression(cfg):
     err = float((nat_l - ref_l).abs().max())
     assert err <= 2e-2 * max(1.0, float(ref_l.abs().max())) and abs(nat_loss - ref_loss) <= 1e-2 * abs(ref_loss), (err, nat_loss, ref_loss)
     for (name, _), a, b in zip(d.named_parameters(), nat_g, ref_g):
-        peak = float(b.abs().max())
-        if peak < 1e-10:                                   # biases in front of an InstanceNorm
-            assert float(a.abs().max()) <= 1e-6, name
+        if name.endswith(".bias") and name.startswith(("intermediate.", "pre_output.")):
+            # a bias in front of an InstanceNorm has a mathematically zero gradient: exact zeros here, round-off noise there
+            wpeak = float(ref_g[[k for k, _ in d.named_parameters()].index(name.replace(".bias", ".weight"))].abs().max())
+            assert float(a.abs().max()) == 0.0 and float(b.abs().max()) <= 1e-3 * wpeak, name
             continue
         cos = float(torch.nn.functional.cosine_similarity(a.flatten(), b.flatten(), dim=0))
         rel = float((a - b).norm() / b.norm())

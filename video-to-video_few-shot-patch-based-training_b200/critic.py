@@ -103,7 +103,9 @@ class CriticEngine:
             bias = {s.name: torch.zeros(s.cout_p, device=self.device) for s in self.stages if s.bname and not s.norm}
             self._packer = {"pk": pk, "ptrs": tuple(p.data_ptr() for p in params), "bias": bias}
             self._pack_key = None
-        if self._pack_key != key:
+        # while a CUDA graph is being captured the packing is always recorded: a replayed graph must see the parameters as
+        # they are at replay time (warm-up roll-back, load_state_dict between replays), not a host-side cache decision
+        if self._pack_key != key or torch.cuda.is_current_stream_capturing():
             self._packer["pk"].run()
             for s in self.stages:        # biases in front of an InstanceNorm cancel; the others go into the conv epilogue
                 if s.name in self._packer["bias"]:
@@ -351,15 +353,21 @@ class CriticEngine:
 
 
 _KY = ((0, 1), (1, 0), (1, 1), (2, 0))     # original 4x4 tap ky -> (3x3 tap over space-to-depth, phase)
+_S2D4_IDX: Dict[Any, Any] = {}
 
 
 def _s2d4_wgrad_to_param(dw: Tensor, dst: Tensor, cpp: int) -> None:
-    """wgrad of a 4x4 stride-2 stage run as 3x3 conv over the space-to-depth input: [9, 4*cpp, cout_p] -> [cout, cin, 4, 4]"""
+    """wgrad of a 4x4 stride-2 stage run as 3x3 conv over the space-to-depth input: [9, 4*cpp, cout_p] -> [cout, cin, 4, 4]
+    (one gather + one strided copy)"""
     cout, cin = dst.shape[0], dst.shape[1]
+    idx = _S2D4_IDX.get(dw.device)
+    if idx is None:
+        t = torch.tensor([a for a, _ in _KY], device=dw.device)
+        ph = torch.tensor([b for _, b in _KY], device=dw.device)
+        idx = _S2D4_IDX[dw.device] = (t[:, None], t[None, :], ph[:, None], ph[None, :])
     d6 = dw.view(3, 3, 2, 2, cpp, dw.shape[2])              # (ty, tx, py, px, c, co)
-    for ky, (ty, py) in enumerate(_KY):
-        for kx, (tx, px) in enumerate(_KY):
-            dst[:, :, ky, kx].copy_(d6[ty, tx, py, px, :cin, :cout].t())
+    g = d6[idx[0], idx[1], idx[2], idx[3]]                  # (ky, kx, c, co)
+    dst.copy_(g[:, :, :cin, :cout].permute(3, 2, 0, 1))
 
 
 class _CriticFn(torch.autograd.Function):

@@ -352,7 +352,9 @@ class _Engine:
         if slot is None or slot["ptrs"] != tuple(p.data_ptr() for p in g.parameters()):
             slot = self._build_packer(with_dgrad)
             self._wslots[slot_key] = slot
-        if slot["key"] != key:
+        # (under CUDA-graph capture the packing is always recorded: a replayed graph must follow the parameters as they are
+        # at replay time, not a host-side cache decision taken at capture time)
+        if slot["key"] != key or torch.cuda.is_current_stream_capturing():
             slot["packer"].run()
             slot["key"] = key
         return slot["W"]
@@ -445,7 +447,9 @@ class _Engine:
             src = xin if xin is not None else pre
             oh, ow = (2 * src.h, 2 * src.w) if up else (src.h, src.w)
             T = self._T(T_pref, ow)
-            bt = 0 if (up or pre is not None or pair) else self._bt(n, oh, ow, cout)
+            # (training passes only: inference keeps a frame's result bit-independent of the frames that share its pass -
+            # batch tiles change the tile geometry of the statistics partial sums)
+            bt = 0 if (up or pre is not None or pair or not save) else self._bt(n, oh, ow, cout)
             if bt:
                 T, cps = bt, 0
             st = ws.stat(name, cout, oh, ow, 1 if bt else T, dev)
