@@ -357,7 +357,7 @@ def run_native(args):
         "roofline": {"bound": "tensor", "kernel": f"conv_igemm_kernel (conv11 7x7, {160 + CIN}->64, CTA-pair configuration, norm+ReLU of up1 on load)",
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
                      "frac_of_burst_peak": achieved / peaks["bf16_tflops"] if peaks.get("bf16_tflops") else None,
-                     "traffic": traffic, "traffic_algorithmic": int(per_pass * H * W * 2 * (128 + 32 + 16 + 64)),
+                     "traffic": traffic, "traffic_algorithmic": int(per_pass * H * W * 2 * (128 + 32 + CIN + 64)),   # 16-bit reads of the 160+Cin real input channels + the 64-channel store
                      "traffic_source": "profiles/conv11_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one launch)" if traffic else None,
                      "peak_source": f"{peak_src} bf16_tflops_sustained (the kernel is timed inside a {ms_total / 1e3:.1f}-s step loop)",
                      "launch_ms": k_ms, "launches_timed": len(full), "frames_per_launch": per_pass},
