@@ -67,6 +67,7 @@ struct ConvKParams {
   const float* pre_scale;
   const float* pre_shift;
   uint32_t l_stage_bytes;
+  int ws_b;              // issue the T MMAs of a (tap, K step) as one weight-stationary run (B fetched once)
   int VH, VW;            // valid output window (<= H, W): outputs outside it are stored as zero and left out of the statistics
   int bt;                // batch tiles: the T tiles of a CTA are the SAME spatial tile of T consecutive images (small maps)
   uint32_t a_tile16;     // A-descriptor step from tile t to t+1 in 16-byte units: 8 pixels (x-adjacent) or one staged tile (bt)
@@ -352,6 +353,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       const uint32_t b_kstep = (2u * b_kstride) >> 4;
       const uint32_t acc_stride = (uint32_t)p.acc_stride;
       const uint32_t a_tstep = p.a_tile16;
+      const bool ws_b = p.ws_b != 0;
       const uint32_t idesc = p.idesc;
       int bi = 0, cbt = 0, it = 0;
       for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x, cbt += p.n_blk, ++it) {
@@ -396,7 +398,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
                         umma_f16_pair(tmem_base + (uint32_t)t * acc_stride,
                                       desc64(a_tap + (uint32_t)t * a_tstep + (uint32_t)k * a_kstep, a_hi),
                                       desc64(b_lo + (uint32_t)k * b_kstep, b_hi), idesc, (k == 0) ? first : 1u);
-                      else
+                      else if (T > 1 && NI == 1 && ws_b) {
+                        // weight-stationary run over the T tiles: B is fetched from shared memory once per (tap, K step)
+                        const uint32_t dt_ = tmem_base + (uint32_t)t * acc_stride;
+                        const uint64_t ad = desc64(a_tap + (uint32_t)t * a_tstep + (uint32_t)k * a_kstep, a_hi);
+                        const uint64_t bd = desc64(b_lo + (uint32_t)k * b_kstep, b_hi);
+                        const uint32_t en = (k == 0) ? first : 1u;
+                        if (t == 0) umma_f16_ws<0>(dt_, ad, bd, idesc, en);
+                        else if (t == T - 1) umma_f16_ws<2>(dt_, ad, bd, idesc, en);
+                        else umma_f16_ws<1>(dt_, ad, bd, idesc, en);
+                      } else
                         umma_f16(tmem_base + (uint32_t)t * acc_stride,
                                  desc64(a_tap + (uint32_t)t * a_tstep + (uint32_t)k * a_kstep, a_hi),
                                  desc64(b_lo + (uint32_t)k * b_kstep, b_hi), idesc, (k == 0) ? first : 1u);
@@ -1078,6 +1089,13 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
   // hardware's dynamic block scheduling.
   static const int persist_min = getenv("PBT_PERSIST_MIN") ? atoi(getenv("PBT_PERSIST_MIN")) : 3;  // (tuning knob)
   if (!(d->debug_flags & 128) && !d->concurrent && grid >= persist_min * occ * num_sms()) grid = occ * num_sms();  // (bring-up: bit 7 = one unit per CTA)
+  // Weight-stationary MMA runs (tcgen05.mma.ws, B kept in a collector buffer across the T tiles of a (tap, K step)): measured
+  // on B200 (tools/ws_experiment.py, bit-identical results) +5 % on the N = 64 small-footprint layers (smoothers: 941 -> 893 us
+  // per 4 x 1080p frames; their MMA streams are bound by the shared-memory operand fetch, A 4 KB + B 2 KB per MMA), neutral to
+  // -3 % on N = 128 and on the 7x7 layers, so it is on exactly there.  Debug bit 5 forces it on (N in {64, 128, 256}), bit 6 off.
+  p.ws_b = (!pair && T > 1 && ((p.NC == 64 && ew == 4 && ntaps <= 9) ||
+                               ((d->debug_flags & 32) && (p.NC == 64 || p.NC == 128 || p.NC == 256)))) ? 1 : 0;
+  if (d->debug_flags & 64) p.ws_b = 0;
   const int kb = d->blk_c / 16;
   if (pair) {
     PBT_REQUIRE((ew == 4) == (d->ctas_per_sm == 4), "conv: cta_pair + ctas_per_sm=4 shape does not fit the small footprint");
