@@ -241,6 +241,15 @@ def run_native(args):
             return float(t.item())
         return ms
 
+    def all_ranks(ms):
+        """every rank's device time (the slowest one is what counts; the spread shows GPU-to-GPU variation)"""
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            every = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(every, t)
+            return [float(e.item()) for e in every]
+        return [ms]
+
     gen = native_generator(cfg, dev, operand)
     sty = FrameStylizer(gen)
     if os.environ.get("PBT_FRAMES_PER_PASS"):   # experiment knob; the default is the library's
@@ -285,7 +294,8 @@ def run_native(args):
     e1.record()
     barrier()
     launches = _native.LAUNCHES[0] - l0
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    rank_ms = all_ranks(e0.elapsed_time(e1))
+    ms_total = max(rank_ms)
     clk = clocks.stop() if rank == 0 else None
     kt = sty.eng.kernel_timer
     sty.eng.kernel_timer = None
@@ -318,7 +328,7 @@ def run_native(args):
     train = None
     if not args.no_train:
         try:
-            train = train_leg(args, rank, world, dev, operand, barrier, max_over_ranks)
+            train = train_leg(args, rank, world, dev, operand, barrier, max_over_ranks, all_ranks)
         except Exception as e:  # noqa: BLE001 - secondary metric: never lose the headline line over it
             train = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
 
@@ -348,7 +358,7 @@ def run_native(args):
                    "frames_per_step": SEG, "video_frames": VIDEO, "frames_per_generator_pass": per_pass, "frame": [H, W, CIN],
                    "weights": f"tests/golden/{cfg['weights']} (100 reference training steps)",
                    "l2": f"the {min(segs_used * SEG, VIDEO)} resident frames are distinct and each pass streams ~{3.5 * per_pass * H * W / (1080 * 1920):.0f} GB of activations >> 126 MB L2"},
-        "timed_region_s": ms_total / 1e3,
+        "timed_region_s": ms_total / 1e3, "timed_region_s_per_rank": [round(m / 1e3, 4) for m in rank_ms],
         "tflops_algorithmic": flops_per_pixel(CIN) * H * W * value / 1e12,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": SEG * H * W * CIN, "d2h_bytes_per_step": SEG * H * W * 3,
                 "ms_per_step": ms_e2e / args.steps, "timed_region_s": ms_e2e / 1e3, "host_checksum": checksum,
@@ -476,7 +486,7 @@ def synthetic_keyframes(n, h, w, seed):
     return pre, post, ga, fl, mask
 
 
-def train_leg(args, rank, world, dev, operand, barrier, max_over_ranks):
+def train_leg(args, rank, world, dev, operand, barrier, max_over_ranks, all_ranks):
     """config C3: the generator half of the reference training_step (lightning_model.py:211-250,260-292) per rank: sampler
     draw + gather -> forward -> L1*4 -> backward -> (NCCL mean all-reduce) -> clip 0.5 -> Adam, batch 80 x 80x80, Cin 9"""
     import numpy as np
@@ -556,13 +566,31 @@ def train_leg(args, rank, world, dev, operand, barrier, max_over_ranks):
     e1.record()
     barrier()
     ms_s = max_over_ranks(e0.elapsed_time(e1))
+    local = None
+    if world > 1:
+        # after all those graph-replayed steps every rank must hold bit-identical weights (BatchNorm running statistics are
+        # per-rank by design: DDP would overwrite them with rank 0's before each forward, and rank 0 writes the checkpoint)
+        checks["replicas_identical"] = bool(replicas_identical(tg, buffers=False))
+        # how much of the step time is the exchange: the same step captured WITHOUT the gradient all-reduce, every rank on its
+        # own (run last: the replicas diverge from here on).  Its slowest rank bounds what any synchronous step can reach.
+        tg._engine.grad_hook = None
+        lstep = GraphedGeneratorStep(tg, opt, (B, 9, P, P), clip=0.5, grad_sync=None)
+        for _ in range(3):
+            lstep(xs, ts)
+        barrier()
+        e0.record()
+        for _ in range(tsteps):
+            lstep(xs, ts)
+        e1.record()
+        barrier()
+        per_rank = [m / tsteps for m in all_ranks(e0.elapsed_time(e1))]
+        local = {"ms_per_step_per_rank": [round(m, 4) for m in per_rank], "ms_per_step_slowest_rank": max(per_rank),
+                 "allreduce_exposed_ms": ms_s / tsteps - max(per_rank),
+                 "note": "the same graph-replayed step without the gradient exchange, ranks independent"}
     lt = loss.detach().clone().reshape(1)
     if world > 1:
         dist.all_reduce(lt)
         lt /= world
-        # (2) after all those graph-replayed steps every rank must hold bit-identical weights (BatchNorm running statistics
-        # are per-rank by design: DDP would overwrite them with rank 0's before each forward, and rank 0 writes the checkpoint)
-        checks["replicas_identical"] = bool(replicas_identical(tg, buffers=False))
     flops = 3 * flops_per_pixel(9) * P * P * B * world
     res = {"metric": "train patches/s", "value": world * B * tsteps / (ms_p / 1e3), "unit": "patches/s",
            "ms_per_step": ms_p / tsteps, "steps": tsteps,
@@ -575,6 +603,8 @@ def train_leg(args, rank, world, dev, operand, barrier, max_over_ranks):
            "step_only": {"value": world * B * tsteps / (ms_s / 1e3), "ms_per_step": ms_s / tsteps,
                          "tflops_algorithmic": flops / (ms_s / tsteps) / 1e9, "note": "graph replay on a resident batch, sampler excluded"},
            "final_loss_mean_over_ranks": float(lt), "skipped_steps": opt.skipped_steps, **checks}
+    if local is not None:
+        res["without_allreduce"] = local
     if world == 1:
         res["gan_step"] = gan_leg(xs, ts, dev, operand, tsteps, barrier)
     return res
