@@ -124,6 +124,9 @@ typedef struct {
                               * x-adjacent tiles of one image: on patch-sized maps (20x20 ... 40x40) the packed weights are then
                               * streamed from L2 once per T images and no tile columns are wasted.  `stats_partial` is indexed
                               * with pbt_conv_num_tiles(h, w, 1) tiles per image.  Excludes upsample2x / pre / cta_pair */
+  int32_t      tap_pairs;    /* 1 (first layer: 16-channel input whose real channels all sit in the first 8-channel plane, blk_c 16): one
+                              * K = 16 MMA covers that plane at two horizontally adjacent taps (descriptor LBO = one pixel), 4 MMAs
+                              * per 7-tap row instead of 7, and only the first plane is loaded.  `wpack` in pack mode bit 4 */
   int32_t      valid_h, valid_w; /* 0 = whole map; else outputs with y >= valid_h or x >= valid_w are stored as ZERO and left out of
                               * `stats_partial`: a 4x4 / pad 1 / stride 1 conv of the PatchGAN critic (src/models/discriminator.py:105-133)
                               * shrinks the map by one pixel; it runs on the fixed grid with (pad_t, pad_l) = (1, 1) and the zero
@@ -141,7 +144,9 @@ typedef struct {
   int32_t     co, ci, kh, kw;   /* source dims */
   int32_t     mode;     /* bit 0: space-to-depth, bit 1: dgrad, bit 2: CTA-pair layout [cb][half][tap][k/8][n/2][8],
                          * bit 3: with bit 0, the source is a 4x4 stride-2 pad-1 kernel (critic): 3x3 stride-1 pad-1 kernel
-                         * over the space-to-depth input, `reserved` = channels per phase of that input (>= ci, 0 = ci) */
+                         * over the space-to-depth input, `reserved` = channels per phase of that input (>= ci, 0 = ci);
+                         * bit 4: tap-pair layout of a first-layer kernel with ci <= 8: taps = kh * ceil(kw/2), K = 16 =
+                         * (channels 0-7 at tap 2j, channels 0-7 at tap 2j+1), zero where 2j+1 == kw */
   int32_t     k_pad;    /* destination K channels (multiple of 16) */
   int32_t     n_out;    /* destination N rows (multiple of 16) */
   int32_t     n_keep;   /* rows taken from the source, remaining rows are zero */
@@ -230,7 +235,7 @@ int pbt_norm_finalize(const float* partial /* consumed: folded in place */, int3
                       float* scale, float* shift, float* mean_out, float* rstd_out,
                       void* stream);
 
-/* y = act(x*scale[n][c] + shift[n][c]) (+ residual32); any of the outputs may be absent.
+/* y = act(x*scale[n][c] + shift[n][c]) (+ residual32 | residual16); any of the outputs may be absent.
  * Replaces the InstanceNorm/BatchNorm + LeakyReLU/ReLU + residual add modules
  * (src/models/generator.py:36-58,93,99,103,116,120,135).
  * out_s2d (optional) receives the same values space-to-depth'ed:
@@ -247,6 +252,8 @@ typedef struct {
   float*       out32;       /* P8F y */
   pbt_act_t    out_s2d;     /* 16-bit y, space-to-depth */
   int32_t      dtype;
+  pbt_act_t    residual16;  /* 16-bit residual addend (ptr NULL = none; not together with residual32): the inference pass keeps
+                             * the residual stream in 16 bits, like the reference's own `.half()` CUDA inference (generator.py:185) */
 } pbt_norm_apply_desc_t;
 int pbt_norm_apply(const pbt_norm_apply_desc_t* d, void* stream);
 

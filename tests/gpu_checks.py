@@ -32,7 +32,7 @@ def act_ref(v, act):
 
 def check_conv(n=1, cin=16, cout=16, h=16, w=8, kh=1, kw=1, pad_t=0, pad_l=0, T=1, blk_c=16, dt=BF16, seed=0,
                debug_flags=0, in_off=0, in_extra=0, out_off=0, out_extra=0, bias=False, act=ACT_NONE, affine=False,
-               mask=False, addend=False, out32=False, stats=False, head=False, integer=True, store16=True, cps=0, pair=False, bt=False):
+               mask=False, addend=False, out32=False, stats=False, head=False, integer=True, store16=True, cps=0, pair=False, bt=False, tp=0):
     """returns (ok, max_abs_err, message); cps = ctas_per_sm configuration of the kernel"""
     g = torch.Generator(device="cuda").manual_seed(seed)
     if integer:
@@ -44,13 +44,15 @@ def check_conv(n=1, cin=16, cout=16, h=16, w=8, kh=1, kw=1, pad_t=0, pad_l=0, T=
     tdt = torch_dtype(dt)
     x = x.to(tdt).float()
     wt = wt.to(tdt).float()
+    if tp:   # tap-pair mode (first layer): only the first `tp` (<= 8) of the 16 input channels carry weights
+        wt[:, tp:] = 0
     # input lives inside a wider tensor (channel-offset view)
     xfull = P8.empty(n, in_off + cin + in_extra, h, w, dt, zero=True)
     xfull.t.copy_(P8.from_nchw(torch.cat([torch.full((n, in_off, h, w), 7.0, device="cuda"), x,
                                           torch.full((n, in_extra, h, w), -5.0, device="cuda")], 1), dt).t)
     xin = xfull.view(in_off, cin)
-    wp = ops.pack_conv_weight(wt, cin, blk_c, dt, pair=pair)   # pair: CTA-pair (cta_group::2) configuration
-    kwargs = {"cta_pair": pair, "batch_tiles": bt}
+    wp = ops.pack_conv_weight_tap_pairs(wt[:, :tp], dt) if tp else ops.pack_conv_weight(wt, cin, blk_c, dt, pair=pair)
+    kwargs = {"cta_pair": pair, "batch_tiles": bt, "tap_pairs": bool(tp)}
     exp = ref_conv(x, wt, pad_t, pad_l)
     if bias:
         b = _ints((cout,), -4, 4, g)

@@ -61,6 +61,11 @@ CONV_CASES = [
     dict(n=2, cin=64, cout=64, h=24, w=40, kh=3, kw=3, pad_t=1, pad_l=1, T=2, blk_c=32, bias=True, act=1, head=True, integer=False,
          bt=True),
     dict(n=170, cin=64, cout=128, h=20, w=20, kh=3, kw=3, pad_t=1, pad_l=1, T=2, blk_c=32, stats=True, integer=False, bt=True),
+    # tap pairs (first layer, <= 8 real input channels): one K = 16 MMA = one channel plane at two adjacent taps
+    dict(n=2, cin=16, cout=32, h=33, w=50, kh=7, kw=7, pad_t=3, pad_l=3, T=3, blk_c=16, stats=True, cps=4, tp=3),
+    dict(n=1, cin=16, cout=32, h=40, w=24, kh=7, kw=7, pad_t=3, pad_l=3, T=2, blk_c=16, bias=True, act=2, tp=8, integer=False),
+    dict(n=3, cin=16, cout=16, h=16, w=17, kh=3, kw=3, pad_t=1, pad_l=1, T=1, blk_c=16, tp=5),
+    dict(n=2, cin=16, cout=32, h=300, w=500, kh=7, kw=7, pad_t=3, pad_l=3, T=3, blk_c=16, stats=True, cps=4, tp=6),
     # more units than one wave of CTAs: every CTA walks several units (persistent loop, barrier phases carried over)
     dict(n=2, cin=64, cout=128, h=272, w=480, kh=3, kw=3, pad_t=1, pad_l=1, T=2, blk_c=32, stats=True, integer=False),
     dict(n=3, cin=32, cout=64, h=200, w=330, kh=3, kw=3, pad_t=1, pad_l=1, T=2, blk_c=16, bias=True, act=1, head=True,

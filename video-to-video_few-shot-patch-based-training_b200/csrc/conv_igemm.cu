@@ -67,6 +67,9 @@ struct ConvKParams {
   const float* pre_scale;
   const float* pre_shift;
   uint32_t l_stage_bytes;
+  int tp;                // tap pairs (first layer, <= 8 input channels): K = 16 = one 8-channel plane at pixels x and x+1
+  int a_planes;          // channel planes TMA-loaded per block (= blk_p; 1 in tap-pair mode)
+  int KWs, dx_step;      // tap walk along x: dx += dx_step while dx < KWs (KW, 1; tap pairs: KW + 1, 2)
   int ws_b;              // issue the T MMAs of a (tap, K step) as one weight-stationary run (B fetched once)
   int VH, VW;            // valid output window (<= H, W): outputs outside it are stored as zero and left out of the statistics
   int bt;                // batch tiles: the T tiles of a CTA are the SAME spatial tile of T consecutive images (small maps)
@@ -198,7 +201,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   const int txi = rem - tyi * p.tiles_x;                     \
   const int x0 = txi * (p.bt ? 8 : 8 * T);                   \
   const int y0 = tyi * 16;
-  const int ntaps = p.KH * p.KW;
+  const int ntaps = p.tp ? p.KH * (p.KWs / 2) : p.KH * p.KW;   // MMA groups per channel block (tap pairs: 4 per 7-tap row)
   const int ngroups = (ntaps + p.b_group - 1) / p.b_group;
 
 #define PBT_STAMP(slot)                                                         \
@@ -271,13 +274,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
           mbar_wait(&a_empty[sa], ((uint32_t)(c / p.a_stages) & 1u) ^ 1u);
           uint64_t* bar = p.nrm ? &a_land[sa] : &a_full[sa];
           if (p.bt) {   // the same haloed tile of T consecutive images (images past the batch are zero-filled by TMA)
-            mbar_arrive_expect_tx(bar, (uint32_t)(p.blk_p * p.BH * p.BW * 16 * T));
+            mbar_arrive_expect_tx(bar, (uint32_t)(p.a_planes * p.BH * p.BW * 16 * T));
             for (int tt = 0; tt < T; ++tt)
               tma_load_4d(sA + (size_t)sa * p.a_stage_bytes + (size_t)tt * p.a_tile_bytes, &tmapA, bar, (x0 - p.pad_l) * 8,
                           y0 - p.pad_t, cb * p.blk_p, n + tt);
             return;
           }
-          mbar_arrive_expect_tx(bar, (uint32_t)(p.blk_p * p.BH * p.BW * 16));
+          mbar_arrive_expect_tx(bar, (uint32_t)(p.a_planes * p.BH * p.BW * 16));
           if (cb < p.nblk0)
             tma_load_4d(sA + (size_t)sa * p.a_stage_bytes, &tmapP, bar, (x0 - p.pad_l) * 8, y0 - p.pad_t, cb * p.blk_p, n);
           else
@@ -345,7 +348,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       const uint32_t row_bytes = (uint32_t)(p.BW * 16);
       const uint32_t b_kstride = (uint32_t)(NCb * 16);
       // descriptor words: lo = addr>>4 | (LBO>>4)<<16 ; hi = SBO>>4 | version(1)<<14
-      const uint32_t a_lo_const = ((plane_bytes >> 4) & 0x3FFF) << 16;
+      // tap pairs: the second 8-element K group is the SAME plane one pixel (16 bytes) to the right -> LBO = 16 B
+      const uint32_t a_lo_const = p.tp ? (1u << 16) : (((plane_bytes >> 4) & 0x3FFF) << 16);
       const uint32_t a_hi = ((row_bytes >> 4) & 0x3FFF) | (1u << 14);
       const uint32_t b_lo_const = ((b_kstride >> 4) & 0x3FFF) << 16;
       const uint32_t b_hi = (128u >> 4) | (1u << 14);
@@ -416,7 +420,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
               }
             }
             b_lo += chunk16;
-            if (++dx == p.KW) { dx = 0; ++dy; }
+            dx += p.dx_step;
+            if (dx >= p.KWs) { dx = 0; ++dy; }
           }
           if (leader) {
             if (PAIR) umma_commit_pair(&b_empty[sb]);
@@ -968,6 +973,10 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
   p.n_blk = ceil_div(p.Cp, p.blk_p);
   p.KH = d->kh; p.KW = d->kw; p.pad_t = d->pad_t; p.pad_l = d->pad_l;
   const int T = d->tiles_per_cta;
+  const int tp = d->tap_pairs ? 1 : 0;
+  PBT_REQUIRE(!tp || (!up && !has_pre && !d->cta_pair && in.c == 16 && d->blk_c == 16 && !d->batch_tiles),
+              "conv: tap_pairs needs a 16-channel input (<= 8 real channels), blk_c 16, and excludes upsample2x / pre / cta_pair / batch_tiles");
+  p.tp = tp;
   const int bt = d->batch_tiles ? 1 : 0;
   PBT_REQUIRE(!bt || (!up && !has_pre && !d->cta_pair && T >= 2), "conv: batch_tiles needs tiles_per_cta >= 2 and excludes upsample2x / pre / cta_pair");
   p.bt = bt;
@@ -976,7 +985,10 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
   p.acc_stride = (int)round_up((uint32_t)p.NC, 32);
   p.tmem_cols = pow2_cols(T * p.acc_stride);
   PBT_REQUIRE(p.tmem_cols <= 512, "conv: tiles_per_cta*cout exceeds tensor memory (512 columns)");
-  p.BW = (bt ? 8 : 8 * T) + p.KW - 1;
+  p.KWs = tp ? (p.KW + 1) / 2 * 2 : p.KW;
+  p.dx_step = tp ? 2 : 1;
+  p.a_planes = tp ? 1 : p.blk_p;
+  p.BW = (bt ? 8 : 8 * T) + p.KWs - 1;
   p.BH = 16 + p.KH - 1;
   PBT_REQUIRE(p.BW <= 32, "conv: haloed tile wider than 32 pixels (reduce tiles_per_cta)");
   p.tiles_x = ceil_div(p.W, bt ? 8 : 8 * T);
@@ -991,7 +1003,7 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
       PBT_REQUIRE(d->blk_c == 32 && T >= 1 && T <= 3, "conv: cta_pair needs blk_c 32");
   }
   p.idesc = make_idesc_f16(pair ? 256 : 128, p.NC, d->dtype == PBT_BF16 ? 1 : 0, 0, 0);
-  p.a_tile_bytes = round_up((uint32_t)(p.blk_p * p.BH * p.BW * 16), 128);
+  p.a_tile_bytes = round_up((uint32_t)(p.a_planes * p.BH * p.BW * 16), 128);
   p.a_stage_bytes = bt ? (uint32_t)T * p.a_tile_bytes : p.a_tile_bytes;
   p.a_tile16 = bt ? p.a_tile_bytes / 16 : 8;
   p.LBH = (p.BH + 1) / 2 + 2;
@@ -1031,7 +1043,7 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
   PBT_REQUIRE(d->ctas_per_sm == 0 || d->ctas_per_sm == 2 || d->ctas_per_sm == 4, "conv: ctas_per_sm must be 0, 2 or 4");
   const uint32_t a_total = (uint32_t)p.a_stages * p.a_stage_bytes + 2 * p.l_stage_bytes;
   const uint32_t chunk = (uint32_t)(p.blk_p * (pair ? p.NC / 2 : p.NC) * 16);  // one tap of one channel block (this CTA's columns)
-  const int ntaps = p.KH * p.KW;
+  const int ntaps = tp ? p.KH * (p.KWs / 2) : p.KH * p.KW;
   int ew = (d->ctas_per_sm == 4 && !up && (!has_pre || p.BH * p.BW <= 4 * 128) && p.tmem_cols <= 128) ? 4 : 8;  // epilogue warps
   uint32_t smem_bytes = 0;
   for (;;) {
@@ -1064,7 +1076,7 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
 
   CUtensorMap tmap, tmapP;
   int rc = PBT_OK;
-  if (in.c > 0) rc = up ? make_p8_tmap(&tmap, in, p.LBW, p.LBH, p.blk_p) : make_p8_tmap(&tmap, in, p.BW, p.BH, p.blk_p);
+  if (in.c > 0) rc = up ? make_p8_tmap(&tmap, in, p.LBW, p.LBH, p.blk_p) : make_p8_tmap(&tmap, in, p.BW, p.BH, p.a_planes);
   if (rc != PBT_OK) return rc;
   if (has_pre) {
     rc = make_p8_tmap(&tmapP, d->pre, p.BW, p.BH, p.blk_p);

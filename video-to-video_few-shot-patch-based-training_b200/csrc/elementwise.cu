@@ -360,7 +360,7 @@ __global__ void norm_finalize_kernel(const float* __restrict__ partial, int n, i
 
 // ------------------------------------------------------------------ norm apply
 struct NormApplyK {
-  ActView x, out, out_relu, out_s2d;
+  ActView x, out, out_relu, out_s2d, res16;
   const float* scale;
   const float* shift;
   int per_channel, act;
@@ -403,6 +403,12 @@ __global__ void norm_apply_kernel(NormApplyK p) {
       const float4 a1 = *reinterpret_cast<const float4*>(p.residual32 + dense + 4);
       f[0] += a0.x; f[1] += a0.y; f[2] += a0.z; f[3] += a0.w;
       f[4] += a1.x; f[5] += a1.y; f[6] += a1.z; f[7] += a1.w;
+    }
+    if (p.res16.ptr) {
+      float r16[8];
+      unpack8<DT>(*chunk_ptr(p.res16, ni, pl, pix), r16);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] += r16[k];
     }
     if (p.out32) {
       *reinterpret_cast<float4*>(p.out32 + dense) = make_float4(f[0], f[1], f[2], f[3]);
@@ -1309,6 +1315,10 @@ extern "C" int pbt_norm_apply(const pbt_norm_apply_desc_t* d, void* stream_) {
   }
   p.scale = d->scale; p.shift = d->shift; p.per_channel = d->per_channel; p.act = d->act;
   p.residual32 = d->residual32; p.out32 = d->out32;
+  if (d->residual16.ptr) {
+    PBT_REQUIRE(!d->residual32 && same(d->residual16), "norm_apply: residual16 shape mismatch (or both residuals given)");
+    p.res16 = view(d->residual16);
+  }
   PBT_REQUIRE(d->x.n <= 65535 && (long long)d->x.h * d->x.w < (1ll << 31), "norm_apply: tensor too large for one launch");
   DISPATCH_DT(d->dtype, pbt::launch(norm_apply_kernel<DT>, ew_grid3(d->x.h * d->x.w, d->x.c / 8, d->x.n), kEwThreads, 0, st, p));
   PBT_CUDA_CHECK(cudaGetLastError());

@@ -41,9 +41,34 @@ __device__ __forceinline__ float virt(const pbt_pack_job_t& j, int o, int i, int
   return load_src(j, o, c, dy, dx);
 }
 
+// tap-pair layout (mode bit 4): first-layer kernels with ci <= 8.  [tap = ky * ceil(kw/2) + j][k/8 = g][n][k%8 = c] holds
+// w[n][c][ky][2j + g] (zero where c >= ci or 2j + g >= kw): one K = 16 MMA covers two horizontally adjacent taps.
+__device__ __forceinline__ void pack_tap_pairs(const pbt_pack_job_t& j) {
+  const int kwp = (j.kw + 1) / 2;
+  const int taps = j.kh * kwp;
+  const long long total = (long long)taps * 16 * j.n_out;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int per_tap = 16 * j.n_out;
+    const int tap = (int)(e / per_tap);
+    const int r2 = (int)(e - (long long)tap * per_tap);
+    const int g = r2 / (j.n_out * 8);
+    const int r3 = r2 - g * j.n_out * 8;
+    const int n = r3 >> 3, c = r3 & 7;
+    const int ky = tap / kwp, dx = 2 * (tap - ky * kwp) + g;
+    float v = 0.f;
+    if (n < min(j.n_keep, j.co) && c < j.ci && dx < j.kw) v = load_src(j, n, c, ky, dx);
+    if (j.dtype == PBT_BF16) static_cast<__nv_bfloat16*>(j.dst)[e] = __float2bfloat16_rn(v);
+    else static_cast<__half*>(j.dst)[e] = __float2half_rn(v);
+  }
+}
+
 __global__ void pack_weights_kernel(const pbt_pack_job_t* __restrict__ jobs) {
   pdl_sync();
   const pbt_pack_job_t j = jobs[blockIdx.y];
+  if (j.mode & 16) {
+    pack_tap_pairs(j);
+    return;
+  }
   const bool s2d = j.mode & 1, dgrad = j.mode & 2;
   const bool s2d4 = s2d && (j.mode & 8);
   const int vkh = s2d ? (s2d4 ? 3 : 2) : j.kh, vkw = s2d ? (s2d4 ? 3 : 2) : j.kw;

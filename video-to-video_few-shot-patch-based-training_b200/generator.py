@@ -199,7 +199,11 @@ class _Workspace:
         self.rawB = [E(f[2], h4, w4) for _ in range(k)]
         self.hmid = [E(f[2], h4, w4) for _ in range(k)]
         self.a = [E(f[2], h4, w4) for _ in range((nb + 1) if train else 2)]
-        self.r = [torch.empty((n, f[2] // 8, h4, w4, 8), device=dev) for _ in range(2)]
+        # residual stream: fp32 while training (its gradient sums seven branches); the inference pass keeps it in 16 bits
+        # like the reference's own `.half()` CUDA inference (generator.py:185): 8 instead of 12 bytes per element in the
+        # seven HBM-bound residual updates of a frame
+        self.r = [torch.empty((n, f[2] // 8, h4, w4, 8), device=dev) for _ in range(2)] if (train or not eng.residual16) else None
+        self.r16 = None if (train or not eng.residual16) else [E(f[2], h4, w4) for _ in range(2)]
         self.u2in = E(2 * f[2], h2, w2) if train else None   # inference upsamples inside the conv kernel
         self.rawU2 = E(f[4], h2, w2)
         self.u1in = E(f[4] + f[1], h, w) if train else None
@@ -237,6 +241,8 @@ class _Engine:
         # 128-channel layers and the smoothers
         env = lambda k, d: os.environ.get(k, d) == "1"  # noqa: E731
         self.pair_res, self.pair_up, self.pair_smooth = env("PBT_PAIR_RES", "0"), env("PBT_PAIR_UP", "0"), env("PBT_PAIR_SMOOTH", "0")
+        self.use_tap_pairs = env("PBT_TAP_PAIRS", "1")
+        self.residual16 = env("PBT_RESIDUAL16", "1")    # inference: 16-bit residual stream (see _Workspace.r16)
         self.batch_tiles = env("PBT_BATCH_TILES", "1")   # small maps: one CTA = the same tile of two images (see _bt)
         self._saved_stamp = 0     # counts grad-enabled forward passes: a backward must match the pass that saved its activations
         self.bucket = None        # parallel.GradBucket: flat fp32 storage the backward sweep writes the parameter gradients into
@@ -275,6 +281,11 @@ class _Engine:
         if not self.batch_tiles or n < 2 or oh * ow > 40 * 40 or (cout + 31) // 32 * 32 * 2 > 256:
             return 0
         return 2
+
+    def tap_pairs(self) -> bool:
+        """first layer with <= 8 input channels (all real channels in one 8-channel plane): one K = 16 MMA covers that plane
+        at two horizontally adjacent taps, 28 instead of 49 MMAs per tile and half the input bytes (env PBT_TAP_PAIRS=0: off)"""
+        return self.use_tap_pairs and self.gen.input_channels <= 8 and self.cin_p == 16
 
     def _T11(self, w: int) -> int:
         t = self._T(3, w)
@@ -377,7 +388,10 @@ class _Engine:
                    blk_c=self._blk(co), dt=dt, pair=pair)
 
         pr, pu, ps = self._pairs(with_dgrad)
-        fwd("initial", g.initial_conv[0], cp)
+        if self.tap_pairs():
+            pk.add("initial", g.initial_conv[0].weight.detach(), k_pad=16, n_out=f[0], n_keep=f[0], blk_c=16, dt=dt, tap_pairs=True)
+        else:
+            fwd("initial", g.initial_conv[0], cp)
         fwd("down1", g.downsample1[0], 4 * f[0], s2d=True)
         fwd("down2", g.downsample2[0], 4 * f[1], s2d=True)
         for i, blk in enumerate(g.resnet_blocks):
@@ -462,7 +476,8 @@ class _Engine:
             ops.conv_fwd(xin, W[name], cout, k, k, pad, pad, dt, blk_c=self._blk(cin), tiles_per_cta=T, out=raw,
                          stats_partial=None if (frozen or no_norm) else st["partial"], upsample2x=up, pre=pre,
                          pre_scale=None if pre is None else pre_st["scale"], pre_shift=None if pre is None else pre_st["shift"],
-                         pre_act=pre_act, ctas_per_sm=0 if pair else cps, bias=plain_bias, cta_pair=pair, batch_tiles=bool(bt))
+                         pre_act=pre_act, ctas_per_sm=0 if pair else cps, bias=plain_bias, cta_pair=pair, batch_tiles=bool(bt),
+                         tap_pairs=(name == "initial" and self.tap_pairs()))
             if no_norm:
                 if not st.get("identity"):
                     st["scale"].fill_(1.0)
@@ -511,7 +526,11 @@ class _Engine:
                        out_s2d=ws.s2d1)
         st = conv_in("down2", ws.s2d1, f[2], 2, 1, ws.raw2, 2, cps=4)
         nb = len(g.resnet_blocks)
-        r_cur, r_nxt = ws.r[0], ws.r[1]
+        r16 = ws.r16 is not None                # inference: 16-bit residual stream; r_0 is the skip slot of c2cat itself
+        if r16:
+            r_cur, r_nxt = ws.c2cat.view(f[2], f[2]), ws.r16[0]
+        else:
+            r_cur, r_nxt = ws.r[0], ws.r[1]
         a_of = (lambda i: ws.a[i]) if save else (lambda i: ws.a[i % 2])
         last16 = ws.c2cat.view(0, f[2])
         if nb == 0:
@@ -519,7 +538,7 @@ class _Engine:
             ops.norm_apply(ws.raw2, dt, scale=st["scale"], shift=st["shift"], act=ACT_LEAKY, out=last16)
         else:
             ops.norm_apply(ws.raw2, dt, scale=st["scale"], shift=st["shift"], act=ACT_LEAKY, out=ws.c2cat.view(f[2], f[2]),
-                           out32=r_cur, out_relu=a_of(0))
+                           out32=None if r16 else r_cur, out_relu=a_of(0))
         # residual blocks: r_{b+1} = r_b + IN(convB(relu(IN(convA(relu(r_b))))))
         # inference: IN + ReLU of a conv's raw output are applied inside the NEXT conv's shared-memory tile
         # (normalise-on-load), so hmid and the up1 half of cat11 are never written; training keeps them for wgrad
@@ -534,10 +553,15 @@ class _Engine:
                 ops.norm_apply(ws.rawA[k], dt, scale=st["scale"], shift=st["shift"], act=ACT_RELU, out=ws.hmid[k])
                 st = conv_in(f"res{b}.b", ws.hmid[k], f[2], 3, 1, ws.rawB[k], 2, cps=4, pair=pr)
             lastb = b == nb - 1
-            ops.norm_apply(ws.rawB[k], dt, scale=st["scale"], shift=st["shift"], act=ACT_NONE, residual32=r_cur,
-                           out32=None if lastb else r_nxt, out=last16 if lastb else None,
-                           out_relu=None if lastb else a_of(b + 1))
-            r_cur, r_nxt = r_nxt, r_cur
+            if r16:
+                ops.norm_apply(ws.rawB[k], dt, scale=st["scale"], shift=st["shift"], act=ACT_NONE, residual16=r_cur,
+                               out=last16 if lastb else r_nxt, out_relu=None if lastb else a_of(b + 1))
+                r_cur, r_nxt = r_nxt, (ws.r16[1] if b == 0 else r_cur)      # never write into c2cat's skip slot
+            else:
+                ops.norm_apply(ws.rawB[k], dt, scale=st["scale"], shift=st["shift"], act=ACT_NONE, residual32=r_cur,
+                               out32=None if lastb else r_nxt, out=last16 if lastb else None,
+                               out_relu=None if lastb else a_of(b + 1))
+                r_cur, r_nxt = r_nxt, r_cur
         # decoder.  Inference: the bilinear x2 upsample is interpolated inside the conv kernel's producer
         # (upsample2x=True), the upsampled tensors are never written.  Training keeps them: wgrad reads them.
         if save:

@@ -13,7 +13,7 @@ from . import _native as nv
 from ._native import ACT_LEAKY, ACT_NONE, ACT_RELU, BF16, FP16, P8, Act, act_or_null, check, lib, ptr, stream_ptr
 
 __all__ = [
-    "pack_conv_weight", "s2d_weight", "s2d_weight_grad", "dgrad_weight", "conv_fwd", "conv_wgrad", "conv_num_tiles",
+    "pack_conv_weight", "pack_conv_weight_tap_pairs", "s2d_weight", "s2d_weight_grad", "dgrad_weight", "conv_fwd", "conv_wgrad", "conv_num_tiles",
     "norm_finalize", "norm_apply", "upsample2x", "upsample2x_bwd", "norm_bwd", "head_bwd", "channel_sum", "nchw_to_p8",
     "p8_to_nchw", "p8f_to_nchw", "u8hwc_to_p8", "nchw_to_u8hwc", "u8hwc_to_norm_chw", "patch_gather", "mask_dilate7",
     "mask_erode7", "composite_to_u8", "zero_border", "p8s2d_to_nchw",
@@ -38,6 +38,19 @@ def pack_conv_weight(w: torch.Tensor, cin_pad: int, blk_c: int, dt: int, pair: b
             blk = blk.reshape(kh * kw, (c1 - c0) // 8, 2, cout // 2, 8).permute(2, 0, 1, 3, 4)  # [half][tap][k8][co/2][8]
         chunks.append(blk.reshape(-1))
     return torch.cat(chunks).to(nv.torch_dtype(dt)).contiguous()
+
+
+def pack_conv_weight_tap_pairs(w: torch.Tensor, dt: int) -> torch.Tensor:
+    """[cout, cin <= 8, kh, kw] -> tap-pair layout [ky * ceil(kw/2) + j][g][cout][c] = w[cout][c][ky][2j + g] (see include/pbt.h)"""
+    cout, cin, kh, kw = w.shape
+    assert cin <= 8
+    kwp = (kw + 1) // 2
+    t = w.new_zeros((kh, kwp, 2, cout, 8))
+    for j in range(kwp):
+        for g in range(2):
+            if 2 * j + g < kw:
+                t[:, j, g, :, :cin] = w[:, :, :, 2 * j + g].permute(2, 0, 1)
+    return t.reshape(-1).to(nv.torch_dtype(dt)).contiguous()
 
 
 def dgrad_weight(w: torch.Tensor) -> torch.Tensor:
@@ -82,14 +95,16 @@ class WeightPacker:
         self._max = 0
 
     def add(self, name: str, param: torch.Tensor, *, s2d=False, dgrad=False, k_pad: int, n_out: int, n_keep: int, blk_c: int,
-            dt: int, pair: bool = False, s2d4_cpp: int = 0) -> torch.Tensor:
+            dt: int, pair: bool = False, s2d4_cpp: int = 0, tap_pairs: bool = False) -> torch.Tensor:
         """s2d4_cpp > 0 (with s2d): the source is a 4x4 stride-2 pad-1 kernel, packed as the 3x3 stride-1 kernel over the
         space-to-depth input that has s2d4_cpp channels per phase"""
         co, ci, kh, kw = param.shape
-        taps = (9 if s2d4_cpp else 4) if s2d else kh * kw
+        taps = (9 if s2d4_cpp else 4) if s2d else (kh * ((kw + 1) // 2) if tap_pairs else kh * kw)
+        if tap_pairs:
+            assert ci <= 8 and k_pad == 16 and not (s2d or dgrad or pair)
         dst = torch.empty(taps * k_pad * n_out, dtype=nv.torch_dtype(dt), device=self.device)
         assert param.is_contiguous() and param.dtype in (torch.float32, torch.float16)
-        self.jobs.append(nv.PackJob(param.data_ptr(), dst.data_ptr(), co, ci, kh, kw, int(s2d) | (int(dgrad) << 1) | (int(pair) << 2) | (8 if s2d4_cpp else 0),
+        self.jobs.append(nv.PackJob(param.data_ptr(), dst.data_ptr(), co, ci, kh, kw, int(s2d) | (int(dgrad) << 1) | (int(pair) << 2) | (8 if s2d4_cpp else 0) | (16 if tap_pairs else 0),
                                     k_pad, n_out, n_keep, blk_c, dt, int(param.dtype == torch.float16), int(s2d4_cpp)))
         self._src = getattr(self, "_src", []) + [param]   # keep the parameters alive / pointers stable
         self.out[name] = dst
@@ -115,7 +130,7 @@ def conv_fwd(x: P8, wpack: torch.Tensor, cout: int, kh: int, kw: int, pad_t: int
              mask: P8 | None = None, addend32=None, out32=None, out: P8 | None = None, stats_partial=None,
              head_w=None, head_b=None, head_out=None, head_tanh: bool = True, upsample2x: bool = False, debug_flags: int = 0,
              debug_buf=None, pre: P8 | None = None, pre_scale=None, pre_shift=None, pre_act: int = ACT_NONE, ctas_per_sm: int = 0, cta_pair: bool = False, concurrent: bool = False, batch_tiles: bool = False,
-             valid_hw=None) -> None:
+             valid_hw=None, tap_pairs: bool = False) -> None:
     """`pre` (raw output of the previous conv) supplies the first channels, normalised + activated on load; `x` (may be
     None then) the remaining ones."""
     d = nv.ConvDesc()
@@ -126,6 +141,7 @@ def conv_fwd(x: P8, wpack: torch.Tensor, cout: int, kh: int, kw: int, pad_t: int
     d.cta_pair = int(cta_pair)
     d.concurrent = int(concurrent)
     d.batch_tiles = int(batch_tiles)
+    d.tap_pairs = int(tap_pairs)
     d.valid_h, d.valid_w = (0, 0) if valid_hw is None else (int(valid_hw[0]), int(valid_hw[1]))
     d.wpack = wpack.data_ptr()
     d.cout, d.kh, d.kw, d.pad_t, d.pad_l = cout, kh, kw, pad_t, pad_l
@@ -162,11 +178,13 @@ def norm_finalize(partial, n, tiles, c, count_per_image, scale, shift, *, eps=1e
 
 
 def norm_apply(x: P8, dt: int, *, scale=None, shift=None, per_channel=False, act=ACT_NONE, residual32=None,
-               out: P8 | None = None, out_relu: P8 | None = None, out32=None, out_s2d: P8 | None = None) -> None:
+               out: P8 | None = None, out_relu: P8 | None = None, out32=None, out_s2d: P8 | None = None,
+               residual16: P8 | None = None) -> None:
     d = nv.NormApplyDesc()
     d.x = x.act()
     d.scale, d.shift, d.per_channel, d.act = ptr(scale), ptr(shift), int(per_channel), act
     d.residual32 = ptr(residual32)
+    d.residual16 = act_or_null(residual16)
     d.out, d.out_relu, d.out32, d.out_s2d = act_or_null(out), act_or_null(out_relu), ptr(out32), act_or_null(out_s2d)
     d.dtype = dt
     check(lib().pbt_norm_apply(C.byref(d), stream_ptr()), "pbt_norm_apply")
