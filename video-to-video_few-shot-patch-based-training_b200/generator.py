@@ -463,7 +463,8 @@ class _Engine:
             T = self._T(T_pref, ow)
             # (training passes only: inference keeps a frame's result bit-independent of the frames that share its pass -
             # batch tiles change the tile geometry of the statistics partial sums)
-            bt = 0 if (up or pre is not None or pair or not save) else self._bt(n, oh, ow, cout)
+            tp = name == "initial" and self.tap_pairs()
+            bt = 0 if (up or pre is not None or pair or not save or tp) else self._bt(n, oh, ow, cout)
             if bt:
                 T, cps = bt, 0
             st = ws.stat(name, cout, oh, ow, 1 if bt else T, dev)
@@ -477,7 +478,7 @@ class _Engine:
                          stats_partial=None if (frozen or no_norm) else st["partial"], upsample2x=up, pre=pre,
                          pre_scale=None if pre is None else pre_st["scale"], pre_shift=None if pre is None else pre_st["shift"],
                          pre_act=pre_act, ctas_per_sm=0 if pair else cps, bias=plain_bias, cta_pair=pair, batch_tiles=bool(bt),
-                         tap_pairs=(name == "initial" and self.tap_pairs()))
+                         tap_pairs=tp)
             if no_norm:
                 if not st.get("identity"):
                     st["scale"].fill_(1.0)
