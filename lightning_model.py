@@ -204,6 +204,14 @@ class StyleTransferModel(_Base):
         if hasattr(opt, "last_grad_norm"):       # FusedClipAdam: the clip is part of the optimiser launch
             opt.step(max_grad_norm=clip)
         else:
+            # torch.optim.Adam (optimizer.*.fused=false) has no skip-on-overflow: a sweep whose fp16 gradients overflowed would
+            # write NaN into the weights.  Replace non-finite gradients by zeros without a host round trip (graph-capturable);
+            # FusedClipAdam skips such a step entirely.
+            grads = [p.grad for p in module.parameters() if p.grad is not None]
+            if grads:
+                finite = torch.stack([torch.isfinite(g).all() for g in grads]).all()
+                for g in grads:
+                    g.copy_(torch.where(finite, torch.nan_to_num(g, nan=0.0, posinf=0.0, neginf=0.0), torch.zeros_like(g)))
             if clip is not None:
                 torch.nn.utils.clip_grad_norm_(module.parameters(), clip)
             opt.step()
