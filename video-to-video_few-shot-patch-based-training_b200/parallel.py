@@ -77,26 +77,38 @@ def replicas_identical(module: torch.nn.Module, buffers: bool = True) -> bool:
 _RES = re.compile(r"resnet_blocks\.(\d+)\.")
 
 
-def group_of(name: str, n_blocks: int = 0) -> int:
-    """0 tail (head, smoothers, conv11) | 1 decoder | 2.. one per residual block, last block first | encoder last"""
+#: how finely the bucket is split into all-reduce groups: "block" = tail | decoder | one group per residual block | encoder
+#: (10 groups), "pairs" = residual blocks two by two (6-7 groups), "coarse" = tail | decoder | trunk + encoder (3 groups, round 1),
+#: "single" = one exchange at the end of the sweep.  Measured at N = 2 by tools/allreduce_groups.py.
+GROUPING = os.environ.get("PBT_AR_GROUPS", "block")
+
+
+def group_of(name: str, n_blocks: int = 0, grouping: str | None = None) -> int:
+    """0 tail (head, smoothers, conv11) | 1 decoder | 2.. residual blocks, last block first | encoder last"""
+    grouping = grouping or GROUPING
+    if grouping == "single":
+        return 0
     if name.startswith(("output.", "smoothers.", "conv11.")):
         return 0
     if name.startswith(("upsample1.", "upsample2.")):
         return 1
+    if grouping == "coarse":
+        return 2
     m = _RES.match(name)
     if m:
-        return 2 + (n_blocks - 1 - int(m.group(1)))
+        k = n_blocks - 1 - int(m.group(1))
+        return 2 + (k // 2 if grouping == "pairs" else k)
     return 2 + n_blocks
 
 
 class GradBucket:
     """flat fp32 storage for the gradients of a parameter set, laid out group by group"""
 
-    def __init__(self, named_params: Sequence[Tuple[str, torch.nn.Parameter]]):
+    def __init__(self, named_params: Sequence[Tuple[str, torch.nn.Parameter]], grouping: str | None = None):
         self.names = [n for n, _ in named_params]
         self.params = [p for _, p in named_params]
         nb = 1 + max([int(m.group(1)) for m in map(_RES.match, self.names) if m] or [-1])
-        grp = [group_of(n, nb) for n in self.names]
+        grp = [group_of(n, nb, grouping) for n in self.names]
         order = sorted(range(len(self.names)), key=lambda i: (grp[i], i))
         self.slices: Dict[str, Tuple[int, int]] = {}
         self.group_of_name: Dict[str, int] = {}
@@ -129,10 +141,10 @@ class GradAllReduce:
     """mean all-reduce of a parameter set's gradients over a GradBucket, overlapped group by group"""
 
     def __init__(self, named_params: Sequence[Tuple[str, torch.nn.Parameter]], world: int | None = None,
-                 bucket: Optional[GradBucket] = None):
+                 bucket: Optional[GradBucket] = None, grouping: str | None = None):
         named_params = list(named_params)
         self.world = world if world is not None else (dist.get_world_size() if dist.is_initialized() else 1)
-        self.bucket = bucket if bucket is not None else GradBucket(named_params)
+        self.bucket = bucket if bucket is not None else GradBucket(named_params, grouping)
         self.names, self.params = self.bucket.names, self.bucket.params
         self.flat, self.slices, self.group_bounds = self.bucket.flat, self.bucket.slices, self.bucket.group_bounds
         self._pending: List = []
