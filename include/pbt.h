@@ -124,6 +124,9 @@ typedef struct {
                               * x-adjacent tiles of one image: on patch-sized maps (20x20 ... 40x40) the packed weights are then
                               * streamed from L2 once per T images and no tile columns are wasted.  `stats_partial` is indexed
                               * with pbt_conv_num_tiles(h, w, 1) tiles per image.  Excludes upsample2x / pre / cta_pair */
+  int32_t      up_raw_channels; /* with upsample2x: the first up_raw_channels channels of `in` (multiple of blk_c) are the RAW output of the
+                              * previous conv; act(x*pre_scale + pre_shift) (pre_scale / pre_shift fp32 [n][up_raw_channels], pre_act) is
+                              * applied to the staged low-res tile before the interpolation, so the normalised tensor is never written */
   int32_t      tap_pairs;    /* 1 (first layer: 16-channel input whose real channels all sit in the first 8-channel plane, blk_c 16): one
                               * K = 16 MMA covers that plane at two horizontally adjacent taps (descriptor LBO = one pixel), 4 MMAs
                               * per 7-tap row instead of 7, and only the first plane is loaded.  `wpack` in pack mode bit 4 */

@@ -487,19 +487,27 @@ def check_conv_norm_on_load(n=2, cpre=64, cin=32, cout=32, h=37, w=45, T=2, blk_
     return ok, err, f"err={err:.4g}"
 
 
-def check_conv_upsample(n=2, cin=64, cout=32, h=20, w=28, T=2, blk_c=32, dt=FP16, seed=11, stats=True, pair=False):
+def check_conv_upsample(n=2, cin=64, cout=32, h=20, w=28, T=2, blk_c=32, dt=FP16, seed=11, stats=True, pair=False, raw_c=0):
     """conv3x3(pad 1) over the bilinear x2 (align_corners=True) upsample of a low-res input, interpolated in-kernel"""
     g = torch.Generator(device="cuda").manual_seed(seed)
     tdt = torch_dtype(dt)
     x = torch.randn((n, cin, h, w), generator=g, device="cuda").to(tdt).float()
     wt = (torch.randn((cout, cin, 3, 3), generator=g, device="cuda") * 0.05).to(tdt).float()
-    up = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True).to(tdt).float()
+    kw_raw = {}
+    xa = x
+    if raw_c:   # the first raw_c channels are raw conv outputs: relu(x*scale + shift) is applied to the low-res tile on load
+        sc = torch.rand((n, raw_c), generator=g, device="cuda") + 0.5
+        sh = torch.randn((n, raw_c), generator=g, device="cuda") * 0.3
+        xa = x.clone()
+        xa[:, :raw_c] = torch.relu(x[:, :raw_c] * sc[:, :, None, None] + sh[:, :, None, None]).to(tdt).float()
+        kw_raw = dict(pre_scale=sc, pre_shift=sh, pre_act=ACT_RELU, up_raw_channels=raw_c)
+    up = F.interpolate(xa, scale_factor=2, mode="bilinear", align_corners=True).to(tdt).float()
     exp = ref_conv(up, wt, 1, 1)
     out = P8.empty(n, cout, 2 * h, 2 * w, dt)
     tiles = ops.conv_num_tiles(2 * h, 2 * w, T)
     part = torch.full((n, tiles, 2, cout), float("nan"), device="cuda") if stats else None
     ops.conv_fwd(P8.from_nchw(x, dt), ops.pack_conv_weight(wt, cin, blk_c, dt, pair=pair), cout, 3, 3, 1, 1, dt, blk_c=blk_c,
-                 tiles_per_cta=T, out=out, stats_partial=part, upsample2x=True, cta_pair=pair)
+                 tiles_per_cta=T, out=out, stats_partial=part, upsample2x=True, cta_pair=pair, **kw_raw)
     torch.cuda.synchronize()
     got = out.to_nchw().double()
     err = (got - exp).abs().max().item()

@@ -87,6 +87,9 @@ def test_conv_fwd(case):
 @pytest.mark.parametrize("kw", [dict(), dict(cin=192, cout=128, h=16, w=16), dict(n=3, cin=256, cout=128, h=10, w=12),
                                 dict(cin=64, cout=64, h=24, w=24, T=3, dt=0), dict(cin=32, cout=16, h=5, w=7, T=1),
                                 dict(n=2, cin=64, cout=64, h=136, w=200, T=2),
+                                # raw leading channels normalised + activated inside the staged low-res tile
+                                dict(cin=192, cout=128, h=16, w=16, raw_c=128), dict(n=3, cin=64, cout=32, h=10, w=12, T=1, raw_c=64),
+                                dict(n=2, cin=96, cout=64, h=136, w=200, T=2, raw_c=32),
                                 # upsample-on-load in the CTA-pair configuration (odd and even unit counts, persistent CTAs)
                                 dict(pair=True), dict(n=1, cin=192, cout=128, h=18, w=20, pair=True),
                                 dict(n=3, cin=256, cout=128, h=10, w=12, T=1, pair=True),

@@ -40,7 +40,7 @@ class ConvDesc(C.Structure):
         ("mask", Act), ("addend32", C.c_void_p), ("out32", C.c_void_p), ("out", Act),
         ("stats_partial", C.c_void_p), ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("head_out", C.c_void_p),
         ("head_tanh", C.c_int32), ("upsample2x", C.c_int32), ("pre", Act), ("pre_scale", C.c_void_p), ("pre_shift", C.c_void_p),
-        ("pre_act", C.c_int32), ("ctas_per_sm", C.c_int32), ("cta_pair", C.c_int32), ("concurrent", C.c_int32), ("batch_tiles", C.c_int32), ("tap_pairs", C.c_int32), ("valid_h", C.c_int32), ("valid_w", C.c_int32), ("debug_flags", C.c_int32), ("debug_buf", C.c_void_p),
+        ("pre_act", C.c_int32), ("ctas_per_sm", C.c_int32), ("cta_pair", C.c_int32), ("concurrent", C.c_int32), ("batch_tiles", C.c_int32), ("up_raw_channels", C.c_int32), ("tap_pairs", C.c_int32), ("valid_h", C.c_int32), ("valid_w", C.c_int32), ("debug_flags", C.c_int32), ("debug_buf", C.c_void_p),
     ]
 
 

@@ -67,6 +67,7 @@ struct ConvKParams {
   const float* pre_scale;
   const float* pre_shift;
   uint32_t l_stage_bytes;
+  int up_nrm;            // upsample-on-load whose first nblk0 channel blocks are raw conv outputs (normalised in the staged low-res tile)
   int tp;                // tap pairs (first layer, <= 8 input channels): K = 16 = one 8-channel plane at pixels x and x+1
   int a_planes;          // channel planes TMA-loaded per block (= blk_p; 1 in tap-pair mode)
   int KWs, dx_step;      // tap walk along x: dx += dx_step while dx < KWs (KW, 1; tap pairs: KW + 1, 2)
@@ -500,6 +501,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         dsto[qq] = pos * 16;
       }
       const int l_plane = p.LBH * p.LBW * 16, a_plane = npos * 16;
+      if (p.up_nrm) {   // the first nblk0 channel blocks of the low-res input are RAW conv outputs: their norm + activation table
+        for (int i = et; i < p.pre_c; i += 32 * EW) {
+          const int nn = min(n, p.n_img - 1);
+          s_norm[i] = __ldg(&p.pre_scale[(long long)nn * p.pre_c + i]);
+          s_norm[p.pre_c + i] = __ldg(&p.pre_shift[(long long)nn * p.pre_c + i]);
+        }
+        asm volatile("bar.sync 3, %0;" ::"r"(32 * EW) : "memory");
+      }
       for (int cb = 0; cb < p.n_blk; ++cb) {
         const int c = cbt + cb;
         const int sa = c % p.a_stages, sl = c & 1;
@@ -507,6 +516,29 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         mbar_wait(&a_empty[sa], ((uint32_t)(c / p.a_stages) & 1u) ^ 1u);
         const uint8_t* src = sL + (size_t)sl * p.l_stage_bytes;
         uint8_t* dstA = sA + (size_t)sa * p.a_stage_bytes;
+        if (p.up_nrm && cb < p.nblk0) {
+          // normalise + activate the staged LOW-RES tile in place (each low-res pixel once, ~4x fewer than the interpolated
+          // positions), then interpolate: bilinear(act(x*s+t)) exactly as the reference upsamples the activated tensor
+          // (src/models/generator.py:204-206 feeding :13).  All transform threads must see the finished tile: named barrier.
+          uint8_t* stg = sL + (size_t)sl * p.l_stage_bytes;
+          const int lpos = p.LBH * p.LBW;
+          for (int i = et; i < lpos * p.blk_p; i += 32 * EW) {
+            const int pln = i / lpos, pos = i - pln * lpos;
+            const int ch = (cb * p.blk_p + pln) * 8;
+            uint4* ptr = reinterpret_cast<uint4*>(stg + (size_t)pln * l_plane + (size_t)pos * 16);
+            float v[8];
+            unpack8_rt(dt, *ptr, v);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              float t = fmaf(v[k], s_norm[ch + k], s_norm[p.pre_c + ch + k]);
+              if (p.pre_act == PBT_ACT_RELU) t = fmaxf(t, 0.f);
+              else if (p.pre_act == PBT_ACT_LEAKY02) t = t > 0.f ? t : 0.2f * t;
+              v[k] = t;
+            }
+            *ptr = pack8_rt(dt, v);
+          }
+          asm volatile("bar.sync 3, %0;" ::"r"(32 * EW) : "memory");
+        }
 #pragma unroll
         for (int qq = 0; qq < 2; ++qq) {
           if (!has[qq]) continue;
@@ -970,6 +1002,12 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
   p.blk_p = d->blk_c / 8;
   p.nrm = has_pre; p.nblk0 = has_pre ? d->pre.c / d->blk_c : 0; p.pre_c = has_pre ? d->pre.c : 0;
   p.pre_act = d->pre_act; p.pre_scale = d->pre_scale; p.pre_shift = d->pre_shift;
+  if (up && d->up_raw_channels > 0) {
+    // upsample-on-load over an input whose FIRST up_raw_channels channels are the raw output of the previous conv
+    PBT_REQUIRE(!has_pre && d->pre_scale && d->pre_shift && d->up_raw_channels % d->blk_c == 0 && d->up_raw_channels <= in.c &&
+                    d->up_raw_channels <= 256, "conv: up_raw_channels needs pre_scale / pre_shift and a multiple of blk_c <= cin, 256");
+    p.up_nrm = 1; p.nblk0 = d->up_raw_channels / d->blk_c; p.pre_c = d->up_raw_channels;
+  }
   p.n_blk = ceil_div(p.Cp, p.blk_p);
   p.KH = d->kh; p.KW = d->kw; p.pad_t = d->pad_t; p.pad_l = d->pad_l;
   const int T = d->tiles_per_cta;

@@ -241,6 +241,7 @@ class _Engine:
         # 128-channel layers and the smoothers
         env = lambda k, d: os.environ.get(k, d) == "1"  # noqa: E731
         self.pair_res, self.pair_up, self.pair_smooth = env("PBT_PAIR_RES", "0"), env("PBT_PAIR_UP", "0"), env("PBT_PAIR_SMOOTH", "0")
+        self.fold_up = env("PBT_FOLD_UP", "1")          # inference: up2's norm + ReLU applied inside up1's upsample-on-load
         self.use_tap_pairs = env("PBT_TAP_PAIRS", "1")
         self.residual16 = env("PBT_RESIDUAL16", "1")    # inference: 16-bit residual stream (see _Workspace.r16)
         self.batch_tiles = env("PBT_BATCH_TILES", "1")   # small maps: one CTA = the same tile of two images (see _bt)
@@ -454,7 +455,8 @@ class _Engine:
         if not u8_hwc and x.dtype not in (torch.float32, torch.float16):
             x = x.float()
 
-        def conv_in(name, xin, cout, k, pad, raw, T_pref, up=False, pre=None, pre_st=None, pre_act=ACT_NONE, cps=0, pair=False):
+        def conv_in(name, xin, cout, k, pad, raw, T_pref, up=False, pre=None, pre_st=None, pre_act=ACT_NONE, cps=0, pair=False,
+                    up_raw=0):
             """conv (bias skipped: a constant per channel is removed by the following InstanceNorm) + IN statistics;
             up=True: xin is the low-res tensor, the conv consumes its bilinear x2 upsample (interpolated in-kernel);
             pre: raw output of the previous conv, its InstanceNorm (pre_st) + activation applied on load"""
@@ -476,7 +478,8 @@ class _Engine:
                 plain_bias = None if cb is None else cb.detach().float()
             ops.conv_fwd(xin, W[name], cout, k, k, pad, pad, dt, blk_c=self._blk(cin), tiles_per_cta=T, out=raw,
                          stats_partial=None if (frozen or no_norm) else st["partial"], upsample2x=up, pre=pre,
-                         pre_scale=None if pre is None else pre_st["scale"], pre_shift=None if pre is None else pre_st["shift"],
+                         pre_scale=None if pre_st is None else pre_st["scale"], pre_shift=None if pre_st is None else pre_st["shift"],
+                         up_raw_channels=up_raw,
                          pre_act=pre_act, ctas_per_sm=0 if pair else cps, bias=plain_bias, cta_pair=pair, batch_tiles=bool(bt),
                          tap_pairs=tp)
             if no_norm:
@@ -573,9 +576,15 @@ class _Engine:
             ops.upsample2x(ws.c1cat.view(f[4], f[1]), ws.u1in.view(f[4], f[1]), dt)
             st = conv_in("up1", ws.u1in, f[4], 3, 1, ws.rawU1, 2)
         else:
-            st = conv_in("up2", ws.c2cat, f[4], 3, 1, ws.rawU2, 2, up=True, pair=pu)
-            ops.norm_apply(ws.rawU2, dt, scale=st["scale"], shift=st["shift"], act=ACT_RELU, out=ws.c1cat.view(0, f[4]))
-            st = conv_in("up1", ws.c1cat, f[4], 3, 1, ws.rawU1, 2, up=True, pair=pu)
+            # the raw output of up2 goes straight into its slot of up1's input; up1 normalises + activates it inside the staged
+            # low-res tile before interpolating (up_raw_channels), so that normalise pass never touches HBM either
+            fold = self.fold_up and f[4] % self._blk(f[4] + f[1]) == 0 and f[4] <= 256
+            st = conv_in("up2", ws.c2cat, f[4], 3, 1, ws.c1cat.view(0, f[4]) if fold else ws.rawU2, 2, up=True, pair=pu)
+            if fold:
+                st = conv_in("up1", ws.c1cat, f[4], 3, 1, ws.rawU1, 2, up=True, pair=pu, pre_st=st, pre_act=ACT_RELU, up_raw=f[4])
+            else:
+                ops.norm_apply(ws.rawU2, dt, scale=st["scale"], shift=st["shift"], act=ACT_RELU, out=ws.c1cat.view(0, f[4]))
+                st = conv_in("up1", ws.c1cat, f[4], 3, 1, ws.rawU1, 2, up=True, pair=pu)
         if not nol_11:
             ops.norm_apply(ws.rawU1, dt, scale=st["scale"], shift=st["shift"], act=ACT_RELU, out=ws.cat11.view(0, f[4]))
         # conv11 + smoothers + fused head

@@ -130,7 +130,7 @@ def conv_fwd(x: P8, wpack: torch.Tensor, cout: int, kh: int, kw: int, pad_t: int
              mask: P8 | None = None, addend32=None, out32=None, out: P8 | None = None, stats_partial=None,
              head_w=None, head_b=None, head_out=None, head_tanh: bool = True, upsample2x: bool = False, debug_flags: int = 0,
              debug_buf=None, pre: P8 | None = None, pre_scale=None, pre_shift=None, pre_act: int = ACT_NONE, ctas_per_sm: int = 0, cta_pair: bool = False, concurrent: bool = False, batch_tiles: bool = False,
-             valid_hw=None, tap_pairs: bool = False) -> None:
+             valid_hw=None, tap_pairs: bool = False, up_raw_channels: int = 0) -> None:
     """`pre` (raw output of the previous conv) supplies the first channels, normalised + activated on load; `x` (may be
     None then) the remaining ones."""
     d = nv.ConvDesc()
@@ -142,6 +142,7 @@ def conv_fwd(x: P8, wpack: torch.Tensor, cout: int, kh: int, kw: int, pad_t: int
     d.concurrent = int(concurrent)
     d.batch_tiles = int(batch_tiles)
     d.tap_pairs = int(tap_pairs)
+    d.up_raw_channels = int(up_raw_channels)
     d.valid_h, d.valid_w = (0, 0) if valid_hw is None else (int(valid_hw[0]), int(valid_hw[1]))
     d.wpack = wpack.data_ptr()
     d.cout, d.kh, d.kw, d.pad_t, d.pad_l = cout, kh, kw, pad_t, pad_l
