@@ -244,6 +244,7 @@ class _Engine:
         # inference: up2's norm + ReLU applied inside up1's upsample-on-load (built and tested; measured 20.25 -> 20.36 ms per
         # 4-frame pass - up1's transform warps are on its critical path, the saved 0.2-ms normalise pass does not pay: off)
         self.fold_up = env("PBT_FOLD_UP", "0")
+        self.ws_up, self.ws_res = env("PBT_WS_UP", "0"), env("PBT_WS_RES", "0")   # weight-stationary MMA runs on the N = 128 layers
         self.use_tap_pairs = env("PBT_TAP_PAIRS", "1")
         self.residual16 = env("PBT_RESIDUAL16", "1")    # inference: 16-bit residual stream (see _Workspace.r16)
         self.batch_tiles = env("PBT_BATCH_TILES", "1")   # small maps: one CTA = the same tile of two images (see _bt)
@@ -481,7 +482,7 @@ class _Engine:
             ops.conv_fwd(xin, W[name], cout, k, k, pad, pad, dt, blk_c=self._blk(cin), tiles_per_cta=T, out=raw,
                          stats_partial=None if (frozen or no_norm) else st["partial"], upsample2x=up, pre=pre,
                          pre_scale=None if pre_st is None else pre_st["scale"], pre_shift=None if pre_st is None else pre_st["shift"],
-                         up_raw_channels=up_raw,
+                         up_raw_channels=up_raw, debug_flags=32 if ((up and self.ws_up) or (name.startswith("res") and self.ws_res)) else 0,
                          pre_act=pre_act, ctas_per_sm=0 if pair else cps, bias=plain_bias, cta_pair=pair, batch_tiles=bool(bt),
                          tap_pairs=tp)
             if no_norm:
