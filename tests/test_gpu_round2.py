@@ -229,3 +229,50 @@ def test_native_critic_matches_the_tensor_library_expression(cfg):
     print(f"{cfg} n={n}: logits err {err:.2e}, loss {nat_loss:.6f}/{ref_loss:.6f}, dL/dx cosine {cos:.5f} rel {rel:.4f}")
     assert cos > 0.999 and rel < 3e-2, (cos, rel)
     d.native = True
+
+
+def test_sampler_at_full_hd_keyframes_matches_the_oracle_cut():
+    """the C3 sampler at its real size (1080p keyframes, two guide sources, patch 80, batch 80): draws follow the oracle's
+    bookkeeping (numpy RNG + k-th-unused selection) and every gathered patch equals the oracle's `_cut_patch` restatement on
+    the resident images, including centres near the frame border"""
+    from oracle import sampler_oracle as so
+    from pbt_b200.sampler import StyleTransferDataset
+    rng = np.random.RandomState(3)
+    H, W, K = 1080, 1920, 2
+    rgb = lambda: [rng.randint(0, 256, (H, W, 3)).astype(np.uint8) for _ in range(K)]  # noqa: E731
+    pre, post, g1, g2 = rgb(), rgb(), rgb(), rgb()
+    masks = []
+    for i in range(K):
+        m = np.zeros((H, W), np.uint8)
+        m[:60, :90] = 255                      # touches the top-left corner: clamped, zero-padded patches
+        m[H - 50:, W - 70:] = 200              # bottom-right corner
+        m[400:700, 800:1300] = 255
+        masks.append(m)
+    ds = StyleTransferDataset.from_arrays(pre, post, masks, 80, additional={"gauss": g1, "flow": g2})
+    # the oracle's draw bookkeeping on the same valid lists
+    left = [list(range(len(v))) for v in ds._valid_np]
+    idx = rng.randint(0, len(ds), 160).tolist()
+    np.random.seed(11)
+    batch_a = ds.sample_batch(idx[:80])
+    batch_b = ds.sample_batch(idx[80:])
+    np.random.seed(11)
+    exp = []
+    for i in idx:
+        img = i % K
+        if not left[img]:
+            left[img] = list(range(len(ds._valid_np[img])))
+        c = np.random.randint(0, len(left[img]))
+        y, x = ds._valid_np[img][left[img].pop(c)]
+        exp.append((img, int(y), int(x)))
+    got = torch.cat([batch_a["positions"], batch_b["positions"]]).tolist()
+    assert got == [list(e) for e in exp]
+    assert any(y < 40 or x < 40 or y > H - 40 or x > W - 40 for _, y, x in exp), "no border patch in the draw"
+    res = {k: [t.cpu().numpy() for t in v] for k, v in (("pre", ds.images_pre), ("post", ds.images_post),
+                                                          ("gauss", ds.additional_channel_data["gauss"]),
+                                                          ("flow", ds.additional_channel_data["flow"]))}
+    for b, batch in enumerate((batch_a, batch_b)):
+        comb, pst = batch["combined_input"].cpu().numpy(), batch["post"].cpu().numpy()
+        for j in range(0, 80, 7):
+            img, y, x = exp[b * 80 + j]
+            ref = np.concatenate([so.cut_patch(res[k][img], y, x, 80) for k in ("pre", "gauss", "flow")], 0)
+            assert np.array_equal(comb[j], ref) and np.array_equal(pst[j], so.cut_patch(res["post"][img], y, x, 80)), (b, j)
