@@ -102,7 +102,8 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor, want_input_grad: 
     # fills the GPU (a 128->128 3x3 wgrad is ~180 CTAs, its dgrad ~480 of 592 slots).  Their parameter gradients are
     # published (grad hook -> all-reduce bucket) at the join points, on the main stream.
     main = torch.cuda.current_stream(dev)
-    side = eng.side_stream()
+    sides = eng.side_streams()
+    n_side = [0]
     keep = []
     last_dw = [None]
 
@@ -112,6 +113,8 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor, want_input_grad: 
         ordered behind the side stream without holding up the data-gradient chain); returns the event that marks the side
         job's completion (wait for it before overwriting x or dy)"""
         dw = Z(k * k, x.c, dy.c)
+        side = sides[n_side[0] % len(sides)]
+        n_side[0] += 1
         fork = torch.cuda.Event()
         fork.record(main)
         side.wait_event(fork)
@@ -126,10 +129,11 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor, want_input_grad: 
         return done
 
     def join():
-        """main stream waits for the side stream"""
-        ev = torch.cuda.Event()
-        ev.record(side)
-        main.wait_event(ev)
+        """main stream waits for the side streams"""
+        for side in sides:
+            ev = torch.cuda.Event()
+            ev.record(side)
+            main.wait_event(ev)
         keep.clear()
 
     bn_mode, no_norm = eng.norm_mode() == "batch", eng.norm_mode() == "none"
