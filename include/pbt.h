@@ -257,6 +257,13 @@ typedef struct {
   int32_t      dtype;
   pbt_act_t    residual16;  /* 16-bit residual addend (ptr NULL = none; not together with residual32): the inference pass keeps
                              * the residual stream in 16 bits, like the reference's own `.half()` CUDA inference (generator.py:185) */
+  /* fused InstanceNorm finalize (training passes, <= 64 tiles per image): when `partial` (the conv's [n][tiles][2][c] per-tile
+   * sums) is given, scale = rstd and shift = -mean*rstd are computed inside this launch from it (count pixels per image, eps)
+   * and WRITTEN to `scale` / `shift` for later consumers, replacing a separate pbt_norm_finalize launch */
+  const float* partial;
+  int32_t      tiles;
+  int64_t      count;
+  float        eps;
 } pbt_norm_apply_desc_t;
 int pbt_norm_apply(const pbt_norm_apply_desc_t* d, void* stream);
 

@@ -55,7 +55,7 @@ class NormApplyDesc(C.Structure):
     _fields_ = [
         ("x", Act), ("scale", C.c_void_p), ("shift", C.c_void_p), ("per_channel", C.c_int32), ("act", C.c_int32),
         ("residual32", C.c_void_p), ("out", Act), ("out_relu", Act), ("out32", C.c_void_p), ("out_s2d", Act),
-        ("dtype", C.c_int32), ("residual16", Act),
+        ("dtype", C.c_int32), ("residual16", Act), ("partial", C.c_void_p), ("tiles", C.c_int32), ("count", C.c_int64), ("eps", C.c_float),
     ]
 
 

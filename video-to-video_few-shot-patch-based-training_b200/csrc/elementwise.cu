@@ -366,6 +366,14 @@ struct NormApplyK {
   int per_channel, act;
   const float* residual32;
   float* out32;
+  // fused InstanceNorm finalize: scale / shift are computed here from the conv's per-tile (sum, sumsq) partials and also
+  // written out (block x == 0) for the backward pass, instead of a separate pbt_norm_finalize launch
+  const float* partial;
+  float* scale_out;
+  float* shift_out;
+  int tiles;
+  double inv_count;
+  float eps;
 };
 
 template <int DT>
@@ -380,7 +388,32 @@ __global__ void norm_apply_kernel(NormApplyK p) {
     sc[k] = 1.f;
     sh[k] = 0.f;
   }
-  if (p.scale) {
+  if (p.partial) {
+    // per-image statistics of this block's 8 channels: the first 16 threads add up the tiles (double, fixed order - the same
+    // arithmetic as norm_finalize_kernel), everyone reads the result from shared memory
+    __shared__ double s_ss[16];
+    if (threadIdx.x < 16) {
+      const int which = threadIdx.x >> 3, k = threadIdx.x & 7;
+      const float* pp = p.partial + (long long)ni * p.tiles * 2 * p.x.c + (long long)which * p.x.c + pl * 8 + k;
+      double a = 0.0;
+      for (int t = 0; t < p.tiles; ++t) a += (double)pp[(long long)t * 2 * p.x.c];
+      s_ss[threadIdx.x] = a * p.inv_count;     // mean, mean of squares
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const double mean = s_ss[k];
+      double var = s_ss[8 + k] - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float rstd = (float)(1.0 / sqrt(var + (double)p.eps));
+      sc[k] = rstd;
+      sh[k] = -(float)mean * rstd;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 8) {
+      p.scale_out[(long long)ni * p.x.c + pl * 8 + threadIdx.x] = sc[threadIdx.x];
+      p.shift_out[(long long)ni * p.x.c + pl * 8 + threadIdx.x] = sh[threadIdx.x];
+    }
+  } else if (p.scale) {
     const long long so = (p.per_channel ? 0 : (long long)ni * p.x.c) + pl * 8;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -388,10 +421,11 @@ __global__ void norm_apply_kernel(NormApplyK p) {
       sh[k] = __ldg(&p.shift[so + k]);
     }
   }
+  const bool affine = p.scale || p.partial;
   for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < hw; pix += gridDim.x * blockDim.x) {
     float f[8];
     unpack8<DT>(*chunk_ptr(p.x, ni, pl, pix), f);
-    if (p.scale) {
+    if (affine) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) f[k] = fmaf(f[k], sc[k], sh[k]);
     }
@@ -1315,6 +1349,13 @@ extern "C" int pbt_norm_apply(const pbt_norm_apply_desc_t* d, void* stream_) {
   }
   p.scale = d->scale; p.shift = d->shift; p.per_channel = d->per_channel; p.act = d->act;
   p.residual32 = d->residual32; p.out32 = d->out32;
+  if (d->partial) {
+    PBT_REQUIRE(d->scale && d->shift && !d->per_channel && d->tiles > 0 && d->tiles <= 64 && d->count > 0,
+                "norm_apply: fused finalize needs scale / shift outputs, per-image statistics, 1..64 tiles and a pixel count");
+    p.partial = d->partial; p.scale_out = const_cast<float*>(d->scale); p.shift_out = const_cast<float*>(d->shift);
+    p.tiles = d->tiles; p.inv_count = 1.0 / (double)d->count; p.eps = d->eps;
+    p.scale = nullptr; p.shift = nullptr;
+  }
   if (d->residual16.ptr) {
     PBT_REQUIRE(!d->residual32 && same(d->residual16), "norm_apply: residual16 shape mismatch (or both residuals given)");
     p.res16 = view(d->residual16);

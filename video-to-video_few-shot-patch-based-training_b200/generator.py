@@ -244,6 +244,7 @@ class _Engine:
         # inference: up2's norm + ReLU applied inside up1's upsample-on-load (built and tested; measured 20.25 -> 20.36 ms per
         # 4-frame pass - up1's transform warps are on its critical path, the saved 0.2-ms normalise pass does not pay: off)
         self.fold_up = env("PBT_FOLD_UP", "0")
+        self.fuse_finalize = env("PBT_FUSE_FINALIZE", "1")   # training: InstanceNorm finalize inside the consuming norm_apply
         self.ws_up, self.ws_res = env("PBT_WS_UP", "0"), env("PBT_WS_RES", "0")   # weight-stationary MMA runs on the N = 128 layers
         self.use_tap_pairs = env("PBT_TAP_PAIRS", "1")
         self.residual16 = env("PBT_RESIDUAL16", "1")    # inference: 16-bit residual stream (see _Workspace.r16)
@@ -459,7 +460,7 @@ class _Engine:
             x = x.float()
 
         def conv_in(name, xin, cout, k, pad, raw, T_pref, up=False, pre=None, pre_st=None, pre_act=ACT_NONE, cps=0, pair=False,
-                    up_raw=0):
+                    up_raw=0, defer=False):
             """conv (bias skipped: a constant per channel is removed by the following InstanceNorm) + IN statistics;
             up=True: xin is the low-res tensor, the conv consumes its bilinear x2 upsample (interpolated in-kernel);
             pre: raw output of the previous conv, its InstanceNorm (pre_st) + activation applied on load"""
@@ -492,6 +493,12 @@ class _Engine:
                     st["identity"] = True
                 return st
             if not bn_mode:
+                if defer and save and st["tiles"] <= 64 and self.fuse_finalize:
+                    # the consuming norm_apply computes scale / shift from the partial sums itself (and stores them for the
+                    # backward pass): one launch less per normalised layer on the critical path of the training step
+                    st["deferred"] = dict(partial=st["partial"], tiles=st["tiles"], count=oh * ow, eps=EPS)
+                    return st
+                st.pop("deferred", None)
                 ops.norm_finalize(st["partial"], n, st["tiles"], cout, oh * ow, st["scale"], st["shift"], eps=EPS)
                 return st
             # norm_layer='batch_norm' (reference :83-87): the same scale/shift tables, filled from batch statistics pooled
@@ -518,6 +525,10 @@ class _Engine:
             bn.num_batches_tracked += 1
             return st
 
+        def napply(x, st, **kw):
+            """norm_apply with the layer's statistics; a deferred finalize (see conv_in) is computed inside this launch"""
+            ops.norm_apply(x, dt, scale=st["scale"], shift=st["shift"], **(st.pop("deferred", None) or {}), **kw)
+
         # input -> tail channels of cat11 (pad channels zeroed every call)
         xin = ws.cat11.view(f[4] + f[0], cp)
         if u8_hwc:
@@ -525,13 +536,13 @@ class _Engine:
         else:
             ops.nchw_to_p8(x, xin, dt)
         # encoder
-        st = conv_in("initial", xin, f[0], 7, 3, ws.raw0, 3, cps=4)
-        ops.norm_apply(ws.raw0, dt, scale=st["scale"], shift=st["shift"], act=ACT_LEAKY, out=ws.cat11.view(f[4], f[0]),
+        st = conv_in("initial", xin, f[0], 7, 3, ws.raw0, 3, cps=4, defer=True)
+        napply(ws.raw0, st, act=ACT_LEAKY, out=ws.cat11.view(f[4], f[0]),
                        out_s2d=ws.s2d0)
-        st = conv_in("down1", ws.s2d0, f[1], 2, 1, ws.raw1, 2, cps=4)
-        ops.norm_apply(ws.raw1, dt, scale=st["scale"], shift=st["shift"], act=ACT_LEAKY, out=ws.c1cat.view(f[4], f[1]),
+        st = conv_in("down1", ws.s2d0, f[1], 2, 1, ws.raw1, 2, cps=4, defer=True)
+        napply(ws.raw1, st, act=ACT_LEAKY, out=ws.c1cat.view(f[4], f[1]),
                        out_s2d=ws.s2d1)
-        st = conv_in("down2", ws.s2d1, f[2], 2, 1, ws.raw2, 2, cps=4)
+        st = conv_in("down2", ws.s2d1, f[2], 2, 1, ws.raw2, 2, cps=4, defer=True)
         nb = len(g.resnet_blocks)
         r16 = ws.r16 is not None                # inference: 16-bit residual stream; r_0 is the skip slot of c2cat itself
         if r16:
@@ -541,10 +552,10 @@ class _Engine:
         a_of = (lambda i: ws.a[i]) if save else (lambda i: ws.a[i % 2])
         last16 = ws.c2cat.view(0, f[2])
         if nb == 0:
-            ops.norm_apply(ws.raw2, dt, scale=st["scale"], shift=st["shift"], act=ACT_LEAKY, out=ws.c2cat.view(f[2], f[2]))
-            ops.norm_apply(ws.raw2, dt, scale=st["scale"], shift=st["shift"], act=ACT_LEAKY, out=last16)
+            napply(ws.raw2, st, act=ACT_LEAKY, out=ws.c2cat.view(f[2], f[2]))
+            napply(ws.raw2, st, act=ACT_LEAKY, out=last16)
         else:
-            ops.norm_apply(ws.raw2, dt, scale=st["scale"], shift=st["shift"], act=ACT_LEAKY, out=ws.c2cat.view(f[2], f[2]),
+            napply(ws.raw2, st, act=ACT_LEAKY, out=ws.c2cat.view(f[2], f[2]),
                            out32=None if r16 else r_cur, out_relu=a_of(0))
         # residual blocks: r_{b+1} = r_b + IN(convB(relu(IN(convA(relu(r_b))))))
         # inference: IN + ReLU of a conv's raw output are applied inside the NEXT conv's shared-memory tile
@@ -553,19 +564,19 @@ class _Engine:
         nol_11 = not save and f[4] % 32 == 0 and f[4] <= 256 and g.append_smoothers
         for b in range(nb):
             k = b if save else 0
-            st = conv_in(f"res{b}.a", a_of(b), f[2], 3, 1, ws.rawA[k], 2, cps=4, pair=pr)
+            st = conv_in(f"res{b}.a", a_of(b), f[2], 3, 1, ws.rawA[k], 2, cps=4, pair=pr, defer=not nol_res)
             if nol_res:
                 st = conv_in(f"res{b}.b", None, f[2], 3, 1, ws.rawB[k], 2, pre=ws.rawA[k], pre_st=st, pre_act=ACT_RELU, pair=pr)
             else:
-                ops.norm_apply(ws.rawA[k], dt, scale=st["scale"], shift=st["shift"], act=ACT_RELU, out=ws.hmid[k])
-                st = conv_in(f"res{b}.b", ws.hmid[k], f[2], 3, 1, ws.rawB[k], 2, cps=4, pair=pr)
+                napply(ws.rawA[k], st, act=ACT_RELU, out=ws.hmid[k])
+                st = conv_in(f"res{b}.b", ws.hmid[k], f[2], 3, 1, ws.rawB[k], 2, cps=4, pair=pr, defer=True)
             lastb = b == nb - 1
             if r16:
-                ops.norm_apply(ws.rawB[k], dt, scale=st["scale"], shift=st["shift"], act=ACT_NONE, residual16=r_cur,
+                napply(ws.rawB[k], st, act=ACT_NONE, residual16=r_cur,
                                out=last16 if lastb else r_nxt, out_relu=None if lastb else a_of(b + 1))
                 r_cur, r_nxt = r_nxt, (ws.r16[1] if b == 0 else r_cur)      # never write into c2cat's skip slot
             else:
-                ops.norm_apply(ws.rawB[k], dt, scale=st["scale"], shift=st["shift"], act=ACT_NONE, residual32=r_cur,
+                napply(ws.rawB[k], st, act=ACT_NONE, residual32=r_cur,
                                out32=None if lastb else r_nxt, out=last16 if lastb else None,
                                out_relu=None if lastb else a_of(b + 1))
                 r_cur, r_nxt = r_nxt, r_cur
@@ -577,7 +588,7 @@ class _Engine:
             # IN + ReLU of the up2 output are applied on load by the upsample kernel (never materialised at H/2)
             ops.upsample2x(ws.rawU2, ws.u1in.view(0, f[4]), dt, scale=st["scale"], shift=st["shift"], act=ACT_RELU)
             ops.upsample2x(ws.c1cat.view(f[4], f[1]), ws.u1in.view(f[4], f[1]), dt)
-            st = conv_in("up1", ws.u1in, f[4], 3, 1, ws.rawU1, 2)
+            st = conv_in("up1", ws.u1in, f[4], 3, 1, ws.rawU1, 2, defer=True)
         else:
             # the raw output of up2 goes straight into its slot of up1's input; up1 normalises + activates it inside the staged
             # low-res tile before interpolating (up_raw_channels), so that normalise pass never touches HBM either
@@ -589,7 +600,7 @@ class _Engine:
                 ops.norm_apply(ws.rawU2, dt, scale=st["scale"], shift=st["shift"], act=ACT_RELU, out=ws.c1cat.view(0, f[4]))
                 st = conv_in("up1", ws.c1cat, f[4], 3, 1, ws.rawU1, 2, up=True, pair=pu)
         if not nol_11:
-            ops.norm_apply(ws.rawU1, dt, scale=st["scale"], shift=st["shift"], act=ACT_RELU, out=ws.cat11.view(0, f[4]))
+            napply(ws.rawU1, st, act=ACT_RELU, out=ws.cat11.view(0, f[4]))
         # conv11 + smoothers + fused head
         ev = self.kernel_timer
         if ev is not None:

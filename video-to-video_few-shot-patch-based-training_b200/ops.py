@@ -180,12 +180,15 @@ def norm_finalize(partial, n, tiles, c, count_per_image, scale, shift, *, eps=1e
 
 def norm_apply(x: P8, dt: int, *, scale=None, shift=None, per_channel=False, act=ACT_NONE, residual32=None,
                out: P8 | None = None, out_relu: P8 | None = None, out32=None, out_s2d: P8 | None = None,
-               residual16: P8 | None = None) -> None:
+               residual16: P8 | None = None, partial=None, tiles: int = 0, count: int = 0, eps: float = 1e-5) -> None:
+    """`partial` (with tiles, count, eps): fused InstanceNorm finalize - scale / shift are computed from the conv's per-tile sums
+    inside the launch and written to `scale` / `shift`"""
     d = nv.NormApplyDesc()
     d.x = x.act()
     d.scale, d.shift, d.per_channel, d.act = ptr(scale), ptr(shift), int(per_channel), act
     d.residual32 = ptr(residual32)
     d.residual16 = act_or_null(residual16)
+    d.partial, d.tiles, d.count, d.eps = ptr(partial), int(tiles), int(count), float(eps)
     d.out, d.out_relu, d.out32, d.out_s2d = act_or_null(out), act_or_null(out_relu), ptr(out32), act_or_null(out_s2d)
     d.dtype = dt
     check(lib().pbt_norm_apply(C.byref(d), stream_ptr()), "pbt_norm_apply")
