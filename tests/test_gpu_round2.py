@@ -276,3 +276,23 @@ def test_sampler_at_full_hd_keyframes_matches_the_oracle_cut():
             img, y, x = exp[b * 80 + j]
             ref = np.concatenate([so.cut_patch(res[k][img], y, x, 80) for k in ("pre", "gauss", "flow")], 0)
             assert np.array_equal(comb[j], ref) and np.array_equal(pst[j], so.cut_patch(res["post"][img], y, x, 80)), (b, j)
+
+
+def test_fused_finalize_switch_gives_identical_results():
+    """`_Engine.fuse_finalize` (InstanceNorm scale / shift computed inside the consuming norm_apply launch) is the same
+    arithmetic in the same order: outputs, running statistics and gradients must not change"""
+    vec = np.load(os.path.join(GOLD, "gen_c3_vectors.npz"))
+    x, t = torch.from_numpy(vec["x"][:8]).cuda(), torch.from_numpy(vec["target"][:8]).cuda()
+    res = []
+    for fused in (False, True):
+        g = _small_gen().train()
+        y0 = g(x[:1])                      # builds the engine
+        g._engine.fuse_finalize = fused
+        g.zero_grad(set_to_none=True)
+        y = g(x)
+        (torch.nn.functional.l1_loss(y, t) * 4.0).backward()
+        res.append((y.detach().clone(), [p.grad.detach().clone() for p in g.parameters()]))
+    assert torch.equal(res[0][0], res[1][0])
+    for a, b in zip(res[0][1], res[1][1]):
+        peak = float(a.abs().max())
+        assert float((a - b).abs().max()) <= 4e-3 * peak + 1e-12      # wgrad atomics reorder fp32 sums run to run

@@ -244,7 +244,9 @@ class _Engine:
         # inference: up2's norm + ReLU applied inside up1's upsample-on-load (built and tested; measured 20.25 -> 20.36 ms per
         # 4-frame pass - up1's transform warps are on its critical path, the saved 0.2-ms normalise pass does not pay: off)
         self.fold_up = env("PBT_FOLD_UP", "0")
-        self.fuse_finalize = env("PBT_FUSE_FINALIZE", "1")   # training: InstanceNorm finalize inside the consuming norm_apply
+        # training: InstanceNorm finalize inside the consuming norm_apply launch (built and tested; measured at C3 5.69 -> 5.72 ms
+        # per step - the per-CTA tile sum costs more than the launch that programmatic dependent launch already hides: off)
+        self.fuse_finalize = env("PBT_FUSE_FINALIZE", "0")
         self.ws_up, self.ws_res = env("PBT_WS_UP", "0"), env("PBT_WS_RES", "0")   # weight-stationary MMA runs on the N = 128 layers
         self.use_tap_pairs = env("PBT_TAP_PAIRS", "1")
         self.residual16 = env("PBT_RESIDUAL16", "1")    # inference: 16-bit residual stream (see _Workspace.r16)
