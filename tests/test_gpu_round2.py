@@ -296,3 +296,31 @@ def test_fused_finalize_switch_gives_identical_results():
     for a, b in zip(res[0][1], res[1][1]):
         peak = float(a.abs().max())
         assert float((a - b).abs().max()) <= 4e-3 * peak + 1e-12      # wgrad atomics reorder fp32 sums run to run
+
+
+def test_forty_training_steps_track_the_oracle():
+    """config C1 shape (batch 40 x 32x32, Cin 3): forty G-only steps (L1*4, clip 0.5, Adam 4e-4 / wd 1e-5) on two alternating real
+    patch batches through the graph-replayed native step against the fp32 oracle's trajectory on the host cores"""
+    from oracle import generator_oracle as go
+    from pbt_b200.graphs import GraphedGeneratorStep
+    from pbt_b200.optim import FusedClipAdam
+    vec = np.load(os.path.join(GOLD, "gen_c3_vectors.npz"))
+    z = np.load(os.path.join(GOLD, "gen_c3_trained.npz"))
+    sd = {k: torch.from_numpy(z[k]).clone() for k in z.files}
+    x, t = torch.from_numpy(vec["x"]), torch.from_numpy(vec["target"])
+    batches = [(x, t), (x.flip(0).flip(3).contiguous(), t.flip(0).flip(3).contiguous())]
+    torch.set_num_threads(os.cpu_count() or 1)
+    st = go.AdamState([k for k, v in sd.items() if v.is_floating_point() and "running_" not in k])
+    ref = [float(go.g_only_train_step(sd, st, *batches[i % 2])) for i in range(40)]
+    g = _small_gen().train()
+    opt = FusedClipAdam(g.parameters(), lr=4e-4, betas=(0.9, 0.999), weight_decay=1e-5, max_grad_norm=0.5)
+    step = GraphedGeneratorStep(g, opt, tuple(x.shape), clip=0.5)
+    got = [float(step(batches[i % 2][0].cuda(), batches[i % 2][1].cuda())) for i in range(40)]
+    worst = max(abs(a - b) / b for a, b in zip(got, ref))
+    print(f"native {got[0]:.4f} -> {got[-1]:.4f}, oracle {ref[0]:.4f} -> {ref[-1]:.4f}, worst relative gap {worst:.4f}, skipped {opt.skipped_steps}")
+    assert got[-1] < 0.8 * got[0] and worst < 0.05 and opt.skipped_steps == 0
+    # the trained weights stay close to the oracle's (same trajectory, 16-bit operand noise only)
+    for k, p in g.named_parameters():
+        if k.endswith(".weight") and p.dim() == 4:
+            a, b = p.detach().cpu(), sd[k]
+            assert float((a - b).norm() / b.norm()) < 0.05, k
