@@ -24,7 +24,8 @@ FLAGS = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 NIMG = 1
 if len(sys.argv) > 2 and sys.argv[2] == "train":     # C3 training shapes: 80 patches
     NIMG = 80
-    cases = [("res 128->128 3x3 @20x20 x80 T1 cps4 +stats", 128, 128, 3, 20, 20, 1, 32, True, 4),
+    cases = [("res 128->128 3x3 @20x20 x80 T2 BATCH TILES +stats", 128, 128, 3, 20, 20, 2, 32, True, 0, False, False, True),
+             ("res 128->128 3x3 @20x20 x80 T1 cps4 +stats", 128, 128, 3, 20, 20, 1, 32, True, 4),
              ("res 128->128 3x3 @20x20 x80 T1 cps2 +stats", 128, 128, 3, 20, 20, 1, 32, True, 0),
              ("up2 256->128 3x3 @40x40 x80 T2", 256, 128, 3, 40, 40, 2, 32, True, 0),
              ("smooth 64->64 3x3 @80x80 x80 T2 blk16 cps4", 64, 64, 3, 80, 80, 2, 16, False, 4)]
@@ -32,23 +33,25 @@ for name, cin, cout, k, h, w, T, blk, stats, *rest in cases:
     cps = rest[0] if rest else 0
     pair = rest[1] if len(rest) > 1 else False
     up = rest[2] if len(rest) > 2 else False
+    bt = rest[3] if len(rest) > 3 else False
     x = P8.empty(NIMG, cin, h // 2 if up else h, w // 2 if up else w, dt)
     x.t.normal_()
     wp = ops.pack_conv_weight(torch.randn((cout, cin, k, k), device="cuda") * 0.05, cin, blk, dt, pair=pair)
     out = P8.empty(NIMG, cout, h, w, dt)
-    tiles = ops.conv_num_tiles(h, w, T)
+    tiles = ops.conv_num_tiles(h, w, 1 if bt else T)
     part = torch.empty((NIMG, tiles, 2, cout), device="cuda") if stats else None
-    dbg = torch.zeros((tiles * NIMG, 8), dtype=torch.int64, device="cuda")
+    n_cta = tiles * ((NIMG + T - 1) // T if bt else NIMG)
+    dbg = torch.zeros((n_cta, 8), dtype=torch.int64, device="cuda")
     for _ in range(2):
         ops.conv_fwd(x, wp, cout, k, k, k // 2, k // 2, dt, blk_c=blk, tiles_per_cta=T, out=out, stats_partial=part, debug_buf=dbg, debug_flags=FLAGS | 128, upsample2x=up,
-                     ctas_per_sm=cps, cta_pair=pair)
+                     ctas_per_sm=cps, cta_pair=pair, batch_tiles=bt)
     torch.cuda.synchronize()
     d = dbg.cpu().double()
     t0 = d[:, 0:1]
     rel = d[:, 1:7] - t0
     med = rel.median(0).values
     names = ["setup done", "first A landed", "MMA issue done", "acc ready (epi start)", "epilogue done", "exit"]
-    print(f"== {name}: {tiles * NIMG} CTAs; median cycles since CTA start:")
+    print(f"== {name}: {n_cta} CTAs; median cycles since CTA start:")
     for nm, v in zip(names, med.tolist()):
         print(f"     {nm:24s} {v:10.0f}")
     # per-SM occupancy of time: CTAs per SM and total span
