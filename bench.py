@@ -207,7 +207,9 @@ def run_reference(args):
         "impl": "reference", "metric": cfg["metric"], "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": cfg["what"], "frame": [h, w, c], "frames_per_step": 1},
+        "config": {"workload": cfg["what"], "frame": [h, w, c], "video_frames": cfg["video"], "frames_per_step": 1,
+                   "weights": f"tests/golden/{cfg['weights']} (100 reference training steps)",
+                   "sample": "one whole frame per step: a bounded sample of the native arm's 200-frame step"},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
@@ -354,7 +356,8 @@ def run_native(args):
         "metric": cfg["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": operand + " operands, f32 accumulate", "data": "synthetic",
-        "config": {"workload": cfg["what"] + "; frames sharded by FrameStylizer.stylize_video (one contiguous range per GPU, no collective)",
+        "config": {"workload": cfg["what"],
+                   "sharding": "FrameStylizer.stylize_video: one contiguous frame range per GPU, no collective",
                    "frames_per_step": SEG, "video_frames": VIDEO, "frames_per_generator_pass": per_pass, "frame": [H, W, CIN],
                    "weights": f"tests/golden/{cfg['weights']} (100 reference training steps)",
                    "l2": f"the {min(segs_used * SEG, VIDEO)} resident frames are distinct and each pass streams ~{3.5 * per_pass * H * W / (1080 * 1920):.0f} GB of activations >> 126 MB L2"},
