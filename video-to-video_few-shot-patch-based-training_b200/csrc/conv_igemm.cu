@@ -1088,7 +1088,9 @@ extern "C" int pbt_conv_fwd(const pbt_conv_desc_t* d, void* stream_) {
     const uint32_t tail = 8u * (2 * 2 + 2 * 8 + 1) + 16 + (uint32_t)(ew * 2 * p.NC * 4 * (bt ? T : 1)) + (ew == 8 ? 3 * 4 * 32 * 3 * 4 : 0) +
                           8 * 14 + (uint32_t)(2 * p.pre_c * 4) + 128;
     const uint32_t budget = ew == 4 ? 55 * 1024 : 112 * 1024;
-    int group = (int)((ew == 4 ? 8192u : 16384u) / chunk);
+    static const unsigned stage_big = getenv("PBT_B_STAGE_BYTES") ? (unsigned)atoi(getenv("PBT_B_STAGE_BYTES")) : 16384u;  // (tuning knob)
+    static const unsigned stage_small = getenv("PBT_B_STAGE_BYTES_SMALL") ? (unsigned)atoi(getenv("PBT_B_STAGE_BYTES_SMALL")) : 8192u;
+    int group = (int)((ew == 4 ? stage_small : stage_big) / chunk);
     if (group < 1) group = 1;
     if (group > ntaps) group = ntaps;
     int stages = 4;
