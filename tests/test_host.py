@@ -229,3 +229,28 @@ def test_index_loader_gives_every_rank_the_same_number_of_steps():
         assert len(batches) == len(ld) == 2 and sum(len(b) for b in batches) == 81
         seen += [i for b in batches for i in b]
     assert set(seen) == set(range(161)) and len(seen) == 162       # one wrapped-around index, as DistributedSampler pads
+
+
+def test_non_fused_adam_path_never_writes_non_finite_weights():
+    """optimizer.*.fused=false uses torch.optim.Adam, which has no skip-on-overflow: `_clip_and_step` replaces non-finite
+    gradients (fp16 overflow in a backward sweep) by zeros so that the weights stay finite"""
+    import torch
+    from lightning_model import StyleTransferModel
+    tcfg = {"batch_size": 2, "reconstruction_weight": 4.0, "adversarial_weight": 0.5, "use_image_loss": True,
+            "reconstruction_criterion": "L1Loss", "adversarial_criterion": "MSELoss", "use_gradient_clipping": True,
+            "gradient_clip_val": 0.5, "cuda_graph": False, "use_adversarial_loss": False}
+    adam = {"lr": 4e-4, "betas": [0.9, 0.999], "weight_decay": 1e-5, "fused": False}
+    m = StyleTransferModel({"args": {"input_channels": 3, "use_bias": True}}, None, tcfg, {"generator": dict(adam)},
+                           {"additional_channels": {}})
+    (opt,) = m.configure_optimizers()
+    assert isinstance(opt, torch.optim.Adam)
+    w0 = [p.detach().clone() for p in m.generator.parameters()]
+    for i, p in enumerate(m.generator.parameters()):
+        p.grad = torch.full_like(p, float("inf") if i == 3 else 1e-3)
+    m._clip_and_step(opt, m.generator)
+    assert all(torch.isfinite(p).all() for p in m.generator.parameters())
+    for i, p in enumerate(m.generator.parameters()):
+        p.grad = torch.full_like(p, 1e-3)
+    m._clip_and_step(opt, m.generator)
+    assert all(torch.isfinite(p).all() for p in m.generator.parameters())
+    assert any(not torch.equal(a, p.detach()) for a, p in zip(w0, m.generator.parameters()))
