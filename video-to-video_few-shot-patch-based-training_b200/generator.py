@@ -251,6 +251,7 @@ class _Engine:
         self.use_tap_pairs = env("PBT_TAP_PAIRS", "1")
         self.residual16 = env("PBT_RESIDUAL16", "1")    # inference: 16-bit residual stream (see _Workspace.r16)
         self.batch_tiles = env("PBT_BATCH_TILES", "1")   # small maps: one CTA = the same tile of two images (see _bt)
+        self._pack_bwd_done = None   # event: the side-stream packing of the data-gradient weights of this step has finished
         self._saved_stamp = 0     # counts grad-enabled forward passes: a backward must match the pass that saved its activations
         self.bucket = None        # parallel.GradBucket: flat fp32 storage the backward sweep writes the parameter gradients into
         self.kernel_timer = None  # bench.py: list collecting (start event, end event, frames) around the dominant kernel (conv11)
@@ -374,6 +375,17 @@ class _Engine:
         # at replay time, not a host-side cache decision taken at capture time)
         if slot["key"] != key or torch.cuda.is_current_stream_capturing():
             slot["packer"].run()
+            self._pack_bwd_done = None
+            if slot["packer_bwd"] is not None:
+                main = torch.cuda.current_stream(self.device)
+                side = self.side_streams()[0]
+                fork = torch.cuda.Event()
+                fork.record(main)
+                side.wait_event(fork)
+                with torch.cuda.stream(side):
+                    slot["packer_bwd"].run()
+                    self._pack_bwd_done = torch.cuda.Event()
+                    self._pack_bwd_done.record(side)
             slot["key"] = key
         return slot["W"]
 
@@ -381,6 +393,9 @@ class _Engine:
         g, dt, cp = self.gen, self.dt, self.cin_p
         f = g.filters
         pk = ops.WeightPacker(self.device)
+        # the data-gradient forms are first read by the backward sweep: they get their own launch, which runs on a side
+        # stream underneath the forward pass instead of in front of it (see _weights)
+        pkd = ops.WeightPacker(self.device) if with_dgrad else None
 
         def fwd(name, conv, k_pad, s2d=False, blk=None, pair=False):
             co = conv.weight.shape[0]
@@ -391,8 +406,8 @@ class _Engine:
             co, ci = conv.weight.shape[0], conv.weight.shape[1]
             vi = 4 * ci if s2d else ci
             n_keep = vi if keep is None else keep
-            pk.add(name + ".d", conv.weight.detach(), s2d=s2d, dgrad=True, k_pad=co, n_out=n_out or _pad16(n_keep), n_keep=n_keep,
-                   blk_c=self._blk(co), dt=dt, pair=pair)
+            pkd.add(name + ".d", conv.weight.detach(), s2d=s2d, dgrad=True, k_pad=co, n_out=n_out or _pad16(n_keep), n_keep=n_keep,
+                    blk_c=self._blk(co), dt=dt, pair=pair)
 
         pr, pu, ps = self._pairs(with_dgrad)
         if self.tap_pairs():
@@ -430,6 +445,8 @@ class _Engine:
                 dgr("conv11x", g.conv11[0], n_out=self.cat11x_channels())
                 dgr("initial", g.initial_conv[0])
         W: Dict[str, Any] = dict(pk.out)
+        if pkd is not None:
+            W.update(pkd.out)
 
         def f32(t):
             return None if t is None else (t.detach() if t.dtype == torch.float32 else t.detach().float())
@@ -439,7 +456,8 @@ class _Engine:
         W["head_b"] = f32(g.output[0].bias)
         W["b11"] = f32(g.conv11[0].bias)
         W["bs0"], W["bs3"] = (f32(g.smoothers[0].bias), f32(g.smoothers[3].bias)) if g.append_smoothers else (None, None)
-        return {"packer": pk, "W": W, "key": None, "ptrs": tuple(p.data_ptr() for p in g.parameters())}
+        return {"packer": pk, "packer_bwd": pkd if (pkd is not None and pkd.jobs) else None, "W": W, "key": None,
+                "ptrs": tuple(p.data_ptr() for p in g.parameters())}
 
     # -------------------------------------------------------------- forward
     def forward(self, x: Tensor, save: bool, u8_hwc: bool = False) -> Tensor:

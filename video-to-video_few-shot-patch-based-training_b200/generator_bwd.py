@@ -102,6 +102,9 @@ def generator_backward(eng, gy: torch.Tensor, y: torch.Tensor, want_input_grad: 
     # fills the GPU (a 128->128 3x3 wgrad is ~180 CTAs, its dgrad ~480 of 592 slots).  Their parameter gradients are
     # published (grad hook -> all-reduce bucket) at the join points, on the main stream.
     main = torch.cuda.current_stream(dev)
+    if getattr(eng, "_pack_bwd_done", None) is not None:
+        main.wait_event(eng._pack_bwd_done)      # the data-gradient weights were packed on a side stream during the forward pass
+        eng._pack_bwd_done = None
     sides = eng.side_streams()
     n_side = [0]
     keep = []
