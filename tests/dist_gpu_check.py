@@ -65,6 +65,28 @@ def main():
     cnt = torch.tensor([hi - lo], device=dev)
     dist.all_reduce(cnt)
     assert int(cnt) == 9
+    # (4) the reference-shaped trainer end to end under torchrun: unseeded ranks, adversarial branch on, CUDA-graph steps,
+    # early-stop / top-k decisions on rank-averaged losses; afterwards generator and critic replicas are bit-identical
+    import tempfile
+    import lightning_model as lm
+    from pbt_b200.config import compose
+    from pbt_b200.trainer import Trainer
+    mini = os.path.join(GOLD, "mini_dataset")
+    tmp = tempfile.mkdtemp(prefix=f"pbt_dist_{rank}_")
+    cfg = compose(os.path.join(ROOT, "config"), "config",
+                  [f"data.dir_pre={mini}/input", f"data.dir_post={mini}/output", f"data.dir_mask={mini}/mask", "data.patch_size=32",
+                   f"data.additional_channels.point_vector.path={mini}/guide", "training.batch_size=8", f"training.output_dir={tmp}",
+                   "+training.max_steps=5", "training.max_epochs=1", "training.log_every_n_steps=2"])
+    model = lm.StyleTransferModel(cfg.model.generator, cfg.model.discriminator, cfg.training, cfg.optimizer, cfg.data,
+                                  cfg.model.perception_loss)
+    tr = Trainer(max_epochs=1, max_steps=5, output_dir=tmp, log_every_n_steps=2)
+    tr.fit(model)
+    assert tr.global_step == 5
+    assert replicas_identical(model.generator, buffers=False), "trainer: generator replicas diverged"
+    assert replicas_identical(model.discriminator, buffers=False), "trainer: critic replicas diverged"
+    if rank == 0:
+        assert os.path.exists(os.path.join(tmp, "checkpoints", "last.ckpt"))
+    model._graphed = None
     del step                      # a live CUDA graph that captured NCCL work keeps the communicator busy at shutdown
     torch.cuda.synchronize()
     dist.barrier()
