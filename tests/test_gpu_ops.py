@@ -200,6 +200,37 @@ def test_bad_arguments_raise():
         ops.conv_fwd(x, w, 16, 1, 1, 0, 0, 0, blk_c=16, tiles_per_cta=1, out=P8.empty(1, 16, 16, 16, 0))
 
 
+def test_bad_arguments_of_the_round2_entry_points_raise():
+    """shape / mode violations come back as an error code that the wrapper raises - never a silent wrong answer"""
+    import ctypes as C
+    from pbt_b200 import ops
+    from pbt_b200._native import P8, lib, stream_ptr
+    x = P8.empty(2, 16, 20, 20, 1)
+    w = torch.zeros(49 * 16 * 32, device="cuda", dtype=torch.float16)
+    out = P8.empty(2, 32, 20, 20, 1)
+    with pytest.raises(RuntimeError, match="batch_tiles"):          # batch tiles need >= 2 tiles per CTA
+        ops.conv_fwd(x, w, 32, 3, 3, 1, 1, 1, blk_c=16, tiles_per_cta=1, out=out, batch_tiles=True)
+    with pytest.raises(RuntimeError, match="tap_pairs"):            # tap pairs and batch tiles exclude each other
+        ops.conv_fwd(x, w, 32, 7, 7, 3, 3, 1, blk_c=16, tiles_per_cta=2, out=out, batch_tiles=True, tap_pairs=True)
+    with pytest.raises(RuntimeError, match="valid window"):
+        ops.conv_fwd(x, w, 32, 3, 3, 1, 1, 1, blk_c=16, tiles_per_cta=2, out=out, valid_hw=(21, 20))
+    with pytest.raises(RuntimeError, match="up_raw_channels"):      # raw leading channels need their scale / shift tables
+        ops.conv_fwd(P8.empty(2, 32, 10, 10, 1), torch.zeros(9 * 32 * 32, device="cuda", dtype=torch.float16), 32, 3, 3, 1, 1, 1,
+                     blk_c=32, tiles_per_cta=2, out=out, upsample2x=True, up_raw_channels=32)
+    a = x.act()
+    assert lib().pbt_zero_border(C.byref(a), 21, 20, stream_ptr()) != 0
+    r = P8.empty(2, 16, 20, 20, 1)
+    with pytest.raises(RuntimeError, match="residual16"):           # both residual kinds at once
+        ops.norm_apply(x, 1, residual32=torch.zeros((2, 2, 20, 20, 8), device="cuda"), residual16=r, out=P8.empty(2, 16, 20, 20, 1))
+    with pytest.raises(RuntimeError, match="fused finalize"):       # > 64 tiles per image cannot be finalised inside the launch
+        ops.norm_apply(x, 1, scale=torch.zeros((2, 16), device="cuda"), shift=torch.zeros((2, 16), device="cuda"),
+                       partial=torch.zeros((2, 100, 2, 16), device="cuda"), tiles=100, count=400, out=P8.empty(2, 16, 20, 20, 1))
+    y = torch.zeros((1, 3, 8, 8), device="cuda")
+    with pytest.raises(AssertionError):                             # a mask without the uint8 frame
+        ops.composite_to_u8(y, torch.zeros((1, 8, 8, 3), dtype=torch.uint8, device="cuda"), None, torch.ones((1, 8, 8), device="cuda"))
+    torch.cuda.synchronize()
+
+
 @pytest.mark.parametrize("kw", [dict(), dict(clip=None), dict(wd=0.0, steps=3)], ids=["clip", "noclip", "nowd"])
 def test_fused_clip_adam_matches_torch(kw):
     ok, err, msg = gc.check_fused_clip_adam(**kw)
