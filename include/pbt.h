@@ -362,6 +362,22 @@ int pbt_patch_gather(const float* const* src_ptrs, int32_t n_src, int32_t n_imag
  * mask pixel > 0 in the 7x7 window. mask: uint8 [h][w] (already thresholded 0/255). */
 int pbt_mask_dilate7(const uint8_t* mask, int32_t h, int32_t w, uint8_t* out, void* stream);
 
+/* Perceptual (VGG feature) term of the generator loss, reference src/models/perception.py:93-143 and
+ * lightning_model.py:270-275: loss = mean((features(generated) - features(target))^2) over the concatenated taps.
+ * `f` is ONE feature tensor of 2*n_pairs images - [0, n_pairs) from the generated patches, [n_pairs, 2*n_pairs) from the
+ * targets - so both feature passes are a single batch through the conv kernels.  flags: 1 = `g` already holds the gradient
+ * arriving from the layers behind `f` (it is added to), 2 = `f` is a ReLU output (the gradient is masked with f > 0),
+ * 4 = `f` is a tap: *loss += loss_mul * sum (f_gen - f_tgt)^2 and g += grad_mul * (f_gen - f_tgt).  `g` (n_pairs images,
+ * same c/h/w; may be NULL when only the value is wanted) is dL/df of the generated half in the caller's fixed gradient scale.
+ * `partial`: scratch of >= 4096 floats; `counter`: one uint32, zero before the first call (the kernel returns it to zero);
+ * the sum is formed in a fixed order (no float atomics), so *loss is reproducible. */
+int pbt_feature_mse(const pbt_act_t* f, int32_t n_pairs, float grad_mul, int32_t flags, const pbt_act_t* g, float* partial,
+                    uint32_t* counter, float* loss, float loss_mul, int32_t dtype, void* stream);
+/* 2x2 stride-2 max pooling of a P8 tensor (torchvision VGG `features[4]`, floor mode) and its transpose: the gradient of a
+ * window goes to its first maximum in row-major order; dx may cover only the first dx->n images of x */
+int pbt_maxpool2(const pbt_act_t* x, const pbt_act_t* y, int32_t dtype, void* stream);
+int pbt_maxpool2_bwd(const pbt_act_t* x, const pbt_act_t* dy, const pbt_act_t* dx, int32_t dtype, void* stream);
+
 /* zero everything outside the valid window [0,valid_h) x [0,valid_w) of a 16-bit P8 tensor (critic maps that shrink by one
  * pixel per 4x4 stride-1 layer live on a fixed grid; the zero border is the next layer's padding) */
 int pbt_zero_border(const pbt_act_t* t, int32_t valid_h, int32_t valid_w, void* stream);

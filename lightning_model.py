@@ -298,9 +298,12 @@ class StyleTransferModel(_Base):
             losses["margin_loss"] = self.reconstruction_criterion(generated, batch["post"]) * \
                 self.training_config["reconstruction_weight"]
         if self.perception_loss_model is not None:      # reference lightning_model.py:270-275
-            _, fake_features = self.perception_loss_model(generated)
-            _, target_features = self.perception_loss_model(batch["post"].detach())
-            losses["g_perception_loss"] = ((fake_features - target_features) ** 2).mean() * self.perception_loss_weight
+            pm = self.perception_loss_model
+            if hasattr(pm, "feature_mse"):              # PerceptualVGG19: native kernels on CUDA (pbt_b200/perceptual.py)
+                per = pm.feature_mse(generated, batch["post"])
+            else:
+                per = ((pm(generated)[1] - pm(batch["post"].detach())[1]) ** 2).mean()
+            losses["g_perception_loss"] = per * self.perception_loss_weight
         if self.discriminator is not None:              # reference lightning_model.py:277-283
             # only dL/d(generated) is needed from this pass: the critic's own gradients of the generator loss are
             # discarded by the reference (opt_d.zero_grad() opens the next step), so they are not computed at all

@@ -1,10 +1,15 @@
 """``PerceptualVGG19`` under the reference's import path (reference src/models/perception.py:9-143): frozen VGG19
 feature taps for the perceptual term of the generator loss (reference lightning_model.py:270-275).
 
-Library module by design: the taps the shipped configuration uses (``feature_layers: [0, 3, 5]``) are the first three
-VGG convolutions on patch-sized inputs, evaluated by torchvision / cuDNN.  The ImageNet weights cannot be downloaded on
-an offline box, so ``path=None`` raises a clear error unless torchvision finds them in its local cache; ``path=<file>``
-loads a custom checkpoint exactly like the reference does (8x8 classifier head with ``num_classes`` outputs).
+``forward`` / ``get_features`` return the flattened taps like the reference (tensor-library ops: a consumer of raw feature
+matrices gets exactly the reference's tensors).  The training step does not need the matrices, only
+``((features(generated) - features(target)) ** 2).mean()`` and its gradient: ``feature_mse`` computes that on the native
+kernels (``pbt_b200/perceptual.py``: both passes as one batch through ``pbt_conv_fwd``, taps reduced in place) whenever the
+module is on a CUDA device with frozen weights, and ``perceptual_loss`` routes through it.
+
+The ImageNet weights cannot be downloaded on an offline box, so ``path=None`` raises a clear error unless torchvision finds
+them in its local cache; ``path=<file>`` loads a custom checkpoint exactly like the reference does (8x8 classifier head with
+``num_classes`` outputs); ``from_features`` wraps an already built feature stack.
 """
 import os
 from typing import List, Optional, Tuple
@@ -45,6 +50,24 @@ class PerceptualVGG19(nn.Module):
             for p in self.parameters():
                 p.requires_grad = False
 
+    @classmethod
+    def from_features(cls, features: nn.Sequential, feature_layers: List[int], use_normalization: bool = True,
+                      requires_grad: bool = False) -> "PerceptualVGG19":
+        """the same module around an existing VGG ``features`` stack (weights already loaded by the caller)"""
+        self = cls.__new__(cls)
+        nn.Module.__init__(self)
+        holder = nn.Module()
+        holder.features = features
+        self.model = holder.float().eval()
+        self.feature_layers = sorted(int(i) for i in feature_layers)
+        self.use_normalization = bool(use_normalization)
+        self.register_buffer("mean", torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1))
+        self.register_buffer("std", torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1))
+        if not requires_grad:
+            for p in self.parameters():
+                p.requires_grad = False
+        return self
+
     def normalize(self, x: Tensor) -> Tensor:
         """[-1, 1] images -> ImageNet-normalised (identity when use_normalization is off)"""
         return (0.5 * (x + 1.0) - self.mean) / self.std if self.use_normalization else x
@@ -63,5 +86,23 @@ class PerceptualVGG19(nn.Module):
     def forward(self, x: Tensor) -> Tuple[None, Tensor]:
         return None, self.get_features(self.normalize(x))
 
+    def native_unsupported(self, x: Tensor):
+        """None when ``feature_mse`` runs on the native kernels for `x`, else the reason it takes the tensor-library route"""
+        if not x.is_cuda:
+            return "not on a CUDA device"
+        from pbt_b200 import perceptual
+        return perceptual.supported(self, x)
+
+    def feature_mse(self, generated: Tensor, target: Tensor) -> Tensor:
+        """``((features(generated) - features(target)) ** 2).mean()`` (reference lightning_model.py:272-274), the target a
+        constant.  Native kernels on CUDA; configurations they do not cover (trainable VGG weights, taps deeper than the
+        256-channel stages, odd patch sizes) evaluate the reference expression."""
+        if self.native_unsupported(generated) is None:
+            from pbt_b200 import perceptual
+            return perceptual.feature_mse(self, generated, target.detach())
+        return ((self(generated)[1] - self(target.detach())[1]) ** 2).mean()
+
     def perceptual_loss(self, y_pred: Tensor, y_true: Tensor) -> Tensor:
+        if self.native_unsupported(y_pred) is None and not y_true.requires_grad:
+            return self.feature_mse(y_pred, y_true)
         return F.mse_loss(self(y_pred)[1], self(y_true)[1])

@@ -254,3 +254,34 @@ def test_non_fused_adam_path_never_writes_non_finite_weights():
     m._clip_and_step(opt, m.generator)
     assert all(torch.isfinite(p).all() for p in m.generator.parameters())
     assert any(not torch.equal(a, p.detach()) for a, p in zip(w0, m.generator.parameters()))
+
+
+def test_perceptual_plan_follows_the_reference_tap_semantics():
+    """host logic of the native perceptual loss (pbt_b200/perceptual.py): which tensors are tapped / rectified, and which
+    configurations are handed back to the reference expression"""
+    import torch
+    from pbt_b200 import perceptual
+    from src.models.perception import PerceptualVGG19
+    C, R, M = torch.nn.Conv2d, torch.nn.ReLU, torch.nn.MaxPool2d
+    stack = lambda: torch.nn.Sequential(C(3, 64, 3, padding=1), R(True), C(64, 64, 3, padding=1), R(True), M(2, 2),  # noqa: E731
+                                        C(64, 128, 3, padding=1), R(True))
+    mod = PerceptualVGG19.from_features(stack(), [5, 0, 3], use_normalization=False)
+    assert mod.feature_layers == [0, 3, 5] and not any(p.requires_grad for p in mod.parameters())
+    nodes = perceptual.plan(mod)
+    # conv 0 is tapped as a view and rectified by the in-place ReLU behind it; conv 5's ReLU (index 6) is never executed
+    assert [(n.kind, n.index, n.relu, n.taps) for n in nodes] == [("conv", 0, True, 1), ("conv", 2, True, 1), ("pool", 4, False, 0),
+                                                                   ("conv", 5, False, 1)]
+    both = perceptual.plan(PerceptualVGG19.from_features(stack(), [0, 1], use_normalization=False))
+    assert [(n.relu, n.taps) for n in both] == [(True, 2)]          # index 0 and index 1 are the same (rectified) tensor, twice
+    x = torch.zeros(2, 3, 32, 32)
+    assert mod.native_unsupported(x) == "not on a CUDA device"
+    y = torch.rand(2, 3, 16, 16) * 2 - 1
+    assert float(mod.feature_mse(y, y)) == 0.0                        # the reference expression on the CPU
+    wide = torch.nn.Sequential(C(3, 512, 3, padding=1))
+    assert "wider than 256" in perceptual.plan(PerceptualVGG19.from_features(wide, [0], use_normalization=False))
+    bn = torch.nn.Sequential(C(3, 64, 3, padding=1), torch.nn.BatchNorm2d(64), R(True))
+    assert "no native kernel" in perceptual.plan(PerceptualVGG19.from_features(bn, [2], use_normalization=False))
+    k5 = torch.nn.Sequential(C(3, 64, 5, padding=2))
+    assert "3x3" in perceptual.plan(PerceptualVGG19.from_features(k5, [0], use_normalization=False))
+    tr = PerceptualVGG19.from_features(stack(), [0], use_normalization=False, requires_grad=True)
+    assert "trainable" in perceptual.plan(tr)

@@ -1185,6 +1185,146 @@ __global__ void grad_scale_feedback_kernel(const float* __restrict__ probe, long
   }
 }
 
+// ------------------------------------------------------------------ perceptual (feature) loss
+// The feature tensor holds 2*nb images: [0, nb) are the features of the generated patches, [nb, 2*nb) of the targets.
+// flags: 1 = `g` already holds the gradient that arrives from the layers behind this tensor (add to it), 2 = the tensor is a
+// ReLU output (mask the gradient with f > 0), 4 = the tensor is a tap (contributes taps * sum (f - t)^2 to the loss and
+// gmul * (f - t) to the gradient).  The squared-difference sum is reduced without float atomics: per-block partial, and the
+// block that finishes last adds all partials in index order (double) to *loss, so the value is the same on every run.
+template <int DT>
+__global__ void feature_mse_kernel(ActView f, int nb, float gmul, int flags, ActView g, float* __restrict__ partial,
+                                   unsigned* counter, float* loss, float loss_mul) {
+  pdl_sync();
+  const long long hw = (long long)f.h * f.w;
+  const int planes = f.c / 8;
+  const long long total = (long long)nb * planes * hw;
+  const bool acc_in = flags & 1, relu = flags & 2, tap = flags & 4;
+  float sq = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i % hw;
+    const int pl = (int)((i / hw) % planes);
+    const int ni = (int)(i / (hw * planes));
+    float a[8], b[8], gv[8];
+    unpack8<DT>(*chunk_ptr(f, ni, pl, pix), a);
+    if (tap) unpack8<DT>(*chunk_ptr(f, ni + nb, pl, pix), b);
+    if (g.ptr && acc_in) unpack8<DT>(*chunk_ptr(g, ni, pl, pix), gv);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float v = (g.ptr && acc_in) ? gv[k] : 0.f;
+      if (tap) {
+        const float d = a[k] - b[k];
+        sq = fmaf(d, d, sq);
+        v = fmaf(gmul, d, v);
+      }
+      gv[k] = (relu && !(a[k] > 0.f)) ? 0.f : v;
+    }
+    if (g.ptr) *chunk_ptr(g, ni, pl, pix) = pack8<DT>(gv);
+  }
+  if (!tap) return;
+  __shared__ double red[kEwThreads / 32];
+  __shared__ bool last;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = (double)sq;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w2 = 0; w2 < kEwThreads / 32; ++w2) t += red[w2];
+    partial[blockIdx.x] = (float)t;
+    __threadfence();
+    last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  double t = 0.0;
+  for (int b2 = threadIdx.x; b2 < (int)gridDim.x; b2 += blockDim.x) t += (double)__ldcg(&partial[b2]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w2 = 0; w2 < kEwThreads / 32; ++w2) s += red[w2];
+    *loss += (float)(s * (double)loss_mul);
+    *counter = 0u;
+  }
+}
+
+// 2x2 stride-2 max pooling (floor mode) and its transpose; the gradient goes to the FIRST maximum of the window in
+// row-major order, as the tensor library's max_pool2d does
+template <int DT>
+__global__ void maxpool2_kernel(ActView x, ActView y) {
+  pdl_sync();
+  const long long ohw = (long long)y.h * y.w;
+  const int planes = y.c / 8;
+  const long long total = (long long)y.n * planes * ohw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long opix = i % ohw;
+    const int pl = (int)((i / ohw) % planes);
+    const int ni = (int)(i / (ohw * planes));
+    const int oy = (int)(opix / y.w), ox = (int)(opix - (long long)oy * y.w);
+    const long long p00 = (long long)(2 * oy) * x.w + 2 * ox;
+    float m[8], v[8];
+    unpack8<DT>(*chunk_ptr(x, ni, pl, p00), m);
+    const long long off[3] = {p00 + 1, p00 + x.w, p00 + x.w + 1};
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      unpack8<DT>(*chunk_ptr(x, ni, pl, off[q]), v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) m[k] = (v[k] > m[k]) ? v[k] : m[k];
+    }
+    *chunk_ptr(y, ni, pl, opix) = pack8<DT>(m);
+  }
+}
+
+template <int DT>
+__global__ void maxpool2_bwd_kernel(ActView x, ActView dy, ActView dx) {
+  pdl_sync();
+  const long long ohw = (long long)dy.h * dy.w;
+  const int planes = dy.c / 8;
+  const long long total = (long long)dx.n * planes * ohw;
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long opix = i % ohw;
+    const int pl = (int)((i / ohw) % planes);
+    const int ni = (int)(i / (ohw * planes));
+    const int oy = (int)(opix / dy.w), ox = (int)(opix - (long long)oy * dy.w);
+    const long long p00 = (long long)(2 * oy) * x.w + 2 * ox;
+    const long long off[4] = {p00, p00 + 1, p00 + x.w, p00 + x.w + 1};
+    float m[8], v[8], gy[8], o[4][8];
+    int arg[8];
+    unpack8<DT>(*chunk_ptr(x, ni, pl, off[0]), m);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) arg[k] = 0;
+#pragma unroll
+    for (int q = 1; q < 4; ++q) {
+      unpack8<DT>(*chunk_ptr(x, ni, pl, off[q]), v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (v[k] > m[k]) { m[k] = v[k]; arg[k] = q; }
+    }
+    unpack8<DT>(*chunk_ptr(dy, ni, pl, opix), gy);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[q][k] = (arg[k] == q) ? gy[k] : 0.f;
+      *chunk_ptr(dx, ni, pl, off[q]) = pack8<DT>(o[q]);
+    }
+    // odd sizes: the last row / column is outside every window
+    if ((x.w & 1) && ox == dy.w - 1) {
+      *chunk_ptr(dx, ni, pl, p00 + 2) = zero4;
+      *chunk_ptr(dx, ni, pl, p00 + x.w + 2) = zero4;
+    }
+    if ((x.h & 1) && oy == dy.h - 1) {
+      *chunk_ptr(dx, ni, pl, p00 + 2 * (long long)x.w) = zero4;
+      *chunk_ptr(dx, ni, pl, p00 + 2 * (long long)x.w + 1) = zero4;
+      if ((x.w & 1) && ox == dy.w - 1) *chunk_ptr(dx, ni, pl, p00 + 2 * (long long)x.w + 2) = zero4;
+    }
+  }
+}
+
 }  // namespace pbt
 
 using namespace pbt;
@@ -1560,6 +1700,49 @@ extern "C" int pbt_make_grad_scale(const float* amax, float target, float* scale
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   PBT_REQUIRE(amax && scale2 && target > 0.f, "make_grad_scale: bad arguments");
   pbt::launch(make_grad_scale_kernel, 1, 1, 0, st, amax, target, scale2, adjust);
+  PBT_CUDA_CHECK(cudaGetLastError());
+  return PBT_OK;
+}
+
+extern "C" int pbt_feature_mse(const pbt_act_t* f, int32_t n_pairs, float grad_mul, int32_t flags, const pbt_act_t* g,
+                               float* partial, uint32_t* counter, float* loss, float loss_mul, int32_t dtype, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  PBT_REQUIRE(f && act_ok(*f) && n_pairs > 0 && f->n >= 2 * n_pairs && (flags & ~7) == 0, "feature_mse: bad feature tensor");
+  PBT_REQUIRE(!(flags & 4) || (partial && counter && loss), "feature_mse: a tap needs partial / counter / loss");
+  pbt_act_t none;
+  memset(&none, 0, sizeof(none));
+  if (g && g->ptr) {
+    PBT_REQUIRE(act_ok(*g) && g->n >= n_pairs && g->c == f->c && g->h == f->h && g->w == f->w, "feature_mse: gradient shape");
+  } else {
+    PBT_REQUIRE(flags & 4, "feature_mse: nothing to do");
+    g = &none;
+  }
+  const long long items = (long long)n_pairs * (f->c / 8) * f->h * f->w;
+  int grid = ew_grid(items);
+  if (grid > 4096) grid = 4096;          // `partial` holds one float per block
+  DISPATCH_DT(dtype, pbt::launch(feature_mse_kernel<DT>, grid, kEwThreads, 0, st, view(*f), n_pairs, grad_mul, flags, view(*g), partial,
+                                 counter, loss, loss_mul));
+  PBT_CUDA_CHECK(cudaGetLastError());
+  return PBT_OK;
+}
+
+extern "C" int pbt_maxpool2(const pbt_act_t* x, const pbt_act_t* y, int32_t dtype, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  PBT_REQUIRE(x && y && act_ok(*x) && act_ok(*y) && y->n == x->n && y->c == x->c && y->h == x->h / 2 && y->w == x->w / 2,
+              "maxpool2: bad tensors");
+  const long long items = (long long)y->n * (y->c / 8) * y->h * y->w;
+  DISPATCH_DT(dtype, pbt::launch(maxpool2_kernel<DT>, ew_grid(items), kEwThreads, 0, st, view(*x), view(*y)));
+  PBT_CUDA_CHECK(cudaGetLastError());
+  return PBT_OK;
+}
+
+extern "C" int pbt_maxpool2_bwd(const pbt_act_t* x, const pbt_act_t* dy, const pbt_act_t* dx, int32_t dtype, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  PBT_REQUIRE(x && dy && dx && act_ok(*x) && act_ok(*dy) && act_ok(*dx), "maxpool2_bwd: bad tensors");
+  PBT_REQUIRE(dx->n <= x->n && dy->n >= dx->n && dx->c == x->c && dy->c == x->c && dx->h == x->h && dx->w == x->w &&
+                  dy->h == x->h / 2 && dy->w == x->w / 2, "maxpool2_bwd: shapes");
+  const long long items = (long long)dx->n * (dy->c / 8) * dy->h * dy->w;
+  DISPATCH_DT(dtype, pbt::launch(maxpool2_bwd_kernel<DT>, ew_grid(items), kEwThreads, 0, st, view(*x), view(*dy), view(*dx)));
   PBT_CUDA_CHECK(cudaGetLastError());
   return PBT_OK;
 }

@@ -290,6 +290,26 @@ def p8s2d_to_nchw(x: P8, cpp: int, c: int, out: torch.Tensor, dt: int, mul=None)
     check(lib().pbt_p8s2d_to_nchw_f32(C.byref(a), cpp, c, out.data_ptr(), ptr(mul), dt, stream_ptr()), "pbt_p8s2d_to_nchw_f32")
 
 
+def feature_mse(f: P8, n_pairs: int, dt: int, *, g: P8 | None = None, grad_mul: float = 0.0, accumulate: bool = False,
+                relu: bool = False, tap: bool = True, partial=None, counter=None, loss=None, loss_mul: float = 1.0) -> None:
+    """one tensor of the perceptual loss: squared difference of the two halves of `f` into *loss, its gradient (and the
+    ReLU mask) into `g`"""
+    a, b = f.act(), act_or_null(g)
+    flags = int(accumulate) | (int(relu) << 1) | (int(tap) << 2)
+    check(lib().pbt_feature_mse(C.byref(a), n_pairs, grad_mul, flags, C.byref(b), ptr(partial), ptr(counter), ptr(loss),
+                                loss_mul, dt, stream_ptr()), "pbt_feature_mse")
+
+
+def maxpool2(x: P8, y: P8, dt: int) -> None:
+    a, b = x.act(), y.act()
+    check(lib().pbt_maxpool2(C.byref(a), C.byref(b), dt, stream_ptr()), "pbt_maxpool2")
+
+
+def maxpool2_bwd(x: P8, dy: P8, dx: P8, dt: int) -> None:
+    a, b, c = x.act(), dy.act(), dx.act()
+    check(lib().pbt_maxpool2_bwd(C.byref(a), C.byref(b), C.byref(c), dt, stream_ptr()), "pbt_maxpool2_bwd")
+
+
 def mask_erode7(mask_u8: torch.Tensor, out: torch.Tensor) -> None:
     """mask_u8 uint8 [n,h,w] (thresholded) -> out fp32 [n,h,w]: 1 where the whole 7x7 window is set (reference generator.py:327-351)"""
     n, h, w = mask_u8.shape
