@@ -643,10 +643,35 @@ def gan_leg(xs, ts, dev, operand, tsteps, barrier):
         e1.record()
         barrier()
         ms_g = e0.elapsed_time(e1) / tsteps
-        return {"value": B / (ms_g / 1e3), "unit": "patches/s", "ms_per_step": ms_g,
-                "workload": "C3 shape, critic (DiscriminatorN_IN 12 filters, 2 layers) + generator update, one generator forward "
-                            "shared by both halves, one CUDA-graph replay",
-                "g_total_loss": float(gout["g_total_loss"]), "d_total_loss": float(gout["d_total_loss"])}
+        res = {"value": B / (ms_g / 1e3), "unit": "patches/s", "ms_per_step": ms_g,
+               "workload": "C3 shape, critic (DiscriminatorN_IN 12 filters, 2 layers) + generator update, one generator forward "
+                           "shared by both halves, one CUDA-graph replay",
+               "g_total_loss": float(gout["g_total_loss"]), "d_total_loss": float(gout["d_total_loss"])}
+        # the reference's default three-term generator loss (config/model/default.yaml:29-37): + 6.0 x VGG19 taps [0, 3, 5].  The
+        # ImageNet checkpoint is not available offline: the taps run on a seeded VGG19 prefix of the same shapes (same cost).
+        try:
+            from pbt_b200.perceptual import vgg19_prefix
+            from src.models.perception import PerceptualVGG19
+            gm._graphed = None
+            gm.perception_loss_model = PerceptualVGG19.from_features(vgg19_prefix(6), [0, 3, 5], use_normalization=False).to(dev)
+            gm.perception_loss_weight = 6.0
+            for i in range(4):
+                gm.graphed_training_step(gbatch, i)
+            barrier()
+            e0.record()
+            for i in range(tsteps):
+                gout = gm.graphed_training_step(gbatch, i)
+            e1.record()
+            barrier()
+            ms_p = e0.elapsed_time(e1) / tsteps
+            res["with_perceptual"] = {"ms_per_step": ms_p, "value": B / (ms_p / 1e3), "unit": "patches/s",
+                                      "workload": "the same step + the perceptual term (VGG19 features [0, 3, 5], weight 6.0) on the "
+                                                  "native kernels; synthetic VGG weights",
+                                      "native_taps": gm.perception_loss_model.native_unsupported(ts) is None,
+                                      "g_perception_loss": float(gout["g_perception_loss"])}
+        except Exception as e:  # noqa: BLE001
+            res["with_perceptual"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+        return res
     except Exception as e:  # noqa: BLE001 - secondary figure: never fail the bench line over it
         return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
 

@@ -10,25 +10,9 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _vgg_prefix(depth: int, seed: int = 5, bias_std: float = 0.05):
-    """features[0 .. depth) of torchvision's VGG19 (configuration E), kaiming-normal weights like torchvision's initialiser;
-    biases are non-zero so that the epilogue bias is exercised"""
-    cfg = [64, 64, "M", 128, 128, "M", 256, 256, 256, 256, "M"]
-    layers, cin = [], 3
-    for v in cfg:
-        if v == "M":
-            layers.append(torch.nn.MaxPool2d(kernel_size=2, stride=2))
-        else:
-            layers += [torch.nn.Conv2d(cin, v, 3, padding=1), torch.nn.ReLU(inplace=True)]
-            cin = v
-    seq = torch.nn.Sequential(*layers[:depth])
-    g = torch.Generator().manual_seed(seed)
-    for m in seq:
-        if isinstance(m, torch.nn.Conv2d):
-            fan_out = m.out_channels * 9
-            m.weight.data = torch.randn(m.weight.shape, generator=g) * (2.0 / fan_out) ** 0.5
-            m.bias.data = torch.randn(m.bias.shape, generator=g) * bias_std
-    return seq
+def _vgg_prefix(depth: int, seed: int = 5):
+    from pbt_b200.perceptual import vgg19_prefix
+    return vgg19_prefix(depth, seed)
 
 
 def _module(layers, norm, depth=None, seed=5):
@@ -223,3 +207,42 @@ def test_generator_step_with_the_native_perceptual_term():
         ps = 10 * np.log10(peak * peak / float(((got.double() - want.double()) ** 2).mean()))
         print(f"{k}: cosine {cos:.5f} psnr {ps:.1f} dB")
         assert cos > 0.99 and ps >= 40.0, k
+
+
+def test_three_term_step_graphed_equals_eager():
+    """the reference's default generator loss (L1 x 4 + VGG taps x 6 + adversarial x 0.5, config/model/default.yaml) as one
+    CUDA-graph replay: same losses and same weights as the eager step, two steps in a row"""
+    import os
+    from lightning_model import StyleTransferModel
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g_sd = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(gold, "gen_c3_trained.npz")).items()}
+    vec = np.load(os.path.join(gold, "gen_c3_vectors.npz"))
+    x, post = torch.from_numpy(vec["x"][:8]).contiguous().cuda(), torch.from_numpy(vec["target"][:8]).contiguous().cuda()
+    tcfg = {"batch_size": 8, "reconstruction_weight": 4.0, "adversarial_weight": 0.5, "use_image_loss": True,
+            "reconstruction_criterion": "L1Loss", "adversarial_criterion": "MSELoss", "use_gradient_clipping": True,
+            "gradient_clip_val": 0.5}
+    adam = {"lr": 0.0004, "betas": [0.9, 0.999], "weight_decay": 0.00001}
+    d_args = dict(input_channels=3, num_filters=12, n_layers=2, use_noise=False, noise_sigma=0.2, norm_layer="instance_norm", use_bias=True)
+    runs = {}
+    for graphed in (False, True):
+        torch.manual_seed(2024)
+        m = StyleTransferModel({"args": {"input_channels": 3, "use_bias": True}}, {"type": "DiscriminatorN_IN", "args": dict(d_args)},
+                               dict(tcfg, cuda_graph=graphed), {"generator": dict(adam), "discriminator": dict(adam)},
+                               {"additional_channels": {}})
+        m.generator.load_state_dict(g_sd, strict=True)
+        m.perception_loss_model, m.perception_loss_weight = _module([0, 3, 5], False), 6.0
+        m = m.cuda().train()
+        m._optimizers = m.configure_optimizers()
+        hist = []
+        for step in range(2):
+            out = m.graphed_training_step({"combined_input": x, "post": post}, step) if graphed else m.full_step(x, post)
+            hist.append({k: float(v) for k, v in out.items() if k != "loss"})
+        runs[graphed] = (hist, {k: v.detach().clone() for k, v in m.generator.state_dict().items()})
+        assert getattr(m.perception_loss_model, "_native_engine", None) is not None
+    for a, b in zip(*[runs[g][0] for g in (False, True)]):
+        assert set(a) == set(b) and "g_perception_loss" in a and a["g_perception_loss"] > 0
+        for k in a:
+            assert b[k] == pytest.approx(a[k], rel=2e-3, abs=1e-6), k
+    for k, v in runs[False][1].items():
+        if v.is_floating_point():
+            assert (v - runs[True][1][k]).abs().max().item() <= 1.7e-3, k     # two Adam steps of <= 4e-4 each; sign noise on ~0 gradients

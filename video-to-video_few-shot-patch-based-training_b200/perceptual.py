@@ -274,6 +274,29 @@ class _PerceptualFn(torch.autograd.Function):
         return (gy * gl).to(ctx.y_dtype), None, None
 
 
+def vgg19_prefix(depth: int, seed: int = 5, bias_std: float = 0.05) -> torch.nn.Sequential:
+    """``features[0:depth]`` of torchvision's VGG19 (configuration E: conv3x3 + in-place ReLU, 2x2 max pooling), weights drawn
+    like torchvision's initialiser (kaiming-normal, fan-out) under `seed`, small non-zero biases.  For tests and benchmarks
+    on boxes without the ImageNet checkpoint; training uses ``PerceptualVGG19(path=...)`` / the torchvision cache."""
+    cfg = [64, 64, "M", 128, 128, "M", 256, 256, 256, 256, "M", 512, 512, 512, 512, "M", 512, 512, 512, 512, "M"]
+    layers, cin = [], 3
+    for v in cfg:
+        if len(layers) >= depth:
+            break
+        if v == "M":
+            layers.append(torch.nn.MaxPool2d(kernel_size=2, stride=2))
+        else:
+            layers += [torch.nn.Conv2d(cin, v, 3, padding=1), torch.nn.ReLU(inplace=True)]
+            cin = v
+    seq = torch.nn.Sequential(*layers[:depth])
+    g = torch.Generator().manual_seed(seed)
+    for m in seq:
+        if isinstance(m, torch.nn.Conv2d):
+            m.weight.data = torch.randn(m.weight.shape, generator=g) * (2.0 / (m.out_channels * 9)) ** 0.5
+            m.bias.data = torch.randn(m.bias.shape, generator=g) * bias_std
+    return seq
+
+
 def feature_mse(module, y: Tensor, target: Tensor) -> Tensor:
     """``((features(y) - features(target)) ** 2).mean()`` of a ``PerceptualVGG19`` on the native kernels, differentiable
     w.r.t. `y` (the target is a constant, as at reference lightning_model.py:273)"""
