@@ -1,5 +1,6 @@
 """a few eager adversarial training steps at the C3 shape (for ncu launch lists):
-python tools/gan_step_once.py [N CIN P [STEPS]]"""
+python tools/gan_step_once.py [N CIN P [STEPS [perceptual]]]     (a 5th argument adds the VGG19 tap term, weight 6.0: the
+reference's default three-term generator loss; synthetic VGG weights)"""
 import os
 import sys
 
@@ -18,6 +19,11 @@ torch.manual_seed(0)
 m = StyleTransferModel({"args": {"input_channels": cin, "use_bias": True}},
                        {"args": {"input_channels": 3, "num_filters": 12, "n_layers": 2, "use_bias": True}}, tcfg,
                        {"generator": dict(adam), "discriminator": dict(adam)}, {"additional_channels": {}}).cuda().train()
+if len(sys.argv) > 5:
+    from pbt_b200.perceptual import vgg19_prefix
+    from src.models.perception import PerceptualVGG19
+    m.perception_loss_model = PerceptualVGG19.from_features(vgg19_prefix(6), [0, 3, 5], use_normalization=False).cuda()
+    m.perception_loss_weight = 6.0
 m._optimizers = m.configure_optimizers()
 x = torch.rand(n, cin, p, p, device="cuda") * 2 - 1
 t = torch.rand(n, 3, p, p, device="cuda") * 2 - 1
