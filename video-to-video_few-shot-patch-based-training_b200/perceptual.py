@@ -89,11 +89,20 @@ def supported(module, x: Tensor) -> Optional[str]:
     """None when the native path can evaluate `module` on `x`, else the reason"""
     if not x.is_cuda or x.dim() != 4:
         return "not a CUDA NCHW batch"
-    p = getattr(module, "_native_plan", None)
-    if p is None:
-        p = module._native_plan = plan(module)
+    key = (tuple(module.feature_layers), len(module.model.features))
+    cached = getattr(module, "_native_plan", None)
+    if cached is None or cached[0] != key:
+        cached = (key, plan(module))
+        object.__setattr__(module, "_native_plan", cached)
+        object.__setattr__(module, "_native_engine", None)
+    p = cached[1]
     if isinstance(p, str):
+        if "trainable" in p and not any(q.requires_grad for q in module.model.features.parameters()):
+            object.__setattr__(module, "_native_plan", None)      # frozen since the plan was made: plan again
+            return supported(module, x)
         return p
+    if any(q.requires_grad for q in module.model.features.parameters()):
+        return "the VGG weights are trainable (requires_grad=True)"
     pools = sum(1 for nd in p if nd.kind == "pool")
     if x.shape[1] != p[0].cin:
         return "channel count does not match the first convolution"
