@@ -240,3 +240,17 @@ def test_fused_clip_adam_matches_torch(kw):
 def test_fused_l1_loss_matches_torch():
     ok, err, msg = gc.check_fused_l1()
     assert ok, msg
+
+
+def test_guard_bands_catch_an_out_of_bounds_write(monkeypatch):
+    """the PBT_GUARD debug mode itself: a write one element past a guarded allocation is reported"""
+    import pbt_b200._native as nv
+    monkeypatch.setattr(nv, "GUARD_ELEMS", 64)
+    t = nv.P8.empty(1, 8, 4, 4, nv.FP16)
+    assert nv.check_guards() >= 1
+    flat = [f for r, f, k in nv._guards if r() is t.t][0]
+    flat[64 + t.t.numel()] = 1.0
+    with pytest.raises(RuntimeError, match="out of bounds"):
+        nv.check_guards()
+    flat.view(torch.int16)[64 + t.t.numel()] = nv._SENTINEL
+    nv._guards.clear()
