@@ -362,6 +362,39 @@ int pbt_patch_gather(const float* const* src_ptrs, int32_t n_src, int32_t n_imag
  * mask pixel > 0 in the 7x7 window. mask: uint8 [h][w] (already thresholded 0/255). */
 int pbt_mask_dilate7(const uint8_t* mask, int32_t h, int32_t w, uint8_t* out, void* stream);
 
+/* The residual trunk of GeneratorJ (reference src/models/generator.py:18-58,107-110,223-224) on patch-sized maps as ONE launch:
+ * r_{b+1} = r_b + IN(convB(relu(IN(convA(relu(r_b)))))) for b = 0 .. n_blocks-1, 128 -> 128 channels, 3x3 pad 1, InstanceNorm
+ * (biased variance, eps) over each image.  One CTA owns one image and keeps the running activation in shared memory (row pitch
+ * w+2: the pad pixels are the zero halo); requires 128 channels and h*(w+2) <= 512 (pbt_res_trunk_supported).  It writes
+ * everything the layer-by-layer path saves for the backward sweep:
+ *   a[0]           in : relu(r_0)                                  a[b+1]   out: relu(r_{b+1}) (b+1 < n_blocks)
+ *   raw_a[b]       out: convA output, 16 bit                       hmid[b]  out: relu(IN(raw_a[b]))
+ *   raw_b[b]       out: convB output, 16 bit                       scale_x / shift_x [n][128] out: rstd, -mean*rstd of raw_x[b]
+ *   residual32     in/out: r_0 -> r_{n_blocks-1} fp32 [n][16][h][w][8] (the last block's sum only goes to last16)
+ *   last16         out: r_{n_blocks} in 16 bit (may be a channel view)
+ * w_a / w_b: pbt_pack_weights output (forward form, blk_c 32, k_pad 128, n_out 128).  Conv biases are not applied: a constant
+ * per channel is removed by the InstanceNorm that follows. */
+#define PBT_TRUNK_MAX_BLOCKS 16
+typedef struct {
+  int32_t n_blocks, dtype;
+  float eps;
+  int32_t reserved;
+  pbt_act_t a[PBT_TRUNK_MAX_BLOCKS];
+  pbt_act_t raw_a[PBT_TRUNK_MAX_BLOCKS];
+  pbt_act_t hmid[PBT_TRUNK_MAX_BLOCKS];
+  pbt_act_t raw_b[PBT_TRUNK_MAX_BLOCKS];
+  const void* w_a[PBT_TRUNK_MAX_BLOCKS];
+  const void* w_b[PBT_TRUNK_MAX_BLOCKS];
+  float* scale_a[PBT_TRUNK_MAX_BLOCKS];
+  float* shift_a[PBT_TRUNK_MAX_BLOCKS];
+  float* scale_b[PBT_TRUNK_MAX_BLOCKS];
+  float* shift_b[PBT_TRUNK_MAX_BLOCKS];
+  float* residual32;
+  pbt_act_t last16;
+} pbt_res_trunk_desc_t;
+int pbt_res_trunk_supported(int32_t channels, int32_t h, int32_t w);   /* 1 / 0 */
+int pbt_res_trunk_fwd(const pbt_res_trunk_desc_t* d, void* stream);
+
 /* Perceptual (VGG feature) term of the generator loss, reference src/models/perception.py:93-143 and
  * lightning_model.py:270-275: loss = mean((features(generated) - features(target))^2) over the concatenated taps.
  * `f` is ONE feature tensor of 2*n_pairs images - [0, n_pairs) from the generated patches, [n_pairs, 2*n_pairs) from the

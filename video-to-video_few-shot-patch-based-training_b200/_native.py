@@ -83,6 +83,20 @@ class NormBwdDesc(C.Structure):
     ]
 
 
+TRUNK_MAX_BLOCKS = 16
+
+
+class ResTrunkDesc(C.Structure):
+    """pbt_res_trunk_desc_t"""
+
+    _fields_ = [("n_blocks", C.c_int32), ("dtype", C.c_int32), ("eps", C.c_float), ("reserved", C.c_int32),
+                ("a", Act * TRUNK_MAX_BLOCKS), ("raw_a", Act * TRUNK_MAX_BLOCKS), ("hmid", Act * TRUNK_MAX_BLOCKS),
+                ("raw_b", Act * TRUNK_MAX_BLOCKS), ("w_a", C.c_void_p * TRUNK_MAX_BLOCKS), ("w_b", C.c_void_p * TRUNK_MAX_BLOCKS),
+                ("scale_a", C.c_void_p * TRUNK_MAX_BLOCKS), ("shift_a", C.c_void_p * TRUNK_MAX_BLOCKS),
+                ("scale_b", C.c_void_p * TRUNK_MAX_BLOCKS), ("shift_b", C.c_void_p * TRUNK_MAX_BLOCKS),
+                ("residual32", C.c_void_p), ("last16", Act)]
+
+
 _lib = None
 
 
@@ -131,6 +145,8 @@ def lib() -> C.CDLL:
         "pbt_zero_border": (C.c_int, [C.POINTER(Act), i32, i32, vp]),
         "pbt_p8s2d_to_nchw_f32": (C.c_int, [C.POINTER(Act), i32, i32, vp, vp, i32, vp]),
         "pbt_composite_to_u8": (C.c_int, [vp, vp, i32, vp, i32, i32, i32, vp, vp]),
+        "pbt_res_trunk_supported": (C.c_int, [i32, i32, i32]),
+        "pbt_res_trunk_fwd": (C.c_int, [C.POINTER(ResTrunkDesc), vp]),
         "pbt_feature_mse": (C.c_int, [C.POINTER(Act), i32, f32, i32, C.POINTER(Act), vp, vp, vp, f32, i32, vp]),
         "pbt_maxpool2": (C.c_int, [C.POINTER(Act), C.POINTER(Act), i32, vp]),
         "pbt_maxpool2_bwd": (C.c_int, [C.POINTER(Act), C.POINTER(Act), C.POINTER(Act), i32, vp]),
@@ -156,7 +172,7 @@ EXPORTED_SYMBOLS = [
     "pbt_conv_wgrad", "pbt_norm_finalize", "pbt_norm_apply", "pbt_upsample2x", "pbt_upsample2x_bwd",
     "pbt_norm_bwd_reduce", "pbt_norm_bwd_apply", "pbt_norm_bwd_fused", "pbt_clip_adam_step", "pbt_l1_loss_fwd_bwd", "pbt_tile_gather", "pbt_tile_blend", "pbt_tile_finish", "pbt_head_bwd", "pbt_channel_sum", "pbt_nchw_to_p8",
     "pbt_p8_to_nchw_f32", "pbt_p8f_to_nchw_f32", "pbt_u8hwc_to_p8", "pbt_nchw_to_u8hwc", "pbt_u8hwc_to_norm_chw",
-    "pbt_patch_gather", "pbt_mask_dilate7", "pbt_mask_erode7", "pbt_composite_to_u8", "pbt_zero_border", "pbt_p8s2d_to_nchw_f32", "pbt_feature_mse", "pbt_maxpool2", "pbt_maxpool2_bwd", "pbt_absmax_f32", "pbt_make_grad_scale", "pbt_grad_scale_feedback", "pbt_ostree_reset",
+    "pbt_patch_gather", "pbt_mask_dilate7", "pbt_mask_erode7", "pbt_composite_to_u8", "pbt_zero_border", "pbt_p8s2d_to_nchw_f32", "pbt_feature_mse", "pbt_maxpool2", "pbt_maxpool2_bwd", "pbt_res_trunk_supported", "pbt_res_trunk_fwd", "pbt_absmax_f32", "pbt_make_grad_scale", "pbt_grad_scale_feedback", "pbt_ostree_reset",
     "pbt_ostree_take", "pbt_pack_weights",
 ]
 

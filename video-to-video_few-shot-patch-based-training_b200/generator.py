@@ -251,6 +251,9 @@ class _Engine:
         self.use_tap_pairs = env("PBT_TAP_PAIRS", "1")
         self.residual16 = env("PBT_RESIDUAL16", "1")    # inference: 16-bit residual stream (see _Workspace.r16)
         self.batch_tiles = env("PBT_BATCH_TILES", "1")   # small maps: one CTA = the same tile of two images (see _bt)
+        # training passes on patch-sized maps (128 channels, h/4 * (w/4 + 2) <= 512): the whole residual trunk is ONE launch, one
+        # CTA per image with the running activation resident in shared memory (csrc/res_trunk.cu) instead of 6 launches per block
+        self.fused_trunk = env("PBT_FUSED_TRUNK", "1")
         self._pack_bwd_done = None   # event: the side-stream packing of the data-gradient weights of this step has finished
         self._saved_stamp = 0     # counts grad-enabled forward passes: a backward must match the pass that saved its activations
         self.bucket = None        # parallel.GradBucket: flat fp32 storage the backward sweep writes the parameter gradients into
@@ -582,7 +585,16 @@ class _Engine:
         # (normalise-on-load), so hmid and the up1 half of cat11 are never written; training keeps them for wgrad
         nol_res = not save and f[2] % self._blk(f[2]) == 0 and f[2] <= 256
         nol_11 = not save and f[4] % 32 == 0 and f[4] <= 256 and g.append_smoothers
-        for b in range(nb):
+        fused_trunk = (save and self.fused_trunk and 1 <= nb <= 16 and not (bn_mode or no_norm or pr or r16)
+                       and ops.res_trunk_supported(f[2], h4, w4))
+        if fused_trunk:
+            sts = [[ws.stat(f"res{b}.{ab}", f[2], h4, w4, 2, dev) for b in range(nb)] for ab in "ab"]
+            for st_ in sts[0] + sts[1]:
+                st_.pop("deferred", None)
+            ops.res_trunk_fwd(ws.a[:nb], ws.rawA[:nb], ws.hmid[:nb], ws.rawB[:nb], [W[f"res{b}.a"] for b in range(nb)],
+                              [W[f"res{b}.b"] for b in range(nb)], [(s_["scale"], s_["shift"]) for s_ in sts[0]],
+                              [(s_["scale"], s_["shift"]) for s_ in sts[1]], r_cur, last16, dt, eps=EPS)
+        for b in range(0 if fused_trunk else nb):
             k = b if save else 0
             st = conv_in(f"res{b}.a", a_of(b), f[2], 3, 1, ws.rawA[k], 2, cps=4, pair=pr, defer=not nol_res)
             if nol_res:

@@ -290,6 +290,30 @@ def p8s2d_to_nchw(x: P8, cpp: int, c: int, out: torch.Tensor, dt: int, mul=None)
     check(lib().pbt_p8s2d_to_nchw_f32(C.byref(a), cpp, c, out.data_ptr(), ptr(mul), dt, stream_ptr()), "pbt_p8s2d_to_nchw_f32")
 
 
+def res_trunk_supported(channels: int, h: int, w: int) -> bool:
+    return bool(lib().pbt_res_trunk_supported(channels, h, w))
+
+
+def res_trunk_fwd(a, raw_a, hmid, raw_b, w_a, w_b, stats_a, stats_b, residual32: torch.Tensor, last16: P8, dt: int,
+                  eps: float = 1e-5) -> None:
+    """the whole residual trunk in one launch (csrc/res_trunk.cu).  a / raw_a / hmid / raw_b: lists of P8 [n, 128, h, w], one per
+    block (a[0] is the input relu(r_0), a[1:] are written); stats_x: lists of (scale, shift) fp32 [n, 128] tables, written;
+    residual32: r_0 on entry (fp32 [n, 16, h, w, 8]); last16: r_nb in 16 bit"""
+    nb = len(raw_a)
+    assert len(a) == nb and len(hmid) == nb and len(raw_b) == nb and len(w_a) == nb and len(w_b) == nb
+    assert residual32.dtype == torch.float32 and residual32.is_contiguous()
+    d = nv.ResTrunkDesc()
+    d.n_blocks, d.dtype, d.eps = nb, dt, float(eps)
+    for b in range(min(nb, nv.TRUNK_MAX_BLOCKS)):
+        d.a[b], d.raw_a[b], d.hmid[b], d.raw_b[b] = a[b].act(), raw_a[b].act(), hmid[b].act(), raw_b[b].act()
+        d.w_a[b], d.w_b[b] = w_a[b].data_ptr(), w_b[b].data_ptr()
+        d.scale_a[b], d.shift_a[b] = stats_a[b][0].data_ptr(), stats_a[b][1].data_ptr()
+        d.scale_b[b], d.shift_b[b] = stats_b[b][0].data_ptr(), stats_b[b][1].data_ptr()
+    d.residual32 = residual32.data_ptr()
+    d.last16 = last16.act()
+    check(lib().pbt_res_trunk_fwd(C.byref(d), stream_ptr()), "pbt_res_trunk_fwd")
+
+
 def feature_mse(f: P8, n_pairs: int, dt: int, *, g: P8 | None = None, grad_mul: float = 0.0, accumulate: bool = False,
                 relu: bool = False, tap: bool = True, partial=None, counter=None, loss=None, loss_mul: float = 1.0) -> None:
     """one tensor of the perceptual loss: squared difference of the two halves of `f` into *loss, its gradient (and the
