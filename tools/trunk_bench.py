@@ -79,4 +79,5 @@ if hasattr(lib(), "pbt_debug_trunk_cycles"):
     torch.cuda.synchronize()
     lib().pbt_debug_trunk_cycles(buf)
     names = ["MMA warp waits for weights", "MMA warp waits for the map", "epilogue waits for accumulators (x4 warps)", "pass 1", "pass 2", "pass 3"]
-    print("block 0 cycles per conv: " + ", ".join(f"{nm} {buf[i] / (2 * nb):.0f}" for i, nm in enumerate(names)))
+    if any(buf):      # only a -DPBT_TRUNK_DBG=1 build of csrc/res_trunk.cu counts
+        print("block 0 cycles per conv: " + ", ".join(f"{nm} {buf[i] / (2 * nb):.0f}" for i, nm in enumerate(names)))
