@@ -264,18 +264,18 @@ def _guarded(shape, dtype, device, zero):
     else:
         body.view(torch.int16).fill_(_SENTINEL)           # "uninitialised" memory is poison too
     t = body.view(shape)
-    _guards[:] = [(r, f, k) for r, f, k in _guards if r() is not None]
-    _guards.append((weakref.ref(t), flat, numel))
+    _guards[:] = [e for e in _guards if e[0]() is not None]
+    _guards.append((weakref.ref(t), flat, numel, GUARD_ELEMS))
     return t
 
 
 def check_guards() -> int:
     """verify the sentinel bands of every live guarded allocation; returns how many were checked"""
-    _guards[:] = [(r, f, k) for r, f, k in _guards if r() is not None]
+    _guards[:] = [e for e in _guards if e[0]() is not None]
     bad = []
-    for _, flat, numel in _guards:
+    for _, flat, numel, band in _guards:
         bits = flat.view(torch.int16)
-        ok = (bits[:GUARD_ELEMS] == _SENTINEL).all() & (bits[GUARD_ELEMS + numel:] == _SENTINEL).all()
+        ok = (bits[:band] == _SENTINEL).all() & (bits[band + numel:] == _SENTINEL).all()
         bad.append(~ok)
     if bad and bool(torch.stack(bad).any()):
         which = [i for i, b in enumerate(bad) if bool(b)]
