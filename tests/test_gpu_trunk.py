@@ -75,7 +75,7 @@ def _run(n, h, w, nb, seed, dt_name="fp16"):
 
 
 @pytest.mark.parametrize("n,h,w,nb", [(3, 20, 20, 2), (2, 8, 8, 1), (5, 16, 16, 3), (2, 12, 40, 2), (1, 20, 20, 7), (2, 4, 4, 2),
-                                      (160, 20, 20, 7)])
+                                      (160, 20, 20, 7), (3, 1, 1, 1), (2, 2, 6, 2), (1, 3, 100, 1)])
 def test_fused_trunk_matches_the_block_chain(n, h, w, nb):
     worst = _run(n, h, w, nb, seed=n * 1000 + h * 10 + nb)
     print(f"n={n} {h}x{w} blocks={nb}: " + ", ".join(f"{k} {v:.2e}" for k, v in worst.items()))
@@ -86,6 +86,7 @@ def test_fused_trunk_bf16_and_bad_arguments():
     _run(2, 20, 20, 2, seed=77, dt_name="bf16")
     assert ops.res_trunk_supported(128, 20, 20) and ops.res_trunk_supported(128, 8, 8)
     assert not ops.res_trunk_supported(128, 24, 24) and not ops.res_trunk_supported(64, 20, 20)
+    assert not ops.res_trunk_supported(128, 3, 126)        # 384 rows, but the 128-pixel pitch makes the halo rows too large for shared memory
     from pbt_b200._native import FP16, P8
     E = lambda c, h, w: P8.empty(1, c, h, w, FP16)  # noqa: E731
     st = [(torch.empty(1, 128, device="cuda"), torch.empty(1, 128, device="cuda"))]
