@@ -89,6 +89,35 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
   }
 }
 
+// Waits that are known to be long (a whole MMA phase or epilogue of a fused kernel): try_wait with a suspend-time hint parks the
+// thread in hardware until the phase completes (or the hint expires) instead of spinning through the issue slots of the warps
+// that do the work; wake-up is immediate, unlike a nanosleep back-off.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+#if PBT_WATCHDOG
+  const long long t0 = clock64();
+#endif
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+#if PBT_WATCHDOG
+    if (clock64() - t0 > 4000000000ll) {
+      printf("pbt: mbarrier watchdog block %d thread %d bar %u parity %u\n", (int)blockIdx.x, (int)threadIdx.x, smem_u32(bar), parity);
+      __trap();
+    }
+#endif
+  }
+}
+
 // ---------------------------------------------------------------- TMA
 // 4-D tiled tensor load: global (tensor map) -> shared, completion on mbarrier.
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2,

@@ -78,8 +78,7 @@ __device__ __forceinline__ uint64_t tdesc(uint32_t lo, uint32_t hi) { return ((u
 
 template <int DT>
 __global__ void __launch_bounds__(kTrunkThreads, 1) res_trunk_fwd_kernel(const __grid_constant__ TrunkParams p) {
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  extern __shared__ __align__(128) uint8_t smem[];   // used directly: pointer arithmetic on the array keeps LDS / STS (no generic accesses)
   uint8_t* sX = smem;                                                   // [16 planes][rows_alloc (+1)][16 B]
   uint8_t* sB = sX + (size_t)kTPlanes * p.plane_bytes;                  // weight ring
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)kTStages * kTStageBytes);
@@ -143,7 +142,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) res_trunk_fwd_kernel(const _
         for (int cb = 0; cb < kTC / 32; ++cb)
           for (int g = 0; g < 9 / kTStageTaps; ++g, ++bi) {
             const int sb = bi % kTStages;
-            mbar_wait(&b_empty[sb], ((uint32_t)(bi / kTStages) & 1u) ^ 1u);
+            mbar_wait_parked(&b_empty[sb], ((uint32_t)(bi / kTStages) & 1u) ^ 1u);
             mbar_arrive_expect_tx(&b_full[sb], kTStageBytes);
             bulk_load_1d(sB + (size_t)sb * kTStageBytes, wsrc + ((size_t)cb * 9 + (size_t)g * kTStageTaps) * kTChunk, kTStageBytes,
                          &b_full[sb]);
@@ -162,7 +161,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) res_trunk_fwd_kernel(const _
     int bi = 0;
     for (int ci = 0; ci < nconv; ++ci) {
       if (ci > 0) {
-        TDBG(1, mbar_wait(x_ready, (uint32_t)(ci - 1) & 1u));      // the map holds this conv's input, the accumulators are drained
+        TDBG(1, mbar_wait_parked(x_ready, (uint32_t)(ci - 1) & 1u));      // the map holds this conv's input, the accumulators are drained
         tc_fence_after();
       }
       for (int cb = 0; cb < kTC / 32; ++cb)
@@ -211,7 +210,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) res_trunk_fwd_kernel(const _
       const int b = ci >> 1;
       const bool second = ci & 1;
       const bool last = second && b == p.nb - 1;
-      TDBG(2, mbar_wait_backoff(acc_full, (uint32_t)ci & 1u, 64));
+      TDBG(2, mbar_wait_parked(acc_full, (uint32_t)ci & 1u));
       tc_fence_after();
       const long long t_p1 = PBT_TRUNK_DBG ? clock64() : 0;
       // pass 1: accumulators -> 16 bit -> map (pad / overrun rows: zero) and global raw output
