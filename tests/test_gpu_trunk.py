@@ -97,3 +97,38 @@ def test_fused_trunk_bf16_and_bad_arguments():
     with pytest.raises(RuntimeError, match="res_trunk"):      # mismatching tensor
         ops.res_trunk_fwd([E(128, 8, 8)], [E(128, 8, 8)], [E(128, 8, 4)], [E(128, 8, 8)], wp, wp, st, st,
                           torch.zeros(1, 16, 8, 8, 8, device="cuda"), E(128, 8, 8), FP16)
+
+
+def test_generator_step_is_the_same_with_and_without_the_fused_trunk():
+    """whole GeneratorJ training pass (forward, loss, backward) with the trunk as one launch against the layer-by-layer launches:
+    both are 16-bit-operand evaluations of the same arithmetic, so they agree far inside the tolerance against the fp32 oracle"""
+    import os
+    import numpy as np
+    from pbt_b200.generator import GeneratorJ, _Engine
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sd = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(gold, "gen_cin9_trained.npz")).items()}
+    vec = np.load(os.path.join(gold, "gen_cin9_vectors.npz"))
+    x, t = torch.from_numpy(vec["p80_x"]).cuda(), torch.from_numpy(vec["p80_target"]).cuda()
+    out = {}
+    for fused in (True, False):
+        g = GeneratorJ(input_channels=9, use_bias=True)
+        g.load_state_dict(sd, strict=True)
+        g = g.cuda().train()
+        g._engine = _Engine(g)
+        g._engine.fused_trunk = fused
+        from pbt_b200._native import LAUNCHES
+        l0 = LAUNCHES[0]
+        y = g(x)
+        fwd_launches = LAUNCHES[0] - l0
+        loss = torch.nn.functional.l1_loss(y, t) * 4.0
+        loss.backward()
+        out[fused] = (y.detach(), float(loss.detach()), {k: p.grad.detach().clone() for k, p in g.named_parameters()}, fwd_launches)
+    yf, lf, gf, nf = out[True]
+    yl, ll, gl, nl = out[False]
+    assert nl - nf == 6 * 7 - 1                       # 7 blocks x (2 convs + 2 finalize + 2 apply) -> one launch
+    assert float((yf - yl).abs().max()) < 4e-3 and abs(lf - ll) < 2e-3 * abs(ll)
+    for k in gf:
+        if float(gl[k].abs().max()) < 1e-6:           # biases in front of an InstanceNorm: zero gradient
+            continue
+        cos = float(torch.nn.functional.cosine_similarity(gf[k].flatten().double(), gl[k].flatten().double(), dim=0))
+        assert cos > 0.995, (k, cos)
